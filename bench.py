@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — LUBM Q1-Q7 queries/sec (geomean) on B200, with roofline and CPU baseline.
+
+Contract:
+  step     = one pass over the query mix Q1..Q7 (each query executed once)
+  value    = geomean over Q1..Q7 of 1 / mean device latency (CUDA events on the engine's stream, store
+             and plan resident in HBM, blind mode = the reference's global_silent=1 protocol)
+  e2e      = same metric through the public C-ABI call wk_query_execute with HOST buffers: the plan
+             goes host->device inside the call, the projected result table comes back device->host
+             into pinned memory inside the timed region (non-blind)
+  roofline = the dominant kernel (largest share of device time): algorithmic bytes
+             / CUDA-event duration vs the measured HBM peak in MEASURED_PEAKS.json
+  --impl reference : the CPU oracle (faithful restatement of the reference engine; the reference
+             itself cannot be built here) timed on the host cores with the same store arrays.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+HEAVY = (1, 2, 3, 7)
+QUERIES = (1, 2, 3, 4, 5, 6, 7)
+
+
+def geomean(xs):
+    xs = [max(float(x), 1e-12) for x in xs]
+    return math.exp(sum(math.log(x) for x in xs) / len(xs))
+
+
+def load_plans(plan):
+    from conftest import load_query
+    return {q: load_query(q, plan)[:3] for q in QUERIES}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for i, nm in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_dataset(args):
+    from wukong_b200 import datagen, host
+    t0 = time.time()
+    tr = datagen.lubm(args.scale, seed=args.seed)
+    t1 = time.time()
+    hs = host.HostStore(tr)
+    t2 = time.time()
+    info = {"triples": int(tr.shape[0]), "keys": int(hs.num_keys), "gen_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2),
+            "header_mb": round(hs.num_slots * 16 / 1e6, 1), "edges_mb": round(hs.num_edges * 4 / 1e6, 1)}
+    return tr, hs, info
+
+
+def cpu_oracle_times(hs, plans, threads, heavy_reps, light_reps):
+    """per-query mean latency (us) of the CPU oracle engine on the product-built store arrays"""
+    from oracle import oracle as O
+    ost = O.Store.wrap(hs.vertices(), hs.edges(), hs.segs())
+    out = {}
+    for q in QUERIES:
+        pats, nvars, req = plans[q]
+        heavy = q in HEAVY
+        reps = heavy_reps if heavy else light_reps
+        mt = threads if heavy else 1
+        O.run_query([ost], pats, nvars, req, mt_factor=mt, blind=False, threaded=heavy)   # warm
+        us = []
+        for _ in range(reps):
+            r = O.run_query([ost], pats, nvars, req, mt_factor=mt, blind=False, threaded=heavy)
+            assert r.status == 0
+            us.append(r.usec)
+        out[q] = (float(np.mean(us)), int(r.rows), mt)
+    return out
+
+
+def peak_hbm():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    tr, hs, info = build_dataset(args)
+    plans = load_plans(args.plan)
+    threads = args.cpu_threads or os.cpu_count()
+    # each step = one bounded pass: heavy queries once with all host threads, light queries 50x
+    lat = {q: [] for q in QUERIES}
+    t_start = time.time()
+    for it in range(args.warmup + args.steps):
+        res = cpu_oracle_times(hs, plans, threads, 1, 50)
+        if it >= args.warmup:
+            for q in QUERIES:
+                lat[q].append(res[q][0])
+    mean = {q: float(np.mean(lat[q])) for q in QUERIES}
+    qps = [1e6 / mean[q] for q in QUERIES]
+    value = geomean(qps)
+    line = {"impl": "reference", "metric": "lubm_q1_q7_geomean_queries_per_sec", "value": value, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sum(mean.values()) / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "LUBM-%d Q1-Q7 (%s), seeded LUBM-shaped generator" % (args.scale, args.plan),
+                       "triples": info["triples"], "non_blind": True},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
+                             "sample": "per step: Q1,Q2,Q3,Q7 once with mt_factor=%d threads, Q4-Q6 50x single thread; "
+                                       "execute_patterns + projection only" % threads},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "latency_us": {"q%d" % q: mean[q] for q in QUERIES},
+            "wall_s": round(time.time() - t_start, 1)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="wukong_b200")
+    ap.add_argument("--scale", type=int, default=40, help="number of universities (LUBM-<scale>)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--plan", default="osdi16_plan")
+    ap.add_argument("--rbuf-mb", type=int, default=0)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    from wukong_b200 import capi, host
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+        if rank != 0:
+            ge.build()   # libraries exist by now; loads them
+    if capi.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+
+    tr, hs, info = build_dataset(args)
+    plans = load_plans(args.plan)
+    gst = hs.upload(local_rank)
+    rbuf = (args.rbuf_mb << 20) if args.rbuf_mb else max(256 << 20, min(16 << 30, int(info["triples"]) * 48))
+    eng = capi.Engine(gst, rbuf_bytes=rbuf)
+    out_tbl, _keep = capi.pinned_array(min(rbuf // 4, 1 << 28))
+
+    def barrier():
+        eng.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------
+    rows = {}
+    for _ in range(args.warmup):
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            _, _, r, c = host.time_query(eng, pats, nvars, req, 1, blind=False, table=out_tbl, flush=True)
+            rows[q] = (r, c)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_region0 = time.time()
+    # ---- timed: device-resident (value) and end-to-end (e2e), K steps, L2 flushed between queries ----
+    dev_us = {q: [] for q in QUERIES}
+    e2e_us = {q: [] for q in QUERIES}
+    eng.set_profiling(1)
+    for _ in range(args.steps):
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            _, d, _, _ = host.time_query(eng, pats, nvars, req, 1, blind=True, flush=True, device_times=True)
+            dev_us[q].append(float(d[0]))
+    eng.set_profiling(0)
+    for _ in range(args.steps):
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            w, _, _, _ = host.time_query(eng, pats, nvars, req, 1, blind=False, table=out_tbl, flush=True)
+            e2e_us[q].append(float(w[0]))
+    barrier()
+    t_region = time.time() - t_region0
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+
+    # ---- roofline of the dominant kernel (per-step CUDA events; separate pass) ---------------------------
+    eng.set_profiling(2)
+    agg = {}
+    for _ in range(max(3, min(args.steps, 10))):
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            eng.flush_l2()
+            rc, _, _, _ = eng.query(pats, nvars, req, blind=True)
+            assert rc == 0
+            for i, s in enumerate(eng.step_stats()):
+                a = agg.setdefault((q, i, s["kind"]), {"us": [], "bytes": s["algo_bytes"], "in_rows": s["in_rows"],
+                                                       "out_rows": s["out_rows"], "in_cols": s["in_cols"]})
+                a["us"].append(s["device_us"])
+    eng.set_profiling(0)
+    kern = [(k, v) for k, v in agg.items() if k[2] in ("k2u", "k2k", "k2c") and np.mean(v["us"]) > 0]
+    roof = None
+    steps_table = []
+    for k, v in sorted(agg.items()):
+        us = float(np.mean(v["us"])) if v["us"] else 0.0
+        steps_table.append({"q": k[0], "step": k[1], "kind": k[2], "in_rows": int(v["in_rows"]), "out_rows": int(v["out_rows"]),
+                            "algo_bytes": int(v["bytes"]), "device_us": round(us, 2),
+                            "gbs": round(v["bytes"] / us / 1e3, 1) if us > 0 else None})
+    if kern:
+        (kq, ki, kk), v = max(kern, key=lambda kv: float(np.mean(kv[1]["us"])))
+        us = float(np.mean(v["us"]))
+        peak, peak_src = peak_hbm()
+        ach = v["bytes"] / us / 1e3   # GB/s
+        roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": None, "kernel": "step_kernel<%s> (q%d step %d: %d rows x %d cols -> %d rows)" %
+                (kk, kq, ki, v["in_rows"], v["in_cols"], v["out_rows"]),
+                "algo_bytes_per_launch": int(v["bytes"]), "us_per_launch": round(us, 2), "peak_source": peak_src}
+
+    # ---- reduce over ranks (max latency), compute the metric ----------------------------------------------------
+    dev_mean = np.array([np.mean(dev_us[q]) for q in QUERIES])
+    e2e_mean = np.array([np.mean(e2e_us[q]) for q in QUERIES])
+    if dist is not None:
+        import torch
+        t = torch.tensor(np.concatenate([dev_mean, e2e_mean]), device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        arr = t.cpu().numpy()
+        dev_mean, e2e_mean = arr[:7], arr[7:]
+    # replicas: every rank answers its own stream of queries => whole-job rate = world x per-replica rate
+    value = geomean(world * 1e6 / dev_mean)
+    e2e = geomean(world * 1e6 / e2e_mean)
+    d2h = sum(rows[q][0] * rows[q][1] * 4 + 8 for q in QUERIES)
+    h2d = sum(len(plans[q][0]) * 16 + len(plans[q][2]) * 4 for q in QUERIES)
+
+    line = {"metric": "lubm_q1_q7_geomean_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dev_mean.sum() / 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "LUBM-%d Q1-Q7 (%s), seeded LUBM-shaped generator" % (args.scale, args.plan),
+                       "triples": info["triples"], "keys": info["keys"], "store_mb": info["header_mb"] + info["edges_mb"],
+                       "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                       "l2": "flushed (384 MB memset) before every timed query",
+                       "value_mode": "blind (row count only), device-resident", "e2e_mode": "non-blind, table D2H into pinned memory"},
+            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "latency_us": {"device": {"q%d" % q: round(float(dev_mean[i]), 2) for i, q in enumerate(QUERIES)},
+                           "e2e": {"q%d" % q: round(float(e2e_mean[i]), 2) for i, q in enumerate(QUERIES)}},
+            "rows": {"q%d" % q: int(rows[q][0]) for q in QUERIES}, "steps_table": steps_table,
+            "dataset": info, "timed_region_s": round(t_region, 2)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = args.cpu_threads or os.cpu_count()
+        res = cpu_oracle_times(hs, plans, threads, 3, 200)
+        cq = [1e6 / res[q][0] for q in QUERIES]
+        for q in QUERIES:
+            assert res[q][1] == rows[q][0], "GPU and CPU oracle disagree on q%d rows" % q
+        line["cpu_baseline"] = {"value": geomean(cq), "unit": "queries/s", "cores": threads, "kind": "port",
+                                "sample": "oracle engine on the same store arrays: Q1,Q2,Q3,Q7 3x with mt_factor=%d threads, "
+                                          "Q4-Q6 200x single thread; execute_patterns + projection" % threads,
+                                "latency_us": {"q%d" % q: round(res[q][0], 2) for q in QUERIES}}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/*
+ * wukong_b200 — C ABI of the B200-native graph-exploration engine.
+ *
+ * This is the drop-in boundary for ONE path of SJTU-IPADS/wukong: per-triple-pattern frontier
+ * expansion over the predicate-indexed cluster-hash graph store.  The reference has no plugin
+ * API; its one host->device seam is core/gpu/gpu_hash.hpp (GPUEngineParam + free functions,
+ * gpu_hash.hpp:43-150) consumed by the GPUEngineCuda method set (gpu_engine_cuda.hpp:45-409).
+ * Every entry point below names the reference interface it replaces (file:line relative to the
+ * reference tree).  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Conventions
+ *  - every function returns an int status: 0 = SUCCESS, 1..12 = the reference's error codes
+ *    (utils/errors.hpp:28-43), >= 100 = engine errors (CUDA failure, buffer overflow, bad args).
+ *    No exception crosses the ABI; the reference-side wrapper rethrows WukongException(code).
+ *  - one caller thread per wk_engine_t (like the single GPUAgent thread, gpu_agent.hpp:245-290);
+ *    several engines may share one wk_store_t.
+ *  - the binding table lives on the device between calls (engine-owned double buffer, like
+ *    GPUMem::res_inbuf/res_outbuf, gpu_mem.hpp:116-124) in the reference's layout: row-major
+ *    uint32 sid_t, nrows x ncols (query.hpp:425-443).
+ *  - `out_rows` may be NULL: the call is then only enqueued (no host synchronisation), which is
+ *    how a whole plan is chained without a sync per pattern.
+ */
+#ifndef WUKONG_B200_H
+#define WUKONG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint32_t wk_sid_t;  /* core/type.hpp:34-38 (sid_t, DTYPE_64BIT off) */
+
+enum { WK_DIR_IN = 0, WK_DIR_OUT = 1 };            /* core/type.hpp:127 dir_t */
+enum { WK_PREDICATE_ID = 0, WK_TYPE_ID = 1 };      /* store/vertex.hpp:38 */
+#define WK_NBITS_IDX 17                            /* store/vertex.hpp:34 */
+#define WK_ASSOCIATIVITY 8                         /* store/gstore.hpp:967 */
+
+/* status codes: utils/errors.hpp:28-43, then engine-specific */
+enum {
+    WK_SUCCESS = 0, WK_UNKNOWN_ERROR, WK_SYNTAX_ERROR, WK_UNKNOWN_PATTERN, WK_ATTR_DISABLE,
+    WK_NO_REQUIRED_VAR, WK_UNSUPPORT_UNION, WK_OBJ_ERROR, WK_VERTEX_INVALID, WK_UNKNOWN_SUB,
+    WK_SETTING_ERROR, WK_FIRST_PATTERN_ERROR, WK_UNKNOWN_FILTER,
+    WK_ERR_CUDA = 100,        /* a CUDA runtime call failed (reference: CUDA_ASSERT aborts, utils/gpu.hpp:26-37) */
+    WK_ERR_BAD_ARG = 101,
+    WK_ERR_RBUF_OVERFLOW = 102, /* result does not fit the result buffer (reference: ASSERT, gpu_engine_cuda.hpp:185) */
+    WK_ERR_NO_SEGMENT = 103,  /* pattern names a (pid,dir) segment that is not in the store */
+    WK_ERR_NO_DEVICE = 104,
+    WK_ERR_COMM = 105
+};
+
+/* 128-bit slot of the cluster-hash header region: store/vertex.hpp:152-155 (vertex_t).
+ *   key = ikey_t raw bits:  dir:1 | pid:17 | vid:46   (vertex.hpp:47-50)
+ *   ptr = iptr_t raw bits:  size:28 | off:34 | type:2 (vertex.hpp:116-119)               */
+typedef struct { uint64_t key; uint64_t ptr; } wk_vertex_t;
+
+/* one (index, pid, dir) segment: segid_t + rdf_seg_meta_t, store/meta.hpp:53-204.
+ * ext_start/ext_num describe the segment's indirect-header extent (informational: probes follow
+ * the chain pointers stored in the slots, so any number of extents works). */
+typedef struct {
+    int32_t index;   /* 0 normal segment, 1 index segment (vid == 0 keys)  */
+    int32_t dir;
+    uint32_t pid;
+    uint32_t _pad;
+    uint64_t num_keys, num_buckets, bucket_start, num_edges, edge_start, ext_start, ext_num;
+} wk_segmeta_t;
+
+/* one triple pattern after planning: SPARQLQuery::Pattern, core/query.hpp:95-116.
+ * ids < 0 are variables (-1, -2, ...), ids >= 0 constants. */
+typedef struct { int32_t subject, predicate, direction, object; } wk_pattern_t;
+
+typedef struct wk_store wk_store_t;
+typedef struct wk_engine wk_engine_t;
+
+/* per-step execution record of the last wk_query_execute (profiling mode only for device_us) */
+typedef struct {
+    int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project */
+    int32_t in_cols;
+    uint64_t in_rows, out_rows;
+    uint64_t buckets_visited;   /* sum over rows of L_i                      */
+    uint64_t edges_touched;     /* sum d_i (k2u) / sum s_i (k2k,k2c) / d (i2u,c2u)          */
+    uint64_t algo_bytes;        /* algorithmic bytes of the step, SURVEY.md §8d formula      */
+    float device_us;            /* CUDA-event time of the step's kernel(s); 0 if not profiled */
+    int32_t launches;
+} wk_step_stats_t;
+
+const char *wk_strerror(int code);
+int wk_version(void);
+int wk_device_count(int *count);
+
+/* ---- store ------------------------------------------------------------------------------------
+ * Replaces GPUCache(gmem, vertex_t*, edge_t*, map<segid_t, rdf_seg_meta_t>) (gpu_cache.hpp:425-467)
+ * and its segment paging: the whole store is uploaded once into flat HBM arrays. The host arrays
+ * stay owned by the caller (GStore::vertices / GStore::edges, gstore.hpp:962-963). */
+int wk_store_create(int device, const wk_vertex_t *vertices, uint64_t num_slots,
+                    const wk_sid_t *edges, uint64_t num_edges,
+                    const wk_segmeta_t *segs, int nsegs, wk_store_t **out);
+/* Adopt arrays that already live on `device` (e.g. produced by a device-side builder). */
+int wk_store_adopt(int device, wk_vertex_t *d_vertices, uint64_t num_slots, wk_sid_t *d_edges,
+                   uint64_t num_edges, const wk_segmeta_t *segs, int nsegs, int take_ownership,
+                   wk_store_t **out);
+int wk_store_destroy(wk_store_t *store);
+/* host-side probe of one key through the device arrays (debug / gsck-style checks) */
+int wk_store_get_edges(wk_store_t *store, wk_sid_t vid, wk_sid_t pid, int dir,
+                       wk_sid_t *dst, uint64_t cap, uint64_t *size);
+
+/* ---- engine -----------------------------------------------------------------------------------
+ * Replaces GPUEngineCuda(sid, GPUCache*, GPUMem*, GPUStreamPool*) (gpu_engine_cuda.hpp:80-85).
+ * rbuf_bytes is the size of EACH of the two result buffers (Global::gpu_rbuf_size_mb). */
+int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out);
+int wk_engine_destroy(wk_engine_t *engine);
+/* 0 off; 1 = CUDA events around each wk_query_execute (device time of the whole pattern phase);
+ * 2 = additionally one event pair per step (wk_step_stats_t.device_us) */
+int wk_engine_set_profiling(wk_engine_t *engine, int level);
+int wk_engine_sync(wk_engine_t *engine);                     /* CUDA_STREAM_SYNC */
+int wk_engine_reset(wk_engine_t *engine);                    /* empty table, 0 columns */
+
+/* load_result_buf(const Result&) / (const char*, size), gpu_engine_cuda.hpp:89-105 */
+int wk_table_upload(wk_engine_t *engine, const wk_sid_t *table, uint64_t nrows, int ncols);
+/* last-pattern device->host copy (thrust::copy into new_table), gpu_engine_cuda.hpp:189-196 */
+int wk_table_download(wk_engine_t *engine, wk_sid_t *dst, uint64_t cap_words,
+                      uint64_t *nrows, int *ncols);
+int wk_table_info(wk_engine_t *engine, uint64_t *nrows, int *ncols);
+
+/* ---- pattern primitives: GPUEngineCuda methods (gpu_engine_cuda.hpp:107-362) and the two seeds
+ * the reference keeps on the CPU (gpu_engine.hpp:63-123); semantics = core/engine/sparql.hpp ---- */
+/* index_to_unknown, sparql.hpp:194-231 (mt slicing :211-221) */
+int wk_index_to_unknown(wk_engine_t *engine, wk_sid_t tpid, int dir, int mt_tid, int mt_factor,
+                        uint64_t *out_rows);
+/* const_to_unknown, sparql.hpp:238-285 */
+int wk_const_to_unknown(wk_engine_t *engine, wk_sid_t vid, wk_sid_t pid, int dir, uint64_t *out_rows);
+/* known_to_unknown, sparql.hpp:295-407 / gpu_engine_cuda.hpp:112-197 */
+int wk_known_to_unknown(wk_engine_t *engine, int col_start, wk_sid_t pid, int dir, uint64_t *out_rows);
+/* known_to_known, sparql.hpp:416-476 / gpu_engine_cuda.hpp:199-281 */
+int wk_known_to_known(wk_engine_t *engine, int col_start, wk_sid_t pid, int dir, int col_end,
+                      uint64_t *out_rows);
+/* known_to_const, sparql.hpp:484-549 / gpu_engine_cuda.hpp:283-362 */
+int wk_known_to_const(wk_engine_t *engine, int col_start, wk_sid_t pid, int dir, wk_sid_t end_const,
+                      uint64_t *out_rows);
+/* final_process projection, sparql.hpp:1507-1550: out[i][j] = in[i][cols[j]] */
+int wk_project(wk_engine_t *engine, const int32_t *cols, int ncols_out, uint64_t *out_rows);
+
+/* ---- whole pattern phase: SPARQLEngine::execute_patterns + final_process for one engine
+ * (sparql.hpp:1113-1154, 1424-1551), i.e. what GPUAgent::execute_sparql_query drives
+ * (gpu_agent.hpp:170-243).  Dispatches each step by (var_stat(subject), var_stat(object)) exactly
+ * like execute_one_pattern (sparql.hpp:938-1061) and runs the plan without a host sync per step.
+ * blind != 0 mirrors Result::blind / Global::silent: only the row count comes back.
+ * If table != NULL (non-blind) the projected table is copied into it (cap in words). */
+int wk_query_execute(wk_engine_t *engine, const wk_pattern_t *patterns, int npatterns, int nvars,
+                     const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor,
+                     int blind, wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols);
+/* stats of the last wk_query_execute / primitive calls since the last reset */
+int wk_engine_num_steps(wk_engine_t *engine);
+int wk_engine_step_stats(wk_engine_t *engine, int step, wk_step_stats_t *out);
+uint64_t wk_engine_launch_count(wk_engine_t *engine);   /* kernels launched by this engine so far */
+/* device time (CUDA events on the engine's stream) of the last wk_query_execute; profiling >= 1 */
+int wk_engine_last_query_device_us(wk_engine_t *engine, float *us);
+/* measurement helpers: evict the L2 (overwrite a scratch buffer larger than L2, then sync) and
+ * page-locked host buffers for the host<->device copies of the end-to-end path */
+int wk_engine_flush_l2(wk_engine_t *engine);
+int wk_host_alloc(uint64_t bytes, void **out);
+int wk_host_free(void *ptr);
+
+/* ---- sharded execution (one process per GPU): generate_sub_query / gpu_shuffle_result_buf +
+ * gpu_split_result_buf (sparql.hpp:746-799; gpu_hash.cu:599-760; gpu_engine_cuda.hpp:364-407) --- */
+/* Bucketise the current table by row[col_start] % nparts into contiguous per-destination runs.
+ * part_rows[nparts] receives the run lengths (synchronises). */
+int wk_partition(wk_engine_t *engine, int col_start, int nparts, uint64_t *part_rows);
+/* Device pointer + rows of partition `part` after wk_partition (borrowed; valid until next call) */
+int wk_partition_ptr(wk_engine_t *engine, int part, const wk_sid_t **d_ptr, uint64_t *rows);
+/* Join a communicator: nccl_unique_id is the 128-byte ncclUniqueId created by rank 0. */
+int wk_comm_unique_id(void *id128);
+int wk_comm_init(wk_engine_t *engine, int nranks, int rank, const void *id128);
+/* wk_partition + all-to-all(v) of the partitions over NCCL; afterwards the table holds exactly the
+ * rows whose row[col_start] % nranks == rank. */
+int wk_exchange(wk_engine_t *engine, int col_start, uint64_t *out_rows);
+/* Sharded whole-query execution: like wk_query_execute, with the store sharded by vid % nranks
+ * and an exchange before every step whose start variable is not local (need_fork_join,
+ * sparql.hpp:802-814).  out_rows is this rank's share of the result. */
+int wk_query_execute_sharded(wk_engine_t *engine, const wk_pattern_t *patterns, int npatterns, int nvars,
+                             const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor,
+                             int blind, wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WUKONG_B200_H */

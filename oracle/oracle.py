@@ -114,7 +114,10 @@ class Store:
     def wrap(cls, vertices, edges, segs, num_servers=1, sid=0):
         v = np.ascontiguousarray(vertices, dtype=np.uint64).reshape(-1, 2)
         e = np.ascontiguousarray(edges, dtype=np.uint32)
-        sa = (SegMeta * len(segs))(*segs)
+        sa = (SegMeta * len(segs))()
+        for i, sg in enumerate(segs):   # accepts any struct with the same field names
+            for f, _t in SegMeta._fields_:
+                setattr(sa[i], f, getattr(sg, f))
         h = lib().wko_store_wrap(num_servers, sid, _ptr(v), v.shape[0], _ptr(e), e.shape[0],
                                  C.cast(sa, C.c_void_p), len(segs))
         return cls(h, keep=(v, e, sa))

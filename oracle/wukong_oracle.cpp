@@ -10,7 +10,7 @@
 //  and the reference cannot be compiled here (boost/TBB/MPI/zmq absent), so
 // this oracle is pinned only by (i) the gsck structural invariants (gchecker.hpp:132-360)
 // restated in wko_store_check, (ii) an independent brute-force triple-scan joiner in
-// tests/bruteforce.py, and (iii) committed golden fixtures generated from it (tests/golden/).
+// tests/sparql_mini.py (bruteforce_bgp), and (iii) committed golden fixtures generated from it (tests/golden/).
 // => "parity unpinned" against reference binaries; see DESIGN.md.
 //
 // All file:line citations are relative to /root/reference/.
@@ -872,9 +872,10 @@ static void run_query(Cluster &cl, const std::vector<Pattern> &patterns, int nva
             fin.append_result(acc);
         }
         fin.blind = blind;
-        fin.update_nrows();
-        final_process(fin);
-        if (blind) { fin.row_num = fin.get_row_num(); fin.result_table.clear(); }   // shrink(), query.hpp:619-630
+        // blind replies carry only row_num (accumulated by append_result, query.hpp:536-545); the
+        // table itself is dropped by shrink() (query.hpp:619-630) and final_process is skipped
+        if (!blind) { fin.update_nrows(); final_process(fin); }
+        else fin.result_table.clear();
     } catch (OracleError &e) {
         fin.status_code = e.code;   // sparql.hpp:1663-1667
         fin.result_table.clear();

@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/wukong_b200.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from conftest import ROOT
+from oracle import oracle as O
+from wukong_b200 import capi
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "wukong_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(wk_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree():
+    assert _header_symbols() == sorted(capi.DECLARED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    for name in _header_symbols():
+        assert hasattr(L, name), name
+    assert L.wk_version() >= 100
+    assert b"overflow" in L.wk_strerror(capi.WK_ERR_RBUF_OVERFLOW)
+
+
+def test_device_arithmetic_matches_oracle():
+    # the hash / key packing / multiply-shift modulo compiled into the CUDA library (host instances
+    # of the same __host__ __device__ functions the kernels use) against the oracle's
+    L, Lo = capi.lib(), O.lib()
+    rng = np.random.default_rng(3)
+    for k in [0, 1, (1 << 64) - 1] + [int(x) for x in rng.integers(0, 1 << 63, 2000)]:
+        assert L.wk_selftest_hash(k) == Lo.wko_hash_u64(k)
+    for vid, pid, d in [(0, 1, 0), (131072, 5, 1), ((1 << 32) - 1, (1 << 17) - 1, 1)]:
+        assert L.wk_selftest_make_key(vid, pid, d) == Lo.wko_make_key(vid, pid, d)
+    ds = [1, 2, 3, 5, 7, 8, 255, 256, 98317, 196613, 12582917, 201326611, 1610612741, (1 << 31) - 1, (1 << 32) - 1]
+    ds += [int(x) for x in rng.integers(1, 1 << 32, 200)]
+    for d in ds:
+        ns = [0, 1, d - 1, d, d + 1, (1 << 64) - 1, (1 << 63), (1 << 63) - 1] + [int(x) for x in rng.integers(0, 1 << 63, 300)]
+        ns += [(int(x) << 1) | 1 for x in rng.integers(1 << 62, 1 << 63, 100)]
+        for n in ns:
+            assert L.wk_selftest_fastmod(n, d) == n % d, (n, d)
+
+
+def test_compute_fails_loudly_without_gpu():
+    if capi.device_count() > 0:
+        return
+    v = np.zeros((8, 2), dtype=np.uint64)
+    e = np.zeros(1, dtype=np.uint32)
+    seg = capi.SegMeta()
+    seg.num_buckets = 1
+    try:
+        capi.Store(v, e, [seg])
+    except capi.WukongError as ex:
+        assert ex.code in (capi.WK_ERR_NO_DEVICE, capi.WK_ERR_CUDA)
+    else:
+        raise AssertionError("store creation must fail without a device (no CPU fallback)")

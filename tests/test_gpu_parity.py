@@ -1,0 +1,251 @@
+"""GPU parity tests: every CUDA path is called through the C ABI and compared bit-exactly (as a
+multiset of rows) with the CPU oracle on the same store arrays and the same inputs."""
+import numpy as np
+import pytest
+
+import sparql_mini as M
+from conftest import PLANS, load_query, rows_equal
+from oracle import oracle as O
+from wukong_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+P = {n: i for i, n in enumerate(M.LUBM_INDEX)}
+def pid(name): return P[M.UB + name + ">"]
+TYPE = 1
+
+
+@pytest.fixture(scope="module")
+def eng1(gstore1):
+    e = capi.Engine(gstore1, rbuf_bytes=64 << 20)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng2(gstore2):
+    e = capi.Engine(gstore2, rbuf_bytes=64 << 20)
+    yield e
+    e.close()
+
+
+def test_store_probe_matches_oracle(gstore1, ostore1, lubm1):
+    rng = np.random.default_rng(0)
+    t = lubm1[rng.integers(0, lubm1.shape[0], 60)]
+    for s, p, o in t.tolist():
+        assert (gstore1.get_edges(s, p, O.OUT) == ostore1.get_edges(s, p, O.OUT)).all()
+        assert (gstore1.get_edges(o, p, O.IN) == ostore1.get_edges(o, p, O.IN)).all()
+    assert gstore1.get_edges(12345, 5, O.OUT).size == 0
+
+
+@pytest.mark.parametrize("mt", [(0, 1), (0, 3), (2, 3), (1, 2)])
+def test_index_to_unknown(eng1, ostore1, mt):
+    for tp, d in [(pid("Course"), O.IN), (pid("GraduateStudent"), O.IN), (pid("memberOf"), O.IN),
+                  (pid("memberOf"), O.OUT), (pid("undergraduateDegreeFrom"), O.OUT)]:
+        want = ostore1.primitive(O.I2U, None, 0, tp, O.PREDICATE_ID, d, mt_tid=mt[0], mt_factor=mt[1])
+        eng1.reset()
+        n = eng1.index_to_unknown(tp, d, mt[0], mt[1])
+        got = eng1.download()
+        assert n == want.shape[0]
+        # a seed is a plain slice copy: identical order, not only the same multiset
+        assert (got == want).all()
+
+
+def test_const_to_unknown(eng1, ostore1):
+    dept0 = M.lubm_str2id("<http://www.Department0.University0.edu>")
+    univ0 = M.lubm_str2id("<http://www.University0.edu>")
+    for vid, p, d in [(dept0, pid("worksFor"), O.IN), (univ0, pid("subOrganizationOf"), O.IN),
+                      (dept0, pid("subOrganizationOf"), O.OUT), (dept0, pid("advisor"), O.IN)]:
+        want = ostore1.primitive(O.C2U, None, 0, vid, p, d)
+        eng1.reset()
+        n = eng1.const_to_unknown(vid, p, d)
+        assert n == want.shape[0]
+        got = eng1.download()
+        assert got.shape[0] == want.shape[0]
+        if n:
+            assert (got == want).all()
+
+
+def _seed_table(ostore, tp, d=O.IN, extra_cols=0, seed=0):
+    t = ostore.primitive(O.I2U, None, 0, tp, O.PREDICATE_ID, d)
+    if extra_cols:
+        rng = np.random.default_rng(seed)
+        t = np.concatenate([rng.integers(1 << 17, 1 << 20, (t.shape[0], extra_cols), dtype=np.uint32), t], axis=1)
+    return t
+
+
+@pytest.mark.parametrize("extra_cols", [0, 1, 2, 5])
+def test_known_to_unknown(eng1, ostore1, extra_cols):
+    cases = [(pid("GraduateStudent"), pid("memberOf"), O.OUT), (pid("Course"), pid("name"), O.OUT),
+             (pid("FullProfessor"), pid("advisor"), O.IN),          # fan-out > SMALL_DEG for some rows
+             (pid("Department"), pid("memberOf"), O.IN),            # hundreds of edges per row (warp path)
+             (pid("UndergraduateStudent"), pid("undergraduateDegreeFrom"), O.OUT),   # all misses
+             (pid("University"), pid("subOrganizationOf"), O.IN)]
+    for tp, p, d in cases:
+        tbl = _seed_table(ostore1, tp, extra_cols=extra_cols)
+        C = tbl.shape[1]
+        want = ostore1.primitive(O.K2U, tbl, C, C - 1, p, d)
+        eng1.upload(tbl)
+        n = eng1.known_to_unknown(C - 1, p, d)
+        got = eng1.download()
+        assert n == want.shape[0], (tp, p, d)
+        assert rows_equal(got, want), (tp, p, d)
+
+
+def test_known_to_unknown_type_index(eng1, ostore1):
+    # pid == TYPE_ID && dir == IN goes through the index segment (sparql.hpp:339-340)
+    tbl = np.array([[pid("Course")], [pid("FullProfessor")], [pid("University")], [9999]], dtype=np.uint32)
+    want = ostore1.primitive(O.K2U, tbl, 1, 0, TYPE, O.IN)
+    eng1.upload(tbl)
+    eng1.known_to_unknown(0, TYPE, O.IN)
+    assert rows_equal(eng1.download(), want)
+    # ... and the forward direction: every vertex -> its types
+    tbl = _seed_table(ostore1, pid("GraduateStudent"))
+    want = ostore1.primitive(O.K2U, tbl, 1, 0, TYPE, O.OUT)
+    eng1.upload(tbl)
+    eng1.known_to_unknown(0, TYPE, O.OUT)
+    assert rows_equal(eng1.download(), want)
+
+
+def test_hub_fanout(eng1, ostore1):
+    # the shared telephone literal has every person as IN-neighbour (thousands of edges for one row)
+    tel = 1 << 17
+    tbl = np.array([[7, tel], [8, 123456], [9, tel]], dtype=np.uint32)
+    want = ostore1.primitive(O.K2U, tbl, 2, 1, pid("telephone"), O.IN)
+    assert want.shape[0] > 10000
+    eng1.upload(tbl)
+    n = eng1.known_to_unknown(1, pid("telephone"), O.IN)
+    assert n == want.shape[0]
+    assert rows_equal(eng1.download(), want)
+    # filter over the same hub list (warp-cooperative scan, first/last/missing element)
+    lst = ostore1.get_edges(tel, pid("telephone"), O.IN)
+    for target in (int(lst[0]), int(lst[-1]), int(lst[len(lst) // 2]), 424242):
+        tbl = np.array([[tel, target], [tel, target + 1], [5, target]], dtype=np.uint32)
+        want = ostore1.primitive(O.K2K, tbl, 2, 0, pid("telephone"), O.IN, a_end=1)
+        eng1.upload(tbl)
+        eng1.known_to_known(0, pid("telephone"), O.IN, 1)
+        assert rows_equal(eng1.download(), want)
+        want = ostore1.primitive(O.K2C, tbl, 2, 0, pid("telephone"), O.IN, a_end=target)
+        eng1.upload(tbl)
+        eng1.known_to_const(0, pid("telephone"), O.IN, target)
+        assert rows_equal(eng1.download(), want)
+
+
+@pytest.mark.parametrize("extra_cols", [0, 2])
+def test_known_to_const_and_known(eng1, ostore1, extra_cols):
+    # k2c: type checks
+    for tp, typ in [(pid("memberOf"), pid("GraduateStudent")), (pid("memberOf"), pid("UndergraduateStudent")),
+                    (pid("worksFor"), pid("FullProfessor")), (pid("takesCourse"), pid("TeachingAssistant"))]:
+        tbl = _seed_table(ostore1, tp, extra_cols=extra_cols)
+        C = tbl.shape[1]
+        want = ostore1.primitive(O.K2C, tbl, C, C - 1, TYPE, O.OUT, a_end=typ)
+        eng1.upload(tbl)
+        n = eng1.known_to_const(C - 1, TYPE, O.OUT, typ)
+        assert n == want.shape[0]
+        assert rows_equal(eng1.download(), want)
+    # k2k: (student, dept) pairs filtered by advisor/worksFor consistency
+    tbl = _seed_table(ostore1, pid("advisor"), extra_cols=extra_cols)
+    C = tbl.shape[1]
+    t2 = ostore1.primitive(O.K2U, tbl, C, C - 1, pid("advisor"), O.OUT)
+    t3 = ostore1.primitive(O.K2U, t2, C + 1, C - 1, pid("takesCourse"), O.OUT)
+    want = ostore1.primitive(O.K2K, t3, C + 2, C, pid("teacherOf"), O.OUT, a_end=C + 1)
+    eng1.upload(t3)
+    n = eng1.known_to_known(C, pid("teacherOf"), O.OUT, C + 1)
+    assert n == want.shape[0] and n > 0
+    assert rows_equal(eng1.download(), want)
+
+
+def test_edge_cases(eng1, ostore1):
+    # empty input table
+    eng1.upload(np.zeros((0, 2), dtype=np.uint32), ncols=2)
+    assert eng1.known_to_unknown(1, pid("memberOf"), O.OUT) == 0
+    assert eng1.download().shape[0] == 0
+    # ragged sizes around the 256-row tile
+    base = _seed_table(ostore1, pid("takesCourse"))
+    for n in (1, 31, 32, 33, 255, 256, 257, 511, 513, 1000):
+        tbl = base[:n]
+        want = ostore1.primitive(O.K2U, tbl, 1, 0, pid("takesCourse"), O.OUT)
+        eng1.upload(tbl)
+        assert eng1.known_to_unknown(0, pid("takesCourse"), O.OUT) == want.shape[0]
+        assert rows_equal(eng1.download(), want)
+    # projection
+    tbl = np.arange(40, dtype=np.uint32).reshape(10, 4)
+    eng1.upload(tbl)
+    eng1.project([3, 0, 0])
+    assert (eng1.download() == tbl[:, [3, 0, 0]]).all()
+    # missing segment -> engine error, not a crash
+    eng1.upload(tbl)
+    with pytest.raises(capi.WukongError) as ei:
+        eng1.known_to_unknown(0, 77, O.OUT)
+    assert ei.value.code == capi.WK_ERR_NO_SEGMENT
+    # result buffer overflow is reported, not written past the end
+    small = capi.Engine(eng1.store, rbuf_bytes=8192)
+    tel = 1 << 17
+    small.upload(np.array([[tel]], dtype=np.uint32))
+    with pytest.raises(capi.WukongError) as ei:
+        small.known_to_unknown(0, pid("telephone"), O.IN)
+    assert ei.value.code == capi.WK_ERR_RBUF_OVERFLOW
+    small.close()
+
+
+def test_chained_without_sync(eng1, ostore1):
+    # a whole pattern chain enqueued without any host synchronisation in between
+    eng1.reset()
+    eng1.index_to_unknown(pid("FullProfessor"), O.IN, sync=False)
+    eng1.known_to_unknown(0, pid("advisor"), O.IN, sync=False)
+    eng1.known_to_const(1, TYPE, O.OUT, pid("UndergraduateStudent"), sync=False)
+    eng1.known_to_unknown(1, pid("takesCourse"), O.OUT, sync=False)
+    eng1.known_to_known(0, pid("teacherOf"), O.OUT, 2, sync=False)
+    got = eng1.download()
+    t = ostore1.primitive(O.I2U, None, 0, pid("FullProfessor"), O.PREDICATE_ID, O.IN)
+    t = ostore1.primitive(O.K2U, t, 1, 0, pid("advisor"), O.IN)
+    t = ostore1.primitive(O.K2C, t, 2, 1, TYPE, O.OUT, a_end=pid("UndergraduateStudent"))
+    t = ostore1.primitive(O.K2U, t, 2, 1, pid("takesCourse"), O.OUT)
+    t = ostore1.primitive(O.K2K, t, 3, 0, pid("teacherOf"), O.OUT, a_end=2)
+    assert rows_equal(got, t)
+    st = eng1.step_stats()
+    assert [s["kind"] for s in st] == ["i2u", "k2u", "k2c", "k2u", "k2k"]
+    assert st[-1]["out_rows"] == t.shape[0]
+    assert all(s["buckets_visited"] >= 1 for s in st)
+
+
+@pytest.mark.parametrize("q", range(1, 8))
+def test_queries_match_oracle(q, eng1, eng2, ostore1, ostore2):
+    for eng, ost in ((eng1, ostore1), (eng2, ostore2)):
+        for plan in PLANS:
+            pats, nvars, req, _ = load_query(q, plan)
+            want = O.run_query([ost], pats, nvars, req, mt_factor=1)
+            rc, rows, cols, tbl = eng.query(pats, nvars, req, mt_tid=0, mt_factor=1)
+            assert rc == 0
+            assert rows == want.rows and cols == want.cols, (q, plan)
+            assert rows_equal(tbl, want.table), (q, plan)
+            rc, rows_b, cols_b, _ = eng.query(pats, nvars, req, blind=True)
+            assert rc == 0 and rows_b == want.rows
+
+
+def test_mt_slices_partition_the_result(eng1, ostore1):
+    # mt_factor replicas (sparql.hpp:1064-1089): the union of the slices equals the whole result
+    for q in (1, 2, 7):
+        pats, nvars, req, _ = load_query(q, "osdi16_plan")
+        want = O.run_query([ostore1], pats, nvars, req, mt_factor=1)
+        parts = []
+        for tid in range(3):
+            rc, rows, cols, tbl = eng1.query(pats, nvars, req, mt_tid=tid, mt_factor=3)
+            assert rc == 0
+            if rows:
+                parts.append(tbl.copy())
+        got = np.concatenate(parts) if parts else np.zeros((0, want.cols), np.uint32)
+        assert rows_equal(got, want.table)
+
+
+def test_query_errors(eng1):
+    # same status codes as the reference engine (utils/errors.hpp) / the oracle
+    rc, *_ = eng1.query([(-1, 5, O.OUT, -2)], 2, [-1])
+    assert rc == 9          # UNKNOWN_SUB
+    univ0 = M.lubm_str2id("<http://www.University0.edu>")
+    rc, *_ = eng1.query([(18, 1, O.IN, -1), (univ0, 7, O.IN, -2)], 2, [-1])
+    assert rc == 11         # FIRST_PATTERN_ERROR
+    rc, *_ = eng1.query([(18, 5, O.IN, -1)], 1, [-1])
+    assert rc == 7          # OBJ_ERROR
+    rc, *_ = eng1.query([(18, 1, O.IN, -1)], 1, [])
+    assert rc == 5          # NO_REQUIRED_VAR

@@ -62,7 +62,7 @@ def build_cuda(force=False, verbose=False):
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", os.path.join(CSRC, "kernels")]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += srcs + ["-o", LIB_CUDA, "-lnccl"]
+    cmd += srcs + ["-o", LIB_CUDA]
     print("[build]", " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
     return LIB_CUDA

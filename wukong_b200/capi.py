@@ -1,0 +1,298 @@
+"""ctypes binding of the C ABI declared in include/wukong_b200.h (libwukong_b200.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_CUDA = os.path.join(_HERE, "libwukong_b200.so")
+
+IN, OUT = 0, 1
+PREDICATE_ID, TYPE_ID = 0, 1
+KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project"]
+
+WK_SUCCESS = 0
+WK_ERR_CUDA, WK_ERR_BAD_ARG, WK_ERR_RBUF_OVERFLOW, WK_ERR_NO_SEGMENT, WK_ERR_NO_DEVICE, WK_ERR_COMM = 100, 101, 102, 103, 104, 105
+
+
+class WukongError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        msg = lib().wk_strerror(code).decode() if _lib is not None else "?"
+        super().__init__("wukong_b200 status %d (%s) %s" % (code, msg, what))
+
+
+class SegMeta(C.Structure):
+    _fields_ = [("index", C.c_int32), ("dir", C.c_int32), ("pid", C.c_uint32), ("_pad", C.c_uint32),
+                ("num_keys", C.c_uint64), ("num_buckets", C.c_uint64), ("bucket_start", C.c_uint64),
+                ("num_edges", C.c_uint64), ("edge_start", C.c_uint64), ("ext_start", C.c_uint64),
+                ("ext_num", C.c_uint64)]
+
+
+class StepStats(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("in_cols", C.c_int32), ("in_rows", C.c_uint64), ("out_rows", C.c_uint64),
+                ("buckets_visited", C.c_uint64), ("edges_touched", C.c_uint64), ("algo_bytes", C.c_uint64),
+                ("device_us", C.c_float), ("launches", C.c_int32)]
+
+
+# every symbol include/wukong_b200.h declares (checked by tests/test_capi_symbols.py)
+DECLARED_SYMBOLS = [
+    "wk_strerror", "wk_version", "wk_device_count", "wk_store_create", "wk_store_adopt", "wk_store_destroy",
+    "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_sync",
+    "wk_engine_reset", "wk_table_upload", "wk_table_download", "wk_table_info", "wk_index_to_unknown",
+    "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_project",
+    "wk_query_execute", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
+    "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libwukong_b200.so.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_CUDA):
+        raise RuntimeError("libwukong_b200.so is missing: run `python -m wukong_b200.build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_CUDA, mode=C.RTLD_GLOBAL)
+    u64, u32, i32, vp, ci = C.c_uint64, C.c_uint32, C.c_int32, C.c_void_p, C.c_int
+    pu64 = C.POINTER(u64)
+    L.wk_strerror.restype = C.c_char_p
+    L.wk_strerror.argtypes = [ci]
+    L.wk_device_count.argtypes = [C.POINTER(ci)]
+    L.wk_store_create.argtypes = [ci, vp, u64, vp, u64, vp, ci, C.POINTER(vp)]
+    L.wk_store_adopt.argtypes = [ci, vp, u64, vp, u64, vp, ci, ci, C.POINTER(vp)]
+    L.wk_store_destroy.argtypes = [vp]
+    L.wk_store_get_edges.argtypes = [vp, u32, u32, ci, vp, u64, pu64]
+    L.wk_engine_create.argtypes = [vp, u64, C.POINTER(vp)]
+    L.wk_engine_destroy.argtypes = [vp]
+    L.wk_engine_set_profiling.argtypes = [vp, ci]
+    L.wk_engine_sync.argtypes = [vp]
+    L.wk_engine_reset.argtypes = [vp]
+    L.wk_table_upload.argtypes = [vp, vp, u64, ci]
+    L.wk_table_download.argtypes = [vp, vp, u64, pu64, C.POINTER(ci)]
+    L.wk_table_info.argtypes = [vp, pu64, C.POINTER(ci)]
+    L.wk_index_to_unknown.argtypes = [vp, u32, ci, ci, ci, pu64]
+    L.wk_const_to_unknown.argtypes = [vp, u32, u32, ci, pu64]
+    L.wk_known_to_unknown.argtypes = [vp, ci, u32, ci, pu64]
+    L.wk_known_to_known.argtypes = [vp, ci, u32, ci, ci, pu64]
+    L.wk_known_to_const.argtypes = [vp, ci, u32, ci, u32, pu64]
+    L.wk_project.argtypes = [vp, vp, ci, pu64]
+    L.wk_query_execute.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
+    L.wk_engine_num_steps.argtypes = [vp]
+    L.wk_engine_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
+    L.wk_engine_launch_count.restype = u64
+    L.wk_engine_launch_count.argtypes = [vp]
+    L.wk_engine_last_query_device_us.argtypes = [vp, C.POINTER(C.c_float)]
+    L.wk_engine_flush_l2.argtypes = [vp]
+    L.wk_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.wk_host_free.argtypes = [vp]
+    L.wk_selftest_hash.restype = u64
+    L.wk_selftest_hash.argtypes = [u64]
+    L.wk_selftest_fastmod.restype = u64
+    L.wk_selftest_fastmod.argtypes = [u64, u64]
+    L.wk_selftest_make_key.restype = u64
+    L.wk_selftest_make_key.argtypes = [u64, u32, u32]
+    _lib = L
+    return L
+
+
+def _check(rc, what=""):
+    if rc != 0:
+        raise WukongError(rc, what)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    n = C.c_int(0)
+    lib().wk_device_count(C.byref(n))
+    return n.value
+
+
+class Store:
+    """GPU-resident graph store (wk_store_t)."""
+
+    def __init__(self, vertices, edges, segs, device=0):
+        v = np.ascontiguousarray(vertices, dtype=np.uint64).reshape(-1, 2)
+        e = np.ascontiguousarray(edges, dtype=np.uint32)
+        sa = (SegMeta * len(segs))()
+        for i, s in enumerate(segs):
+            for f, _t in SegMeta._fields_:
+                setattr(sa[i], f, getattr(s, f))
+        h = C.c_void_p()
+        _check(lib().wk_store_create(device, _ptr(v), v.shape[0], _ptr(e), e.shape[0], C.cast(sa, C.c_void_p),
+                                     len(segs), C.byref(h)), "wk_store_create")
+        self.h = h
+        self.device = device
+
+    @classmethod
+    def adopt(cls, d_vertices, num_slots, d_edges, num_edges, segs, device=0, take_ownership=True):
+        self = cls.__new__(cls)
+        sa = (SegMeta * len(segs))(*segs)
+        h = C.c_void_p()
+        _check(lib().wk_store_adopt(device, d_vertices, num_slots, d_edges, num_edges, C.cast(sa, C.c_void_p),
+                                    len(segs), 1 if take_ownership else 0, C.byref(h)), "wk_store_adopt")
+        self.h = h
+        self.device = device
+        return self
+
+    def get_edges(self, vid, pid, d, cap=1 << 20):
+        out = np.empty(cap, dtype=np.uint32)
+        n = C.c_uint64(0)
+        _check(lib().wk_store_get_edges(self.h, vid, pid, d, _ptr(out), cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wk_store_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One query engine (wk_engine_t): device-resident binding table + pattern primitives."""
+
+    def __init__(self, store, rbuf_bytes=256 << 20):
+        self.store = store
+        h = C.c_void_p()
+        _check(lib().wk_engine_create(store.h, rbuf_bytes, C.byref(h)), "wk_engine_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().wk_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_profiling(self, level):
+        _check(lib().wk_engine_set_profiling(self.h, int(level)))
+
+    def last_query_device_us(self):
+        us = C.c_float(0)
+        _check(lib().wk_engine_last_query_device_us(self.h, C.byref(us)))
+        return us.value
+
+    def reset(self):
+        _check(lib().wk_engine_reset(self.h))
+
+    def sync(self):
+        _check(lib().wk_engine_sync(self.h))
+
+    def upload(self, table, ncols=None):
+        t = np.ascontiguousarray(table, dtype=np.uint32)
+        if ncols is None:
+            ncols = t.shape[1]
+        t = t.reshape(-1, ncols) if ncols else t.reshape(0, 0)
+        _check(lib().wk_table_upload(self.h, _ptr(t) if t.size else None, t.shape[0], ncols))
+
+    def info(self):
+        n, c = C.c_uint64(0), C.c_int(0)
+        _check(lib().wk_table_info(self.h, C.byref(n), C.byref(c)))
+        return n.value, c.value
+
+    def download(self):
+        n, c = self.info()
+        out = np.empty((max(n, 1), max(c, 1)), dtype=np.uint32)
+        n2, c2 = C.c_uint64(0), C.c_int(0)
+        _check(lib().wk_table_download(self.h, _ptr(out), out.size, C.byref(n2), C.byref(c2)))
+        return out[: n2.value, : c2.value].copy() if c2.value else np.zeros((0, 0), np.uint32)
+
+    def _rows(self, sync):
+        return C.byref(C.c_uint64(0)) if sync else None
+
+    def index_to_unknown(self, tpid, d, mt_tid=0, mt_factor=1, sync=True):
+        n = C.c_uint64(0)
+        _check(lib().wk_index_to_unknown(self.h, tpid, d, mt_tid, mt_factor, C.byref(n) if sync else None))
+        return n.value
+
+    def const_to_unknown(self, vid, pid, d, sync=True):
+        n = C.c_uint64(0)
+        _check(lib().wk_const_to_unknown(self.h, vid, pid, d, C.byref(n) if sync else None))
+        return n.value
+
+    def known_to_unknown(self, col_start, pid, d, sync=True):
+        n = C.c_uint64(0)
+        _check(lib().wk_known_to_unknown(self.h, col_start, pid, d, C.byref(n) if sync else None))
+        return n.value
+
+    def known_to_known(self, col_start, pid, d, col_end, sync=True):
+        n = C.c_uint64(0)
+        _check(lib().wk_known_to_known(self.h, col_start, pid, d, col_end, C.byref(n) if sync else None))
+        return n.value
+
+    def known_to_const(self, col_start, pid, d, end_const, sync=True):
+        n = C.c_uint64(0)
+        _check(lib().wk_known_to_const(self.h, col_start, pid, d, end_const, C.byref(n) if sync else None))
+        return n.value
+
+    def project(self, cols, sync=True):
+        a = np.array(cols, dtype=np.int32)
+        n = C.c_uint64(0)
+        _check(lib().wk_project(self.h, _ptr(a), len(cols), C.byref(n) if sync else None))
+        return n.value
+
+    def query(self, patterns, nvars, required_vars, mt_tid=0, mt_factor=1, blind=False, out=None):
+        """wk_query_execute.  Returns (status, rows, cols, table-or-None)."""
+        p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+        rv = np.array(required_vars, dtype=np.int32)
+        n, c = C.c_uint64(0), C.c_int(0)
+        if blind:
+            rc = lib().wk_query_execute(self.h, _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv), mt_tid, mt_factor, 1,
+                                        None, 0, C.byref(n), C.byref(c))
+            return rc, n.value, c.value, None
+        if out is None:
+            out = self._out_buf
+        rc = lib().wk_query_execute(self.h, _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv), mt_tid, mt_factor, 0,
+                                    _ptr(out), out.size, C.byref(n), C.byref(c))
+        tbl = None
+        if rc == 0:
+            tbl = out.reshape(-1)[: n.value * c.value].reshape(n.value, c.value) if c.value else np.zeros((0, 0), np.uint32)
+        return rc, n.value, c.value, tbl
+
+    _out_cache = None
+
+    @property
+    def _out_buf(self):
+        if self._out_cache is None:
+            self._out_cache = np.empty(64 << 20, dtype=np.uint32)
+        return self._out_cache
+
+    def flush_l2(self):
+        _check(lib().wk_engine_flush_l2(self.h))
+
+    def step_stats(self):
+        n = lib().wk_engine_num_steps(self.h)
+        out = []
+        for i in range(n):
+            s = StepStats()
+            _check(lib().wk_engine_step_stats(self.h, i, C.byref(s)))
+            out.append(dict(kind=KIND_NAMES[s.kind], in_cols=s.in_cols, in_rows=s.in_rows, out_rows=s.out_rows,
+                            buckets_visited=s.buckets_visited, edges_touched=s.edges_touched,
+                            algo_bytes=s.algo_bytes, device_us=s.device_us, launches=s.launches))
+        return out
+
+    def launch_count(self):
+        return lib().wk_engine_launch_count(self.h)
+
+
+def pinned_array(nwords):
+    """uint32 numpy array backed by page-locked host memory (cudaHostAlloc)."""
+    p = C.c_void_p()
+    _check(lib().wk_host_alloc(nwords * 4, C.byref(p)), "wk_host_alloc")
+    arr = np.frombuffer((C.c_uint32 * nwords).from_address(p.value), dtype=np.uint32)
+    return arr, p

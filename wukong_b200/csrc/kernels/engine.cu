@@ -1,0 +1,1209 @@
+// wukong_b200 GPU engine: kernels + C-ABI (include/wukong_b200.h).  sm_100a only.
+//
+// Design (B200-first, not a port of the reference's core/gpu):
+//   * the whole cluster-hash store lives in flat HBM arrays (no segment paging / block maps);
+//   * one fused kernel per pattern step: probe -> multiplicity -> tile scan -> materialise,
+//     persistent grid sized from the SM count, row counts stay on the device between steps
+//     so a plan runs without a host synchronisation per pattern (the reference does 5 launches,
+//     a D2H copy and 2 stream syncs per pattern: gpu_engine_cuda.hpp:112-197);
+//   * const-start ("light") plans run as ONE single-CTA kernel that interprets the plan and
+//     reports through mapped pinned memory (launch-latency bound, not bandwidth bound);
+//   * completion/row counts come back through a mapped pinned record, not a cudaMemcpy.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "wukong_b200.h"
+#include "wk_device.cuh"
+
+using namespace wk;
+
+// =============================================================================================
+// device-side control block and kernels
+// =============================================================================================
+enum { MAX_STEPS = 60, MAX_LIGHT_STEPS = 24 };
+enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5 };
+
+struct CtlBlock {
+    uint64_t counts[MAX_STEPS + 4];       // counts[s] = rows of the table that step s reads
+    uint64_t stats[2 * (MAX_STEPS + 4)];  // per step: buckets visited, edges touched
+    uint32_t status;                      // sticky: bit0 = result buffer overflow
+    uint32_t _pad;
+};
+
+struct HostRec {   // lives in mapped pinned host memory
+    volatile uint64_t seq;
+    uint64_t rows;
+    uint32_t status;
+    int32_t resume_step;     // light kernel: first step it did NOT run (== nsteps when finished)
+    uint32_t table_in_host;  // light kernel: projected table was written to the mapped staging area
+    uint32_t _pad;
+};
+
+struct SeedParam {
+    const uint4 *vertices;
+    const uint32_t *edges;
+    uint32_t *out;
+    uint64_t *out_count;
+    uint64_t out_cap_rows;
+    uint64_t *stats;
+    uint32_t *status;
+    uint64_t key;
+    uint64_t bucket_start;
+    FastMod fm;
+    int32_t mt_tid, mt_factor;
+};
+
+struct ProjParam {
+    const uint32_t *in;
+    uint32_t *out;
+    const uint64_t *in_count;
+    uint64_t *out_count;
+    uint64_t out_cap_rows;
+    uint32_t *status;
+    int32_t C, Cn;
+    int8_t cols[MAX_COLS];
+};
+
+__device__ __forceinline__ void flush_stats(uint64_t *stats, uint64_t visited, uint64_t edges) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        visited += __shfl_down_sync(0xFFFFFFFFu, visited, o);
+        edges += __shfl_down_sync(0xFFFFFFFFu, edges, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (visited) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)visited);
+        if (edges) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)edges);
+    }
+}
+
+// ---- known_to_{unknown,known,const}: one persistent fused kernel ---------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(CTA_THREADS) step_kernel(const StepParam p) {
+    extern __shared__ uint32_t dyn_rows[];
+    __shared__ TileSmem sm;
+    if (__ldcg(p.status) != 0) return;   // an earlier step overflowed: its output is not usable
+    const uint64_t N = ld_count(p.in_count);
+    uint64_t acc_visited = 0, acc_edges = 0;
+    for (uint64_t tile = blockIdx.x; tile * TILE_ROWS < N; tile += gridDim.x) {
+        const uint64_t row0 = tile * TILE_ROWS;
+        const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
+        process_tile<MODE>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
+    }
+    flush_stats(p.stats, acc_visited, acc_edges);
+}
+
+// ---- probe of ONE key by the first 8 lanes of a warp (seeds) ---------------------------------------
+__device__ __forceinline__ uint64_t probe_single(const uint4 *__restrict__ vertices, uint64_t key, uint64_t bucket,
+                                                 int lane, uint32_t &visited) {
+    uint64_t result = 0;
+    visited = 0;
+    while (true) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (lane < 8) v = ld_slot(vertices + (bucket * 8 + lane));
+        const uint64_t kk = (uint64_t)v.x | ((uint64_t)v.y << 32);
+        const uint64_t pp = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, lane < 7 && kk == key && kk != 0);
+        const uint64_t chain = __shfl_sync(0xFFFFFFFFu, kk, 7);
+        visited++;
+        if (hit) {
+            result = __shfl_sync(0xFFFFFFFFu, pp, __ffs(hit) - 1);
+            break;
+        }
+        if (chain == 0) break;
+        bucket = chain >> WK_KEY_VID_SHIFT;
+    }
+    return result;
+}
+
+// body shared by seed_kernel and the fused light kernel.  nblocks/bid describe the cooperating CTAs.
+__device__ __forceinline__ void seed_body(const SeedParam &p, uint64_t *s_ptr, uint32_t bid, uint32_t nblocks) {
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        uint32_t visited;
+        const uint64_t bucket = p.bucket_start + fastmod(hash_u64(p.key), p.fm);
+        const uint64_t ptr = probe_single(p.vertices, p.key, bucket, tid, visited);
+        if (tid == 0) {
+            *s_ptr = ptr;
+            if (bid == 0) atomicAdd((unsigned long long *)&p.stats[0], (unsigned long long)visited);
+        }
+    }
+    __syncthreads();
+    const uint64_t ptr = *s_ptr;
+    const uint64_t size = ptr_size(ptr), off = ptr_off(ptr);
+    // mt slicing exactly as sparql.hpp:211-221: length = sz / mt_factor, the last one takes the tail
+    const uint64_t start = (uint64_t)(p.mt_tid % p.mt_factor);
+    const uint64_t length = size / (uint64_t)p.mt_factor;
+    const uint64_t begin = start * length;
+    const uint64_t len = (start == (uint64_t)p.mt_factor - 1) ? (size - begin) : length;
+    if (len > p.out_cap_rows) {
+        if (bid == 0 && tid == 0) { atomicOr(p.status, 1u); *p.out_count = len; }
+        return;
+    }
+    const uint32_t *src = p.edges + off + begin;
+    for (uint64_t k = (uint64_t)bid * CTA_THREADS + tid; k < len; k += (uint64_t)nblocks * CTA_THREADS) p.out[k] = ld_edge(src + k);
+    if (bid == 0 && tid == 0) {
+        *p.out_count = len;
+        atomicAdd((unsigned long long *)&p.stats[1], (unsigned long long)len);
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) seed_kernel(const SeedParam p) {
+    __shared__ uint64_t s_ptr;
+    if (__ldcg(p.status) != 0) return;
+    seed_body(p, &s_ptr, blockIdx.x, gridDim.x);
+}
+
+// ---- final_process projection -------------------------------------------------------------------
+__device__ __forceinline__ void project_body(const ProjParam &p, uint64_t N, uint32_t bid, uint32_t nblocks) {
+    if (N > p.out_cap_rows) {
+        if (bid == 0 && threadIdx.x == 0) atomicOr(p.status, 1u);
+        return;
+    }
+    const uint64_t nwords = N * (uint64_t)p.Cn;
+    for (uint64_t w = (uint64_t)bid * CTA_THREADS + threadIdx.x; w < nwords; w += (uint64_t)nblocks * CTA_THREADS) {
+        const uint64_t r = w / (uint32_t)p.Cn;
+        const uint32_t j = (uint32_t)(w - r * (uint32_t)p.Cn);
+        p.out[w] = ld_table(p.in + r * (uint64_t)p.C + p.cols[j]);
+    }
+    if (bid == 0 && threadIdx.x == 0) *p.out_count = N;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) project_kernel(const ProjParam p) {
+    if (__ldcg(p.status) != 0) return;
+    project_body(p, ld_count(p.in_count), blockIdx.x, gridDim.x);
+}
+
+// ---- bookkeeping kernels -------------------------------------------------------------------------
+__global__ void set_count_kernel(uint64_t *dst, uint64_t v) { *dst = v; }
+
+__global__ void rebase_kernel(CtlBlock *ctl, int from, int to) {
+    const uint64_t v = ctl->counts[from];
+    for (int i = 0; i < MAX_STEPS + 4; i++) ctl->counts[i] = 0;
+    for (int i = 0; i < 2 * (MAX_STEPS + 4); i++) ctl->stats[i] = 0;
+    ctl->counts[to] = v;
+}
+
+__global__ void finish_kernel(const uint64_t *count, const uint32_t *status, HostRec *rec, uint64_t seq, int resume) {
+    rec->rows = ld_count(count);
+    rec->status = __ldcg(status);
+    rec->resume_step = resume;
+    rec->table_in_host = 0;
+    __threadfence_system();
+    rec->seq = seq;
+}
+
+// ---- fused single-CTA interpreter for const-start ("light") plans ------------------------------------
+struct LightStep {
+    SegParam seg;
+    uint64_t key;          // seeds
+    int32_t kind, C;
+    int32_t col_start, col_end;
+    uint32_t end_const, inv_c;
+    int32_t mt_tid, mt_factor;
+};
+
+struct LightPlan {
+    const uint4 *vertices;
+    const uint32_t *edges;
+    uint32_t *buf[2];
+    CtlBlock *ctl;
+    HostRec *rec;
+    uint32_t *host_table;       // mapped staging area (device pointer), may be null
+    uint64_t host_table_words;
+    uint64_t cap_words;         // per result buffer
+    uint64_t escalate_rows;     // hand over to the multi-CTA path beyond this many rows
+    uint64_t seq;
+    int32_t nsteps, first_step; // steps [first_step, nsteps) are run; table of step s is in buf[s & 1]
+    int32_t do_project, proj_n, final_cols, _pad;
+    int8_t proj_cols[MAX_COLS];
+    LightStep steps[MAX_LIGHT_STEPS];
+};
+
+__global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
+    extern __shared__ uint32_t dyn_rows[];
+    __shared__ TileSmem sm;
+    __shared__ uint64_t s_ptr;
+    const int tid = threadIdx.x;
+    CtlBlock *ctl = plan.ctl;
+    int s = plan.first_step;
+    int ncols_final = plan.final_cols;
+    bool stopped = false;
+    for (; s < plan.nsteps; s++) {
+        const LightStep &ls = plan.steps[s];
+        uint32_t *in = plan.buf[s & 1], *out = plan.buf[(s + 1) & 1];
+        uint64_t acc_visited = 0, acc_edges = 0;
+        if (ls.kind == KIND_I2U || ls.kind == KIND_C2U) {
+            SeedParam sp;
+            sp.vertices = plan.vertices; sp.edges = plan.edges; sp.out = out;
+            sp.out_count = &ctl->counts[s + 1]; sp.out_cap_rows = plan.cap_words;
+            sp.stats = &ctl->stats[2 * s]; sp.status = &ctl->status;
+            sp.key = ls.key; sp.bucket_start = ls.seg.bucket_start; sp.fm = ls.seg.fm;
+            sp.mt_tid = ls.mt_tid; sp.mt_factor = ls.mt_factor;
+            seed_body(sp, &s_ptr, 0, 1);
+        } else {
+            StepParam p;
+            p.vertices = plan.vertices; p.edges = plan.edges; p.in = in; p.out = out;
+            p.in_count = &ctl->counts[s]; p.out_count = &ctl->counts[s + 1];
+            const int Cout = (ls.kind == KIND_K2U) ? ls.C + 1 : ls.C;
+            p.out_cap_rows = plan.cap_words / (uint64_t)Cout;
+            p.stats = &ctl->stats[2 * s]; p.status = &ctl->status;
+            p.seg = ls.seg; p.C = ls.C; p.col_start = ls.col_start; p.col_end = ls.col_end;
+            p.end_const = ls.end_const; p.inv_c = ls.inv_c; p._pad = 0;
+            const uint64_t N = ld_count(p.in_count);
+            for (uint64_t row0 = 0; row0 < N; row0 += TILE_ROWS) {
+                const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
+                if (ls.kind == KIND_K2U) process_tile<MODE_K2U>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
+                else if (ls.kind == KIND_K2K) process_tile<MODE_K2K>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
+                else process_tile<MODE_K2C>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
+            }
+            flush_stats(&ctl->stats[2 * s], acc_visited, acc_edges);
+        }
+        __syncthreads();   // this CTA's global writes (table, counters) are visible to all its threads
+        if (__ldcg(&ctl->status) != 0) { stopped = true; s++; break; }
+        if (s + 1 < plan.nsteps && ld_count(&ctl->counts[s + 1]) > plan.escalate_rows) { stopped = true; s++; break; }
+    }
+    const int done_steps = s;   // table now in buf[done_steps & 1], rows in counts[done_steps]
+    uint64_t rows = ld_count(&ctl->counts[done_steps]);
+    uint32_t table_in_host = 0;
+    const uint32_t status = __ldcg(&ctl->status);
+    if (!stopped && status == 0 && plan.do_project && rows > 0) {
+        // final_process projection, straight into the mapped staging area when it fits
+        ProjParam pp;
+        pp.in = plan.buf[done_steps & 1];
+        pp.in_count = &ctl->counts[done_steps];
+        pp.out_count = &ctl->counts[done_steps + 1];
+        pp.status = &ctl->status;
+        pp.C = ncols_final; pp.Cn = plan.proj_n;
+        for (int i = 0; i < MAX_COLS; i++) pp.cols[i] = plan.proj_cols[i];
+        const uint64_t words = rows * (uint64_t)plan.proj_n;
+        if (plan.host_table && words <= plan.host_table_words) {
+            pp.out = plan.host_table; pp.out_cap_rows = rows;
+            table_in_host = 1;
+        } else {
+            pp.out = plan.buf[(done_steps + 1) & 1]; pp.out_cap_rows = plan.cap_words / (uint64_t)plan.proj_n;
+        }
+        project_body(pp, rows, 0, 1);
+        __threadfence_system();   // every thread's stores (possibly to mapped host memory) before the record
+        __syncthreads();
+    }
+    if (tid == 0) {
+        HostRec *rec = plan.rec;
+        rec->rows = rows;
+        rec->status = __ldcg(&ctl->status);
+        rec->resume_step = done_steps;
+        rec->table_in_host = table_in_host;
+        __threadfence_system();
+        rec->seq = plan.seq;
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess) {                                                                      \
+            fprintf(stderr, "[wukong_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                    cudaGetErrorString(_e));                                                          \
+            return WK_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+typedef std::tuple<int, uint32_t, int> SegKey;   // (index, pid, dir)
+
+struct wk_store {
+    int device = 0;
+    uint4 *d_vertices = nullptr;
+    uint32_t *d_edges = nullptr;
+    uint64_t num_slots = 0, num_edges = 0;
+    bool owns = true;
+    std::map<SegKey, wk_segmeta_t> segs;
+};
+
+struct StepRecord {
+    int kind = 0, in_cols = 0, launches = 0;
+    int s = 0;   // index into CtlBlock::counts / stats
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+struct wk_engine {
+    wk_store *store = nullptr;
+    cudaStream_t stream = nullptr;
+    uint32_t *buf[2] = {nullptr, nullptr};
+    uint64_t cap_words = 0;
+    CtlBlock *d_ctl = nullptr;
+    HostRec *h_rec = nullptr, *d_rec = nullptr;
+    uint32_t *h_stage = nullptr, *d_stage = nullptr;
+    uint64_t stage_words = 0;
+    int ncols = 0;
+    int step = 0;           // table is in buf[step & 1], its row count in ctl.counts[step]
+    uint64_t seq = 0;
+    int profiling = 0;   // 0 off, 1 query-level CUDA events, 2 also per-step events
+    cudaEvent_t q_ev0 = nullptr, q_ev1 = nullptr;
+    bool q_timed = false;
+    int num_sms = 148;
+    int occ[3] = {1, 1, 1};
+    uint64_t launches = 0;
+    uint64_t light_escalate_rows = 4096;
+    void *d_flush = nullptr;             // > L2-sized scratch for wk_engine_flush_l2
+    size_t flush_bytes = 0;
+    std::vector<StepRecord> recs;        // one per step since the last reset
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_next = 0;
+    // snapshot of per-step stats taken at the last synchronising call
+    std::vector<wk_step_stats_t> stats;
+};
+
+static const char *k_errs[] = {"success", "unknown error", "syntax error", "unsupported triple pattern",
+                               "attribute support disabled", "no required variables", "unsupported UNION",
+                               "object should not be an index", "subject or object is not valid",
+                               "triple pattern should not start from unknown subject", "setting error",
+                               "const_X_X or index_X_X must be the first pattern", "unsupported filter"};
+
+static inline bool is_tpid(int64_t id) { return id > 1 && id < (1 << WK_NBITS_IDX); }
+
+static const wk_segmeta_t *find_seg(const wk_store *st, int index, uint32_t pid, int dir) {
+    auto it = st->segs.find(SegKey(index, pid, dir));
+    if (it == st->segs.end() || it->second.num_buckets == 0) return nullptr;
+    return &it->second;
+}
+// segment of a key, store/meta.hpp:143-153 (segid_t(const ikey_t&))
+static const wk_segmeta_t *seg_of_key(const wk_store *st, uint64_t vid, uint32_t pid, int dir) {
+    return vid == 0 ? find_seg(st, 1, WK_PREDICATE_ID, dir) : find_seg(st, 0, pid, dir);
+}
+
+static SegParam make_segparam(const wk_segmeta_t *m, uint32_t pid, int dir, bool index_mode) {
+    SegParam s;
+    s.bucket_start = m->bucket_start;
+    s.fm = make_fastmod(m->num_buckets);
+    s.pid = pid;
+    s.dir = (uint32_t)dir;
+    s.index_mode = index_mode ? 1u : 0u;
+    s._pad = 0;
+    return s;
+}
+
+static cudaEvent_t get_event(wk_engine *e) {
+    if (e->event_next == e->event_pool.size()) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+        e->event_pool.push_back(ev);
+    }
+    return e->event_pool[e->event_next++];
+}
+
+static StepRecord &begin_step(wk_engine *e, int kind, int in_cols) {
+    e->recs.emplace_back();
+    StepRecord &r = e->recs.back();
+    r.kind = kind;
+    r.in_cols = in_cols;
+    r.s = e->step;
+    if (e->profiling >= 2) {
+        r.ev0 = get_event(e);
+        r.ev1 = get_event(e);
+        if (r.ev0 && r.ev1) { cudaEventRecord(r.ev0, e->stream); r.timed = true; }
+    }
+    return r;
+}
+static void end_step(wk_engine *e, StepRecord &r, int launches) {
+    r.launches = launches;
+    e->launches += launches;
+    if (r.timed) cudaEventRecord(r.ev1, e->stream);
+}
+
+static int reset_ctl(wk_engine *e) {
+    CUDA_TRY(cudaMemsetAsync(e->d_ctl, 0, sizeof(CtlBlock), e->stream));
+    e->step = 0;
+    e->recs.clear();
+    e->event_next = 0;
+    return WK_SUCCESS;
+}
+
+// make room for one more step in the control block (keeps buffer parity)
+static int ensure_step_room(wk_engine *e) {
+    if (e->step < MAX_STEPS) return WK_SUCCESS;
+    const int to = e->step & 1;
+    rebase_kernel<<<1, 1, 0, e->stream>>>(e->d_ctl, e->step, to);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    e->step = to;
+    e->recs.clear();
+    e->event_next = 0;
+    return WK_SUCCESS;
+}
+
+// wait for the mapped completion record (spin; falls back to stream status to catch faults)
+static int wait_record(wk_engine *e, uint64_t seq) {
+    uint32_t spins = 0;
+    while (e->h_rec->seq != seq) {
+        if ((++spins & 0x3FF) == 0) {
+            cudaError_t q = cudaStreamQuery(e->stream);
+            if (q == cudaSuccess) {
+                if (e->h_rec->seq == seq) break;
+                CUDA_TRY(cudaStreamSynchronize(e->stream));
+                if (e->h_rec->seq == seq) break;
+                fprintf(stderr, "[wukong_b200] completion record missing (seq %llu)\n", (unsigned long long)seq);
+                return WK_ERR_CUDA;
+            } else if (q != cudaErrorNotReady) {
+                CUDA_TRY(q);
+            }
+        }
+    }
+    return WK_SUCCESS;
+}
+
+// enqueue the completion record for the current table and wait for it
+static int sync_rows(wk_engine *e, uint64_t *rows) {
+    const uint64_t seq = ++e->seq;
+    finish_kernel<<<1, 1, 0, e->stream>>>(&e->d_ctl->counts[e->step], &e->d_ctl->status, e->d_rec, seq, e->step);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    int rc = wait_record(e, seq);
+    if (rc) return rc;
+    if (rows) *rows = e->h_rec->rows;
+    if (e->h_rec->status & 1u) return WK_ERR_RBUF_OVERFLOW;
+    return WK_SUCCESS;
+}
+
+static size_t rows_smem(int C) { return (size_t)TILE_ROWS * (size_t)(C | 1) * sizeof(uint32_t); }
+
+template <int MODE>
+static int launch_step(wk_engine *e, const StepParam &p) {
+    const int grid = e->num_sms * e->occ[MODE];
+    step_kernel<MODE><<<grid, CTA_THREADS, rows_smem(p.C), e->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return WK_SUCCESS;
+}
+
+// ---- enqueue one known_to_* step on the multi-CTA path ------------------------------------------
+static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, int dir, int col_end, uint32_t end_const) {
+    if (e->ncols <= 0 || e->ncols > MAX_COLS - 1) return e->ncols <= 0 ? WK_FIRST_PATTERN_ERROR : WK_ERR_BAD_ARG;
+    if (col_start < 0 || col_start >= e->ncols) return WK_VERTEX_INVALID;
+    if (kind == KIND_K2K && (col_end < 0 || col_end >= e->ncols)) return WK_VERTEX_INVALID;
+    if (dir != WK_DIR_IN && dir != WK_DIR_OUT) return WK_ERR_BAD_ARG;
+    const bool index_mode = (kind == KIND_K2U && pid == WK_TYPE_ID && dir == WK_DIR_IN);   // sparql.hpp:339-340
+    const wk_segmeta_t *m = index_mode ? find_seg(e->store, 1, WK_PREDICATE_ID, dir) : find_seg(e->store, 0, pid, dir);
+    if (!m) return WK_ERR_NO_SEGMENT;
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    const int s = e->step;
+    StepParam p;
+    memset(&p, 0, sizeof(p));
+    p.vertices = e->store->d_vertices;
+    p.edges = e->store->d_edges;
+    p.in = e->buf[s & 1];
+    p.out = e->buf[(s + 1) & 1];
+    p.in_count = &e->d_ctl->counts[s];
+    p.out_count = &e->d_ctl->counts[s + 1];
+    const int Cout = (kind == KIND_K2U) ? e->ncols + 1 : e->ncols;
+    p.out_cap_rows = e->cap_words / (uint64_t)Cout;
+    p.stats = &e->d_ctl->stats[2 * s];
+    p.status = &e->d_ctl->status;
+    p.seg = make_segparam(m, pid, dir, index_mode);
+    p.C = e->ncols;
+    p.col_start = col_start;
+    p.col_end = col_end;
+    p.end_const = end_const;
+    p.inv_c = ((1u << 20) + (uint32_t)e->ncols - 1) / (uint32_t)e->ncols;
+    StepRecord &r = begin_step(e, kind, e->ncols);
+    if (kind == KIND_K2U) rc = launch_step<MODE_K2U>(e, p);
+    else if (kind == KIND_K2K) rc = launch_step<MODE_K2K>(e, p);
+    else rc = launch_step<MODE_K2C>(e, p);
+    if (rc) return rc;
+    end_step(e, r, 1);
+    e->step = s + 1;
+    e->ncols = Cout;
+    return WK_SUCCESS;
+}
+
+static int enqueue_seed(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int dir, int mt_tid, int mt_factor) {
+    if (e->ncols != 0) return WK_FIRST_PATTERN_ERROR;
+    if (dir != WK_DIR_IN && dir != WK_DIR_OUT) return WK_ERR_BAD_ARG;
+    if (mt_factor < 1) mt_factor = 1;
+    const wk_segmeta_t *m = seg_of_key(e->store, vid, pid, dir);
+    if (!m) return WK_ERR_NO_SEGMENT;
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    const int s = e->step;
+    SeedParam p;
+    memset(&p, 0, sizeof(p));
+    p.vertices = e->store->d_vertices;
+    p.edges = e->store->d_edges;
+    p.out = e->buf[(s + 1) & 1];
+    p.out_count = &e->d_ctl->counts[s + 1];
+    p.out_cap_rows = e->cap_words;
+    p.stats = &e->d_ctl->stats[2 * s];
+    p.status = &e->d_ctl->status;
+    p.key = make_key(vid, pid, (uint32_t)dir);
+    p.bucket_start = m->bucket_start;
+    p.fm = make_fastmod(m->num_buckets);
+    p.mt_tid = mt_tid;
+    p.mt_factor = mt_factor;
+    StepRecord &r = begin_step(e, kind, 0);
+    seed_kernel<<<e->num_sms * 2, CTA_THREADS, 0, e->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    end_step(e, r, 1);
+    e->step = s + 1;
+    e->ncols = 1;
+    return WK_SUCCESS;
+}
+
+static int enqueue_project(wk_engine *e, const int32_t *cols, int n) {
+    if (n <= 0 || n > MAX_COLS) return WK_NO_REQUIRED_VAR;
+    if (e->ncols <= 0) return WK_ERR_BAD_ARG;
+    for (int i = 0; i < n; i++)
+        if (cols[i] < 0 || cols[i] >= e->ncols) return WK_VERTEX_INVALID;
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    const int s = e->step;
+    ProjParam p;
+    memset(&p, 0, sizeof(p));
+    p.in = e->buf[s & 1];
+    p.out = e->buf[(s + 1) & 1];
+    p.in_count = &e->d_ctl->counts[s];
+    p.out_count = &e->d_ctl->counts[s + 1];
+    p.out_cap_rows = e->cap_words / (uint64_t)n;
+    p.status = &e->d_ctl->status;
+    p.C = e->ncols;
+    p.Cn = n;
+    for (int i = 0; i < n; i++) p.cols[i] = (int8_t)cols[i];
+    StepRecord &r = begin_step(e, KIND_PROJECT, e->ncols);
+    project_kernel<<<e->num_sms * 4, CTA_THREADS, 0, e->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    end_step(e, r, 1);
+    e->step = s + 1;
+    e->ncols = n;
+    return WK_SUCCESS;
+}
+
+// copy per-step counters back and derive the algorithmic bytes
+static int snapshot_stats(wk_engine *e) {
+    CtlBlock h;
+    CUDA_TRY(cudaMemcpyAsync(&h, e->d_ctl, sizeof(CtlBlock), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->stats.clear();
+    for (size_t i = 0; i < e->recs.size(); i++) {
+        const StepRecord &r = e->recs[i];
+        const int s = r.s;
+        wk_step_stats_t st;
+        memset(&st, 0, sizeof(st));
+        st.kind = r.kind;
+        st.in_cols = r.in_cols;
+        st.in_rows = (r.kind == KIND_I2U || r.kind == KIND_C2U) ? 0 : h.counts[s];
+        st.out_rows = h.counts[s + 1];
+        st.buckets_visited = h.stats[2 * s];
+        st.edges_touched = h.stats[2 * s + 1];
+        st.launches = r.launches;
+        const uint64_t C = (uint64_t)r.in_cols, N = st.in_rows, R = st.out_rows;
+        switch (r.kind) {
+        case KIND_K2U: st.algo_bytes = 4 * C * N + 128 * st.buckets_visited + 4 * st.edges_touched + 4 * (C + 1) * R; break;
+        case KIND_K2K:
+        case KIND_K2C: st.algo_bytes = 4 * C * N + 128 * st.buckets_visited + 4 * st.edges_touched + 4 * C * R; break;
+        case KIND_I2U:
+        case KIND_C2U: st.algo_bytes = 128 * st.buckets_visited + 4 * R + 4 * R; break;
+        default: st.algo_bytes = 4 * C * R + 4 * (uint64_t)e->ncols * R; break;
+        }
+        if (r.timed) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r.ev0, r.ev1) == cudaSuccess) st.device_us = ms * 1000.0f;
+        }
+        e->stats.push_back(st);
+    }
+    return WK_SUCCESS;
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char *wk_strerror(int code) {
+    if (code >= 0 && code <= WK_UNKNOWN_FILTER) return k_errs[code];
+    switch (code) {
+    case WK_ERR_CUDA: return "CUDA runtime error";
+    case WK_ERR_BAD_ARG: return "bad argument";
+    case WK_ERR_RBUF_OVERFLOW: return "result buffer overflow (raise rbuf_bytes / global_gpu_rbuf_size_mb)";
+    case WK_ERR_NO_SEGMENT: return "no such (pid, dir) segment in the store";
+    case WK_ERR_NO_DEVICE: return "no CUDA device";
+    case WK_ERR_COMM: return "communicator not initialised";
+    default: return "unknown status";
+    }
+}
+
+int wk_version(void) { return 100; }
+
+int wk_device_count(int *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = (e == cudaSuccess) ? n : 0;
+    return (e == cudaSuccess && n > 0) ? WK_SUCCESS : WK_ERR_NO_DEVICE;
+}
+
+static int store_set_segs(wk_store *st, const wk_segmeta_t *segs, int nsegs) {
+    for (int i = 0; i < nsegs; i++) {
+        if (segs[i].num_buckets >= (1ull << 32)) return WK_ERR_BAD_ARG;
+        if (segs[i].num_buckets && segs[i].bucket_start + segs[i].num_buckets > st->num_slots / WK_ASSOCIATIVITY) return WK_ERR_BAD_ARG;
+        st->segs[SegKey(segs[i].index, segs[i].pid, segs[i].dir)] = segs[i];
+    }
+    return WK_SUCCESS;
+}
+
+int wk_store_create(int device, const wk_vertex_t *vertices, uint64_t num_slots, const wk_sid_t *edges,
+                    uint64_t num_edges, const wk_segmeta_t *segs, int nsegs, wk_store_t **out) {
+    if (!vertices || !segs || !out || num_slots == 0 || (num_slots % WK_ASSOCIATIVITY) != 0) return WK_ERR_BAD_ARG;
+    if (num_slots / WK_ASSOCIATIVITY >= (1ull << 32)) return WK_ERR_BAD_ARG;   // bucket ids are 32-bit on the device
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return WK_ERR_NO_DEVICE;
+    CUDA_TRY(cudaSetDevice(device));
+    wk_store *st = new wk_store();
+    st->device = device;
+    st->num_slots = num_slots;
+    st->num_edges = num_edges;
+    int rc = store_set_segs(st, segs, nsegs);
+    if (rc) { delete st; return rc; }
+    CUDA_TRY(cudaMalloc((void **)&st->d_vertices, num_slots * sizeof(uint4)));
+    CUDA_TRY(cudaMalloc((void **)&st->d_edges, (num_edges ? num_edges : 1) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(st->d_vertices, vertices, num_slots * sizeof(uint4), cudaMemcpyHostToDevice));
+    if (num_edges) CUDA_TRY(cudaMemcpy(st->d_edges, edges, num_edges * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    *out = st;
+    return WK_SUCCESS;
+}
+
+int wk_store_adopt(int device, wk_vertex_t *d_vertices, uint64_t num_slots, wk_sid_t *d_edges, uint64_t num_edges,
+                   const wk_segmeta_t *segs, int nsegs, int take_ownership, wk_store_t **out) {
+    if (!d_vertices || !segs || !out || num_slots == 0 || (num_slots % WK_ASSOCIATIVITY) != 0) return WK_ERR_BAD_ARG;
+    if (num_slots / WK_ASSOCIATIVITY >= (1ull << 32)) return WK_ERR_BAD_ARG;
+    wk_store *st = new wk_store();
+    st->device = device;
+    st->num_slots = num_slots;
+    st->num_edges = num_edges;
+    st->d_vertices = (uint4 *)d_vertices;
+    st->d_edges = d_edges;
+    st->owns = take_ownership != 0;
+    int rc = store_set_segs(st, segs, nsegs);
+    if (rc) { delete st; return rc; }
+    *out = st;
+    return WK_SUCCESS;
+}
+
+int wk_store_destroy(wk_store_t *st) {
+    if (!st) return WK_ERR_BAD_ARG;
+    if (st->owns) {
+        cudaSetDevice(st->device);
+        if (st->d_vertices) cudaFree(st->d_vertices);
+        if (st->d_edges) cudaFree(st->d_edges);
+    }
+    delete st;
+    return WK_SUCCESS;
+}
+
+int wk_store_get_edges(wk_store_t *st, wk_sid_t vid, wk_sid_t pid, int dir, wk_sid_t *dst, uint64_t cap, uint64_t *size) {
+    if (!st || !size) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(st->device));
+    const wk_segmeta_t *m = seg_of_key(st, vid, pid, dir);
+    if (!m) return WK_ERR_NO_SEGMENT;
+    const uint64_t key = make_key(vid, pid, (uint32_t)dir);
+    uint64_t bucket = m->bucket_start + hash_u64(key) % m->num_buckets;
+    *size = 0;
+    while (true) {
+        wk_vertex_t b[WK_ASSOCIATIVITY];
+        CUDA_TRY(cudaMemcpy(b, st->d_vertices + bucket * WK_ASSOCIATIVITY, sizeof(b), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < WK_ASSOCIATIVITY - 1; i++) {
+            if (b[i].key == key) {
+                const uint64_t sz = ptr_size(b[i].ptr), off = ptr_off(b[i].ptr);
+                *size = sz;
+                if (dst && sz <= cap && sz) CUDA_TRY(cudaMemcpy(dst, st->d_edges + off, sz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+                return WK_SUCCESS;
+            }
+        }
+        if (b[WK_ASSOCIATIVITY - 1].key == 0) return WK_SUCCESS;
+        bucket = b[WK_ASSOCIATIVITY - 1].key >> WK_KEY_VID_SHIFT;
+        if (bucket >= st->num_slots / WK_ASSOCIATIVITY) return WK_ERR_BAD_ARG;
+    }
+}
+
+int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) {
+    if (!store || !out || rbuf_bytes < 4096) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(store->device));
+    wk_engine *e = new wk_engine();
+    e->store = store;
+    e->cap_words = rbuf_bytes / sizeof(uint32_t);
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc((void **)&e->buf[0], e->cap_words * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&e->buf[1], e->cap_words * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&e->d_ctl, sizeof(CtlBlock)));
+    CUDA_TRY(cudaHostAlloc((void **)&e->h_rec, sizeof(HostRec), cudaHostAllocMapped));
+    memset((void *)e->h_rec, 0, sizeof(HostRec));
+    CUDA_TRY(cudaHostGetDevicePointer((void **)&e->d_rec, (void *)e->h_rec, 0));
+    e->stage_words = (1u << 20) / sizeof(uint32_t);   // 1 MiB zero-copy staging for small results
+    CUDA_TRY(cudaHostAlloc((void **)&e->h_stage, e->stage_words * sizeof(uint32_t), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void **)&e->d_stage, (void *)e->h_stage, 0));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, store->device));
+    e->num_sms = prop.multiProcessorCount;
+    // resident CTAs per SM of each fused kernel (persistent grid = SMs x occupancy)
+    const size_t smem = rows_smem(4);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[MODE_K2U], step_kernel<MODE_K2U>, CTA_THREADS, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[MODE_K2K], step_kernel<MODE_K2K>, CTA_THREADS, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[MODE_K2C], step_kernel<MODE_K2C>, CTA_THREADS, smem));
+    for (int i = 0; i < 3; i++)
+        if (e->occ[i] < 1) e->occ[i] = 1;
+    int rc = reset_ctl(e);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return WK_SUCCESS;
+}
+
+int wk_engine_destroy(wk_engine_t *e) {
+    if (!e) return WK_ERR_BAD_ARG;
+    cudaSetDevice(e->store->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->d_flush) cudaFree(e->d_flush);
+    if (e->q_ev0) cudaEventDestroy(e->q_ev0);
+    if (e->q_ev1) cudaEventDestroy(e->q_ev1);
+    cudaFree(e->buf[0]);
+    cudaFree(e->buf[1]);
+    cudaFree(e->d_ctl);
+    cudaFreeHost((void *)e->h_rec);
+    cudaFreeHost((void *)e->h_stage);
+    cudaStreamDestroy(e->stream);
+    delete e;
+    return WK_SUCCESS;
+}
+
+int wk_engine_set_profiling(wk_engine_t *e, int on) {
+    if (!e) return WK_ERR_BAD_ARG;
+    e->profiling = on < 0 ? 0 : on;
+    if (e->profiling && !e->q_ev0) {
+        CUDA_TRY(cudaSetDevice(e->store->device));
+        CUDA_TRY(cudaEventCreate(&e->q_ev0));
+        CUDA_TRY(cudaEventCreate(&e->q_ev1));
+    }
+    return WK_SUCCESS;
+}
+
+int wk_engine_sync(wk_engine_t *e) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return WK_SUCCESS;
+}
+
+int wk_engine_reset(wk_engine_t *e) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    e->ncols = 0;
+    return reset_ctl(e);
+}
+
+int wk_table_upload(wk_engine_t *e, const wk_sid_t *table, uint64_t nrows, int ncols) {
+    if (!e || ncols < 0 || ncols >= MAX_COLS || (nrows && ncols && !table)) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (nrows * (uint64_t)ncols > e->cap_words) return WK_ERR_RBUF_OVERFLOW;
+    int rc = reset_ctl(e);
+    if (rc) return rc;
+    e->ncols = ncols;
+    if (nrows && ncols) {
+        CUDA_TRY(cudaMemcpyAsync(e->buf[0], table, nrows * (uint64_t)ncols * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        set_count_kernel<<<1, 1, 0, e->stream>>>(&e->d_ctl->counts[0], nrows);
+        CUDA_TRY(cudaGetLastError());
+        e->launches++;
+    }
+    return WK_SUCCESS;
+}
+
+int wk_table_info(wk_engine_t *e, uint64_t *nrows, int *ncols) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    uint64_t rows = 0;
+    int rc = sync_rows(e, &rows);
+    if (nrows) *nrows = rows;
+    if (ncols) *ncols = e->ncols;
+    return rc;
+}
+
+int wk_table_download(wk_engine_t *e, wk_sid_t *dst, uint64_t cap_words, uint64_t *nrows, int *ncols) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    uint64_t rows = 0;
+    int rc = sync_rows(e, &rows);
+    if (nrows) *nrows = rows;
+    if (ncols) *ncols = e->ncols;
+    if (rc) return rc;
+    const uint64_t words = rows * (uint64_t)e->ncols;
+    if (words > cap_words) return WK_ERR_BAD_ARG;
+    if (words && dst) {
+        CUDA_TRY(cudaMemcpyAsync(dst, e->buf[e->step & 1], words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return WK_SUCCESS;
+}
+
+static int finish_call(wk_engine *e, int rc, uint64_t *out_rows) {
+    if (rc) return rc;
+    if (out_rows) return sync_rows(e, out_rows);
+    return WK_SUCCESS;
+}
+
+int wk_index_to_unknown(wk_engine_t *e, wk_sid_t tpid, int dir, int mt_tid, int mt_factor, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_seed(e, KIND_I2U, 0, tpid, dir, mt_tid, mt_factor), out_rows);
+}
+
+int wk_const_to_unknown(wk_engine_t *e, wk_sid_t vid, wk_sid_t pid, int dir, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_seed(e, KIND_C2U, vid, pid, dir, 0, 1), out_rows);
+}
+
+int wk_known_to_unknown(wk_engine_t *e, int col_start, wk_sid_t pid, int dir, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_known(e, KIND_K2U, col_start, pid, dir, 0, 0), out_rows);
+}
+
+int wk_known_to_known(wk_engine_t *e, int col_start, wk_sid_t pid, int dir, int col_end, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_known(e, KIND_K2K, col_start, pid, dir, col_end, 0), out_rows);
+}
+
+int wk_known_to_const(wk_engine_t *e, int col_start, wk_sid_t pid, int dir, wk_sid_t end_const, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_known(e, KIND_K2C, col_start, pid, dir, 0, end_const), out_rows);
+}
+
+int wk_project(wk_engine_t *e, const int32_t *cols, int n, uint64_t *out_rows) {
+    if (!e || !cols) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_project(e, cols, n), out_rows);
+}
+
+// ---- whole pattern phase ---------------------------------------------------------------------------
+struct PlannedStep {
+    int kind;
+    int col_start, col_end;
+    uint32_t pid, end_const;
+    int dir;
+    uint64_t vid;   // seeds
+    int in_cols;
+};
+
+// Resolve each pattern to a primitive exactly like execute_one_pattern (sparql.hpp:938-1061),
+// tracking var -> column like Result::add_var2col (query.hpp:378-395).
+static int plan_steps(const wk_pattern_t *pats, int npat, int nvars, std::vector<int> &v2c, std::vector<PlannedStep> &steps) {
+    const int NO_RESULT = 0xFFFF;
+    if (npat <= 0 || nvars <= 0 || nvars > 4096) return npat <= 0 ? WK_SYNTAX_ERROR : WK_ERR_BAD_ARG;
+    v2c.assign(nvars, NO_RESULT);
+    int ncols = 0;
+    auto var2col = [&](int32_t vid, int &col) -> int {
+        if (vid >= 0) return WK_VERTEX_INVALID;
+        const int idx = -(vid + 1);
+        if (idx < 0 || idx >= nvars) return WK_VERTEX_INVALID;
+        col = v2c[idx];
+        return WK_SUCCESS;
+    };
+    enum { KNOWN = 0, UNKNOWN = 1, CONST = 2 };
+    auto var_stat = [&](int32_t vid, int &st) -> int {
+        if (vid >= 0) { st = CONST; return WK_SUCCESS; }
+        int col;
+        int rc = var2col(vid, col);
+        if (rc) return rc;
+        st = (col == NO_RESULT) ? UNKNOWN : KNOWN;
+        return WK_SUCCESS;
+    };
+    for (int i = 0; i < npat; i++) {
+        const wk_pattern_t &pt = pats[i];
+        PlannedStep ps;
+        memset(&ps, 0, sizeof(ps));
+        ps.dir = pt.direction;
+        ps.in_cols = ncols;
+        if (pt.direction != WK_DIR_IN && pt.direction != WK_DIR_OUT) return WK_ERR_BAD_ARG;
+        if (i == 0 && is_tpid(pt.subject)) {   // start_from_index(), query.hpp:660-682
+            if (pt.predicate != WK_PREDICATE_ID && pt.predicate != WK_TYPE_ID) return WK_OBJ_ERROR;
+            int col;
+            int rc = var2col(pt.object, col);
+            if (rc) return rc;
+            if (col != NO_RESULT) return WK_UNKNOWN_PATTERN;   // index_to_known: not on the device path
+            if (ncols != 0) return WK_FIRST_PATTERN_ERROR;
+            ps.kind = KIND_I2U;
+            ps.vid = 0;
+            ps.pid = (uint32_t)pt.subject;
+            v2c[-(pt.object + 1)] = 0;
+            ncols = 1;
+            steps.push_back(ps);
+            continue;
+        }
+        int sp, ss, so;
+        int rc = var_stat(pt.predicate, sp);
+        if (rc) return rc;
+        if (sp != CONST) return WK_UNKNOWN_PATTERN;   // variable predicates need VERSATILE
+        if ((rc = var_stat(pt.subject, ss)) || (rc = var_stat(pt.object, so))) return rc;
+        ps.pid = (uint32_t)pt.predicate;
+        if (ss == CONST && so == UNKNOWN) {
+            if (ncols != 0) return WK_FIRST_PATTERN_ERROR;
+            ps.kind = KIND_C2U;
+            ps.vid = (uint64_t)pt.subject;
+            v2c[-(pt.object + 1)] = ncols;
+            ncols += 1;
+        } else if (ss == KNOWN && so == CONST) {
+            ps.kind = KIND_K2C;
+            ps.col_start = v2c[-(pt.subject + 1)];
+            ps.end_const = (uint32_t)pt.object;
+        } else if (ss == KNOWN && so == KNOWN) {
+            ps.kind = KIND_K2K;
+            ps.col_start = v2c[-(pt.subject + 1)];
+            ps.col_end = v2c[-(pt.object + 1)];
+        } else if (ss == KNOWN && so == UNKNOWN) {
+            ps.kind = KIND_K2U;
+            ps.col_start = v2c[-(pt.subject + 1)];
+            v2c[-(pt.object + 1)] = ncols;
+            ncols += 1;
+        } else if (ss == UNKNOWN) {
+            return WK_UNKNOWN_SUB;
+        } else {
+            return WK_UNKNOWN_PATTERN;   // CONST/CONST, CONST/KNOWN (const_to_known) not on the device path
+        }
+        if (ncols >= MAX_COLS) return WK_ERR_BAD_ARG;
+        steps.push_back(ps);
+    }
+    return WK_SUCCESS;
+}
+
+static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt_tid, int mt_factor, bool project,
+                     const std::vector<int32_t> &proj_cols, int final_cols) {
+    LightPlan lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.vertices = e->store->d_vertices;
+    lp.edges = e->store->d_edges;
+    lp.buf[0] = e->buf[0];
+    lp.buf[1] = e->buf[1];
+    lp.ctl = e->d_ctl;
+    lp.rec = e->d_rec;
+    lp.host_table = e->d_stage;
+    lp.host_table_words = e->stage_words;
+    lp.cap_words = e->cap_words;
+    lp.escalate_rows = e->light_escalate_rows;
+    lp.nsteps = (int)steps.size();
+    lp.first_step = 0;
+    lp.do_project = project ? 1 : 0;
+    lp.proj_n = (int)proj_cols.size();
+    lp.final_cols = final_cols;
+    for (size_t i = 0; i < proj_cols.size(); i++) lp.proj_cols[i] = (int8_t)proj_cols[i];
+    int maxC = 1;
+    for (size_t i = 0; i < steps.size(); i++) {
+        const PlannedStep &ps = steps[i];
+        LightStep &ls = lp.steps[i];
+        ls.kind = ps.kind;
+        ls.C = ps.in_cols;
+        ls.col_start = ps.col_start;
+        ls.col_end = ps.col_end;
+        ls.end_const = ps.end_const;
+        ls.mt_tid = mt_tid;
+        ls.mt_factor = mt_factor < 1 ? 1 : mt_factor;
+        if (ps.in_cols > maxC) maxC = ps.in_cols;
+        if (ps.kind == KIND_I2U || ps.kind == KIND_C2U) {
+            const wk_segmeta_t *m = seg_of_key(e->store, ps.vid, ps.pid, ps.dir);
+            if (!m) return WK_ERR_NO_SEGMENT;
+            ls.seg = make_segparam(m, ps.pid, ps.dir, false);
+            ls.key = make_key(ps.vid, ps.pid, (uint32_t)ps.dir);
+        } else {
+            const bool index_mode = (ps.kind == KIND_K2U && ps.pid == WK_TYPE_ID && ps.dir == WK_DIR_IN);
+            const wk_segmeta_t *m = index_mode ? find_seg(e->store, 1, WK_PREDICATE_ID, ps.dir) : find_seg(e->store, 0, ps.pid, ps.dir);
+            if (!m) return WK_ERR_NO_SEGMENT;
+            ls.seg = make_segparam(m, ps.pid, ps.dir, index_mode);
+            ls.inv_c = ((1u << 20) + (uint32_t)ps.in_cols - 1) / (uint32_t)ps.in_cols;
+        }
+    }
+    lp.seq = ++e->seq;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->profiling >= 2) { ev0 = get_event(e); ev1 = get_event(e); if (ev0) cudaEventRecord(ev0, e->stream); }
+    light_query_kernel<<<1, CTA_THREADS, rows_smem(maxC), e->stream>>>(lp);
+    CUDA_TRY(cudaGetLastError());
+    if (ev0 && ev1) cudaEventRecord(ev1, e->stream);
+    e->launches++;
+    int rc = wait_record(e, lp.seq);
+    if (rc) return rc;
+    // one record per step the fused kernel actually ran; the single launch (and its event time)
+    // is attributed to the first of them
+    const int ran = e->h_rec->resume_step;
+    for (int i = 0; i < ran && i < (int)steps.size(); i++) {
+        e->recs.emplace_back();
+        StepRecord &r = e->recs.back();
+        r.kind = steps[i].kind;
+        r.in_cols = steps[i].in_cols;
+        r.s = i;
+        r.launches = (i == 0) ? 1 : 0;
+        if (i == 0 && ev0 && ev1) { r.ev0 = ev0; r.ev1 = ev1; r.timed = true; }
+    }
+    return WK_SUCCESS;
+}
+
+int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns, int nvars,
+                     const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor, int blind,
+                     wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols) {
+    if (!e || !patterns) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (out_rows) *out_rows = 0;
+    if (out_cols) *out_cols = 0;
+    std::vector<int> v2c;
+    std::vector<PlannedStep> steps;
+    int rc = plan_steps(patterns, npatterns, nvars, v2c, steps);
+    if (rc) return rc;
+    if ((int)steps.size() > MAX_STEPS - 2) return WK_ERR_BAD_ARG;
+    const int final_cols = steps.back().in_cols + ((steps.back().kind == KIND_K2K || steps.back().kind == KIND_K2C) ? 0 : 1);
+    // projection columns (final_process, sparql.hpp:1507-1550)
+    std::vector<int32_t> proj_cols;
+    // final_process raises NO_REQUIRED_VAR only when there is a non-empty table to project
+    // (sparql.hpp:1425-1426, 1511): run the pattern phase first and report afterwards
+    const bool no_required = !blind && (nrequired <= 0 || !required_vars);
+    const bool want_table = !blind && !no_required;
+    if (want_table) {
+        for (int i = 0; i < nrequired; i++) {
+            const int idx = -(required_vars[i] + 1);
+            if (required_vars[i] >= 0 || idx >= nvars) return WK_VERTEX_INVALID;
+            if (v2c[idx] == 0xFFFF) return WK_VERTEX_INVALID;
+            proj_cols.push_back(v2c[idx]);
+        }
+        if (nrequired > MAX_COLS) return WK_ERR_BAD_ARG;
+    }
+    e->q_timed = false;
+    if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
+    rc = reset_ctl(e);
+    if (rc) return rc;
+    e->ncols = 0;
+
+    uint64_t rows = 0;
+    int cols = final_cols;
+    bool table_in_host = false;
+    size_t next = 0;
+    const bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS;
+    if (light) {
+        rc = run_light(e, steps, mt_tid, mt_factor, want_table, proj_cols, final_cols);
+        if (rc) return rc;
+        if (e->h_rec->status & 1u) return WK_ERR_RBUF_OVERFLOW;
+        next = (size_t)e->h_rec->resume_step;
+        e->step = (int)next;
+        e->ncols = (next == steps.size()) ? final_cols : steps[next].in_cols;
+        rows = e->h_rec->rows;
+        if (next == steps.size()) {
+            table_in_host = e->h_rec->table_in_host != 0;
+            if (want_table && rows > 0 && !table_in_host) { e->step += 1; }   // projected into the other buffer
+            if (want_table && rows > 0) { cols = nrequired; e->ncols = nrequired; }
+        }
+    }
+    if (next < steps.size()) {
+        // multi-CTA path: one fused kernel per remaining step, no host sync in between
+        for (size_t i = next; i < steps.size(); i++) {
+            const PlannedStep &ps = steps[i];
+            if (ps.kind == KIND_I2U) rc = enqueue_seed(e, KIND_I2U, 0, ps.pid, ps.dir, mt_tid, mt_factor);
+            else if (ps.kind == KIND_C2U) rc = enqueue_seed(e, KIND_C2U, ps.vid, ps.pid, ps.dir, 0, 1);
+            else rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const);
+            if (rc) return rc;
+        }
+        if (want_table) {
+            rc = enqueue_project(e, proj_cols.data(), nrequired);
+            if (rc) return rc;
+        }
+        rc = sync_rows(e, &rows);
+        if (rc) return rc;
+        if (want_table) {
+            // final_process leaves an empty table untouched (sparql.hpp:1425-1426)
+            cols = rows > 0 ? nrequired : final_cols;
+        }
+    }
+    if (e->profiling) { CUDA_TRY(cudaEventRecord(e->q_ev1, e->stream)); e->q_timed = true; }
+    if (out_rows) *out_rows = rows;
+    if (out_cols) *out_cols = cols;
+    if (no_required && rows > 0) return WK_NO_REQUIRED_VAR;
+    if (want_table && rows > 0 && table) {
+        const uint64_t words = rows * (uint64_t)cols;
+        if (words > cap_words) return WK_ERR_BAD_ARG;
+        if (table_in_host) {
+            memcpy(table, e->h_stage, words * sizeof(uint32_t));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(table, e->buf[e->step & 1], words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+            CUDA_TRY(cudaStreamSynchronize(e->stream));
+        }
+    }
+    return WK_SUCCESS;
+}
+
+int wk_engine_num_steps(wk_engine_t *e) {
+    if (!e) return 0;
+    if (cudaSetDevice(e->store->device) != cudaSuccess) return 0;
+    if (snapshot_stats(e) != WK_SUCCESS) return 0;
+    return (int)e->stats.size();
+}
+
+int wk_engine_step_stats(wk_engine_t *e, int step, wk_step_stats_t *out) {
+    if (!e || !out || step < 0 || step >= (int)e->stats.size()) return WK_ERR_BAD_ARG;
+    *out = e->stats[step];
+    return WK_SUCCESS;
+}
+
+uint64_t wk_engine_launch_count(wk_engine_t *e) { return e ? e->launches : 0; }
+
+// Evict the L2 between timed iterations: overwrite a scratch buffer larger than the 126 MB L2.
+int wk_engine_flush_l2(wk_engine_t *e) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (!e->d_flush) {
+        e->flush_bytes = (size_t)384 << 20;
+        CUDA_TRY(cudaMalloc(&e->d_flush, e->flush_bytes));
+    }
+    static int v = 0;
+    CUDA_TRY(cudaMemsetAsync(e->d_flush, ++v & 0xFF, e->flush_bytes, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return WK_SUCCESS;
+}
+
+int wk_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return WK_SUCCESS;
+}
+
+int wk_host_free(void *p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return WK_SUCCESS;
+}
+
+int wk_engine_last_query_device_us(wk_engine_t *e, float *us) {
+    if (!e || !us) return WK_ERR_BAD_ARG;
+    *us = 0;
+    if (!e->q_timed) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    CUDA_TRY(cudaEventSynchronize(e->q_ev1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->q_ev0, e->q_ev1));
+    *us = ms * 1000.0f;
+    return WK_SUCCESS;
+}
+
+// ---- sharded execution: implemented in a later milestone -------------------------------------------
+int wk_partition(wk_engine_t *, int, int, uint64_t *) { return WK_ERR_COMM; }
+int wk_partition_ptr(wk_engine_t *, int, const wk_sid_t **, uint64_t *) { return WK_ERR_COMM; }
+int wk_comm_unique_id(void *) { return WK_ERR_COMM; }
+int wk_comm_init(wk_engine_t *, int, int, const void *) { return WK_ERR_COMM; }
+int wk_exchange(wk_engine_t *, int, uint64_t *) { return WK_ERR_COMM; }
+int wk_query_execute_sharded(wk_engine_t *, const wk_pattern_t *, int, int, const int32_t *, int, int, int, int,
+                             wk_sid_t *, uint64_t, uint64_t *, int *) { return WK_ERR_COMM; }
+
+// ---- self-test hooks (host-side arithmetic shared with the kernels; callable without a GPU) ----------
+uint64_t wk_selftest_hash(uint64_t key) { return hash_u64(key); }
+uint64_t wk_selftest_fastmod(uint64_t n, uint64_t d) { FastMod f = make_fastmod(d); return fastmod(n, f); }
+uint64_t wk_selftest_make_key(uint64_t vid, uint32_t pid, uint32_t dir) { return make_key(vid, pid, dir); }
+
+}  // extern "C"

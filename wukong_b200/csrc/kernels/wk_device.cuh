@@ -1,0 +1,358 @@
+// Device-side building blocks of the frontier-expansion engine (sm_100a).
+//
+// Semantics follow the reference's probe (store/gstore.hpp:242-248, 341-361, 393-410) and key
+// layout (store/vertex.hpp:47-66, 116-119); the implementation is a B200-first design:
+//   * a bucket is 8 x 16 B = 128 B = one L2/HBM line: 8 lanes fetch it with one LDG.128 each
+//     (one wavefront per probe), 4 probes per warp instruction, 8 instructions in flight per warp;
+//   * the per-segment modulo is a multiply-shift (no 64-bit division on the device);
+//   * tables are staged per 256-row tile in shared memory, output space is claimed per tile with
+//     one 64-bit atomic, rows are written with coalesced stores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wk {
+
+// ---- key / pointer bit layout ---------------------------------------------------------------
+// ikey_t: dir:1 | pid:17 | vid:46 (LSB first)  => raw = vid<<18 | pid<<1 | dir
+// iptr_t: size:28 | off:34 | type:2
+#define WK_KEY_VID_SHIFT 18
+#define WK_PTR_SIZE_BITS 28
+#define WK_PTR_OFF_BITS 34
+
+__host__ __device__ __forceinline__ uint64_t make_key(uint64_t vid, uint32_t pid, uint32_t dir) {
+    return (vid << WK_KEY_VID_SHIFT) | ((uint64_t)pid << 1) | (uint64_t)dir;
+}
+__host__ __device__ __forceinline__ uint32_t ptr_size(uint64_t p) { return (uint32_t)(p & ((1ull << WK_PTR_SIZE_BITS) - 1)); }
+__host__ __device__ __forceinline__ uint64_t ptr_off(uint64_t p) { return (p >> WK_PTR_SIZE_BITS) & ((1ull << WK_PTR_OFF_BITS) - 1); }
+
+// Thomas Wang 64-bit mix (the reference's math::hash_u64, utils/math.hpp:58-67) of the raw key.
+__host__ __device__ __forceinline__ uint64_t hash_u64(uint64_t key) {
+    key = (~key) + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+// ---- n % d for a launch-invariant d (round-up multiply-shift with 65-bit magic) --------------
+struct FastMod {
+    uint64_t magic;
+    uint64_t d;
+    uint32_t shift;
+    uint32_t _pad;
+};
+
+__host__ __device__ __forceinline__ uint64_t mulhi64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+
+inline FastMod make_fastmod(uint64_t d) {
+    FastMod f;
+    f.d = d;
+    f._pad = 0;
+    if (d <= 1) { f.magic = 0; f.shift = 0; return f; }   // n % 1 == 0, handled in fastmod()
+    const uint32_t fl = 63u - (uint32_t)__builtin_clzll(d);
+    if ((d & (d - 1)) == 0) {
+        f.magic = 0;
+        f.shift = fl - 1;
+    } else {
+        const unsigned __int128 num = (unsigned __int128)1 << (64 + fl);
+        uint64_t m = (uint64_t)(num / d);
+        const uint64_t rem = (uint64_t)(num % d);
+        m += m;
+        const uint64_t twice_rem = rem + rem;
+        if (twice_rem >= d || twice_rem < rem) m += 1;
+        f.magic = m + 1;
+        f.shift = fl;
+    }
+    return f;
+}
+
+__host__ __device__ __forceinline__ uint64_t fastmod(uint64_t n, const FastMod &f) {
+    if (f.d <= 1) return 0;
+    const uint64_t q0 = mulhi64(f.magic, n);
+    const uint64_t t = ((n - q0) >> 1) + q0;
+    const uint64_t q = t >> f.shift;
+    return n - q * f.d;
+}
+
+// ---- memory access helpers --------------------------------------------------------------------
+// store arrays are immutable while an engine runs: read-only (non-coherent) path
+__device__ __forceinline__ uint4 ld_slot(const uint4 *p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t ld_edge(const uint32_t *p) { return __ldg(p); }
+// binding tables are rewritten by every step (and re-read inside the fused light kernel):
+// read them through L2 only so that no stale L1 line can ever be observed
+__device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ uint64_t ld_count(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
+
+// ---- per-step parameters (passed by value) ---------------------------------------------------
+enum { MODE_K2U = 0, MODE_K2K = 1, MODE_K2C = 2 };
+enum { TILE_ROWS = 256, CTA_THREADS = 256, MAX_COLS = 32 };
+static constexpr uint32_t BUCKET_NONE = 0xFFFFFFFFu;
+static constexpr int SMALL_DEG = 8;       // rows with <= SMALL_DEG outputs are written by their owner thread
+static constexpr int SERIAL_SCAN = 32;    // filter edge lists up to this length are scanned by the owner thread
+
+struct SegParam {
+    uint64_t bucket_start;
+    FastMod fm;          // % num_buckets
+    uint32_t pid, dir;
+    uint32_t index_mode; // 1: key = [0 | cur | dir] (type-index lookup of a known vertex)
+    uint32_t _pad;
+};
+
+struct StepParam {
+    const uint4 *vertices;
+    const uint32_t *edges;
+    const uint32_t *in;
+    uint32_t *out;
+    const uint64_t *in_count;
+    uint64_t *out_count;
+    uint64_t out_cap_rows;
+    uint64_t *stats;      // [0] buckets visited, [1] edges touched
+    uint32_t *status;     // sticky error word
+    SegParam seg;
+    int32_t C;            // input columns
+    int32_t col_start, col_end;
+    uint32_t end_const;
+    uint32_t inv_c;       // ceil(2^20 / C) for idx -> (row, col)
+    uint32_t _pad;
+};
+
+__device__ __forceinline__ uint64_t step_key(const SegParam &s, uint32_t cur) {
+    // index_mode: the reference builds ikey_t(0, cur, d) whose 17-bit pid bitfield truncates cur
+    // (vertex.hpp:47-60); mask the same way so an out-of-range id can never alias a vid field
+    return s.index_mode ? make_key(0, cur & ((1u << 17) - 1), s.dir) : make_key(cur, s.pid, s.dir);
+}
+
+// shared-memory working set of one tile
+struct TileSmem {
+    uint32_t cur[TILE_ROWS];
+    uint32_t bucket[TILE_ROWS];
+    uint32_t next[TILE_ROWS];
+    uint32_t _pad0;
+    uint64_t ptr[TILE_ROWS];
+    uint64_t wsum[CTA_THREADS / 32];
+    uint64_t base;
+    uint64_t total;
+};
+
+// ---- cooperative cluster-hash probe of one warp's 32 rows ------------------------------------
+// Before the call: sm.bucket[row] = first bucket (BUCKET_NONE for inactive rows), sm.cur[row] =
+// probed vertex id, sm.ptr[row] = 0, sm.next[row] = 0, followed by __syncwarp().
+// After the call sm.ptr[row] holds the raw iptr_t of the key (0 = miss).  Returns the number of
+// buckets this lane's own row visited (L_i).
+__device__ __forceinline__ uint32_t warp_probe(const uint4 *__restrict__ vertices, const SegParam &seg,
+                                               TileSmem &sm, int warp_row0, int lane, bool active) {
+    const int slot = lane & 7;
+    const int grp = lane >> 3;
+    const int my_row = warp_row0 + lane;
+    bool pending = active;
+    uint32_t visited = 0;
+    while (true) {
+        uint32_t b[8];
+        uint4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) b[r] = sm.bucket[warp_row0 + 4 * r + grp];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            v[r] = make_uint4(0, 0, 0, 0);
+            if (b[r] != BUCKET_NONE) v[r] = ld_slot(vertices + ((uint64_t)b[r] * 8 + slot));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if (b[r] != BUCKET_NONE) {
+                const int j = warp_row0 + 4 * r + grp;
+                const uint64_t kk = (uint64_t)v[r].x | ((uint64_t)v[r].y << 32);
+                if (slot < 7) {
+                    if (kk == step_key(seg, sm.cur[j])) sm.ptr[j] = (uint64_t)v[r].z | ((uint64_t)v[r].w << 32);
+                } else {
+                    // last slot: key.vid is the next bucket of the chain (0 / empty key = end)
+                    sm.next[j] = (uint32_t)(kk >> WK_KEY_VID_SHIFT);
+                }
+            }
+        }
+        __syncwarp();
+        if (pending) {
+            visited++;
+            if (sm.ptr[my_row] != 0) pending = false;
+            else if (sm.next[my_row] == 0) pending = false;   // miss
+            else { sm.bucket[my_row] = sm.next[my_row]; sm.next[my_row] = 0; }
+        }
+        if (!pending) sm.bucket[my_row] = BUCKET_NONE;
+        const bool more = __any_sync(0xFFFFFFFFu, pending);
+        __syncwarp();
+        if (!more) break;
+    }
+    return visited;
+}
+
+// block-wide exclusive scan of one uint64 per thread; returns exclusive prefix, total in sm.total
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t x, TileSmem &sm, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    uint64_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) sm.wsum[warp] = incl;
+    __syncthreads();
+    uint64_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CTA_THREADS / 32; w++) {
+        const uint64_t s = sm.wsum[w];
+        if (w < warp) woff += s;
+        tot += s;
+    }
+    if (tid == 0) sm.total = tot;
+    return woff + incl - x;
+}
+
+// ---- one 256-row tile of a known_to_{unknown,known,const} step --------------------------------
+// rows: dynamic shared memory, TILE_ROWS x CP words (CP = C | 1 to spread banks)
+template <int MODE>
+__device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, uint32_t nrows, TileSmem &sm,
+                                             uint32_t *rows, uint64_t &acc_visited, uint64_t &acc_edges) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C, CP = C | 1;
+    const int Cout = (MODE == MODE_K2U) ? C + 1 : C;
+
+    // A. stage the tile's input rows (coalesced, L2-only loads)
+    {
+        const uint32_t nwords = nrows * (uint32_t)C;
+        const uint32_t *src = p.in + row0 * (uint64_t)C;
+        for (uint32_t idx = tid; idx < nwords; idx += CTA_THREADS) {
+            const uint32_t r = (uint32_t)(((uint64_t)idx * p.inv_c) >> 20);
+            const uint32_t c = idx - r * (uint32_t)C;
+            rows[r * CP + c] = ld_table(src + idx);
+        }
+    }
+    __syncthreads();
+
+    // B. key -> first bucket
+    const bool active = (uint32_t)tid < nrows;
+    uint32_t cur = 0;
+    if (active) {
+        cur = rows[tid * CP + p.col_start];
+        const uint64_t key = step_key(p.seg, cur);
+        sm.bucket[tid] = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key), p.seg.fm));
+    } else {
+        sm.bucket[tid] = BUCKET_NONE;
+    }
+    sm.cur[tid] = cur;
+    sm.ptr[tid] = 0;
+    sm.next[tid] = 0;
+    __syncwarp();
+
+    // C. probe
+    acc_visited += warp_probe(p.vertices, p.seg, sm, warp * 32, lane, active);
+
+    // D. multiplicity of each row
+    const uint64_t ptr = sm.ptr[tid];
+    const uint32_t size = active ? ptr_size(ptr) : 0;
+    const uint64_t off = ptr_off(ptr);
+    uint32_t mult = 0;
+    if (MODE == MODE_K2U) {
+        mult = size;
+        acc_edges += size;
+    } else {
+        const uint32_t target = (MODE == MODE_K2K) ? (active ? rows[tid * CP + p.col_end] : 0) : p.end_const;
+        bool found = false;
+        if (size <= SERIAL_SCAN) {
+            uint32_t k = 0;
+            for (; k < size; k++)
+                if (ld_edge(p.edges + off + k) == target) { found = true; break; }
+            acc_edges += found ? (k + 1) : size;
+        }
+        // long lists: the whole warp scans one list at a time (coalesced, early exit)
+        uint32_t longmask = __ballot_sync(0xFFFFFFFFu, size > SERIAL_SCAN);
+        while (longmask) {
+            const int src = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const uint32_t s_size = __shfl_sync(0xFFFFFFFFu, size, src);
+            const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
+            const uint32_t s_target = __shfl_sync(0xFFFFFFFFu, target, src);
+            uint32_t scanned = s_size;
+            bool hit = false;
+            for (uint32_t k0 = 0; k0 < s_size; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const bool eq = (k < s_size) && (ld_edge(p.edges + s_off + k) == s_target);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
+                if (m) { hit = true; scanned = k0 + __ffs(m); break; }
+            }
+            if (lane == src) { found = hit; acc_edges += scanned; }
+        }
+        mult = found ? 1u : 0u;
+    }
+
+    // E. claim output space for the tile
+    const uint64_t excl = block_exclusive_scan((uint64_t)mult, sm, tid);
+    __syncthreads();
+    if (tid == 0) {
+        const uint64_t total = sm.total;
+        uint64_t base = 0;
+        if (total) base = atomicAdd((unsigned long long *)p.out_count, (unsigned long long)total);
+        if (base + total > p.out_cap_rows) {
+            atomicOr(p.status, 1u);   // WK_ERR_RBUF_OVERFLOW: counted but not written
+            base = ~0ull;
+        }
+        sm.base = base;
+    }
+    __syncthreads();
+    const uint64_t base = sm.base;
+
+    // F. write the output rows
+    if (base != ~0ull && sm.total != 0) {
+        if (MODE != MODE_K2U) {
+            if (mult) {
+                uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
+                for (int c = 0; c < C; c++) dst[c] = rows[tid * CP + c];
+            }
+        } else {
+            // small fan-out: the owner thread writes its rows
+            if (mult != 0 && mult <= SMALL_DEG) {
+                uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
+                for (uint32_t k = 0; k < mult; k++) {
+                    const uint32_t e = ld_edge(p.edges + off + k);
+                    for (int c = 0; c < C; c++) dst[c] = rows[tid * CP + c];
+                    dst[C] = e;
+                    dst += Cout;
+                }
+            }
+            // larger fan-out: the warp cooperates on one source row at a time; consecutive lanes
+            // write consecutive output words (coalesced) and read consecutive edges
+            uint32_t bigmask = __ballot_sync(0xFFFFFFFFu, mult > SMALL_DEG);
+            while (bigmask) {
+                const int src = __ffs(bigmask) - 1;
+                bigmask &= bigmask - 1;
+                const uint32_t s_mult = __shfl_sync(0xFFFFFFFFu, mult, src);
+                const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
+                const uint64_t s_excl = __shfl_sync(0xFFFFFFFFu, excl, src);
+                const uint32_t *srow = rows + (warp * 32 + src) * CP;
+                uint32_t *dst = p.out + (base + s_excl) * (uint64_t)Cout;
+                const uint64_t nwords = (uint64_t)s_mult * (uint64_t)Cout;
+                // word w of the run: row = w / Cout, col = w % Cout, advanced incrementally
+                uint32_t r = (uint32_t)lane / (uint32_t)Cout;
+                uint32_t c = (uint32_t)lane - r * (uint32_t)Cout;
+                const uint32_t dr = 32u / (uint32_t)Cout, dc = 32u - dr * (uint32_t)Cout;
+                for (uint64_t w = lane; w < nwords; w += 32) {
+                    dst[w] = (c == (uint32_t)C) ? ld_edge(p.edges + s_off + r) : srow[c];
+                    r += dr;
+                    c += dc;
+                    if (c >= (uint32_t)Cout) { c -= (uint32_t)Cout; r++; }
+                }
+            }
+        }
+    }
+    __syncthreads();   // smem is reused by the next tile
+}
+
+}  // namespace wk

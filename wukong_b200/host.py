@@ -1,0 +1,119 @@
+"""ctypes binding of the host-side C++ layer (libwukong_host.so): store builder + Wukong-surface mirror."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi, datagen
+
+
+def lib():
+    L = datagen.lib()
+    if getattr(L, "_wkh_ready", False):
+        return L
+    u64, u32, vp, ci = C.c_uint64, C.c_uint32, C.c_void_p, C.c_int
+    L.wkh_store_build.restype = vp
+    L.wkh_store_build.argtypes = [vp, u64, ci, ci, ci, u64, ci, ci]
+    L.wkh_store_free.argtypes = [vp]
+    L.wkh_store_ok.argtypes = [vp]
+    L.wkh_store_error.restype = C.c_char_p
+    L.wkh_store_error.argtypes = [vp]
+    for f in ("wkh_store_vertices", "wkh_store_edges"):
+        getattr(L, f).restype = vp
+        getattr(L, f).argtypes = [vp]
+    for f in ("wkh_store_num_slots", "wkh_store_num_edges", "wkh_store_num_keys", "wkh_store_num_buckets",
+              "wkh_store_used_ext"):
+        getattr(L, f).restype = u64
+        getattr(L, f).argtypes = [vp]
+    L.wkh_store_num_segs.argtypes = [vp]
+    L.wkh_store_segs.argtypes = [vp, vp]
+    L.wkh_store_get_edges.restype = u64
+    L.wkh_store_get_edges.argtypes = [vp, u32, u32, ci, C.POINTER(vp)]
+    L.wkh_store_upload.argtypes = [vp, ci, C.POINTER(vp)]
+    L.wkh_time_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, ci, ci, vp, vp, C.POINTER(u64),
+                                 C.POINTER(ci)]
+    L._wkh_ready = True
+    return L
+
+
+class HostStore:
+    """Cluster-hash graph store built on the host by the product builder (csrc/store/host_builder.cpp)."""
+
+    def __init__(self, triples, num_servers=1, sid=0, num_normal_preds=datagen.LUBM_NUM_NORMAL_PREDS,
+                 kvstore_bytes=0, est_load_factor=55, gpu_ext_extents=True):
+        t = np.ascontiguousarray(triples, dtype=np.uint32).reshape(-1, 3)
+        self.h = lib().wkh_store_build(t.ctypes.data_as(C.c_void_p), t.shape[0], num_servers, sid, num_normal_preds,
+                                       kvstore_bytes, est_load_factor, 1 if gpu_ext_extents else 0)
+        if not lib().wkh_store_ok(self.h):
+            msg = lib().wkh_store_error(self.h).decode()
+            lib().wkh_store_free(self.h)
+            self.h = None
+            raise RuntimeError("store build failed: " + msg)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().wkh_store_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def num_slots(self):
+        return lib().wkh_store_num_slots(self.h)
+
+    @property
+    def num_edges(self):
+        return lib().wkh_store_num_edges(self.h)
+
+    @property
+    def num_keys(self):
+        return lib().wkh_store_num_keys(self.h)
+
+    def vertices(self):
+        n = self.num_slots
+        return np.frombuffer((C.c_uint64 * (2 * n)).from_address(lib().wkh_store_vertices(self.h)), dtype=np.uint64).reshape(n, 2)
+
+    def edges(self):
+        n = self.num_edges
+        return np.frombuffer((C.c_uint32 * n).from_address(lib().wkh_store_edges(self.h)), dtype=np.uint32)
+
+    def segs(self):
+        n = lib().wkh_store_num_segs(self.h)
+        arr = (capi.SegMeta * n)()
+        lib().wkh_store_segs(self.h, C.cast(arr, C.c_void_p))
+        return list(arr)
+
+    def get_edges(self, vid, pid, d):
+        p = C.c_void_p()
+        n = lib().wkh_store_get_edges(self.h, vid, pid, d, C.byref(p))
+        if n == 0 or not p.value:
+            return np.zeros(0, dtype=np.uint32)
+        return np.frombuffer((C.c_uint32 * n).from_address(p.value), dtype=np.uint32).copy()
+
+    def upload(self, device=0):
+        """-> capi.Store living on `device` (wk_store_create through the C ABI)."""
+        h = C.c_void_p()
+        capi._check(lib().wkh_store_upload(self.h, device, C.byref(h)), "wkh_store_upload")
+        st = capi.Store.__new__(capi.Store)
+        st.h = h
+        st.device = device
+        return st
+
+
+def time_query(engine, patterns, nvars, required_vars, reps, blind=True, table=None, flush=True, mt_tid=0,
+               mt_factor=1, device_times=False):
+    """Timed loop in native code around wk_query_execute.  Returns (wall_us[], dev_us[] or None, rows, cols)."""
+    p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+    rv = np.array(required_vars, dtype=np.int32)
+    wall = np.zeros(reps, dtype=np.float64)
+    dev = np.zeros(reps, dtype=np.float32) if device_times else None
+    rows, cols = C.c_uint64(0), C.c_int(0)
+    rc = lib().wkh_time_query(engine.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars,
+                              rv.ctypes.data_as(C.c_void_p), len(rv), mt_tid, mt_factor, 1 if blind else 0,
+                              table.ctypes.data_as(C.c_void_p) if table is not None else None,
+                              table.size if table is not None else 0, reps, 1 if flush else 0,
+                              wall.ctypes.data_as(C.c_void_p),
+                              dev.ctypes.data_as(C.c_void_p) if dev is not None else None,
+                              C.byref(rows), C.byref(cols))
+    capi._check(rc, "wkh_time_query")
+    return wall, dev, rows.value, cols.value
