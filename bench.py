@@ -54,14 +54,15 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t_mark = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
@@ -69,10 +70,12 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, timed = [], 0, set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
             try:
+                if self.t_mark is not None and ts >= self.t_mark:
+                    timed += 1
                 sm.append(float(r[1]))
                 mx = max(mx, float(r[2]))
                 for i, nm in enumerate(names):
@@ -81,7 +84,8 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": timed,
+                "note": "sampled every 20 ms from the start of warm-up to the end of the timed region"}
 
 
 def build_dataset(args):
@@ -197,7 +201,7 @@ def main():
     tr, hs, info = build_dataset(args)
     plans = load_plans(args.plan)
     gst = hs.upload(local_rank)
-    rbuf = (args.rbuf_mb << 20) if args.rbuf_mb else max(256 << 20, min(16 << 30, int(info["triples"]) * 48))
+    rbuf = (args.rbuf_mb << 20) if args.rbuf_mb else max(256 << 20, min(8 << 30, int(info["triples"]) * 8))
     eng = capi.Engine(gst, rbuf_bytes=rbuf)
     out_tbl, _keep = capi.pinned_array(min(rbuf // 4, 1 << 28))
 
@@ -208,6 +212,9 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
     # ---- warm-up ---------------------------------------------------------------------------------
     rows = {}
     for _ in range(args.warmup):
@@ -216,10 +223,9 @@ def main():
             _, _, r, c = host.time_query(eng, pats, nvars, req, 1, blind=False, table=out_tbl, flush=True)
             rows[q] = (r, c)
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     t_region0 = time.time()
+    sampler.t_mark = t_region0
     # ---- timed: device-resident (value) and end-to-end (e2e), K steps, L2 flushed between queries ----
     dev_us = {q: [] for q in QUERIES}
     e2e_us = {q: [] for q in QUERIES}

@@ -36,6 +36,8 @@ struct CtlBlock {
     uint32_t _pad;
 };
 
+static_assert(sizeof(CtlBlock) % sizeof(uint64_t) == 0, "CtlBlock is cleared in 8-byte words");
+
 struct HostRec {   // lives in mapped pinned host memory
     volatile uint64_t seq;
     uint64_t rows;
@@ -231,6 +233,9 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
     __shared__ uint64_t s_ptr;
     const int tid = threadIdx.x;
     CtlBlock *ctl = plan.ctl;
+    // the fused kernel owns the control block: clear it here instead of a separate memset node
+    for (int i = tid; i < (int)(sizeof(CtlBlock) / sizeof(uint64_t)); i += CTA_THREADS) ((uint64_t *)ctl)[i] = 0;
+    __syncthreads();
     int s = plan.first_step;
     int ncols_final = plan.final_cols;
     bool stopped = false;
@@ -461,10 +466,11 @@ static int wait_record(wk_engine *e, uint64_t seq) {
 }
 
 // enqueue the completion record for the current table and wait for it
-static int sync_rows(wk_engine *e, uint64_t *rows) {
+static int sync_rows(wk_engine *e, uint64_t *rows, cudaEvent_t after = nullptr) {
     const uint64_t seq = ++e->seq;
     finish_kernel<<<1, 1, 0, e->stream>>>(&e->d_ctl->counts[e->step], &e->d_ctl->status, e->d_rec, seq, e->step);
     CUDA_TRY(cudaGetLastError());
+    if (after) cudaEventRecord(after, e->stream);   // device-side end of the query, before the host waits
     e->launches++;
     int rc = wait_record(e, seq);
     if (rc) return rc;
@@ -1032,6 +1038,7 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
     light_query_kernel<<<1, CTA_THREADS, rows_smem(maxC), e->stream>>>(lp);
     CUDA_TRY(cudaGetLastError());
     if (ev0 && ev1) cudaEventRecord(ev1, e->stream);
+    if (e->profiling) { cudaEventRecord(e->q_ev1, e->stream); e->q_timed = true; }
     e->launches++;
     int rc = wait_record(e, lp.seq);
     if (rc) return rc;
@@ -1080,15 +1087,21 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
     }
     e->q_timed = false;
     if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
-    rc = reset_ctl(e);
-    if (rc) return rc;
+    const bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS;
+    if (light) {   // the fused kernel clears the control block itself
+        e->step = 0;
+        e->recs.clear();
+        e->event_next = 0;
+    } else {
+        rc = reset_ctl(e);
+        if (rc) return rc;
+    }
     e->ncols = 0;
 
     uint64_t rows = 0;
     int cols = final_cols;
     bool table_in_host = false;
     size_t next = 0;
-    const bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS;
     if (light) {
         rc = run_light(e, steps, mt_tid, mt_factor, want_table, proj_cols, final_cols);
         if (rc) return rc;
@@ -1116,14 +1129,14 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
             rc = enqueue_project(e, proj_cols.data(), nrequired);
             if (rc) return rc;
         }
-        rc = sync_rows(e, &rows);
+        rc = sync_rows(e, &rows, e->profiling ? e->q_ev1 : nullptr);
         if (rc) return rc;
+        if (e->profiling) e->q_timed = true;
         if (want_table) {
             // final_process leaves an empty table untouched (sparql.hpp:1425-1426)
             cols = rows > 0 ? nrequired : final_cols;
         }
     }
-    if (e->profiling) { CUDA_TRY(cudaEventRecord(e->q_ev1, e->stream)); e->q_timed = true; }
     if (out_rows) *out_rows = rows;
     if (out_cols) *out_cols = cols;
     if (no_required && rows > 0) return WK_NO_REQUIRED_VAR;
