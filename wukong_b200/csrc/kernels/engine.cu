@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -20,13 +21,14 @@
 
 #include "wukong_b200.h"
 #include "wk_device.cuh"
+#include "wk_light.cuh"
 
 using namespace wk;
 
 // =============================================================================================
 // device-side control block and kernels
 // =============================================================================================
-enum { MAX_STEPS = 60, MAX_LIGHT_STEPS = 24 };
+enum { MAX_STEPS = 60 };
 enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5 };
 
 struct CtlBlock {
@@ -38,14 +40,9 @@ struct CtlBlock {
 
 static_assert(sizeof(CtlBlock) % sizeof(uint64_t) == 0, "CtlBlock is cleared in 8-byte words");
 
-struct HostRec {   // lives in mapped pinned host memory
-    volatile uint64_t seq;
-    uint64_t rows;
-    uint32_t status;
-    int32_t resume_step;     // light kernel: first step it did NOT run (== nsteps when finished)
-    uint32_t table_in_host;  // light kernel: projected table was written to the mapped staging area
-    uint32_t _pad;
-};
+// completion record in mapped pinned host memory: wk::LightRecord (32 bytes, two 16-byte stores,
+// validated on the host by record_check instead of a system-scope fence on the device)
+typedef LightRecord HostRec;
 
 struct SeedParam {
     const uint4 *vertices;
@@ -85,8 +82,9 @@ __device__ __forceinline__ void flush_stats(uint64_t *stats, uint64_t visited, u
 }
 
 // ---- known_to_{unknown,known,const}: one persistent fused kernel ---------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(CTA_THREADS) step_kernel(const StepParam p) {
+// BATCH / MINB: probe batch size and minimum resident CTAs per SM (register budget); see DESIGN.md
+template <int MODE, int BATCH, int MINB>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel(const StepParam p) {
     extern __shared__ uint32_t dyn_rows[];
     __shared__ TileSmem sm;
     if (__ldcg(p.status) != 0) return;   // an earlier step overflowed: its output is not usable
@@ -95,7 +93,7 @@ __global__ void __launch_bounds__(CTA_THREADS) step_kernel(const StepParam p) {
     for (uint64_t tile = blockIdx.x; tile * TILE_ROWS < N; tile += gridDim.x) {
         const uint64_t row0 = tile * TILE_ROWS;
         const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
-        process_tile<MODE>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
+        process_tile<MODE, BATCH>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
     }
     flush_stats(p.stats, acc_visited, acc_edges);
 }
@@ -192,120 +190,11 @@ __global__ void rebase_kernel(CtlBlock *ctl, int from, int to) {
 }
 
 __global__ void finish_kernel(const uint64_t *count, const uint32_t *status, HostRec *rec, uint64_t seq, int resume) {
-    rec->rows = ld_count(count);
-    rec->status = __ldcg(status);
-    rec->resume_step = resume;
-    rec->table_in_host = 0;
-    __threadfence_system();
-    rec->seq = seq;
-}
-
-// ---- fused single-CTA interpreter for const-start ("light") plans ------------------------------------
-struct LightStep {
-    SegParam seg;
-    uint64_t key;          // seeds
-    int32_t kind, C;
-    int32_t col_start, col_end;
-    uint32_t end_const, inv_c;
-    int32_t mt_tid, mt_factor;
-};
-
-struct LightPlan {
-    const uint4 *vertices;
-    const uint32_t *edges;
-    uint32_t *buf[2];
-    CtlBlock *ctl;
-    HostRec *rec;
-    uint32_t *host_table;       // mapped staging area (device pointer), may be null
-    uint64_t host_table_words;
-    uint64_t cap_words;         // per result buffer
-    uint64_t escalate_rows;     // hand over to the multi-CTA path beyond this many rows
-    uint64_t seq;
-    int32_t nsteps, first_step; // steps [first_step, nsteps) are run; table of step s is in buf[s & 1]
-    int32_t do_project, proj_n, final_cols, _pad;
-    int8_t proj_cols[MAX_COLS];
-    LightStep steps[MAX_LIGHT_STEPS];
-};
-
-__global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
-    extern __shared__ uint32_t dyn_rows[];
-    __shared__ TileSmem sm;
-    __shared__ uint64_t s_ptr;
-    const int tid = threadIdx.x;
-    CtlBlock *ctl = plan.ctl;
-    // the fused kernel owns the control block: clear it here instead of a separate memset node
-    for (int i = tid; i < (int)(sizeof(CtlBlock) / sizeof(uint64_t)); i += CTA_THREADS) ((uint64_t *)ctl)[i] = 0;
-    __syncthreads();
-    int s = plan.first_step;
-    int ncols_final = plan.final_cols;
-    bool stopped = false;
-    for (; s < plan.nsteps; s++) {
-        const LightStep &ls = plan.steps[s];
-        uint32_t *in = plan.buf[s & 1], *out = plan.buf[(s + 1) & 1];
-        uint64_t acc_visited = 0, acc_edges = 0;
-        if (ls.kind == KIND_I2U || ls.kind == KIND_C2U) {
-            SeedParam sp;
-            sp.vertices = plan.vertices; sp.edges = plan.edges; sp.out = out;
-            sp.out_count = &ctl->counts[s + 1]; sp.out_cap_rows = plan.cap_words;
-            sp.stats = &ctl->stats[2 * s]; sp.status = &ctl->status;
-            sp.key = ls.key; sp.bucket_start = ls.seg.bucket_start; sp.fm = ls.seg.fm;
-            sp.mt_tid = ls.mt_tid; sp.mt_factor = ls.mt_factor;
-            seed_body(sp, &s_ptr, 0, 1);
-        } else {
-            StepParam p;
-            p.vertices = plan.vertices; p.edges = plan.edges; p.in = in; p.out = out;
-            p.in_count = &ctl->counts[s]; p.out_count = &ctl->counts[s + 1];
-            const int Cout = (ls.kind == KIND_K2U) ? ls.C + 1 : ls.C;
-            p.out_cap_rows = plan.cap_words / (uint64_t)Cout;
-            p.stats = &ctl->stats[2 * s]; p.status = &ctl->status;
-            p.seg = ls.seg; p.C = ls.C; p.col_start = ls.col_start; p.col_end = ls.col_end;
-            p.end_const = ls.end_const; p.inv_c = ls.inv_c; p._pad = 0;
-            const uint64_t N = ld_count(p.in_count);
-            for (uint64_t row0 = 0; row0 < N; row0 += TILE_ROWS) {
-                const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
-                if (ls.kind == KIND_K2U) process_tile<MODE_K2U>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
-                else if (ls.kind == KIND_K2K) process_tile<MODE_K2K>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
-                else process_tile<MODE_K2C>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
-            }
-            flush_stats(&ctl->stats[2 * s], acc_visited, acc_edges);
-        }
-        __syncthreads();   // this CTA's global writes (table, counters) are visible to all its threads
-        if (__ldcg(&ctl->status) != 0) { stopped = true; s++; break; }
-        if (s + 1 < plan.nsteps && ld_count(&ctl->counts[s + 1]) > plan.escalate_rows) { stopped = true; s++; break; }
-    }
-    const int done_steps = s;   // table now in buf[done_steps & 1], rows in counts[done_steps]
-    uint64_t rows = ld_count(&ctl->counts[done_steps]);
-    uint32_t table_in_host = 0;
-    const uint32_t status = __ldcg(&ctl->status);
-    if (!stopped && status == 0 && plan.do_project && rows > 0) {
-        // final_process projection, straight into the mapped staging area when it fits
-        ProjParam pp;
-        pp.in = plan.buf[done_steps & 1];
-        pp.in_count = &ctl->counts[done_steps];
-        pp.out_count = &ctl->counts[done_steps + 1];
-        pp.status = &ctl->status;
-        pp.C = ncols_final; pp.Cn = plan.proj_n;
-        for (int i = 0; i < MAX_COLS; i++) pp.cols[i] = plan.proj_cols[i];
-        const uint64_t words = rows * (uint64_t)plan.proj_n;
-        if (plan.host_table && words <= plan.host_table_words) {
-            pp.out = plan.host_table; pp.out_cap_rows = rows;
-            table_in_host = 1;
-        } else {
-            pp.out = plan.buf[(done_steps + 1) & 1]; pp.out_cap_rows = plan.cap_words / (uint64_t)plan.proj_n;
-        }
-        project_body(pp, rows, 0, 1);
-        __threadfence_system();   // every thread's stores (possibly to mapped host memory) before the record
-        __syncthreads();
-    }
-    if (tid == 0) {
-        HostRec *rec = plan.rec;
-        rec->rows = rows;
-        rec->status = __ldcg(&ctl->status);
-        rec->resume_step = done_steps;
-        rec->table_in_host = table_in_host;
-        __threadfence_system();
-        rec->seq = plan.seq;
-    }
+    const uint64_t rows = ld_count(count);
+    const uint64_t sr = (uint64_t)__ldcg(status) | ((uint64_t)(uint32_t)resume << 32);
+    uint64_t *r = (uint64_t *)rec;
+    st_sys_v2u64(r + 2, sr, record_check(seq, rows, sr, 0));
+    st_sys_v2u64(r, seq, rows);
 }
 
 // =============================================================================================
@@ -356,6 +245,7 @@ struct wk_engine {
     bool q_timed = false;
     int num_sms = 148;
     int occ[3] = {1, 1, 1};
+    int variant = 1;
     uint64_t launches = 0;
     uint64_t light_escalate_rows = 4096;
     void *d_flush = nullptr;             // > L2-sized scratch for wk_engine_flush_l2
@@ -445,17 +335,41 @@ static int ensure_step_room(wk_engine *e) {
     return WK_SUCCESS;
 }
 
-// wait for the mapped completion record (spin; falls back to stream status to catch faults)
-static int wait_record(wk_engine *e, uint64_t seq) {
+// Wait for the mapped completion record of sequence number `seq` (spin; falls back to the stream
+// status to catch faults).  The record and an optional zero-copy result table are written without
+// a device-side system fence, so they are accepted only once the record's checksum matches what
+// the host reads (table_cols > 0: the table in h_stage is rows x table_cols words).
+struct RecView { uint64_t rows; uint32_t status; int resume; };
+
+static bool record_valid(wk_engine *e, uint64_t seq, int nsteps_full, int table_cols, RecView &out) {
+    volatile uint64_t *r = (volatile uint64_t *)e->h_rec;
+    if (r[0] != seq) return false;
+    const uint64_t rows = r[1], sr = r[2], check = r[3];
+    uint64_t tsum = 0;
+    const int resume = (int)(uint32_t)(sr >> 32);
+    if (table_cols > 0 && resume == nsteps_full && (uint32_t)sr == 0 && rows > 0) {
+        const uint64_t words = rows * (uint64_t)table_cols;
+        if (words > e->stage_words) return false;
+        const volatile uint32_t *t = (const volatile uint32_t *)e->h_stage;
+        for (uint64_t i = 0; i < words; i++) tsum += table_word_mix(t[i], i);
+    }
+    if (record_check(seq, rows, sr, tsum) != check) return false;
+    out.rows = rows;
+    out.status = (uint32_t)sr;
+    out.resume = resume;
+    return true;
+}
+
+static int wait_record(wk_engine *e, uint64_t seq, int nsteps_full, int table_cols, RecView &out) {
     uint32_t spins = 0;
-    while (e->h_rec->seq != seq) {
+    while (!record_valid(e, seq, nsteps_full, table_cols, out)) {
         if ((++spins & 0x3FF) == 0) {
             cudaError_t q = cudaStreamQuery(e->stream);
             if (q == cudaSuccess) {
-                if (e->h_rec->seq == seq) break;
+                if (record_valid(e, seq, nsteps_full, table_cols, out)) break;
                 CUDA_TRY(cudaStreamSynchronize(e->stream));
-                if (e->h_rec->seq == seq) break;
-                fprintf(stderr, "[wukong_b200] completion record missing (seq %llu)\n", (unsigned long long)seq);
+                if (record_valid(e, seq, nsteps_full, table_cols, out)) break;
+                fprintf(stderr, "[wukong_b200] completion record missing or corrupt (seq %llu)\n", (unsigned long long)seq);
                 return WK_ERR_CUDA;
             } else if (q != cudaErrorNotReady) {
                 CUDA_TRY(q);
@@ -472,19 +386,38 @@ static int sync_rows(wk_engine *e, uint64_t *rows, cudaEvent_t after = nullptr) 
     CUDA_TRY(cudaGetLastError());
     if (after) cudaEventRecord(after, e->stream);   // device-side end of the query, before the host waits
     e->launches++;
-    int rc = wait_record(e, seq);
+    RecView rv;
+    int rc = wait_record(e, seq, -1, 0, rv);
     if (rc) return rc;
-    if (rows) *rows = e->h_rec->rows;
-    if (e->h_rec->status & 1u) return WK_ERR_RBUF_OVERFLOW;
+    if (rows) *rows = rv.rows;
+    if (rv.status & 1u) return WK_ERR_RBUF_OVERFLOW;
     return WK_SUCCESS;
 }
 
 static size_t rows_smem(int C) { return (size_t)TILE_ROWS * (size_t)(C | 1) * sizeof(uint32_t); }
 
+// kernel variants (probe batch, min CTAs/SM); WK_VARIANT selects one for tuning runs
+#define WK_NUM_VARIANTS 4
+#define WK_DEFAULT_VARIANT 1
+typedef void (*StepKernelFn)(const StepParam);
+template <int MODE>
+static StepKernelFn step_kernel_variant(int v) {
+    switch (v) {
+    case 0: return step_kernel<MODE, 8, 1>;
+    case 2: return step_kernel<MODE, 4, 5>;
+    case 3: return step_kernel<MODE, 2, 6>;
+    default: return step_kernel<MODE, 4, 4>;
+    }
+}
+static StepKernelFn step_kernel_fn(int mode, int v) {
+    return mode == MODE_K2U ? step_kernel_variant<MODE_K2U>(v)
+         : mode == MODE_K2K ? step_kernel_variant<MODE_K2K>(v) : step_kernel_variant<MODE_K2C>(v);
+}
+
 template <int MODE>
 static int launch_step(wk_engine *e, const StepParam &p) {
     const int grid = e->num_sms * e->occ[MODE];
-    step_kernel<MODE><<<grid, CTA_THREADS, rows_smem(p.C), e->stream>>>(p);
+    step_kernel_fn(MODE, e->variant)<<<grid, CTA_THREADS, rows_smem(p.C), e->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return WK_SUCCESS;
 }
@@ -757,9 +690,15 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     e->num_sms = prop.multiProcessorCount;
     // resident CTAs per SM of each fused kernel (persistent grid = SMs x occupancy)
     const size_t smem = rows_smem(4);
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[MODE_K2U], step_kernel<MODE_K2U>, CTA_THREADS, smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[MODE_K2K], step_kernel<MODE_K2K>, CTA_THREADS, smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[MODE_K2C], step_kernel<MODE_K2C>, CTA_THREADS, smem));
+    e->variant = WK_DEFAULT_VARIANT;
+    if (const char *ev = getenv("WK_VARIANT")) {
+        const int v = atoi(ev);
+        if (v >= 0 && v < WK_NUM_VARIANTS) e->variant = v;
+    }
+    for (int m = 0; m < 3; m++)
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], step_kernel_fn(m, e->variant), CTA_THREADS, smem));
+    if (getenv("WK_VERBOSE"))
+        fprintf(stderr, "[wukong_b200] variant %d: CTAs/SM k2u=%d k2k=%d k2c=%d, %d SMs\n", e->variant, e->occ[0], e->occ[1], e->occ[2], e->num_sms);
     for (int i = 0; i < 3; i++)
         if (e->occ[i] < 1) e->occ[i] = 1;
     int rc = reset_ctl(e);
@@ -988,26 +927,26 @@ static int plan_steps(const wk_pattern_t *pats, int npat, int nvars, std::vector
 }
 
 static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt_tid, int mt_factor, bool project,
-                     const std::vector<int32_t> &proj_cols, int final_cols) {
+                     const std::vector<int32_t> &proj_cols, RecView &rv) {
     LightPlan lp;
     memset(&lp, 0, sizeof(lp));
     lp.vertices = e->store->d_vertices;
     lp.edges = e->store->d_edges;
     lp.buf[0] = e->buf[0];
     lp.buf[1] = e->buf[1];
-    lp.ctl = e->d_ctl;
+    lp.counts = e->d_ctl->counts;
+    lp.stats = e->d_ctl->stats;
+    lp.status = &e->d_ctl->status;
+    lp.ctl_words = (uint64_t *)e->d_ctl;
+    lp.ctl_nwords = (int)(sizeof(CtlBlock) / sizeof(uint64_t));
     lp.rec = e->d_rec;
     lp.host_table = e->d_stage;
     lp.host_table_words = e->stage_words;
     lp.cap_words = e->cap_words;
-    lp.escalate_rows = e->light_escalate_rows;
     lp.nsteps = (int)steps.size();
-    lp.first_step = 0;
     lp.do_project = project ? 1 : 0;
     lp.proj_n = (int)proj_cols.size();
-    lp.final_cols = final_cols;
     for (size_t i = 0; i < proj_cols.size(); i++) lp.proj_cols[i] = (int8_t)proj_cols[i];
-    int maxC = 1;
     for (size_t i = 0; i < steps.size(); i++) {
         const PlannedStep &ps = steps[i];
         LightStep &ls = lp.steps[i];
@@ -1018,7 +957,6 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
         ls.end_const = ps.end_const;
         ls.mt_tid = mt_tid;
         ls.mt_factor = mt_factor < 1 ? 1 : mt_factor;
-        if (ps.in_cols > maxC) maxC = ps.in_cols;
         if (ps.kind == KIND_I2U || ps.kind == KIND_C2U) {
             const wk_segmeta_t *m = seg_of_key(e->store, ps.vid, ps.pid, ps.dir);
             if (!m) return WK_ERR_NO_SEGMENT;
@@ -1029,23 +967,21 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
             const wk_segmeta_t *m = index_mode ? find_seg(e->store, 1, WK_PREDICATE_ID, ps.dir) : find_seg(e->store, 0, ps.pid, ps.dir);
             if (!m) return WK_ERR_NO_SEGMENT;
             ls.seg = make_segparam(m, ps.pid, ps.dir, index_mode);
-            ls.inv_c = ((1u << 20) + (uint32_t)ps.in_cols - 1) / (uint32_t)ps.in_cols;
         }
     }
     lp.seq = ++e->seq;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->profiling >= 2) { ev0 = get_event(e); ev1 = get_event(e); if (ev0) cudaEventRecord(ev0, e->stream); }
-    light_query_kernel<<<1, CTA_THREADS, rows_smem(maxC), e->stream>>>(lp);
+    light_query_kernel<<<1, CTA_THREADS, 0, e->stream>>>(lp);
     CUDA_TRY(cudaGetLastError());
     if (ev0 && ev1) cudaEventRecord(ev1, e->stream);
     if (e->profiling) { cudaEventRecord(e->q_ev1, e->stream); e->q_timed = true; }
     e->launches++;
-    int rc = wait_record(e, lp.seq);
+    int rc = wait_record(e, lp.seq, (int)steps.size(), project ? (int)proj_cols.size() : 0, rv);
     if (rc) return rc;
     // one record per step the fused kernel actually ran; the single launch (and its event time)
     // is attributed to the first of them
-    const int ran = e->h_rec->resume_step;
-    for (int i = 0; i < ran && i < (int)steps.size(); i++) {
+    for (int i = 0; i < rv.resume && i < (int)steps.size(); i++) {
         e->recs.emplace_back();
         StepRecord &r = e->recs.back();
         r.kind = steps[i].kind;
@@ -1103,17 +1039,18 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
     bool table_in_host = false;
     size_t next = 0;
     if (light) {
-        rc = run_light(e, steps, mt_tid, mt_factor, want_table, proj_cols, final_cols);
+        RecView rv;
+        rc = run_light(e, steps, mt_tid, mt_factor, want_table, proj_cols, rv);
         if (rc) return rc;
-        if (e->h_rec->status & 1u) return WK_ERR_RBUF_OVERFLOW;
-        next = (size_t)e->h_rec->resume_step;
+        if (rv.status & 1u) return WK_ERR_RBUF_OVERFLOW;
+        next = (size_t)rv.resume;
         e->step = (int)next;
         e->ncols = (next == steps.size()) ? final_cols : steps[next].in_cols;
-        rows = e->h_rec->rows;
-        if (next == steps.size()) {
-            table_in_host = e->h_rec->table_in_host != 0;
-            if (want_table && rows > 0 && !table_in_host) { e->step += 1; }   // projected into the other buffer
-            if (want_table && rows > 0) { cols = nrequired; e->ncols = nrequired; }
+        rows = rv.rows;
+        if (next == steps.size() && want_table && rows > 0) {
+            // the fused kernel projected straight into the mapped staging area
+            table_in_host = true;
+            cols = nrequired;
         }
     }
     if (next < steps.size()) {

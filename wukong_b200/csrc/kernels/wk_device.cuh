@@ -149,6 +149,7 @@ struct TileSmem {
 // probed vertex id, sm.ptr[row] = 0, sm.next[row] = 0, followed by __syncwarp().
 // After the call sm.ptr[row] holds the raw iptr_t of the key (0 = miss).  Returns the number of
 // buckets this lane's own row visited (L_i).
+template <int BATCH>   // buckets fetched per lane before the first compare: 8, 4 or 2 (register/MLP trade-off)
 __device__ __forceinline__ uint32_t warp_probe(const uint4 *__restrict__ vertices, const SegParam &seg,
                                                TileSmem &sm, int warp_row0, int lane, bool active) {
     const int slot = lane & 7;
@@ -157,25 +158,29 @@ __device__ __forceinline__ uint32_t warp_probe(const uint4 *__restrict__ vertice
     bool pending = active;
     uint32_t visited = 0;
     while (true) {
-        uint32_t b[8];
-        uint4 v[8];
+#pragma unroll 1
+        for (int part = 0; part < 8 / BATCH; part++) {
+            const int rbase = warp_row0 + part * (4 * BATCH);
+            uint32_t b[BATCH];
+            uint4 v[BATCH];
 #pragma unroll
-        for (int r = 0; r < 8; r++) b[r] = sm.bucket[warp_row0 + 4 * r + grp];
+            for (int r = 0; r < BATCH; r++) b[r] = sm.bucket[rbase + 4 * r + grp];
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            v[r] = make_uint4(0, 0, 0, 0);
-            if (b[r] != BUCKET_NONE) v[r] = ld_slot(vertices + ((uint64_t)b[r] * 8 + slot));
-        }
+            for (int r = 0; r < BATCH; r++) {
+                v[r] = make_uint4(0, 0, 0, 0);
+                if (b[r] != BUCKET_NONE) v[r] = ld_slot(vertices + ((uint64_t)b[r] * 8 + slot));
+            }
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            if (b[r] != BUCKET_NONE) {
-                const int j = warp_row0 + 4 * r + grp;
-                const uint64_t kk = (uint64_t)v[r].x | ((uint64_t)v[r].y << 32);
-                if (slot < 7) {
-                    if (kk == step_key(seg, sm.cur[j])) sm.ptr[j] = (uint64_t)v[r].z | ((uint64_t)v[r].w << 32);
-                } else {
-                    // last slot: key.vid is the next bucket of the chain (0 / empty key = end)
-                    sm.next[j] = (uint32_t)(kk >> WK_KEY_VID_SHIFT);
+            for (int r = 0; r < BATCH; r++) {
+                if (b[r] != BUCKET_NONE) {
+                    const int j = rbase + 4 * r + grp;
+                    const uint64_t kk = (uint64_t)v[r].x | ((uint64_t)v[r].y << 32);
+                    if (slot < 7) {
+                        if (kk == step_key(seg, sm.cur[j])) sm.ptr[j] = (uint64_t)v[r].z | ((uint64_t)v[r].w << 32);
+                    } else {
+                        // last slot: key.vid is the next bucket of the chain (0 / empty key = end)
+                        sm.next[j] = (uint32_t)(kk >> WK_KEY_VID_SHIFT);
+                    }
                 }
             }
         }
@@ -218,7 +223,7 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t x, TileSmem &s
 
 // ---- one 256-row tile of a known_to_{unknown,known,const} step --------------------------------
 // rows: dynamic shared memory, TILE_ROWS x CP words (CP = C | 1 to spread banks)
-template <int MODE>
+template <int MODE, int BATCH>
 __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, uint32_t nrows, TileSmem &sm,
                                              uint32_t *rows, uint64_t &acc_visited, uint64_t &acc_edges) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -253,7 +258,7 @@ __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, 
     __syncwarp();
 
     // C. probe
-    acc_visited += warp_probe(p.vertices, p.seg, sm, warp * 32, lane, active);
+    acc_visited += warp_probe<BATCH>(p.vertices, p.seg, sm, warp * 32, lane, active);
 
     // D. multiplicity of each row
     const uint64_t ptr = sm.ptr[tid];

@@ -1,0 +1,332 @@
+// Lean single-CTA interpreter for const-start ("light") plans.
+//
+// Light queries (LUBM Q4-Q6: a constant, then a handful of steps over tens to hundreds of rows)
+// are bound by dependent-load latency, not bandwidth.  This kernel therefore
+//   * keeps the whole binding table in shared memory across steps (no global round trips),
+//   * issues all probes of a step at once (thread per row, 8 independent 16-byte loads each),
+//     then all edge loads at once (thread per OUTPUT row, binary search in the scanned degrees),
+//   * keeps every counter in shared memory (no global atomics),
+//   * reports through one 32-byte record in mapped pinned memory, validated by a checksum on the
+//     host instead of a system-scope fence on the device.
+// If a table outgrows shared memory the kernel spills it to the engine's global buffer and tells
+// the host at which step to continue on the multi-CTA path.
+//
+// Step semantics: reference core/engine/sparql.hpp:238-285 (const_to_unknown), :295-407
+// (known_to_unknown), :416-476 (known_to_known), :484-549 (known_to_const), :1507-1550 (projection).
+#pragma once
+#include "wk_device.cuh"
+
+namespace wk {
+
+enum { LIGHT_WORDS = 4096, LIGHT_ROWS = 1024, MAX_LIGHT_STEPS = 24 };
+enum { LKIND_I2U = 0, LKIND_C2U = 1, LKIND_K2U = 2, LKIND_K2K = 3, LKIND_K2C = 4 };
+
+struct LightStep {
+    SegParam seg;
+    uint64_t key;          // seeds
+    int32_t kind, C;
+    int32_t col_start, col_end;
+    uint32_t end_const, _pad0;
+    int32_t mt_tid, mt_factor;
+};
+
+// completion record in mapped pinned host memory (32 bytes, written with two 16-byte stores)
+struct LightRecord {
+    uint64_t seq;
+    uint64_t rows;
+    uint64_t status_resume;   // status | resume_step << 32
+    uint64_t check;           // record_check(seq, rows, status_resume, table checksum)
+};
+
+struct LightPlan {
+    const uint4 *vertices;
+    const uint32_t *edges;
+    uint32_t *buf[2];           // engine result buffers (spill target)
+    uint64_t *counts;           // CtlBlock::counts
+    uint64_t *stats;            // CtlBlock::stats
+    uint32_t *status;           // CtlBlock::status
+    uint64_t *ctl_words;        // whole CtlBlock as 8-byte words (cleared here)
+    int32_t ctl_nwords;
+    int32_t nsteps;
+    LightRecord *rec;           // device pointer of the mapped record
+    uint32_t *host_table;       // device pointer of the mapped staging area
+    uint64_t host_table_words;
+    uint64_t cap_words;         // per result buffer
+    uint64_t seq;
+    int32_t do_project, proj_n;
+    int8_t proj_cols[MAX_COLS];
+    LightStep steps[MAX_LIGHT_STEPS];
+};
+
+__host__ __device__ __forceinline__ uint64_t table_word_mix(uint32_t w, uint64_t i) {
+    return ((uint64_t)w + 0x9E3779B97F4A7C15ull) * (2 * i + 1);
+}
+__host__ __device__ __forceinline__ uint64_t record_check(uint64_t seq, uint64_t rows, uint64_t sr, uint64_t tsum) {
+    uint64_t h = seq * 0xD6E8FEB86659FD93ull;
+    h ^= (rows + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h = (h << 31) | (h >> 33);
+    h ^= (sr + 0x2545F4914F6CDD1Dull) * 0x94D049BB133111EBull;
+    h = (h << 29) | (h >> 35);
+    return h + tsum * 0xFF51AFD7ED558CCDull + 1;
+}
+
+__device__ __forceinline__ void st_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys_v2u64(uint64_t *p, uint64_t a, uint64_t b) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+struct LightSmem {
+    uint32_t tab[2][LIGHT_WORDS];
+    uint64_t ptr[LIGHT_ROWS];       // raw iptr_t of each row's key (0 = miss)
+    uint32_t pre[LIGHT_ROWS + 4];   // multiplicities, then their exclusive prefix
+    uint32_t wsum[CTA_THREADS / 32];
+    uint32_t total;
+    uint32_t seed_len;
+    uint64_t seed_ptr;
+    uint64_t red[CTA_THREADS / 32];
+};
+
+// probe one key, thread-serial over the bucket chain, 8 independent slot loads per bucket
+__device__ __forceinline__ uint64_t probe_thread(const uint4 *__restrict__ vertices, uint64_t key, uint64_t bucket,
+                                                 uint32_t &visited) {
+    visited = 0;
+    while (true) {
+        uint4 v[8];
+        const uint4 *b = vertices + bucket * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = ld_slot(b + i);
+        visited++;
+        uint64_t found = 0;
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const uint64_t kk = (uint64_t)v[i].x | ((uint64_t)v[i].y << 32);
+            if (kk == key) found = (uint64_t)v[i].z | ((uint64_t)v[i].w << 32);
+        }
+        if (found) return found;
+        const uint64_t chain = (uint64_t)v[7].x | ((uint64_t)v[7].y << 32);
+        if (chain == 0) return 0;
+        bucket = chain >> WK_KEY_VID_SHIFT;
+    }
+}
+
+// first index k < size with edges[k] == target, scanning 4 independent loads at a time
+__device__ __forceinline__ bool list_contains(const uint32_t *__restrict__ e, uint32_t size, uint32_t target,
+                                              uint32_t &scanned) {
+    for (uint32_t k0 = 0; k0 < size; k0 += 4) {
+        uint32_t x[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) x[j] = (k0 + j < size) ? ld_edge(e + k0 + j) : ~target;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (k0 + j < size && x[j] == target) { scanned = k0 + j + 1; return true; }
+    }
+    scanned = size;
+    return false;
+}
+
+// exclusive scan of sm.pre[0..n) in place (n <= LIGHT_ROWS), total in sm.total
+__device__ __forceinline__ void light_scan(LightSmem &sm, uint32_t n, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i = (uint32_t)tid * 4 + j;
+        v[j] = (i < n) ? sm.pre[i] : 0;
+        s += v[j];
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) sm.wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CTA_THREADS / 32; w++) {
+        const uint32_t x = sm.wsum[w];
+        if (w < warp) woff += x;
+        tot += x;
+    }
+    uint32_t run = woff + incl - s;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i = (uint32_t)tid * 4 + j;
+        if (i < n) sm.pre[i] = run;
+        run += v[j];
+    }
+    if (tid == 0) sm.total = tot;
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, LightSmem &sm, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
+    if ((tid & 31) == 0) sm.red[tid >> 5] = x;
+    __syncthreads();
+    uint64_t t = 0;
+#pragma unroll
+    for (int w = 0; w < CTA_THREADS / 32; w++) t += sm.red[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
+    __shared__ LightSmem sm;
+    const int tid = threadIdx.x;
+    // this kernel owns the control block: clear it here instead of a separate memset node
+    for (int i = tid; i < plan.ctl_nwords; i += CTA_THREADS) plan.ctl_words[i] = 0;
+
+    uint32_t N = 0;          // rows of the current table (in sm.tab[cur])
+    int C = 0;
+    int cur = 0;
+    int s = 0;
+    bool spilled = false;
+    uint32_t status = 0;
+    for (; s < plan.nsteps; s++) {
+        const LightStep &ls = plan.steps[s];
+        const int nxt = cur ^ 1;
+        uint64_t st_visited = 0, st_edges = 0;
+        if (ls.kind == LKIND_C2U || ls.kind == LKIND_I2U) {
+            if (tid < 32) {
+                uint32_t visited;
+                const uint64_t bucket = ls.seg.bucket_start + fastmod(hash_u64(ls.key), ls.seg.fm);
+                // warp-cooperative single probe (8 lanes load the bucket)
+                uint64_t result = 0, b = bucket;
+                visited = 0;
+                while (true) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (tid < 8) v = ld_slot(plan.vertices + (b * 8 + tid));
+                    const uint64_t kk = (uint64_t)v.x | ((uint64_t)v.y << 32);
+                    const uint64_t pp = (uint64_t)v.z | ((uint64_t)v.w << 32);
+                    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, tid < 7 && kk == ls.key && kk != 0);
+                    const uint64_t chain = __shfl_sync(0xFFFFFFFFu, kk, 7);
+                    visited++;
+                    if (hit) { result = __shfl_sync(0xFFFFFFFFu, pp, __ffs(hit) - 1); break; }
+                    if (chain == 0) break;
+                    b = chain >> WK_KEY_VID_SHIFT;
+                }
+                if (tid == 0) { sm.seed_ptr = result; st_visited = visited; }
+            }
+            __syncthreads();
+            const uint64_t ptr = sm.seed_ptr;
+            const uint64_t size = ptr_size(ptr), off = ptr_off(ptr);
+            const uint64_t mtf = (uint64_t)(ls.mt_factor < 1 ? 1 : ls.mt_factor);
+            const uint64_t start = (uint64_t)ls.mt_tid % mtf;
+            const uint64_t length = size / mtf;
+            const uint64_t begin = start * length;
+            const uint64_t len = (start == mtf - 1) ? (size - begin) : length;
+            if (len > LIGHT_ROWS) { spilled = true; break; }   // nothing done yet: resume at this very step
+            for (uint32_t k = tid; k < len; k += CTA_THREADS) sm.tab[nxt][k] = ld_edge(plan.edges + off + begin + k);
+            if (tid == 0) st_edges = len;
+            N = (uint32_t)len;
+            C = 1;
+        } else {
+            const int Cin = ls.C;
+            const int Cout = (ls.kind == LKIND_K2U) ? Cin + 1 : Cin;
+            const uint32_t *tin = sm.tab[cur];
+            // phase 1: all probes of the step in flight at once (thread per row)
+            for (uint32_t r = tid; r < N; r += CTA_THREADS) {
+                const uint32_t c0 = tin[r * Cin + ls.col_start];
+                const uint64_t key = step_key(ls.seg, c0);
+                const uint64_t bucket = ls.seg.bucket_start + fastmod(hash_u64(key), ls.seg.fm);
+                uint32_t visited;
+                const uint64_t ptr = probe_thread(plan.vertices, key, bucket, visited);
+                st_visited += visited;
+                sm.ptr[r] = ptr;
+                const uint32_t size = ptr_size(ptr);
+                if (ls.kind == LKIND_K2U) {
+                    sm.pre[r] = size;
+                    st_edges += size;
+                } else {
+                    const uint32_t target = (ls.kind == LKIND_K2K) ? tin[r * Cin + ls.col_end] : ls.end_const;
+                    uint32_t scanned;
+                    const bool hit = list_contains(plan.edges + ptr_off(ptr), size, target, scanned);
+                    st_edges += scanned;
+                    sm.pre[r] = hit ? 1u : 0u;
+                }
+            }
+            __syncthreads();
+            // phase 2: scan multiplicities
+            light_scan(sm, N, tid);
+            const uint32_t total = sm.total;
+            if (total > LIGHT_ROWS || (uint64_t)total * (uint64_t)Cout > LIGHT_WORDS) { spilled = true; break; }
+            // phase 3: materialise (thread per OUTPUT row: every edge load of the step in flight at once)
+            uint32_t *tout = sm.tab[nxt];
+            if (ls.kind == LKIND_K2U) {
+                for (uint32_t o = tid; o < total; o += CTA_THREADS) {
+                    uint32_t lo = 0, hi = N;   // largest r with pre[r] <= o
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (sm.pre[mid] <= o) lo = mid; else hi = mid;
+                    }
+                    const uint32_t k = o - sm.pre[lo];
+                    const uint32_t e = ld_edge(plan.edges + ptr_off(sm.ptr[lo]) + k);
+                    for (int c = 0; c < Cin; c++) tout[o * Cout + c] = tin[lo * Cin + c];
+                    tout[o * Cout + Cin] = e;
+                }
+            } else {
+                for (uint32_t r = tid; r < N; r += CTA_THREADS) {
+                    const uint32_t p0 = sm.pre[r];
+                    const uint32_t p1 = (r + 1 < N) ? sm.pre[r + 1] : total;
+                    if (p1 != p0)
+                        for (int c = 0; c < Cin; c++) tout[p0 * Cout + c] = tin[r * Cin + c];
+                }
+            }
+            N = total;
+            C = Cout;
+        }
+        // per-step statistics (algorithmic-bytes accounting)
+        const uint64_t v = block_sum_u64(st_visited, sm, tid);
+        const uint64_t e = block_sum_u64(st_edges, sm, tid);
+        if (tid == 0) {
+            plan.stats[2 * s] = v;
+            plan.stats[2 * s + 1] = e;
+            plan.counts[s + 1] = N;
+        }
+        cur = nxt;
+        __syncthreads();
+    }
+    const int done_steps = s;   // steps [0, done_steps) ran; the table (N x C) is in sm.tab[cur]
+    uint64_t tsum = 0;
+    if (spilled) {
+        // hand the table over to the multi-CTA path: buf[done_steps & 1], counts[done_steps]
+        if (done_steps > 0) {
+            uint32_t *dst = plan.buf[done_steps & 1];
+            const uint32_t words = N * (uint32_t)C;
+            if ((uint64_t)words <= plan.cap_words) {
+                for (uint32_t i = tid; i < words; i += CTA_THREADS) dst[i] = sm.tab[cur][i];
+            } else {
+                status = 1;
+            }
+        }
+    } else if (plan.do_project && N > 0) {
+        // final_process projection straight into the mapped staging area
+        const uint32_t words = N * (uint32_t)plan.proj_n;
+        uint64_t part = 0;
+        if ((uint64_t)words <= plan.host_table_words) {
+            for (uint32_t w = tid; w < words; w += CTA_THREADS) {
+                const uint32_t r = w / (uint32_t)plan.proj_n, j = w - r * (uint32_t)plan.proj_n;
+                const uint32_t val = sm.tab[cur][r * C + plan.proj_cols[j]];
+                st_sys_u32(plan.host_table + w, val);
+                part += table_word_mix(val, w);
+            }
+        } else {
+            status = 1;
+        }
+        tsum = block_sum_u64(part, sm, tid);
+    }
+    if (tid == 0) {
+        if (status) *plan.status = status;
+        const uint64_t rows = N;
+        const uint64_t sr = (uint64_t)status | ((uint64_t)(uint32_t)done_steps << 32);
+        uint64_t *rec = (uint64_t *)plan.rec;
+        st_sys_v2u64(rec + 2, sr, record_check(plan.seq, rows, sr, tsum));
+        st_sys_v2u64(rec, plan.seq, rows);
+    }
+}
+
+}  // namespace wk
