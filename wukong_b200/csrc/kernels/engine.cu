@@ -83,7 +83,8 @@ __device__ __forceinline__ void flush_stats(uint64_t *stats, uint64_t visited, u
 
 // ---- known_to_{unknown,known,const}: one persistent fused kernel ---------------------------------
 // BATCH / MINB: probe batch size and minimum resident CTAs per SM (register budget); see DESIGN.md
-template <int MODE, int BATCH, int MINB>
+// CT: compile-time column count (1..4), 0 = read it from the parameters
+template <int MODE, int BATCH, int MINB, int CT>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel(const StepParam p) {
     extern __shared__ uint32_t dyn_rows[];
     __shared__ TileSmem sm;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel(const StepParam
     for (uint64_t tile = blockIdx.x; tile * TILE_ROWS < N; tile += gridDim.x) {
         const uint64_t row0 = tile * TILE_ROWS;
         const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
-        process_tile<MODE, BATCH>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
+        process_tile<MODE, BATCH, CT>(p, row0, nrows, sm, dyn_rows, acc_visited, acc_edges);
     }
     flush_stats(p.stats, acc_visited, acc_edges);
 }
@@ -146,7 +147,14 @@ __device__ __forceinline__ void seed_body(const SeedParam &p, uint64_t *s_ptr, u
         return;
     }
     const uint32_t *src = p.edges + off + begin;
-    for (uint64_t k = (uint64_t)bid * CTA_THREADS + tid; k < len; k += (uint64_t)nblocks * CTA_THREADS) p.out[k] = ld_edge(src + k);
+    const uint64_t stride = (uint64_t)nblocks * CTA_THREADS;
+    uint64_t k = (uint64_t)bid * CTA_THREADS + tid;
+    for (; k + 3 * stride < len; k += 4 * stride) {   // 4 independent loads in flight per thread
+        const uint32_t a0 = ld_edge(src + k), a1 = ld_edge(src + k + stride), a2 = ld_edge(src + k + 2 * stride),
+                       a3 = ld_edge(src + k + 3 * stride);
+        p.out[k] = a0; p.out[k + stride] = a1; p.out[k + 2 * stride] = a2; p.out[k + 3 * stride] = a3;
+    }
+    for (; k < len; k += stride) p.out[k] = ld_edge(src + k);
     if (bid == 0 && tid == 0) {
         *p.out_count = len;
         atomicAdd((unsigned long long *)&p.stats[1], (unsigned long long)len);
@@ -398,26 +406,36 @@ static size_t rows_smem(int C) { return (size_t)TILE_ROWS * (size_t)(C | 1) * si
 
 // kernel variants (probe batch, min CTAs/SM); WK_VARIANT selects one for tuning runs
 #define WK_NUM_VARIANTS 4
-#define WK_DEFAULT_VARIANT 1
+#define WK_DEFAULT_VARIANT 2
 typedef void (*StepKernelFn)(const StepParam);
-template <int MODE>
+template <int MODE, int CT>
 static StepKernelFn step_kernel_variant(int v) {
     switch (v) {
-    case 0: return step_kernel<MODE, 8, 1>;
-    case 2: return step_kernel<MODE, 4, 5>;
-    case 3: return step_kernel<MODE, 2, 6>;
-    default: return step_kernel<MODE, 4, 4>;
+    case 0: return step_kernel<MODE, 8, 1, CT>;
+    case 1: return step_kernel<MODE, 4, 4, CT>;
+    case 3: return step_kernel<MODE, 2, 6, CT>;
+    default: return step_kernel<MODE, 4, 5, CT>;
     }
 }
-static StepKernelFn step_kernel_fn(int mode, int v) {
-    return mode == MODE_K2U ? step_kernel_variant<MODE_K2U>(v)
-         : mode == MODE_K2K ? step_kernel_variant<MODE_K2K>(v) : step_kernel_variant<MODE_K2C>(v);
+template <int MODE>
+static StepKernelFn step_kernel_cols(int v, int C) {
+    switch (C) {
+    case 1: return step_kernel_variant<MODE, 1>(v);
+    case 2: return step_kernel_variant<MODE, 2>(v);
+    case 3: return step_kernel_variant<MODE, 3>(v);
+    case 4: return step_kernel_variant<MODE, 4>(v);
+    default: return step_kernel_variant<MODE, 0>(v);
+    }
+}
+static StepKernelFn step_kernel_fn(int mode, int v, int C) {
+    return mode == MODE_K2U ? step_kernel_cols<MODE_K2U>(v, C)
+         : mode == MODE_K2K ? step_kernel_cols<MODE_K2K>(v, C) : step_kernel_cols<MODE_K2C>(v, C);
 }
 
 template <int MODE>
 static int launch_step(wk_engine *e, const StepParam &p) {
     const int grid = e->num_sms * e->occ[MODE];
-    step_kernel_fn(MODE, e->variant)<<<grid, CTA_THREADS, rows_smem(p.C), e->stream>>>(p);
+    step_kernel_fn(MODE, e->variant, p.C)<<<grid, CTA_THREADS, rows_smem(p.C), e->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return WK_SUCCESS;
 }
@@ -487,7 +505,7 @@ static int enqueue_seed(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int 
     p.mt_tid = mt_tid;
     p.mt_factor = mt_factor;
     StepRecord &r = begin_step(e, kind, 0);
-    seed_kernel<<<e->num_sms * 2, CTA_THREADS, 0, e->stream>>>(p);
+    seed_kernel<<<e->num_sms * 4, CTA_THREADS, 0, e->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     end_step(e, r, 1);
     e->step = s + 1;
@@ -696,7 +714,7 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
         if (v >= 0 && v < WK_NUM_VARIANTS) e->variant = v;
     }
     for (int m = 0; m < 3; m++)
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], step_kernel_fn(m, e->variant), CTA_THREADS, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], step_kernel_fn(m, e->variant, 3), CTA_THREADS, smem));
     if (getenv("WK_VERBOSE"))
         fprintf(stderr, "[wukong_b200] variant %d: CTAs/SM k2u=%d k2k=%d k2c=%d, %d SMs\n", e->variant, e->occ[0], e->occ[1], e->occ[2], e->num_sms);
     for (int i = 0; i < 3; i++)

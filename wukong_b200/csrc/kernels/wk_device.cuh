@@ -134,10 +134,9 @@ __device__ __forceinline__ uint64_t step_key(const SegParam &s, uint32_t cur) {
 
 // shared-memory working set of one tile
 struct TileSmem {
-    uint32_t cur[TILE_ROWS];
+    uint64_t key[TILE_ROWS];      // raw ikey_t each row probes for
     uint32_t bucket[TILE_ROWS];
     uint32_t next[TILE_ROWS];
-    uint32_t _pad0;
     uint64_t ptr[TILE_ROWS];
     uint64_t wsum[CTA_THREADS / 32];
     uint64_t base;
@@ -145,13 +144,13 @@ struct TileSmem {
 };
 
 // ---- cooperative cluster-hash probe of one warp's 32 rows ------------------------------------
-// Before the call: sm.bucket[row] = first bucket (BUCKET_NONE for inactive rows), sm.cur[row] =
-// probed vertex id, sm.ptr[row] = 0, sm.next[row] = 0, followed by __syncwarp().
+// Before the call: sm.bucket[row] = first bucket (BUCKET_NONE for inactive rows), sm.key[row] =
+// the probed key, sm.ptr[row] = 0, sm.next[row] = 0, followed by __syncwarp().
 // After the call sm.ptr[row] holds the raw iptr_t of the key (0 = miss).  Returns the number of
 // buckets this lane's own row visited (L_i).
 template <int BATCH>   // buckets fetched per lane before the first compare: 8, 4 or 2 (register/MLP trade-off)
-__device__ __forceinline__ uint32_t warp_probe(const uint4 *__restrict__ vertices, const SegParam &seg,
-                                               TileSmem &sm, int warp_row0, int lane, bool active) {
+__device__ __forceinline__ uint32_t warp_probe(const uint4 *__restrict__ vertices, TileSmem &sm, int warp_row0,
+                                               int lane, bool active) {
     const int slot = lane & 7;
     const int grp = lane >> 3;
     const int my_row = warp_row0 + lane;
@@ -176,7 +175,7 @@ __device__ __forceinline__ uint32_t warp_probe(const uint4 *__restrict__ vertice
                     const int j = rbase + 4 * r + grp;
                     const uint64_t kk = (uint64_t)v[r].x | ((uint64_t)v[r].y << 32);
                     if (slot < 7) {
-                        if (kk == step_key(seg, sm.cur[j])) sm.ptr[j] = (uint64_t)v[r].z | ((uint64_t)v[r].w << 32);
+                        if (kk == sm.key[j]) sm.ptr[j] = (uint64_t)v[r].z | ((uint64_t)v[r].w << 32);
                     } else {
                         // last slot: key.vid is the next bucket of the chain (0 / empty key = end)
                         sm.next[j] = (uint32_t)(kk >> WK_KEY_VID_SHIFT);
@@ -199,14 +198,29 @@ __device__ __forceinline__ uint32_t warp_probe(const uint4 *__restrict__ vertice
     return visited;
 }
 
-// block-wide exclusive scan of one uint64 per thread; returns exclusive prefix, total in sm.total
-__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t x, TileSmem &sm, int tid) {
+// Block-wide exclusive scan of the per-row multiplicities + output-space claim for the tile.
+// Returns the row's exclusive prefix; sm.total = tile total, sm.base = first output row of the tile
+// (~0 when the result buffer would overflow: counted, flagged, not written).
+__device__ __forceinline__ uint64_t tile_scan_and_claim(uint32_t mult, TileSmem &sm, int tid, const StepParam &p) {
     const int lane = tid & 31, warp = tid >> 5;
-    uint64_t incl = x;
+    uint64_t incl;
+    // a warp whose 32 multiplicities cannot overflow 32 bits (always, except 2^27-edge hubs) scans in 32 bits
+    if (__all_sync(0xFFFFFFFFu, mult < (1u << 26))) {
+        uint32_t x = mult;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += y;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl = x;
+    } else {
+        uint64_t x = mult;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl = x;
     }
     if (lane == 31) sm.wsum[warp] = incl;
     __syncthreads();
@@ -217,17 +231,39 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t x, TileSmem &s
         if (w < warp) woff += s;
         tot += s;
     }
-    if (tid == 0) sm.total = tot;
-    return woff + incl - x;
+    if (tid == 0) {
+        uint64_t base = 0;
+        if (tot) base = atomicAdd((unsigned long long *)p.out_count, (unsigned long long)tot);
+        if (base + tot > p.out_cap_rows) {
+            atomicOr(p.status, 1u);   // WK_ERR_RBUF_OVERFLOW
+            base = ~0ull;
+        }
+        sm.base = base;
+        sm.total = tot;
+    }
+    __syncthreads();
+    return woff + incl - mult;
+}
+
+template <int CT>
+__device__ __forceinline__ void copy_row(uint32_t *__restrict__ dst, const uint32_t *__restrict__ srow, int C) {
+    if (CT > 0) {
+#pragma unroll
+        for (int c = 0; c < CT; c++) dst[c] = srow[c];
+    } else {
+        for (int c = 0; c < C; c++) dst[c] = srow[c];
+    }
 }
 
 // ---- one 256-row tile of a known_to_{unknown,known,const} step --------------------------------
-// rows: dynamic shared memory, TILE_ROWS x CP words (CP = C | 1 to spread banks)
-template <int MODE, int BATCH>
+// rows: dynamic shared memory, TILE_ROWS x CP words (CP = C | 1 to spread banks).
+// CT > 0: the column count is a compile-time constant (C = 1..4 get their own instantiation).
+template <int MODE, int BATCH, int CT>
 __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, uint32_t nrows, TileSmem &sm,
                                              uint32_t *rows, uint64_t &acc_visited, uint64_t &acc_edges) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = p.C, CP = C | 1;
+    const int C = CT > 0 ? CT : p.C;
+    const int CP = C | 1;
     const int Cout = (MODE == MODE_K2U) ? C + 1 : C;
 
     // A. stage the tile's input rows (coalesced, L2-only loads)
@@ -235,7 +271,7 @@ __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, 
         const uint32_t nwords = nrows * (uint32_t)C;
         const uint32_t *src = p.in + row0 * (uint64_t)C;
         for (uint32_t idx = tid; idx < nwords; idx += CTA_THREADS) {
-            const uint32_t r = (uint32_t)(((uint64_t)idx * p.inv_c) >> 20);
+            const uint32_t r = CT > 0 ? idx / (uint32_t)C : (uint32_t)(((uint64_t)idx * p.inv_c) >> 20);
             const uint32_t c = idx - r * (uint32_t)C;
             rows[r * CP + c] = ld_table(src + idx);
         }
@@ -244,32 +280,36 @@ __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, 
 
     // B. key -> first bucket
     const bool active = (uint32_t)tid < nrows;
-    uint32_t cur = 0;
-    if (active) {
-        cur = rows[tid * CP + p.col_start];
-        const uint64_t key = step_key(p.seg, cur);
-        sm.bucket[tid] = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key), p.seg.fm));
-    } else {
-        sm.bucket[tid] = BUCKET_NONE;
+    const uint32_t *myrow = rows + tid * CP;
+    {
+        uint64_t key = 0;
+        uint32_t bucket = BUCKET_NONE;
+        if (active) {
+            key = step_key(p.seg, myrow[p.col_start]);
+            bucket = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key), p.seg.fm));
+        }
+        sm.key[tid] = key;
+        sm.bucket[tid] = bucket;
+        sm.ptr[tid] = 0;
+        sm.next[tid] = 0;
     }
-    sm.cur[tid] = cur;
-    sm.ptr[tid] = 0;
-    sm.next[tid] = 0;
     __syncwarp();
 
     // C. probe
-    acc_visited += warp_probe<BATCH>(p.vertices, p.seg, sm, warp * 32, lane, active);
+    acc_visited += warp_probe<BATCH>(p.vertices, sm, warp * 32, lane, active);
 
     // D. multiplicity of each row
     const uint64_t ptr = sm.ptr[tid];
     const uint32_t size = active ? ptr_size(ptr) : 0;
     const uint64_t off = ptr_off(ptr);
     uint32_t mult = 0;
+    uint32_t e0 = 0;   // K2U: first edge, fetched while the tile's output space is being claimed
     if (MODE == MODE_K2U) {
         mult = size;
         acc_edges += size;
+        if (size != 0 && size <= SMALL_DEG) e0 = ld_edge(p.edges + off);
     } else {
-        const uint32_t target = (MODE == MODE_K2K) ? (active ? rows[tid * CP + p.col_end] : 0) : p.end_const;
+        const uint32_t target = (MODE == MODE_K2K) ? (active ? myrow[p.col_end] : 0) : p.end_const;
         bool found = false;
         if (size <= SERIAL_SCAN) {
             uint32_t k = 0;
@@ -298,38 +338,25 @@ __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, 
         mult = found ? 1u : 0u;
     }
 
-    // E. claim output space for the tile
-    const uint64_t excl = block_exclusive_scan((uint64_t)mult, sm, tid);
-    __syncthreads();
-    if (tid == 0) {
-        const uint64_t total = sm.total;
-        uint64_t base = 0;
-        if (total) base = atomicAdd((unsigned long long *)p.out_count, (unsigned long long)total);
-        if (base + total > p.out_cap_rows) {
-            atomicOr(p.status, 1u);   // WK_ERR_RBUF_OVERFLOW: counted but not written
-            base = ~0ull;
-        }
-        sm.base = base;
-    }
-    __syncthreads();
+    // E. claim output space for the tile (one 64-bit atomic per tile)
+    const uint64_t excl = tile_scan_and_claim(mult, sm, tid, p);
     const uint64_t base = sm.base;
 
     // F. write the output rows
     if (base != ~0ull && sm.total != 0) {
         if (MODE != MODE_K2U) {
-            if (mult) {
-                uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
-                for (int c = 0; c < C; c++) dst[c] = rows[tid * CP + c];
-            }
+            if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
         } else {
             // small fan-out: the owner thread writes its rows
             if (mult != 0 && mult <= SMALL_DEG) {
                 uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
-                for (uint32_t k = 0; k < mult; k++) {
-                    const uint32_t e = ld_edge(p.edges + off + k);
-                    for (int c = 0; c < C; c++) dst[c] = rows[tid * CP + c];
-                    dst[C] = e;
+                copy_row<CT>(dst, myrow, C);
+                dst[C] = e0;
+                for (uint32_t k = 1; k < mult; k++) {
                     dst += Cout;
+                    const uint32_t e = ld_edge(p.edges + off + k);
+                    copy_row<CT>(dst, myrow, C);
+                    dst[C] = e;
                 }
             }
             // larger fan-out: the warp cooperates on one source row at a time; consecutive lanes
