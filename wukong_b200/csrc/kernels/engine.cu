@@ -99,6 +99,38 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel(const StepParam
     flush_stats(p.stats, acc_visited, acc_edges);
 }
 
+// v4: asynchronously staged tiles (see wk_device.cuh).  Dynamic smem: [bucket staging 32 KB][rows 0][rows 1]
+template <int MODE, int MINB, int CT>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v4(const StepParam p) {
+    extern __shared__ __align__(16) unsigned char dyn4[];
+    __shared__ TileSmem4 sm;
+    if (__ldcg(p.status) != 0) return;
+    const uint64_t N = ld_count(p.in_count);
+    const int C = CT > 0 ? CT : p.C;
+    unsigned char *bkt = dyn4;
+    const uint32_t rows_bytes = ((uint32_t)TILE_ROWS * (uint32_t)C * 4u + 15u) & ~15u;
+    uint32_t *rows_buf[2] = {(uint32_t *)(dyn4 + BKT_BYTES), (uint32_t *)(dyn4 + BKT_BYTES + rows_bytes)};
+    uint64_t acc_visited = 0, acc_edges = 0;
+    uint64_t tile = blockIdx.x;
+    int buf = 0;
+    if (tile * TILE_ROWS < N) {
+        const uint64_t row0 = tile * TILE_ROWS;
+        const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
+        stage_rows_async(p.in, row0, nrows, C, rows_buf[0], threadIdx.x);
+    }
+    for (; tile * TILE_ROWS < N; tile += gridDim.x, buf ^= 1) {
+        const uint64_t row0 = tile * TILE_ROWS;
+        const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
+        const uint64_t nrow0 = (tile + gridDim.x) * TILE_ROWS;
+        const bool has_next = nrow0 < N;
+        const uint32_t nnrows = has_next ? (uint32_t)((N - nrow0 < (uint64_t)TILE_ROWS) ? (N - nrow0) : (uint64_t)TILE_ROWS) : 0;
+        process_tile_v4<MODE, CT>(p, row0, nrows, has_next, nrow0, nnrows, sm, bkt, rows_buf[buf], rows_buf[buf ^ 1],
+                                  acc_visited, acc_edges);
+    }
+    cp_async_wait<0>();
+    flush_stats(p.stats, acc_visited, acc_edges);
+}
+
 // ---- probe of ONE key by the first 8 lanes of a warp (seeds) ---------------------------------------
 __device__ __forceinline__ uint64_t probe_single(const uint4 *__restrict__ vertices, uint64_t key, uint64_t bucket,
                                                  int lane, uint32_t &visited) {
@@ -403,9 +435,12 @@ static int sync_rows(wk_engine *e, uint64_t *rows, cudaEvent_t after = nullptr) 
 }
 
 static size_t rows_smem(int C) { return (size_t)TILE_ROWS * (size_t)(C | 1) * sizeof(uint32_t); }
+// v4: bucket staging + double-buffered rows (opt-in to > 48 KB when many columns)
+static size_t rows_smem_v4(int C) { return (size_t)BKT_BYTES + 2 * (((size_t)TILE_ROWS * C * 4 + 15) & ~(size_t)15); }
+static size_t step_smem(const wk_engine *e, int C);
 
 // kernel variants (probe batch, min CTAs/SM); WK_VARIANT selects one for tuning runs
-#define WK_NUM_VARIANTS 4
+#define WK_NUM_VARIANTS 6
 #define WK_DEFAULT_VARIANT 2
 typedef void (*StepKernelFn)(const StepParam);
 template <int MODE, int CT>
@@ -414,6 +449,8 @@ static StepKernelFn step_kernel_variant(int v) {
     case 0: return step_kernel<MODE, 8, 1, CT>;
     case 1: return step_kernel<MODE, 4, 4, CT>;
     case 3: return step_kernel<MODE, 2, 6, CT>;
+    case 4: return step_kernel_v4<MODE, 4, CT>;
+    case 5: return step_kernel_v4<MODE, 5, CT>;
     default: return step_kernel<MODE, 4, 5, CT>;
     }
 }
@@ -432,10 +469,15 @@ static StepKernelFn step_kernel_fn(int mode, int v, int C) {
          : mode == MODE_K2K ? step_kernel_cols<MODE_K2K>(v, C) : step_kernel_cols<MODE_K2C>(v, C);
 }
 
+static size_t step_smem(const wk_engine *e, int C) { return e->variant >= 4 ? rows_smem_v4(C) : rows_smem(C); }
+
 template <int MODE>
 static int launch_step(wk_engine *e, const StepParam &p) {
     const int grid = e->num_sms * e->occ[MODE];
-    step_kernel_fn(MODE, e->variant, p.C)<<<grid, CTA_THREADS, rows_smem(p.C), e->stream>>>(p);
+    StepKernelFn fn = step_kernel_fn(MODE, e->variant, p.C);
+    const size_t smem = step_smem(e, p.C);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<grid, CTA_THREADS, smem, e->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return WK_SUCCESS;
 }
@@ -707,14 +749,13 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     CUDA_TRY(cudaGetDeviceProperties(&prop, store->device));
     e->num_sms = prop.multiProcessorCount;
     // resident CTAs per SM of each fused kernel (persistent grid = SMs x occupancy)
-    const size_t smem = rows_smem(4);
     e->variant = WK_DEFAULT_VARIANT;
     if (const char *ev = getenv("WK_VARIANT")) {
         const int v = atoi(ev);
         if (v >= 0 && v < WK_NUM_VARIANTS) e->variant = v;
     }
     for (int m = 0; m < 3; m++)
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], step_kernel_fn(m, e->variant, 3), CTA_THREADS, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], step_kernel_fn(m, e->variant, 3), CTA_THREADS, step_smem(e, 3)));
     if (getenv("WK_VERBOSE"))
         fprintf(stderr, "[wukong_b200] variant %d: CTAs/SM k2u=%d k2k=%d k2c=%d, %d SMs\n", e->variant, e->occ[0], e->occ[1], e->occ[2], e->num_sms);
     for (int i = 0; i < 3; i++)

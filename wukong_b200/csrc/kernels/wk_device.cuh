@@ -387,4 +387,253 @@ __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, 
     __syncthreads();   // smem is reused by the next tile
 }
 
+
+// =============================================================================================
+// v4 tile pipeline: asynchronous staging (cp.async / LDGSTS) + owner-thread bucket scan
+//
+//  * the tile's input rows are fetched with 16-byte cp.async into a double buffer one tile ahead,
+//  * each bucket (128 B) is fetched by 8 lanes with one 16-byte cp.async each (one L1 wavefront per
+//    probe, no registers held while the loads are in flight) into a per-warp staging area whose
+//    16-byte chunks are XOR-swizzled by the row number,
+//  * the row's owner thread then scans its 7 keys from shared memory: one warp instruction covers
+//    32 rows (the register-staged variant above covers 4), which is what matters once the kernel is
+//    instruction-issue bound,
+//  * rare chain hops (a few % of the rows) are walked by the owner thread straight from global.
+// =============================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct TileSmem4 {
+    uint64_t wsum[CTA_THREADS / 32];
+    uint64_t base;
+    uint64_t total;
+};
+enum { BKT_BYTES = TILE_ROWS * 128 };   // bucket staging area of one CTA
+
+// issue the asynchronous copy of one tile's input rows (nrows x C words, contiguous) into `dst`
+__device__ __forceinline__ void stage_rows_async(const uint32_t *__restrict__ in, uint64_t row0, uint32_t nrows, int C,
+                                                 uint32_t *dst, int tid) {
+    const uint32_t nwords = nrows * (uint32_t)C;
+    const uint32_t *src = in + row0 * (uint64_t)C;   // 16-byte aligned: row0 is a multiple of 256
+    const uint32_t nvec = nwords >> 2;
+    const uint32_t d0 = smem_u32(dst);
+    for (uint32_t i = tid; i < nvec; i += CTA_THREADS) cp_async16(d0 + i * 16, src + i * 4);
+    const uint32_t tail = nwords & 3u;
+    if ((uint32_t)tid < tail) cp_async4(d0 + (nvec * 4 + tid) * 4, src + nvec * 4 + tid);
+    cp_async_commit();
+}
+
+// thread-serial walk of a bucket chain from global memory (slow path: only rows whose first
+// bucket neither holds the key nor ends the chain)
+__device__ __noinline__ uint64_t chain_walk(const uint4 *__restrict__ vertices, uint64_t key, uint64_t bucket,
+                                            uint32_t &visited) {
+    while (true) {
+        const uint4 *b = vertices + bucket * 8;
+        visited++;
+        uint64_t found = 0;
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const uint4 v = ld_slot(b + i);
+            const uint64_t kk = (uint64_t)v.x | ((uint64_t)v.y << 32);
+            if (kk == key) found = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        }
+        if (found) return found;
+        const uint4 v7 = ld_slot(b + 7);
+        const uint64_t chain = (uint64_t)v7.x | ((uint64_t)v7.y << 32);
+        if (chain == 0) return 0;
+        bucket = chain >> WK_KEY_VID_SHIFT;
+    }
+}
+
+template <int MODE, int CT>
+__device__ __forceinline__ void process_tile_v4(const StepParam &p, uint64_t row0, uint32_t nrows, bool has_next,
+                                                uint64_t next_row0, uint32_t next_nrows, TileSmem4 &sm,
+                                                unsigned char *bkt, const uint32_t *rows, uint32_t *rows_next,
+                                                uint64_t &acc_visited, uint64_t &acc_edges) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = CT > 0 ? CT : p.C;
+    const int Cout = (MODE == MODE_K2U) ? C + 1 : C;
+
+    // A. this tile's rows were issued one iteration ago: wait for them
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // B. key -> first bucket; all 8 lanes of a group fetch one bucket with one 16-byte cp.async each
+    const bool active = (uint32_t)tid < nrows;
+    const uint32_t *myrow = rows + tid * C;
+    uint64_t key = 0;
+    uint32_t bucket = BUCKET_NONE;
+    if (active) {
+        key = step_key(p.seg, myrow[p.col_start]);
+        bucket = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key), p.seg.fm));
+    }
+    {
+        const int slot = lane & 7, grp = lane >> 3;
+        const uint32_t wbase = smem_u32(bkt) + (uint32_t)warp * (32 * 128);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int j = 4 * r + grp;
+            const uint32_t b = __shfl_sync(0xFFFFFFFFu, bucket, j);
+            if (b != BUCKET_NONE)
+                cp_async16(wbase + (uint32_t)j * 128 + (uint32_t)((slot ^ (j & 7)) << 4), p.vertices + ((uint64_t)b * 8 + slot));
+        }
+        cp_async_commit();
+    }
+    // prefetch the next tile's rows while this tile is being processed
+    if (has_next) stage_rows_async(p.in, next_row0, next_nrows, C, rows_next, tid);
+    else cp_async_commit();
+    cp_async_wait<1>();   // the bucket group (the rows group may stay in flight)
+    __syncwarp();
+
+    // C. owner thread scans its bucket in shared memory
+    uint64_t ptr = 0;
+    if (active) {
+        const unsigned char *mb = bkt + (warp * 32 + lane) * 128;
+        const int sw = lane & 7;
+        int hit = -1;
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const uint64_t kk = *(const uint64_t *)(mb + ((i ^ sw) << 4));
+            if (kk == key) hit = i;
+        }
+        uint32_t visited = 1;
+        if (hit >= 0) {
+            ptr = *(const uint64_t *)(mb + ((hit ^ sw) << 4) + 8);
+        } else {
+            const uint64_t chain = *(const uint64_t *)(mb + ((7 ^ sw) << 4));
+            if (chain != 0) ptr = chain_walk(p.vertices, key, chain >> WK_KEY_VID_SHIFT, visited);
+        }
+        acc_visited += visited;
+    }
+
+    // D. multiplicity of each row
+    const uint32_t size = active ? ptr_size(ptr) : 0;
+    const uint64_t off = ptr_off(ptr);
+    uint32_t mult = 0;
+    uint32_t e0 = 0;   // K2U: first edge, fetched while the tile's output space is being claimed
+    if (MODE == MODE_K2U) {
+        mult = size;
+        acc_edges += size;
+        if (size != 0 && size <= SMALL_DEG) e0 = ld_edge(p.edges + off);
+    } else {
+        const uint32_t target = (MODE == MODE_K2K) ? (active ? myrow[p.col_end] : 0) : p.end_const;
+        bool found = false;
+        if (size <= SERIAL_SCAN) {
+            uint32_t k = 0;
+            for (; k < size; k++)
+                if (ld_edge(p.edges + off + k) == target) { found = true; break; }
+            acc_edges += found ? (k + 1) : size;
+        }
+        uint32_t longmask = __ballot_sync(0xFFFFFFFFu, size > SERIAL_SCAN);
+        while (longmask) {
+            const int src = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const uint32_t s_size = __shfl_sync(0xFFFFFFFFu, size, src);
+            const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
+            const uint32_t s_target = __shfl_sync(0xFFFFFFFFu, target, src);
+            uint32_t scanned = s_size;
+            bool hitl = false;
+            for (uint32_t k0 = 0; k0 < s_size; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const bool eq = (k < s_size) && (ld_edge(p.edges + s_off + k) == s_target);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
+                if (m) { hitl = true; scanned = k0 + __ffs(m); break; }
+            }
+            if (lane == src) { found = hitl; acc_edges += scanned; }
+        }
+        mult = found ? 1u : 0u;
+    }
+
+    // E. claim output space for the tile (one 64-bit atomic per tile)
+    const int widx = warp;
+    uint64_t incl;
+    if (__all_sync(0xFFFFFFFFu, mult < (1u << 26))) {
+        uint32_t x = mult;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl = x;
+    } else {
+        uint64_t x = mult;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl = x;
+    }
+    if (lane == 31) sm.wsum[widx] = incl;
+    __syncthreads();
+    uint64_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CTA_THREADS / 32; w++) {
+        const uint64_t sx = sm.wsum[w];
+        if (w < warp) woff += sx;
+        tot += sx;
+    }
+    if (tid == 0) {
+        uint64_t b0 = 0;
+        if (tot) b0 = atomicAdd((unsigned long long *)p.out_count, (unsigned long long)tot);
+        if (b0 + tot > p.out_cap_rows) {
+            atomicOr(p.status, 1u);   // WK_ERR_RBUF_OVERFLOW
+            b0 = ~0ull;
+        }
+        sm.base = b0;
+    }
+    __syncthreads();
+    const uint64_t base = sm.base;
+    const uint64_t excl = woff + incl - mult;
+
+    // F. write the output rows
+    if (base != ~0ull && tot != 0) {
+        if (MODE != MODE_K2U) {
+            if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
+        } else {
+            if (mult != 0 && mult <= SMALL_DEG) {
+                uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
+                copy_row<CT>(dst, myrow, C);
+                dst[C] = e0;
+                for (uint32_t k = 1; k < mult; k++) {
+                    dst += Cout;
+                    const uint32_t e = ld_edge(p.edges + off + k);
+                    copy_row<CT>(dst, myrow, C);
+                    dst[C] = e;
+                }
+            }
+            uint32_t bigmask = __ballot_sync(0xFFFFFFFFu, mult > SMALL_DEG);
+            while (bigmask) {
+                const int src = __ffs(bigmask) - 1;
+                bigmask &= bigmask - 1;
+                const uint32_t s_mult = __shfl_sync(0xFFFFFFFFu, mult, src);
+                const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
+                const uint64_t s_excl = __shfl_sync(0xFFFFFFFFu, excl, src);
+                const uint32_t *srow = rows + (warp * 32 + src) * C;
+                uint32_t *dst = p.out + (base + s_excl) * (uint64_t)Cout;
+                const uint64_t nwords = (uint64_t)s_mult * (uint64_t)Cout;
+                uint32_t r = (uint32_t)lane / (uint32_t)Cout;
+                uint32_t c = (uint32_t)lane - r * (uint32_t)Cout;
+                const uint32_t dr = 32u / (uint32_t)Cout, dc = 32u - dr * (uint32_t)Cout;
+                for (uint64_t w = lane; w < nwords; w += 32) {
+                    dst[w] = (c == (uint32_t)C) ? ld_edge(p.edges + s_off + r) : srow[c];
+                    r += dr;
+                    c += dc;
+                    if (c >= (uint32_t)Cout) { c -= (uint32_t)Cout; r++; }
+                }
+            }
+        }
+    }
+    // no trailing barrier: `rows` is double-buffered, the bucket staging area is private to each
+    // warp, and wsum/base are only rewritten after the next tile's first barrier
+}
+
 }  // namespace wk
