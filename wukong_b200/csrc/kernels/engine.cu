@@ -69,18 +69,6 @@ struct ProjParam {
     int8_t cols[MAX_COLS];
 };
 
-__device__ __forceinline__ void flush_stats(uint64_t *stats, uint64_t visited, uint64_t edges) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        visited += __shfl_down_sync(0xFFFFFFFFu, visited, o);
-        edges += __shfl_down_sync(0xFFFFFFFFu, edges, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (visited) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)visited);
-        if (edges) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)edges);
-    }
-}
-
 // ---- known_to_{unknown,known,const}: one persistent fused kernel ---------------------------------
 // BATCH / MINB: probe batch size and minimum resident CTAs per SM (register budget); see DESIGN.md
 // CT: compile-time column count (1..4), 0 = read it from the parameters
@@ -129,6 +117,15 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v4(const StepPa
     }
     cp_async_wait<0>();
     flush_stats(p.stats, acc_visited, acc_edges);
+}
+
+// v5: warp-autonomous pipeline (see wk_device.cuh).  Dynamic smem: [bucket staging 32 KB][8 warps x 3 x rows]
+template <int MODE, int MINB, int CT>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v5(const StepParam p) {
+    extern __shared__ __align__(16) unsigned char dyn5[];
+    __shared__ TileSmem4 sm;
+    if (__ldcg(p.status) != 0) return;
+    step_body_v5<MODE, CT>(p, ld_count(p.in_count), sm, dyn5);
 }
 
 // ---- probe of ONE key by the first 8 lanes of a warp (seeds) ---------------------------------------
@@ -440,7 +437,7 @@ static size_t rows_smem_v4(int C) { return (size_t)BKT_BYTES + 2 * (((size_t)TIL
 static size_t step_smem(const wk_engine *e, int C);
 
 // kernel variants (probe batch, min CTAs/SM); WK_VARIANT selects one for tuning runs
-#define WK_NUM_VARIANTS 6
+#define WK_NUM_VARIANTS 8
 #define WK_DEFAULT_VARIANT 2
 typedef void (*StepKernelFn)(const StepParam);
 template <int MODE, int CT>
@@ -451,6 +448,8 @@ static StepKernelFn step_kernel_variant(int v) {
     case 3: return step_kernel<MODE, 2, 6, CT>;
     case 4: return step_kernel_v4<MODE, 4, CT>;
     case 5: return step_kernel_v4<MODE, 5, CT>;
+    case 6: return step_kernel_v5<MODE, 4, CT>;
+    case 7: return step_kernel_v5<MODE, 5, CT>;
     default: return step_kernel<MODE, 4, 5, CT>;
     }
 }
@@ -469,7 +468,10 @@ static StepKernelFn step_kernel_fn(int mode, int v, int C) {
          : mode == MODE_K2K ? step_kernel_cols<MODE_K2K>(v, C) : step_kernel_cols<MODE_K2C>(v, C);
 }
 
-static size_t step_smem(const wk_engine *e, int C) { return e->variant >= 4 ? rows_smem_v4(C) : rows_smem(C); }
+static size_t rows_smem_v5(int C) { return (size_t)BKT_BYTES + (size_t)(CTA_THREADS / 32) * 3 * 128 * (size_t)C; }
+static size_t step_smem(const wk_engine *e, int C) {
+    return e->variant >= 6 ? rows_smem_v5(C) : e->variant >= 4 ? rows_smem_v4(C) : rows_smem(C);
+}
 
 template <int MODE>
 static int launch_step(wk_engine *e, const StepParam &p) {

@@ -93,6 +93,18 @@ __device__ __forceinline__ uint32_t ld_edge(const uint32_t *p) { return __ldg(p)
 __device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ uint64_t ld_count(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
 
+__device__ __forceinline__ void flush_stats(uint64_t *stats, uint64_t visited, uint64_t edges) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        visited += __shfl_down_sync(0xFFFFFFFFu, visited, o);
+        edges += __shfl_down_sync(0xFFFFFFFFu, edges, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (visited) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)visited);
+        if (edges) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)edges);
+    }
+}
+
 // ---- per-step parameters (passed by value) ---------------------------------------------------
 enum { MODE_K2U = 0, MODE_K2K = 1, MODE_K2C = 2 };
 enum { TILE_ROWS = 256, CTA_THREADS = 256, MAX_COLS = 32 };
@@ -634,6 +646,269 @@ __device__ __forceinline__ void process_tile_v4(const StepParam &p, uint64_t row
     }
     // no trailing barrier: `rows` is double-buffered, the bucket staging area is private to each
     // warp, and wsum/base are only rewritten after the next tile's first barrier
+}
+
+
+// =============================================================================================
+// v5: warp-autonomous software pipeline.  Each warp stages only its own 32 rows of a tile (triple
+// buffered) and its own 32 buckets, so the only CTA-wide synchronisation left is the scan/claim;
+// the buckets of tile t+1 are already in flight while tile t fetches edges, claims space and writes.
+//   cp.async groups of a warp, oldest first, at the top of an iteration:  B(t), R(t+1)
+// =============================================================================================
+__device__ __forceinline__ void stage_warp_rows(const uint32_t *__restrict__ in, uint64_t row0w, uint32_t n, int C,
+                                                uint32_t *dst, int lane) {
+    const uint32_t nwords = n * (uint32_t)C;
+    const uint32_t *src = in + row0w * (uint64_t)C;   // 16-byte aligned: row0w is a multiple of 32
+    const uint32_t nvec = nwords >> 2;
+    const uint32_t d0 = smem_u32(dst);
+    for (uint32_t i = lane; i < nvec; i += 32) cp_async16(d0 + i * 16, src + i * 4);
+    const uint32_t tail = nwords & 3u;
+    if ((uint32_t)lane < tail) cp_async4(d0 + (nvec * 4 + lane) * 4, src + nvec * 4 + lane);
+}
+
+// membership test over a short edge list with 8 independent loads in flight per round
+__device__ __forceinline__ bool list_contains8(const uint32_t *__restrict__ e, uint32_t size, uint32_t target,
+                                               uint32_t &scanned) {
+    for (uint32_t k0 = 0; k0 < size; k0 += 8) {
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = (k0 + j < size) ? ld_edge(e + k0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (k0 + j < size && x[j] == target) { scanned = k0 + j + 1; return true; }
+    }
+    scanned = size;
+    return false;
+}
+
+template <int MODE, int CT>
+__device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, TileSmem4 &sm, unsigned char *dyn) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = CT > 0 ? CT : p.C;
+    const int Cout = (MODE == MODE_K2U) ? C + 1 : C;
+    const uint32_t rowbytes = 128u * (uint32_t)C;                    // 32 rows x C words
+    unsigned char *bkt = dyn + warp * (32 * 128);                    // this warp's bucket staging area
+    unsigned char *rows_base = dyn + BKT_BYTES + (uint32_t)warp * 3u * rowbytes;
+    const uint64_t stride = gridDim.x;
+    uint64_t tile = blockIdx.x;
+    uint64_t acc_visited = 0, acc_edges = 0;
+    if (tile * TILE_ROWS >= N) { flush_stats(p.stats, 0, 0); return; }
+
+    auto warp_n = [&](uint64_t t) -> uint32_t {
+        const uint64_t r0 = t * TILE_ROWS + (uint64_t)warp * 32;
+        return r0 >= N ? 0u : (uint32_t)((N - r0 < 32) ? (N - r0) : 32);
+    };
+    auto rows_buf = [&](uint32_t k) -> uint32_t * { return (uint32_t *)(rows_base + (k % 3u) * rowbytes); };
+    auto issue_buckets = [&](uint32_t bucket) {
+        const int slot = lane & 7, grp = lane >> 3;
+        const uint32_t wbase = smem_u32(bkt);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int j = 4 * r + grp;
+            const uint32_t b = __shfl_sync(0xFFFFFFFFu, bucket, j);
+            if (b != BUCKET_NONE)
+                cp_async16(wbase + (uint32_t)j * 128 + (uint32_t)((slot ^ (j & 7)) << 4), p.vertices + ((uint64_t)b * 8 + slot));
+        }
+    };
+
+    // ---- prologue: rows(t0) -> keys -> B(t0); R(t0+1) ---------------------------------------------
+    uint32_t it = 0;
+    uint32_t n_cur = warp_n(tile);
+    stage_warp_rows(p.in, tile * TILE_ROWS + (uint64_t)warp * 32, n_cur, C, rows_buf(0), lane);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    uint64_t key = 0;
+    {
+        uint32_t bucket = BUCKET_NONE;
+        if ((uint32_t)lane < n_cur) {
+            key = step_key(p.seg, rows_buf(0)[lane * C + p.col_start]);
+            bucket = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key), p.seg.fm));
+        }
+        issue_buckets(bucket);
+        cp_async_commit();
+    }
+    {
+        const uint64_t t1 = tile + stride;
+        stage_warp_rows(p.in, t1 * TILE_ROWS + (uint64_t)warp * 32, warp_n(t1), C, rows_buf(1), lane);
+        cp_async_commit();
+    }
+
+    for (; tile * TILE_ROWS < N; tile += stride, it++) {
+        const bool active = (uint32_t)lane < n_cur;
+        const uint32_t *rows = rows_buf(it);
+        const uint32_t *myrow = rows + lane * C;
+
+        // 1. buckets of this tile (issued one iteration ago)
+        cp_async_wait<1>();
+        __syncwarp();
+
+        // 2. owner thread scans its bucket in shared memory
+        uint64_t ptr = 0;
+        if (active) {
+            const unsigned char *mb = bkt + lane * 128;
+            const int sw = lane & 7;
+            int hit = -1;
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                const uint64_t kk = *(const uint64_t *)(mb + ((i ^ sw) << 4));
+                if (kk == key) hit = i;
+            }
+            uint32_t visited = 1;
+            if (hit >= 0) {
+                ptr = *(const uint64_t *)(mb + ((hit ^ sw) << 4) + 8);
+            } else {
+                const uint64_t chain = *(const uint64_t *)(mb + ((7 ^ sw) << 4));
+                if (chain != 0) ptr = chain_walk(p.vertices, key, chain >> WK_KEY_VID_SHIFT, visited);
+            }
+            acc_visited += visited;
+        }
+        __syncwarp();   // every lane is done with the staging area before it is refilled
+
+        // 3./4. next tile: its rows have landed -> keys -> buckets in flight during the rest of this tile
+        cp_async_wait<0>();
+        __syncwarp();
+        const uint64_t tnext = tile + stride;
+        const uint32_t n_next = warp_n(tnext);
+        uint64_t key_next = 0;
+        {
+            uint32_t bucket = BUCKET_NONE;
+            if ((uint32_t)lane < n_next) {
+                key_next = step_key(p.seg, rows_buf(it + 1)[lane * C + p.col_start]);
+                bucket = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key_next), p.seg.fm));
+            }
+            issue_buckets(bucket);
+            cp_async_commit();
+        }
+        // 5. rows of the tile after next (its buffer was last used by the previous tile)
+        {
+            const uint64_t t2 = tnext + stride;
+            stage_warp_rows(p.in, t2 * TILE_ROWS + (uint64_t)warp * 32, warp_n(t2), C, rows_buf(it + 2), lane);
+            cp_async_commit();
+        }
+
+        // 6a. multiplicity of each row
+        const uint32_t size = active ? ptr_size(ptr) : 0;
+        const uint64_t off = ptr_off(ptr);
+        uint32_t mult = 0;
+        uint32_t e0 = 0;
+        if (MODE == MODE_K2U) {
+            mult = size;
+            acc_edges += size;
+            if (size != 0 && size <= SMALL_DEG) e0 = ld_edge(p.edges + off);
+        } else {
+            const uint32_t target = (MODE == MODE_K2K) ? (active ? myrow[p.col_end] : 0) : p.end_const;
+            bool found = false;
+            if (size <= SERIAL_SCAN) {
+                uint32_t scanned;
+                found = list_contains8(p.edges + off, size, target, scanned);
+                acc_edges += scanned;
+            }
+            uint32_t longmask = __ballot_sync(0xFFFFFFFFu, size > SERIAL_SCAN);
+            while (longmask) {
+                const int src = __ffs(longmask) - 1;
+                longmask &= longmask - 1;
+                const uint32_t s_size = __shfl_sync(0xFFFFFFFFu, size, src);
+                const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
+                const uint32_t s_target = __shfl_sync(0xFFFFFFFFu, target, src);
+                uint32_t scanned = s_size;
+                bool hitl = false;
+                for (uint32_t k0 = 0; k0 < s_size; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    const bool eq = (k < s_size) && (ld_edge(p.edges + s_off + k) == s_target);
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
+                    if (m) { hitl = true; scanned = k0 + __ffs(m); break; }
+                }
+                if (lane == src) { found = hitl; acc_edges += scanned; }
+            }
+            mult = found ? 1u : 0u;
+        }
+
+        // 6b. claim output space for the tile (one 64-bit atomic per tile; the only CTA-wide sync)
+        uint64_t incl;
+        if (__all_sync(0xFFFFFFFFu, mult < (1u << 26))) {
+            uint32_t x = mult;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += y;
+            }
+            incl = x;
+        } else {
+            uint64_t x = mult;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += y;
+            }
+            incl = x;
+        }
+        if (lane == 31) sm.wsum[warp] = incl;
+        __syncthreads();
+        uint64_t woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < CTA_THREADS / 32; w++) {
+            const uint64_t sx = sm.wsum[w];
+            if (w < warp) woff += sx;
+            tot += sx;
+        }
+        if (tid == 0) {
+            uint64_t b0 = 0;
+            if (tot) b0 = atomicAdd((unsigned long long *)p.out_count, (unsigned long long)tot);
+            if (b0 + tot > p.out_cap_rows) {
+                atomicOr(p.status, 1u);   // WK_ERR_RBUF_OVERFLOW
+                b0 = ~0ull;
+            }
+            sm.base = b0;
+        }
+        __syncthreads();
+        const uint64_t base = sm.base;
+        const uint64_t excl = woff + incl - mult;
+
+        // 6c. write the output rows
+        if (base != ~0ull && tot != 0) {
+            if (MODE != MODE_K2U) {
+                if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
+            } else {
+                if (mult != 0 && mult <= SMALL_DEG) {
+                    uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
+                    copy_row<CT>(dst, myrow, C);
+                    dst[C] = e0;
+                    for (uint32_t k = 1; k < mult; k++) {
+                        dst += Cout;
+                        const uint32_t e = ld_edge(p.edges + off + k);
+                        copy_row<CT>(dst, myrow, C);
+                        dst[C] = e;
+                    }
+                }
+                uint32_t bigmask = __ballot_sync(0xFFFFFFFFu, mult > SMALL_DEG);
+                while (bigmask) {
+                    const int src = __ffs(bigmask) - 1;
+                    bigmask &= bigmask - 1;
+                    const uint32_t s_mult = __shfl_sync(0xFFFFFFFFu, mult, src);
+                    const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
+                    const uint64_t s_excl = __shfl_sync(0xFFFFFFFFu, excl, src);
+                    const uint32_t *srow = rows + src * C;
+                    uint32_t *dst = p.out + (base + s_excl) * (uint64_t)Cout;
+                    const uint64_t nwords = (uint64_t)s_mult * (uint64_t)Cout;
+                    uint32_t r = (uint32_t)lane / (uint32_t)Cout;
+                    uint32_t c = (uint32_t)lane - r * (uint32_t)Cout;
+                    const uint32_t dr = 32u / (uint32_t)Cout, dc = 32u - dr * (uint32_t)Cout;
+                    for (uint64_t w = lane; w < nwords; w += 32) {
+                        dst[w] = (c == (uint32_t)C) ? ld_edge(p.edges + s_off + r) : srow[c];
+                        r += dr;
+                        c += dc;
+                        if (c >= (uint32_t)Cout) { c -= (uint32_t)Cout; r++; }
+                    }
+                }
+            }
+        }
+        __syncwarp();   // rows_buf(it) may be refilled two iterations from now; keep the warp together
+        key = key_next;
+        n_cur = n_next;
+    }
+    cp_async_wait<0>();
+    flush_stats(p.stats, acc_visited, acc_edges);
 }
 
 }  // namespace wk
