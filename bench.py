@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="wukong_b200")
-    ap.add_argument("--scale", type=int, default=40, help="number of universities (LUBM-<scale>)")
+    ap.add_argument("--scale", type=int, default=2560, help="number of universities (LUBM-<scale>)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--plan", default="osdi16_plan")
     ap.add_argument("--rbuf-mb", type=int, default=0)

@@ -438,7 +438,7 @@ static size_t step_smem(const wk_engine *e, int C);
 
 // kernel variants (probe batch, min CTAs/SM); WK_VARIANT selects one for tuning runs
 #define WK_NUM_VARIANTS 8
-#define WK_DEFAULT_VARIANT 2
+#define WK_DEFAULT_VARIANT 6
 typedef void (*StepKernelFn)(const StepParam);
 template <int MODE, int CT>
 static StepKernelFn step_kernel_variant(int v) {
@@ -448,9 +448,9 @@ static StepKernelFn step_kernel_variant(int v) {
     case 3: return step_kernel<MODE, 2, 6, CT>;
     case 4: return step_kernel_v4<MODE, 4, CT>;
     case 5: return step_kernel_v4<MODE, 5, CT>;
-    case 6: return step_kernel_v5<MODE, 4, CT>;
     case 7: return step_kernel_v5<MODE, 5, CT>;
-    default: return step_kernel<MODE, 4, 5, CT>;
+    case 2: return step_kernel<MODE, 4, 5, CT>;
+    default: return step_kernel_v5<MODE, 4, CT>;
     }
 }
 template <int MODE>
