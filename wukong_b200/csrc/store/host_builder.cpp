@@ -217,7 +217,7 @@ void build_store(const wk_sid_t *tr, uint64_t n, const StoreBuildOptions &opt, H
         // size from the data: #buckets = #keys * 100 / (ASSOCIATIVITY * est_load_factor) (global.hpp:99-104)
         const uint64_t lf = (uint64_t)std::max(1, std::min(100, opt.est_load_factor));
         st.num_buckets = total_keys * 100 / (ASSOC * lf) + nsegs + 8;
-        st.num_buckets_ext = (opt.gpu_ext_extents ? st.num_buckets * 15 / 100 : 256 * nsegs + st.num_buckets / 4) + nsegs + 8;
+        st.num_buckets_ext = (opt.gpu_ext_extents ? st.num_buckets * 15 / 100 : 512 * nsegs + st.num_buckets) + nsegs + 8;
         cx.num_slots = (st.num_buckets + st.num_buckets_ext) * ASSOC;
         num_entries = total_edges + 1;
     }
