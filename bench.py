@@ -160,6 +160,80 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_sharded(args, rank, world, local_rank, dist):
+    """vid % N sharded store, one exchange (NCCL all-to-all(v)) before every step whose start variable is not local.
+    Strong scaling: the dataset is fixed, every query is answered by all ranks together."""
+    import torch
+    from wukong_b200 import capi, datagen, host
+    t0 = time.time()
+    tr = datagen.lubm_shard(args.scale, world, rank, seed=args.seed)
+    hs = host.HostStore(tr, num_servers=world, sid=rank)
+    t1 = time.time()
+    gst = hs.upload(local_rank)
+    rbuf = (args.rbuf_mb << 20) if args.rbuf_mb else max(256 << 20, min(8 << 30, int(tr.shape[0]) * 8))
+    eng = capi.Engine(gst, rbuf_bytes=rbuf)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(world, rank, uid[0])
+    plans = load_plans(args.plan)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    rows = {}
+    for _ in range(args.warmup):
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            rc, r, c, _ = eng.query_sharded(pats, nvars, req, blind=True)
+            assert rc == 0, rc
+            rows[q] = r
+    launches0 = eng.launch_count()
+    eng.sync(); dist.barrier(); torch.cuda.synchronize()
+    t_region0 = time.time()
+    sampler.t_mark = t_region0
+    eng.set_profiling(1)
+    dev_us = {q: [] for q in QUERIES}
+    wall_us = {q: [] for q in QUERIES}
+    for _ in range(args.steps):
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            eng.flush_l2()
+            dist.barrier()
+            w0 = time.perf_counter_ns()
+            rc, r, c, _ = eng.query_sharded(pats, nvars, req, blind=True)
+            w1 = time.perf_counter_ns()
+            assert rc == 0, rc
+            dev_us[q].append(eng.last_query_device_us())
+            wall_us[q].append((w1 - w0) / 1e3)
+    eng.sync(); dist.barrier(); torch.cuda.synchronize()
+    t_region = time.time() - t_region0
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    stats = eng.comm_stats()
+    t = torch.tensor([np.mean(dev_us[q]) for q in QUERIES] + [np.mean(wall_us[q]) for q in QUERIES], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    lat = t.cpu().numpy()
+    rr = torch.tensor([rows[q] for q in QUERIES] + [stats["rows_sent"], launches], device="cuda", dtype=torch.int64)
+    dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+    rr = rr.cpu().numpy()
+    if rank == 0:
+        dev_mean, wall_mean = lat[:7], lat[7:]
+        line = {"metric": "lubm_q1_q7_geomean_queries_per_sec", "value": geomean(1e6 / dev_mean), "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dev_mean.sum() / 1e3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": "LUBM-%d Q1-Q7 (%s), store sharded by vid %% %d" % (args.scale, args.plan, world),
+                           "parallelism": "sharded x%d, NCCL all-to-all(v) before non-local steps" % world,
+                           "l2": "flushed (384 MB memset) before every timed query", "value_mode": "blind, device-resident"},
+                "e2e": {"value": geomean(1e6 / wall_mean), "unit": "queries/s", "h2d_bytes_per_step": 584, "d2h_bytes_per_step": 56},
+                "gpu_launches": int(rr[8]), "clocks": clocks,
+                "latency_us": {"device": {"q%d" % q: round(float(dev_mean[i]), 2) for i, q in enumerate(QUERIES)},
+                               "wall": {"q%d" % q: round(float(wall_mean[i]), 2) for i, q in enumerate(QUERIES)}},
+                "rows": {"q%d" % q: int(rr[i]) for i, q in enumerate(QUERIES)},
+                "exchange": {"rows_sent_all_ranks": int(rr[7]), "exchanges_per_rank": stats["exchanges"]},
+                "dataset": {"shard_triples_rank0": int(tr.shape[0]), "build_s": round(t1 - t0, 1)}, "timed_region_s": round(t_region, 2)}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +246,8 @@ def main():
     ap.add_argument("--rbuf-mb", type=int, default=0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N>1: replicas (whole store per GPU, weak scaling) or sharded (vid %% N + NCCL all-to-all)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -198,6 +274,9 @@ def main():
     if capi.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
 
+    if world > 1 and args.mode == "sharded":
+        run_sharded(args, rank, world, local_rank, dist)
+        return
     tr, hs, info = build_dataset(args)
     plans = load_plans(args.plan)
     gst = hs.upload(local_rank)

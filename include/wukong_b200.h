@@ -174,6 +174,11 @@ int wk_comm_init(wk_engine_t *engine, int nranks, int rank, const void *id128);
 /* wk_partition + all-to-all(v) of the partitions over NCCL; afterwards the table holds exactly the
  * rows whose row[col_start] % nranks == rank. */
 int wk_exchange(wk_engine_t *engine, int col_start, uint64_t *out_rows);
+int wk_comm_stats(wk_engine_t *engine, uint64_t *exchanges, uint64_t *rows_sent, uint64_t *rows_recv);
+/* Host-only planning helper: out[i] = -1 no exchange before step i, -2 replicate the table to every
+ * shard (type-index lookup of a known variable, sparql.hpp:1091-1110), c >= 0 re-shard by column c
+ * (need_fork_join with local_var, sparql.hpp:802-814).  Needs no GPU. */
+int wk_plan_exchanges(const wk_pattern_t *patterns, int npatterns, int nvars, int32_t *out);
 /* Sharded whole-query execution: like wk_query_execute, with the store sharded by vid % nranks
  * and an exchange before every step whose start variable is not local (need_fork_join,
  * sparql.hpp:802-814).  out_rows is this rank's share of the result. */

@@ -43,6 +43,7 @@ DECLARED_SYMBOLS = [
     "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_project",
     "wk_query_execute", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
     "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
+    "wk_comm_stats", "wk_plan_exchanges",
 ]
 
 _lib = None
@@ -87,6 +88,14 @@ def lib():
     L.wk_engine_launch_count.argtypes = [vp]
     L.wk_engine_last_query_device_us.argtypes = [vp, C.POINTER(C.c_float)]
     L.wk_engine_flush_l2.argtypes = [vp]
+    L.wk_partition.argtypes = [vp, ci, ci, vp]
+    L.wk_partition_ptr.argtypes = [vp, ci, C.POINTER(vp), pu64]
+    L.wk_comm_unique_id.argtypes = [vp]
+    L.wk_comm_init.argtypes = [vp, ci, ci, vp]
+    L.wk_exchange.argtypes = [vp, ci, pu64]
+    L.wk_comm_stats.argtypes = [vp, pu64, pu64, pu64]
+    L.wk_plan_exchanges.argtypes = [vp, ci, ci, vp]
+    L.wk_query_execute_sharded.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
     L.wk_host_alloc.argtypes = [u64, C.POINTER(vp)]
     L.wk_host_free.argtypes = [vp]
     L.wk_selftest_hash.restype = u64
@@ -272,6 +281,43 @@ class Engine:
             self._out_cache = np.empty(64 << 20, dtype=np.uint32)
         return self._out_cache
 
+    # ---- sharded execution ----
+    def comm_init(self, nranks, rank, unique_id_bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id_bytes)
+        _check(lib().wk_comm_init(self.h, nranks, rank, C.cast(buf, C.c_void_p)), "wk_comm_init")
+
+    def partition(self, col, nparts):
+        out = np.zeros(nparts, dtype=np.uint64)
+        _check(lib().wk_partition(self.h, col, nparts, _ptr(out)), "wk_partition")
+        return out
+
+    def exchange(self, col):
+        n = C.c_uint64(0)
+        _check(lib().wk_exchange(self.h, col, C.byref(n)), "wk_exchange")
+        return n.value
+
+    def comm_stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().wk_comm_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(exchanges=a.value, rows_sent=b.value, rows_recv=c.value)
+
+    def query_sharded(self, patterns, nvars, required_vars, mt_tid=0, mt_factor=1, blind=False, out=None):
+        p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+        rv = np.array(required_vars, dtype=np.int32)
+        n, c = C.c_uint64(0), C.c_int(0)
+        if blind:
+            rc = lib().wk_query_execute_sharded(self.h, _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv), mt_tid, mt_factor, 1,
+                                                None, 0, C.byref(n), C.byref(c))
+            return rc, n.value, c.value, None
+        if out is None:
+            out = self._out_buf
+        rc = lib().wk_query_execute_sharded(self.h, _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv), mt_tid, mt_factor, 0,
+                                            _ptr(out), out.size, C.byref(n), C.byref(c))
+        tbl = None
+        if rc == 0:
+            tbl = out.reshape(-1)[: n.value * c.value].reshape(n.value, c.value) if c.value else np.zeros((0, 0), np.uint32)
+        return rc, n.value, c.value, tbl
+
     def flush_l2(self):
         _check(lib().wk_engine_flush_l2(self.h))
 
@@ -296,3 +342,17 @@ def pinned_array(nwords):
     _check(lib().wk_host_alloc(nwords * 4, C.byref(p)), "wk_host_alloc")
     arr = np.frombuffer((C.c_uint32 * nwords).from_address(p.value), dtype=np.uint32)
     return arr, p
+
+
+def comm_unique_id():
+    buf = (C.c_ubyte * 128)()
+    _check(lib().wk_comm_unique_id(C.cast(buf, C.c_void_p)), "wk_comm_unique_id")
+    return bytes(buf)
+
+
+def plan_exchanges(patterns, nvars):
+    """Host-only: per step -1 (no exchange), -2 (replicate to all shards) or the column to re-shard by."""
+    p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+    out = np.zeros(p.shape[0], dtype=np.int32)
+    _check(lib().wk_plan_exchanges(_ptr(p), p.shape[0], nvars, _ptr(out)), "wk_plan_exchanges")
+    return [int(x) for x in out]

@@ -285,6 +285,7 @@ struct wk_engine {
     int variant = 1;
     uint64_t launches = 0;
     uint64_t light_escalate_rows = 4096;
+    struct wk_comm *comm = nullptr;      // sharded execution (wk_comm_init)
     void *d_flush = nullptr;             // > L2-sized scratch for wk_engine_flush_l2
     size_t flush_bytes = 0;
     std::vector<StepRecord> recs;        // one per step since the last reset
@@ -1203,14 +1204,265 @@ int wk_engine_last_query_device_us(wk_engine_t *e, float *us) {
     return WK_SUCCESS;
 }
 
-// ---- sharded execution: implemented in a later milestone -------------------------------------------
-int wk_partition(wk_engine_t *, int, int, uint64_t *) { return WK_ERR_COMM; }
-int wk_partition_ptr(wk_engine_t *, int, const wk_sid_t **, uint64_t *) { return WK_ERR_COMM; }
-int wk_comm_unique_id(void *) { return WK_ERR_COMM; }
-int wk_comm_init(wk_engine_t *, int, int, const void *) { return WK_ERR_COMM; }
-int wk_exchange(wk_engine_t *, int, uint64_t *) { return WK_ERR_COMM; }
-int wk_query_execute_sharded(wk_engine_t *, const wk_pattern_t *, int, int, const int32_t *, int, int, int, int,
-                             wk_sid_t *, uint64_t, uint64_t *, int *) { return WK_ERR_COMM; }
+}  // extern "C"
+
+#include "wk_sharded.cuh"
+
+static int comm_alloc(wk_engine *e, int nranks, int rank) {
+    if (nranks < 1 || nranks > MAX_PARTS || rank < 0 || rank >= nranks) return WK_ERR_BAD_ARG;
+    wk_comm *c = new wk_comm();
+    c->nranks = nranks;
+    c->rank = rank;
+    CUDA_TRY(cudaMalloc((void **)&c->d_counts, MAX_PARTS * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc((void **)&c->d_cursor, MAX_PARTS * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc((void **)&c->d_matrix, (size_t)nranks * MAX_PARTS * sizeof(uint64_t)));
+    CUDA_TRY(cudaHostAlloc((void **)&c->h_matrix, (size_t)nranks * MAX_PARTS * sizeof(uint64_t), cudaHostAllocDefault));
+    e->comm = c;
+    return WK_SUCCESS;
+}
+
+// bucketise the current table (buf[step&1], counts[step]) by row[col] % nparts into buf[(step+1)&1]
+static int partition_table(wk_engine *e, int col, int nparts) {
+    wk_comm *c = e->comm;
+    if (e->ncols <= 0 || col < 0 || col >= e->ncols) return WK_VERTEX_INVALID;
+    if (nparts < 1 || nparts > MAX_PARTS) return WK_ERR_BAD_ARG;
+    const int s = e->step;
+    CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, MAX_PARTS * sizeof(uint64_t), e->stream));
+    const int grid = e->num_sms * 4;
+    part_count_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->buf[s & 1], &e->d_ctl->counts[s], e->ncols, col, (uint32_t)nparts, c->d_counts);
+    part_scan_kernel<<<1, 1, 0, e->stream>>>(c->d_counts, c->d_cursor, (uint32_t)nparts);
+    part_scatter_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->buf[s & 1], &e->d_ctl->counts[s], e->ncols, col, (uint32_t)nparts,
+                                                             c->d_cursor, e->buf[(s + 1) & 1]);
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 3;
+    return WK_SUCCESS;
+}
+
+// all-to-all(v) of the table.  col >= 0: rows go to rank row[col] % nranks, result stays in buf[step&1];
+// col == -2: every rank receives every row (type-index lookups), result in buf[(step+1)&1], step advances.
+static int exchange_table(wk_engine *e, int col, uint64_t *out_rows) {
+    wk_comm *c = e->comm;
+    NcclApi &nc = nccl_api();
+    if (!c || !c->comm || !nc.ok) return WK_ERR_COMM;
+    const int n = c->nranks, me = c->rank, s = e->step, C = e->ncols;
+    if (C <= 0) return WK_ERR_BAD_ARG;
+    const bool dup = (col == -2);
+    if (!dup) {
+        int rc = partition_table(e, col, n);
+        if (rc) return rc;
+    } else {
+        // every destination gets the whole table: counts[d] = N for all d
+        CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, MAX_PARTS * sizeof(uint64_t), e->stream));
+        for (int d = 0; d < n; d++)
+            CUDA_TRY(cudaMemcpyAsync(&c->d_counts[d], &e->d_ctl->counts[s], sizeof(uint64_t), cudaMemcpyDeviceToDevice, e->stream));
+    }
+    // counts: all-gather the per-destination vectors, then every rank knows the whole n x n matrix
+    NCCL_TRY(nc.AllGather(c->d_counts, c->d_matrix, MAX_PARTS, ncclUint64, c->comm, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_matrix, c->d_matrix, (size_t)n * MAX_PARTS * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    // every rank evaluates every rank's receive total, so an overflow is seen by all of them alike
+    bool overflow = false;
+    for (int r = 0; r < n; r++) {
+        uint64_t tot = 0;
+        for (int src = 0; src < n; src++) tot += c->h_matrix[(size_t)src * MAX_PARTS + r];
+        if (tot * (uint64_t)C > e->cap_words) overflow = true;
+    }
+    if (overflow) return WK_ERR_RBUF_OVERFLOW;
+    uint64_t send_off[MAX_PARTS], recv_off[MAX_PARTS], acc = 0, racc = 0;
+    for (int d = 0; d < n; d++) {
+        send_off[d] = dup ? 0 : acc;
+        acc += c->h_matrix[(size_t)me * MAX_PARTS + d];
+        recv_off[d] = racc;
+        racc += c->h_matrix[(size_t)d * MAX_PARTS + me];
+    }
+    const uint32_t *send_base = dup ? e->buf[s & 1] : e->buf[(s + 1) & 1];
+    uint32_t *recv_base = dup ? e->buf[(s + 1) & 1] : e->buf[s & 1];
+    NCCL_TRY(nc.GroupStart());
+    for (int peer = 0; peer < n; peer++) {
+        const uint64_t sc = c->h_matrix[(size_t)me * MAX_PARTS + peer], rcnt = c->h_matrix[(size_t)peer * MAX_PARTS + me];
+        if (peer == me) continue;
+        if (sc) NCCL_TRY(nc.Send(send_base + send_off[peer] * (uint64_t)C, sc * (uint64_t)C, ncclUint32, peer, c->comm, e->stream));
+        if (rcnt) NCCL_TRY(nc.Recv(recv_base + recv_off[peer] * (uint64_t)C, rcnt * (uint64_t)C, ncclUint32, peer, c->comm, e->stream));
+    }
+    NCCL_TRY(nc.GroupEnd());
+    {   // own share: device-to-device copy
+        const uint64_t sc = c->h_matrix[(size_t)me * MAX_PARTS + me];
+        if (sc) CUDA_TRY(cudaMemcpyAsync(recv_base + recv_off[me] * (uint64_t)C, send_base + send_off[me] * (uint64_t)C,
+                                         sc * (uint64_t)C * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+    }
+    const int dst_step = dup ? s + 1 : s;
+    set_count_kernel<<<1, 1, 0, e->stream>>>(&e->d_ctl->counts[dst_step], racc);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    e->step = dst_step;
+    c->exchanges++;
+    c->rows_sent += acc - c->h_matrix[(size_t)me * MAX_PARTS + me];
+    c->rows_recv += racc - c->h_matrix[(size_t)me * MAX_PARTS + me];
+    c->partitioned = false;
+    if (out_rows) *out_rows = racc;
+    return WK_SUCCESS;
+}
+
+extern "C" {
+
+int wk_partition(wk_engine_t *e, int col_start, int nparts, uint64_t *part_rows) {
+    if (!e || !part_rows) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (!e->comm) {
+        int rc = comm_alloc(e, 1, 0);
+        if (rc) return rc;
+    }
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    rc = partition_table(e, col_start, nparts);
+    if (rc) return rc;
+    wk_comm *c = e->comm;
+    CUDA_TRY(cudaMemcpyAsync(c->h_matrix, c->d_counts, MAX_PARTS * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    uint64_t acc = 0;
+    for (int d = 0; d < nparts; d++) {
+        c->part_rows[d] = part_rows[d] = c->h_matrix[d];
+        c->part_off[d] = acc;
+        acc += c->h_matrix[d];
+    }
+    if (acc * (uint64_t)e->ncols > e->cap_words) return WK_ERR_RBUF_OVERFLOW;
+    c->partitioned = true;
+    return WK_SUCCESS;
+}
+
+int wk_partition_ptr(wk_engine_t *e, int part, const wk_sid_t **d_ptr, uint64_t *rows) {
+    if (!e || !e->comm || !e->comm->partitioned || part < 0 || part >= MAX_PARTS || !d_ptr || !rows) return WK_ERR_BAD_ARG;
+    *d_ptr = e->buf[(e->step + 1) & 1] + e->comm->part_off[part] * (uint64_t)e->ncols;
+    *rows = e->comm->part_rows[part];
+    return WK_SUCCESS;
+}
+
+int wk_comm_unique_id(void *id128) {
+    NcclApi &nc = nccl_api();
+    if (!nc.ok || !id128) return WK_ERR_COMM;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NCCL_TRY(nc.GetUniqueId((ncclUniqueId *)id128));
+    return WK_SUCCESS;
+}
+
+int wk_comm_init(wk_engine_t *e, int nranks, int rank, const void *id128) {
+    if (!e || !id128) return WK_ERR_BAD_ARG;
+    NcclApi &nc = nccl_api();
+    if (!nc.ok) return WK_ERR_COMM;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (!e->comm) {
+        int rc = comm_alloc(e, nranks, rank);
+        if (rc) return rc;
+    }
+    e->comm->nranks = nranks;
+    e->comm->rank = rank;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCCL_TRY(nc.CommInitRank(&e->comm->comm, nranks, id, rank));
+    return WK_SUCCESS;
+}
+
+int wk_exchange(wk_engine_t *e, int col_start, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    return exchange_table(e, col_start, out_rows);
+}
+
+int wk_comm_stats(wk_engine_t *e, uint64_t *exchanges, uint64_t *rows_sent, uint64_t *rows_recv) {
+    if (!e || !e->comm) return WK_ERR_COMM;
+    if (exchanges) *exchanges = e->comm->exchanges;
+    if (rows_sent) *rows_sent = e->comm->rows_sent;
+    if (rows_recv) *rows_recv = e->comm->rows_recv;
+    return WK_SUCCESS;
+}
+
+// host-only: which steps of a plan exchange, for `nranks` shards (out[npatterns])
+int wk_plan_exchanges(const wk_pattern_t *patterns, int npatterns, int nvars, int32_t *out) {
+    if (!patterns || !out) return WK_ERR_BAD_ARG;
+    std::vector<int> v2c;
+    std::vector<PlannedStep> steps;
+    int rc = plan_steps(patterns, npatterns, nvars, v2c, steps);
+    if (rc) return rc;
+    std::vector<int> ex;
+    plan_exchanges(steps, ex);
+    for (size_t i = 0; i < ex.size(); i++) out[i] = ex[i];
+    return WK_SUCCESS;
+}
+
+int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns, int nvars,
+                             const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor, int blind,
+                             wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols) {
+    if (!e || !patterns) return WK_ERR_BAD_ARG;
+    if (!e->comm || !e->comm->comm) return WK_ERR_COMM;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (out_rows) *out_rows = 0;
+    if (out_cols) *out_cols = 0;
+    std::vector<int> v2c;
+    std::vector<PlannedStep> steps;
+    int rc = plan_steps(patterns, npatterns, nvars, v2c, steps);
+    if (rc) return rc;
+    if ((int)steps.size() > MAX_STEPS / 2 - 2) return WK_ERR_BAD_ARG;
+    std::vector<int> ex;
+    plan_exchanges(steps, ex);
+    const int final_cols = steps.back().in_cols + ((steps.back().kind == KIND_K2K || steps.back().kind == KIND_K2C) ? 0 : 1);
+    const bool no_required = !blind && (nrequired <= 0 || !required_vars);
+    const bool want_table = !blind && !no_required;
+    std::vector<int32_t> proj_cols;
+    if (want_table) {
+        for (int i = 0; i < nrequired; i++) {
+            const int idx = -(required_vars[i] + 1);
+            if (required_vars[i] >= 0 || idx >= nvars || v2c[idx] == 0xFFFF) return WK_VERTEX_INVALID;
+            proj_cols.push_back(v2c[idx]);
+        }
+    }
+    e->q_timed = false;
+    if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
+    rc = reset_ctl(e);
+    if (rc) return rc;
+    e->ncols = 0;
+    const int n = e->comm->nranks, me = e->comm->rank;
+    for (size_t i = 0; i < steps.size(); i++) {
+        const PlannedStep &ps = steps[i];
+        if (ex[i] != -1) {
+            rc = exchange_table(e, ex[i], nullptr);
+            if (rc) return rc;
+        }
+        if (ps.kind == KIND_I2U) {
+            rc = enqueue_seed(e, KIND_I2U, 0, ps.pid, ps.dir, mt_tid, mt_factor);   // this shard's slice of the index
+        } else if (ps.kind == KIND_C2U) {
+            if ((int)(ps.vid % (uint64_t)n) == me) {
+                rc = enqueue_seed(e, KIND_C2U, ps.vid, ps.pid, ps.dir, 0, 1);       // the constant's owner (proxy.hpp:205)
+            } else {   // empty 1-column table on the other shards
+                rc = ensure_step_room(e);
+                if (!rc) { e->step += 1; e->ncols = 1; }
+            }
+        } else {
+            rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const);
+        }
+        if (rc) return rc;
+    }
+    if (want_table) {
+        rc = enqueue_project(e, proj_cols.data(), nrequired);
+        if (rc) return rc;
+    }
+    uint64_t rows = 0;
+    rc = sync_rows(e, &rows, e->profiling ? e->q_ev1 : nullptr);
+    if (rc) return rc;
+    if (e->profiling) e->q_timed = true;
+    const int cols = want_table ? nrequired : final_cols;
+    if (out_rows) *out_rows = rows;
+    if (out_cols) *out_cols = cols;
+    if (no_required && rows > 0) return WK_NO_REQUIRED_VAR;
+    if (want_table && rows > 0 && table) {
+        const uint64_t words = rows * (uint64_t)cols;
+        if (words > cap_words) return WK_ERR_BAD_ARG;
+        CUDA_TRY(cudaMemcpyAsync(table, e->buf[e->step & 1], words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return WK_SUCCESS;
+}
 
 // ---- self-test hooks (host-side arithmetic shared with the kernels; callable without a GPU) ----------
 uint64_t wk_selftest_hash(uint64_t key) { return hash_u64(key); }

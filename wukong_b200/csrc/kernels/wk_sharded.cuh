@@ -1,0 +1,133 @@
+// Sharded execution: the store is partitioned by vid % nranks (reference utils/math.hpp:51-55,
+// base_loader.hpp:343-351); before a step whose start variable is not the current sharding column
+// the binding table is bucketised by row[col] % nranks and exchanged all-to-all(v) over NCCL
+// (replaces generate_sub_query + the Bundle/RDMA hop: sparql.hpp:746-814, gpu_hash.cu:599-760,
+// gpu_engine_cuda.hpp:364-407).  Included by engine.cu (needs wk_engine internals).
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+// ---- bucketise-by-owner kernels -----------------------------------------------------------------
+enum { MAX_PARTS = 64 };
+
+__global__ void __launch_bounds__(CTA_THREADS) part_count_kernel(const uint32_t *in, const uint64_t *in_count, int C, int col,
+                                                                 uint32_t nparts, uint64_t *counts) {
+    __shared__ uint32_t hist[MAX_PARTS];
+    if (threadIdx.x < MAX_PARTS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t N = ld_count(in_count);
+    for (uint64_t r = (uint64_t)blockIdx.x * CTA_THREADS + threadIdx.x; r < N; r += (uint64_t)gridDim.x * CTA_THREADS)
+        atomicAdd(&hist[ld_table(in + r * (uint64_t)C + col) % nparts], 1u);
+    __syncthreads();
+    if (threadIdx.x < nparts && hist[threadIdx.x]) atomicAdd((unsigned long long *)&counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+__global__ void part_scan_kernel(const uint64_t *counts, uint64_t *cursor, uint32_t nparts) {
+    uint64_t acc = 0;
+    for (uint32_t d = 0; d < nparts; d++) { cursor[d] = acc; acc += counts[d]; }
+}
+
+// each tile reserves a run per destination, then places its rows (order inside a run is free)
+__global__ void __launch_bounds__(CTA_THREADS) part_scatter_kernel(const uint32_t *in, const uint64_t *in_count, int C, int col,
+                                                                   uint32_t nparts, uint64_t *cursor, uint32_t *out) {
+    __shared__ uint32_t hist[MAX_PARTS];
+    __shared__ uint64_t base[MAX_PARTS];
+    const uint64_t N = ld_count(in_count);
+    for (uint64_t t0 = (uint64_t)blockIdx.x * CTA_THREADS; t0 < N; t0 += (uint64_t)gridDim.x * CTA_THREADS) {
+        if (threadIdx.x < MAX_PARTS) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t r = t0 + threadIdx.x;
+        uint32_t d = 0, local = 0;
+        if (r < N) {
+            d = ld_table(in + r * (uint64_t)C + col) % nparts;
+            local = atomicAdd(&hist[d], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < nparts && hist[threadIdx.x])
+            base[threadIdx.x] = atomicAdd((unsigned long long *)&cursor[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+        __syncthreads();
+        if (r < N) {
+            const uint32_t *src = in + r * (uint64_t)C;
+            uint32_t *dst = out + (base[d] + local) * (uint64_t)C;
+            for (int c = 0; c < C; c++) dst[c] = ld_table(src + c);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- NCCL through dlopen (no link-time dependency; shares the copy torch may already have loaded) ----
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+static NcclApi &nccl_api() {
+    static NcclApi api;
+    if (api.h) return api;
+    api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) { fprintf(stderr, "[wukong_b200] cannot load libnccl: %s\n", dlerror()); return api; }
+#define WK_NCCL_SYM(field, name) *(void **)(&api.field) = dlsym(api.h, name)
+    WK_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    WK_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    WK_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    WK_NCCL_SYM(GroupStart, "ncclGroupStart");
+    WK_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    WK_NCCL_SYM(Send, "ncclSend");
+    WK_NCCL_SYM(Recv, "ncclRecv");
+    WK_NCCL_SYM(AllGather, "ncclAllGather");
+    WK_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef WK_NCCL_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.GroupStart && api.GroupEnd && api.Send && api.Recv && api.AllGather;
+    return api;
+}
+
+#define NCCL_TRY(x)                                                                                        \
+    do {                                                                                                   \
+        ncclResult_t _r = (x);                                                                             \
+        if (_r != ncclSuccess) {                                                                           \
+            fprintf(stderr, "[wukong_b200] NCCL error at %s:%d: %s\n", __FILE__, __LINE__,                 \
+                    nccl_api().GetErrorString ? nccl_api().GetErrorString(_r) : "?");                      \
+            return WK_ERR_COMM;                                                                            \
+        }                                                                                                  \
+    } while (0)
+
+struct wk_comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    uint64_t *d_counts = nullptr;    // [MAX_PARTS] rows per destination
+    uint64_t *d_cursor = nullptr;    // [MAX_PARTS] running offsets
+    uint64_t *d_matrix = nullptr;    // [nranks][MAX_PARTS] all-gathered counts
+    uint64_t *h_matrix = nullptr;    // pinned copy
+    uint64_t part_rows[MAX_PARTS] = {0}, part_off[MAX_PARTS] = {0};
+    bool partitioned = false;
+    uint64_t exchanges = 0, rows_sent = 0, rows_recv = 0;
+};
+
+// Which steps need an exchange: out[i] = -1 none, -2 replicate to every rank, c >= 0 re-shard by column c.
+// Mirrors need_fork_join()/local_var (sparql.hpp:802-814) and dispatch(r,false) for type-index
+// lookups of a known variable (sparql.hpp:1091-1110).
+static void plan_exchanges(const std::vector<PlannedStep> &steps, std::vector<int> &out) {
+    out.assign(steps.size(), -1);
+    int shard_col = -1;
+    for (size_t i = 0; i < steps.size(); i++) {
+        const PlannedStep &ps = steps[i];
+        if (ps.kind == KIND_I2U) { shard_col = 0; continue; }     // local index slice: the new column is local
+        if (ps.kind == KIND_C2U) { shard_col = -1; continue; }    // rows only on the owner of the constant
+        if (ps.kind == KIND_K2U && ps.pid == WK_TYPE_ID && ps.dir == WK_DIR_IN) {
+            out[i] = -2;
+            shard_col = ps.in_cols;   // the appended instances are local to the rank that found them
+            continue;
+        }
+        if (ps.col_start != shard_col) { out[i] = ps.col_start; shard_col = ps.col_start; }
+    }
+}

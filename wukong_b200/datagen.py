@@ -50,3 +50,14 @@ def lubm_write_dir(path, num_univs, seed=1):
     if n == 0:
         raise RuntimeError("failed to write dataset to " + path)
     return n
+
+
+def lubm_shard(num_univs, nranks, rank, seed=1, chunk=128):
+    """Triples of a `num_univs` dataset that shard `rank` of `nranks` stores (subject or object owned by it:
+    vid % nranks == rank, reference base_loader.hpp:169-181), generated chunk-wise to bound host memory."""
+    parts = []
+    for u0 in range(0, num_univs, chunk):
+        t = lubm(num_univs, seed=seed, u_begin=u0, u_end=min(num_univs, u0 + chunk))
+        keep = ((t[:, 0] % nranks) == rank) | ((t[:, 2] % nranks) == rank)
+        parts.append(t[keep])
+    return np.concatenate(parts) if parts else np.zeros((0, 3), dtype=np.uint32)
