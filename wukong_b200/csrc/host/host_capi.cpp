@@ -6,6 +6,12 @@
 #include <cstring>
 #include <string>
 
+#include <sstream>
+
+#include "host/dgraph.hpp"
+#include "host/global.hpp"
+#include "host/gpu_engine.hpp"
+#include "host/proxy.hpp"
 #include "store/host_builder.hpp"
 #include "wukong_b200.h"
 
@@ -78,6 +84,90 @@ int wkh_time_query(wk_engine_t *e, const wk_pattern_t *pats, int npat, int nvars
         }
     }
     return WK_SUCCESS;
+}
+
+// ---- Wukong-surface environment: config + string server + graph + engine + proxy of one server ----
+struct HostEnv {
+    wukong::Global global;
+    wukong::StringServer str_server;
+    wukong::DGraph *graph = nullptr;
+    wukong::GPUEngine *engine = nullptr;
+    wukong::Proxy *proxy = nullptr;
+    std::string error;
+    ~HostEnv() { delete proxy; delete engine; delete graph; }
+};
+
+// config_text: "global_* value" lines (must contain global_input_folder).  device < 0: host-only
+// (config / string server / parser / planner / store build are usable without a GPU).
+void *wkh_env_create(const char *config_text, int device) {
+    HostEnv *env = new HostEnv();
+    std::string bad;
+    if (!env->global.load_str(config_text ? config_text : "", &bad)) { env->error = "bad config item: " + bad; return env; }
+    if (env->global.input_folder.empty()) { env->error = "global_input_folder is not set"; return env; }
+    if (!env->str_server.load(env->global.input_folder)) { env->error = "cannot read str_index in " + env->global.input_folder; return env; }
+    env->graph = new wukong::DGraph(0, env->global, device);
+    if (!env->graph->ok()) { env->error = env->graph->error; return env; }
+    if (device >= 0) {
+        env->engine = new wukong::GPUEngine(0, env->graph, env->global);
+        if (!env->engine->ok()) { env->error = env->engine->error; return env; }
+    }
+    env->proxy = new wukong::Proxy(0, 0, &env->str_server, env->engine, &env->global);
+    return env;
+}
+void wkh_env_destroy(void *h) { delete (HostEnv *)h; }
+const char *wkh_env_error(void *h) { return ((HostEnv *)h)->error.c_str(); }
+uint64_t wkh_env_num_triples(void *h) { HostEnv *e = (HostEnv *)h; return e->graph ? e->graph->num_triples : 0; }
+int wkh_env_num_normal_preds(void *h) { HostEnv *e = (HostEnv *)h; return e->graph ? e->graph->num_normal_preds : 0; }
+uint64_t wkh_env_num_keys(void *h) { HostEnv *e = (HostEnv *)h; return e->graph ? e->graph->store.num_keys : 0; }
+int wkh_env_config_int(void *h, const char *key) {
+    wukong::Global &g = ((HostEnv *)h)->global;
+    std::string k(key);
+    if (k == "global_num_engines") return g.num_engines;
+    if (k == "global_mt_threshold") return g.mt_threshold;
+    if (k == "global_silent") return g.silent;
+    if (k == "global_est_load_factor") return g.est_load_factor;
+    if (k == "global_gpu_rbuf_size_mb") return g.gpu_rbuf_size_mb;
+    if (k == "global_enable_planner") return g.enable_planner;
+    if (k == "global_num_threads") return g.num_threads;
+    return -1;
+}
+
+// parse + apply a user-defined plan; patterns come back as (subject, predicate, direction, object)
+int wkh_parse_plan(void *h, const char *query, const char *fmt, int32_t *pats, int max_pats, int *npats, int *nvars,
+                   int32_t *required, int max_req, int *nreq) {
+    HostEnv *env = (HostEnv *)h;
+    if (!env->proxy) return wukong::UNKNOWN_ERROR;
+    std::istringstream is(query), fs(fmt);
+    wukong::SPARQLQuery q;
+    int rc = env->proxy->prepare(is, fs, q);
+    if (rc) return rc;
+    if ((int)q.pattern_group.patterns.size() > max_pats || (int)q.result.required_vars.size() > max_req) return wukong::UNKNOWN_ERROR;
+    *npats = (int)q.pattern_group.patterns.size();
+    for (int i = 0; i < *npats; i++) {
+        const auto &p = q.pattern_group.patterns[i];
+        pats[4 * i] = p.subject; pats[4 * i + 1] = p.predicate; pats[4 * i + 2] = p.direction; pats[4 * i + 3] = p.object;
+    }
+    *nvars = q.result.nvars;
+    *nreq = (int)q.result.required_vars.size();
+    for (int i = 0; i < *nreq; i++) required[i] = q.result.required_vars[i];
+    return wukong::SUCCESS;
+}
+
+// Proxy::run_single_query.  Returns the reply's status code; the (last) reply's table is copied out.
+int wkh_run_single_query(void *h, const char *query, const char *fmt, int mt_factor, int cnt, int per_pattern,
+                         uint32_t *table, uint64_t cap_words, uint64_t *rows, int *cols, double *latency_us) {
+    HostEnv *env = (HostEnv *)h;
+    if (!env->proxy || !env->engine) return WK_ERR_NO_DEVICE;
+    std::istringstream is(query), fs(fmt);
+    wukong::SPARQLQuery reply;
+    wukong::Monitor mon;
+    int rc = env->proxy->run_single_query(is, fs, mt_factor, cnt, per_pattern != 0, reply, mon);
+    if (rows) *rows = (uint64_t)reply.result.row_num;
+    if (cols) *cols = reply.result.col_num;
+    if (latency_us) *latency_us = mon.latency_usec();
+    if (rc == 0 && table && reply.result.result_table.size() <= cap_words)
+        memcpy(table, reply.result.result_table.data(), reply.result.result_table.size() * sizeof(uint32_t));
+    return rc;
 }
 
 }  // extern "C"

@@ -31,6 +31,20 @@ def lib():
     L.wkh_store_upload.argtypes = [vp, ci, C.POINTER(vp)]
     L.wkh_time_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, ci, ci, vp, vp, C.POINTER(u64),
                                  C.POINTER(ci)]
+    L.wkh_env_create.restype = vp
+    L.wkh_env_create.argtypes = [C.c_char_p, ci]
+    L.wkh_env_destroy.argtypes = [vp]
+    L.wkh_env_error.restype = C.c_char_p
+    L.wkh_env_error.argtypes = [vp]
+    L.wkh_env_num_triples.restype = u64
+    L.wkh_env_num_triples.argtypes = [vp]
+    L.wkh_env_num_normal_preds.argtypes = [vp]
+    L.wkh_env_num_keys.restype = u64
+    L.wkh_env_num_keys.argtypes = [vp]
+    L.wkh_env_config_int.argtypes = [vp, C.c_char_p]
+    L.wkh_parse_plan.argtypes = [vp, C.c_char_p, C.c_char_p, vp, ci, C.POINTER(ci), C.POINTER(ci), vp, ci, C.POINTER(ci)]
+    L.wkh_run_single_query.argtypes = [vp, C.c_char_p, C.c_char_p, ci, ci, ci, vp, u64, C.POINTER(u64), C.POINTER(ci),
+                                       C.POINTER(C.c_double)]
     L._wkh_ready = True
     return L
 
@@ -117,3 +131,58 @@ def time_query(engine, patterns, nvars, required_vars, reps, blind=True, table=N
                               C.byref(rows), C.byref(cols))
     capi._check(rc, "wkh_time_query")
     return wall, dev, rows.value, cols.value
+
+
+class Env:
+    """One Wukong-surface server: Global config + StringServer + DGraph + GPUEngine + Proxy (C++, csrc/host/)."""
+
+    def __init__(self, config_text, device=0):
+        self.h = lib().wkh_env_create(config_text.encode(), device)
+        err = lib().wkh_env_error(self.h).decode()
+        if err:
+            lib().wkh_env_destroy(self.h)
+            self.h = None
+            raise RuntimeError(err)
+
+    def close(self):
+        if self.h:
+            lib().wkh_env_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_triples(self):
+        return lib().wkh_env_num_triples(self.h)
+
+    @property
+    def num_normal_preds(self):
+        return lib().wkh_env_num_normal_preds(self.h)
+
+    def config_int(self, key):
+        return lib().wkh_env_config_int(self.h, key.encode())
+
+    def parse_plan(self, query_text, fmt_text):
+        """-> (status, patterns [(s,p,d,o)], nvars, required_vars) from the C++ Parser + Planner::set_plan"""
+        pats = np.zeros((64, 4), dtype=np.int32)
+        req = np.zeros(64, dtype=np.int32)
+        n, nv, nr = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = lib().wkh_parse_plan(self.h, query_text.encode(), fmt_text.encode(), pats.ctypes.data_as(C.c_void_p), 64,
+                                  C.byref(n), C.byref(nv), req.ctypes.data_as(C.c_void_p), 64, C.byref(nr))
+        return rc, [tuple(int(x) for x in r) for r in pats[: n.value]], nv.value, [int(x) for x in req[: nr.value]]
+
+    def run_single_query(self, query_text, fmt_text, mt_factor=1, cnt=1, per_pattern=False, cap_words=1 << 24):
+        """Proxy::run_single_query -> (status, rows, cols, table or None, latency_us)"""
+        out = np.empty(cap_words, dtype=np.uint32)
+        rows, cols, lat = C.c_uint64(0), C.c_int(0), C.c_double(0)
+        rc = lib().wkh_run_single_query(self.h, query_text.encode(), fmt_text.encode(), mt_factor, cnt, 1 if per_pattern else 0,
+                                        out.ctypes.data_as(C.c_void_p), cap_words, C.byref(rows), C.byref(cols), C.byref(lat))
+        tbl = None
+        if rc == 0 and cols.value:
+            n = rows.value * cols.value
+            tbl = out[:n].reshape(rows.value, cols.value).copy() if n <= cap_words else None
+        return rc, rows.value, cols.value, tbl, lat.value
