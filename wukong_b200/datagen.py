@@ -61,3 +61,23 @@ def lubm_shard(num_univs, nranks, rank, seed=1, chunk=128):
         keep = ((t[:, 0] % nranks) == rank) | ((t[:, 2] % nranks) == rank)
         parts.append(t[keep])
     return np.concatenate(parts) if parts else np.zeros((0, 3), dtype=np.uint32)
+
+
+RMAT_PRED, RMAT_TYPE, RMAT_NUM_NORMAL_PREDS = 2, 3, 3   # str_index: __PREDICATE__, rdf:type, <edge>, <Vertex>
+
+
+def rmat(scale, nedges, seed=42, a=0.57, b=0.19, c=0.19, typed=True):
+    """R-MAT power-law graph as ID triples: (s, 2, o) edges, plus (v, 1, 3) for every vertex that occurs."""
+    L = lib()
+    L.wkgen_rmat_edges.restype = C.c_uint64
+    L.wkgen_rmat_edges.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    out = np.empty((nedges, 3), dtype=np.uint32)
+    L.wkgen_rmat_edges(scale, nedges, seed, a, b, c, out.ctypes.data_as(C.c_void_p))
+    if not typed:
+        return out
+    verts = np.unique(np.concatenate([out[:, 0], out[:, 2]]))
+    tt = np.empty((verts.shape[0], 3), dtype=np.uint32)
+    tt[:, 0] = verts
+    tt[:, 1] = 1
+    tt[:, 2] = RMAT_TYPE
+    return np.concatenate([out, tt])
