@@ -155,7 +155,8 @@ int wkh_parse_plan(void *h, const char *query, const char *fmt, int32_t *pats, i
 
 // Proxy::run_single_query.  Returns the reply's status code; the (last) reply's table is copied out.
 int wkh_run_single_query(void *h, const char *query, const char *fmt, int mt_factor, int cnt, int per_pattern,
-                         uint32_t *table, uint64_t cap_words, uint64_t *rows, int *cols, double *latency_us) {
+                         uint32_t *table, uint64_t cap_words, uint64_t *rows, int *cols, double *latency_us,
+                         uint64_t *table_words) {
     HostEnv *env = (HostEnv *)h;
     if (!env->proxy || !env->engine) return WK_ERR_NO_DEVICE;
     std::istringstream is(query), fs(fmt);
@@ -165,6 +166,7 @@ int wkh_run_single_query(void *h, const char *query, const char *fmt, int mt_fac
     if (rows) *rows = (uint64_t)reply.result.row_num;
     if (cols) *cols = reply.result.col_num;
     if (latency_us) *latency_us = mon.latency_usec();
+    if (table_words) *table_words = reply.result.result_table.size();   // 0 for blind / silent replies
     if (rc == 0 && table && reply.result.result_table.size() <= cap_words)
         memcpy(table, reply.result.result_table.data(), reply.result.result_table.size() * sizeof(uint32_t));
     return rc;

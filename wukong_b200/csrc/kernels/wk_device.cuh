@@ -427,6 +427,8 @@ struct TileSmem4 {
     uint64_t wsum[CTA_THREADS / 32];
     uint64_t base;
     uint64_t total;
+    uint64_t pre[CTA_THREADS / 32][32];   // per warp: exclusive prefix of the 32 multiplicities (balanced expand)
+    uint64_t off[CTA_THREADS / 32][32];   // per warp: edge offsets of the 32 rows
 };
 enum { BKT_BYTES = TILE_ROWS * 128 };   // bucket staging area of one CTA
 
@@ -869,37 +871,33 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
         if (base != ~0ull && tot != 0) {
             if (MODE != MODE_K2U) {
                 if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
-            } else {
-                if (mult != 0 && mult <= SMALL_DEG) {
+            } else if (__all_sync(0xFFFFFFFFu, mult <= 1)) {
+                // at most one edge per row (the common case on LUBM): the owner thread writes its row
+                if (mult) {
                     uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
                     copy_row<CT>(dst, myrow, C);
                     dst[C] = e0;
-                    for (uint32_t k = 1; k < mult; k++) {
-                        dst += Cout;
-                        const uint32_t e = ld_edge(p.edges + off + k);
-                        copy_row<CT>(dst, myrow, C);
-                        dst[C] = e;
-                    }
                 }
-                uint32_t bigmask = __ballot_sync(0xFFFFFFFFu, mult > SMALL_DEG);
-                while (bigmask) {
-                    const int src = __ffs(bigmask) - 1;
-                    bigmask &= bigmask - 1;
-                    const uint32_t s_mult = __shfl_sync(0xFFFFFFFFu, mult, src);
-                    const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
-                    const uint64_t s_excl = __shfl_sync(0xFFFFFFFFu, excl, src);
-                    const uint32_t *srow = rows + src * C;
-                    uint32_t *dst = p.out + (base + s_excl) * (uint64_t)Cout;
-                    const uint64_t nwords = (uint64_t)s_mult * (uint64_t)Cout;
-                    uint32_t r = (uint32_t)lane / (uint32_t)Cout;
-                    uint32_t c = (uint32_t)lane - r * (uint32_t)Cout;
-                    const uint32_t dr = 32u / (uint32_t)Cout, dc = 32u - dr * (uint32_t)Cout;
-                    for (uint64_t w = lane; w < nwords; w += 32) {
-                        dst[w] = (c == (uint32_t)C) ? ld_edge(p.edges + s_off + r) : srow[c];
-                        r += dr;
-                        c += dc;
-                        if (c >= (uint32_t)Cout) { c -= (uint32_t)Cout; r++; }
-                    }
+            } else {
+                // load-balanced expand: every lane takes output rows o = lane, lane+32, ... of the warp's run and
+                // finds its source row by binary search in the 32 scanned multiplicities, so skewed degrees
+                // (power-law graphs, hubs) keep all lanes busy and all edge loads independent
+                const uint64_t wexcl = incl - mult;                      // prefix inside the warp
+                const uint64_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                uint64_t *wpre = sm.pre[warp], *woffs = sm.off[warp];
+                wpre[lane] = wexcl;
+                woffs[lane] = off;
+                __syncwarp();
+                uint32_t *dst0 = p.out + (base + woff) * (uint64_t)Cout;
+                for (uint64_t o = lane; o < wtotal; o += 32) {
+                    int r = 0;
+#pragma unroll
+                    for (int st = 16; st > 0; st >>= 1)
+                        if (wpre[r + st] <= o) r += st;
+                    const uint32_t e = ld_edge(p.edges + woffs[r] + (o - wpre[r]));
+                    uint32_t *dst = dst0 + o * (uint64_t)Cout;
+                    copy_row<CT>(dst, rows + r * C, C);
+                    dst[C] = e;
                 }
             }
         }

@@ -44,7 +44,7 @@ def lib():
     L.wkh_env_config_int.argtypes = [vp, C.c_char_p]
     L.wkh_parse_plan.argtypes = [vp, C.c_char_p, C.c_char_p, vp, ci, C.POINTER(ci), C.POINTER(ci), vp, ci, C.POINTER(ci)]
     L.wkh_run_single_query.argtypes = [vp, C.c_char_p, C.c_char_p, ci, ci, ci, vp, u64, C.POINTER(u64), C.POINTER(ci),
-                                       C.POINTER(C.c_double)]
+                                       C.POINTER(C.c_double), C.POINTER(u64)]
     L._wkh_ready = True
     return L
 
@@ -178,11 +178,11 @@ class Env:
     def run_single_query(self, query_text, fmt_text, mt_factor=1, cnt=1, per_pattern=False, cap_words=1 << 24):
         """Proxy::run_single_query -> (status, rows, cols, table or None, latency_us)"""
         out = np.empty(cap_words, dtype=np.uint32)
-        rows, cols, lat = C.c_uint64(0), C.c_int(0), C.c_double(0)
+        rows, cols, lat, nw = C.c_uint64(0), C.c_int(0), C.c_double(0), C.c_uint64(0)
         rc = lib().wkh_run_single_query(self.h, query_text.encode(), fmt_text.encode(), mt_factor, cnt, 1 if per_pattern else 0,
-                                        out.ctypes.data_as(C.c_void_p), cap_words, C.byref(rows), C.byref(cols), C.byref(lat))
+                                        out.ctypes.data_as(C.c_void_p), cap_words, C.byref(rows), C.byref(cols), C.byref(lat),
+                                        C.byref(nw))
         tbl = None
-        if rc == 0 and cols.value:
-            n = rows.value * cols.value
-            tbl = out[:n].reshape(rows.value, cols.value).copy() if n <= cap_words else None
+        if rc == 0 and cols.value and nw.value and nw.value <= cap_words:
+            tbl = out[: nw.value].reshape(-1, cols.value).copy()
         return rc, rows.value, cols.value, tbl, lat.value
