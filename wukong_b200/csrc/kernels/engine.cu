@@ -34,6 +34,8 @@ enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIN
 struct CtlBlock {
     uint64_t counts[MAX_STEPS + 4];       // counts[s] = rows of the table that step s reads
     uint64_t stats[2 * (MAX_STEPS + 4)];  // per step: buckets visited, edges touched
+    uint64_t hq_packed[MAX_STEPS + 4];    // per step: heavy-tile queue (entries:24 | chunks:40)
+    uint64_t hq_ticket[MAX_STEPS + 4];    // per step: chunk ticket dispenser
     uint32_t status;                      // sticky: bit0 = result buffer overflow
     uint32_t _pad;
 };
@@ -126,6 +128,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v5(const StepPa
     __shared__ TileSmem4 sm;
     if (__ldcg(p.status) != 0) return;
     step_body_v5<MODE, CT>(p, ld_count(p.in_count), sm, dyn5);
+}
+
+template <int CT>
+__global__ void __launch_bounds__(CTA_THREADS) expand_heavy_kernel(const StepParam p) {
+    if (__ldcg(p.status) != 0) return;
+    expand_heavy_body<CT>(p);
 }
 
 // ---- probe of ONE key by the first 8 lanes of a warp (seeds) ---------------------------------------
@@ -223,6 +231,7 @@ __global__ void rebase_kernel(CtlBlock *ctl, int from, int to) {
     const uint64_t v = ctl->counts[from];
     for (int i = 0; i < MAX_STEPS + 4; i++) ctl->counts[i] = 0;
     for (int i = 0; i < 2 * (MAX_STEPS + 4); i++) ctl->stats[i] = 0;
+    for (int i = 0; i < MAX_STEPS + 4; i++) { ctl->hq_packed[i] = 0; ctl->hq_ticket[i] = 0; }
     ctl->counts[to] = v;
 }
 
@@ -286,6 +295,8 @@ struct wk_engine {
     uint64_t launches = 0;
     uint64_t light_escalate_rows = 4096;
     struct wk_comm *comm = nullptr;      // sharded execution (wk_comm_init)
+    HeavyTile *d_hq = nullptr;           // heavy-tile queue (skewed fan-out)
+    uint32_t hq_cap = 0;
     void *d_flush = nullptr;             // > L2-sized scratch for wk_engine_flush_l2
     size_t flush_bytes = 0;
     std::vector<StepRecord> recs;        // one per step since the last reset
@@ -479,9 +490,19 @@ static int launch_step(wk_engine *e, const StepParam &p) {
     const int grid = e->num_sms * e->occ[MODE];
     StepKernelFn fn = step_kernel_fn(MODE, e->variant, p.C);
     const size_t smem = step_smem(e, p.C);
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fn<<<grid, CTA_THREADS, smem, e->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
+    if (MODE == MODE_K2U && p.hq_cap) {   // spreads queued heavy tiles over the grid; returns at once when there are none
+        const int g2 = e->num_sms * 4;
+        switch (p.C) {
+        case 1: expand_heavy_kernel<1><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
+        case 2: expand_heavy_kernel<2><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
+        case 3: expand_heavy_kernel<3><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
+        default: expand_heavy_kernel<0><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
     return WK_SUCCESS;
 }
 
@@ -515,12 +536,18 @@ static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, in
     p.col_end = col_end;
     p.end_const = end_const;
     p.inv_c = ((1u << 20) + (uint32_t)e->ncols - 1) / (uint32_t)e->ncols;
+    if (kind == KIND_K2U && e->variant >= 6 && e->d_hq) {
+        p.hq = e->d_hq;
+        p.hq_cap = e->hq_cap;
+        p.hq_packed = &e->d_ctl->hq_packed[s];
+        p.hq_ticket = &e->d_ctl->hq_ticket[s];
+    }
     StepRecord &r = begin_step(e, kind, e->ncols);
     if (kind == KIND_K2U) rc = launch_step<MODE_K2U>(e, p);
     else if (kind == KIND_K2K) rc = launch_step<MODE_K2K>(e, p);
     else rc = launch_step<MODE_K2C>(e, p);
     if (rc) return rc;
-    end_step(e, r, 1);
+    end_step(e, r, p.hq_cap ? 2 : 1);
     e->step = s + 1;
     e->ncols = Cout;
     return WK_SUCCESS;
@@ -742,6 +769,8 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     CUDA_TRY(cudaMalloc((void **)&e->buf[0], e->cap_words * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&e->buf[1], e->cap_words * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&e->d_ctl, sizeof(CtlBlock)));
+    e->hq_cap = 8192;
+    CUDA_TRY(cudaMalloc((void **)&e->d_hq, (size_t)e->hq_cap * sizeof(HeavyTile)));
     CUDA_TRY(cudaHostAlloc((void **)&e->h_rec, sizeof(HostRec), cudaHostAllocMapped));
     memset((void *)e->h_rec, 0, sizeof(HostRec));
     CUDA_TRY(cudaHostGetDevicePointer((void **)&e->d_rec, (void *)e->h_rec, 0));
@@ -781,6 +810,7 @@ int wk_engine_destroy(wk_engine_t *e) {
     cudaFree(e->buf[0]);
     cudaFree(e->buf[1]);
     cudaFree(e->d_ctl);
+    if (e->d_hq) cudaFree(e->d_hq);
     cudaFreeHost((void *)e->h_rec);
     cudaFreeHost((void *)e->h_stage);
     cudaStreamDestroy(e->stream);

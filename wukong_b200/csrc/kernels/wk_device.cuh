@@ -135,7 +135,20 @@ struct StepParam {
     int32_t col_start, col_end;
     uint32_t end_const;
     uint32_t inv_c;       // ceil(2^20 / C) for idx -> (row, col)
-    uint32_t _pad;
+    uint32_t hq_cap;      // capacity of the heavy-tile queue (0 = disabled)
+    struct HeavyTile *hq; // tiles whose fan-out is expanded by expand_heavy_kernel (skewed degrees)
+    uint64_t *hq_packed;  // entries:24 | chunks:40, one atomic keeps both consistent
+    uint64_t *hq_ticket;
+};
+
+// A tile with a large total fan-out is not expanded in place: it only claims its output range and leaves
+// this descriptor; expand_heavy_kernel then spreads its output rows over the whole grid in equal chunks.
+enum { HEAVY_TILE_MIN = 4096, HEAVY_CHUNK = 2048 };
+struct HeavyTile {
+    uint64_t row0, base, total, chunk_base;
+    uint32_t nrows, _pad;
+    uint64_t pre[TILE_ROWS];   // exclusive prefix of the multiplicities inside the tile
+    uint64_t off[TILE_ROWS];   // edge offset of every row
 };
 
 __device__ __forceinline__ uint64_t step_key(const SegParam &s, uint32_t cur) {
@@ -427,6 +440,7 @@ struct TileSmem4 {
     uint64_t wsum[CTA_THREADS / 32];
     uint64_t base;
     uint64_t total;
+    uint64_t qidx;                        // heavy-queue slot of this tile (~0: expand in place)
     uint64_t pre[CTA_THREADS / 32][32];   // per warp: exclusive prefix of the 32 multiplicities (balanced expand)
     uint64_t off[CTA_THREADS / 32][32];   // per warp: edge offsets of the 32 rows
 };
@@ -862,13 +876,35 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
                 b0 = ~0ull;
             }
             sm.base = b0;
+            uint64_t q = ~0ull;
+            if (MODE == MODE_K2U && p.hq_cap && tot >= HEAVY_TILE_MIN && b0 != ~0ull) {
+                const uint64_t nchunks = (tot + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+                const uint64_t pk = atomicAdd((unsigned long long *)p.hq_packed, (unsigned long long)((1ull << 40) + nchunks));
+                const uint64_t idx = pk >> 40;
+                if (idx < p.hq_cap) {
+                    q = idx;
+                    HeavyTile *ht = p.hq + idx;
+                    ht->row0 = tile * TILE_ROWS;
+                    ht->base = b0;
+                    ht->total = tot;
+                    ht->chunk_base = pk & ((1ull << 40) - 1);
+                    ht->nrows = TILE_ROWS;
+                }
+            }
+            sm.qidx = q;
         }
         __syncthreads();
         const uint64_t base = sm.base;
         const uint64_t excl = woff + incl - mult;
+        const uint64_t qidx = (MODE == MODE_K2U) ? sm.qidx : ~0ull;
 
         // 6c. write the output rows
-        if (base != ~0ull && tot != 0) {
+        if (qidx != ~0ull) {
+            // skewed tile: leave the expansion to expand_heavy_kernel
+            HeavyTile *ht = p.hq + qidx;
+            ht->pre[tid] = excl;
+            ht->off[tid] = off;
+        } else if (base != ~0ull && tot != 0) {
             if (MODE != MODE_K2U) {
                 if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
             } else if (__all_sync(0xFFFFFFFFu, mult <= 1)) {
@@ -907,6 +943,74 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
     }
     cp_async_wait<0>();
     flush_stats(p.stats, acc_visited, acc_edges);
+}
+
+// ---- expansion of the queued heavy tiles: output-parallel, equal chunks over the whole grid ----------
+template <int CT>
+__device__ __forceinline__ void expand_heavy_body(const StepParam &p) {
+    __shared__ uint64_t s_pre[TILE_ROWS];
+    __shared__ uint64_t s_off[TILE_ROWS];
+    __shared__ uint64_t s_hdr[4];   // ticket, entry, chunk
+    const int tid = threadIdx.x;
+    const int C = CT > 0 ? CT : p.C;
+    const int Cout = C + 1;
+    const uint64_t packed = ld_count(p.hq_packed);
+    uint64_t count = packed >> 40;
+    if (count > p.hq_cap) count = p.hq_cap;
+    const uint64_t total_chunks = packed & ((1ull << 40) - 1);
+    if (count == 0) return;
+    uint64_t cur = ~0ull, cur_cb = 0, cur_nch = 0;   // thread 0: the entry the previous ticket fell into
+    while (true) {
+        if (tid == 0) {
+            const uint64_t t = atomicAdd((unsigned long long *)p.hq_ticket, 1ull);
+            uint64_t entry = ~0ull, chunk = 0;
+            if (t < total_chunks) {
+                if (cur == ~0ull || t < cur_cb || t >= cur_cb + cur_nch) {
+                    // slot index and chunk_base come from one atomic, so both are monotone: binary search for the
+                    // last queued entry whose chunk_base <= t
+                    uint64_t lo = 0, hi = count;
+                    while (hi - lo > 1) {
+                        const uint64_t mid = (lo + hi) >> 1;
+                        if (ld_count(&p.hq[mid].chunk_base) <= t) lo = mid; else hi = mid;
+                    }
+                    cur = lo;
+                    cur_cb = ld_count(&p.hq[lo].chunk_base);
+                    cur_nch = (ld_count(&p.hq[lo].total) + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+                }
+                if (t >= cur_cb && t - cur_cb < cur_nch) { entry = cur; chunk = t - cur_cb; }
+                else entry = ~1ull;   // ticket of a tile that did not fit the queue and was expanded in place
+            }
+            s_hdr[0] = t; s_hdr[1] = entry; s_hdr[2] = chunk;
+        }
+        __syncthreads();
+        const uint64_t t = s_hdr[0], entry = s_hdr[1], chunk = s_hdr[2];
+        if (t >= total_chunks) break;
+        if (entry < count) {
+            const HeavyTile *ht = p.hq + entry;
+            s_pre[tid] = ht->pre[tid];
+            s_off[tid] = ht->off[tid];
+            __syncthreads();
+            const uint64_t row0 = ht->row0, base = ht->base, total = ht->total;
+            const uint64_t o_end = (chunk + 1) * HEAVY_CHUNK < total ? (chunk + 1) * HEAVY_CHUNK : total;
+            for (uint64_t o = chunk * HEAVY_CHUNK + tid; o < o_end; o += CTA_THREADS) {
+                int r = 0;
+#pragma unroll
+                for (int st = TILE_ROWS / 2; st > 0; st >>= 1)
+                    if (s_pre[r + st] <= o) r += st;
+                const uint32_t e = ld_edge(p.edges + s_off[r] + (o - s_pre[r]));
+                uint32_t *dst = p.out + (base + o) * (uint64_t)Cout;
+                const uint32_t *src = p.in + (row0 + r) * (uint64_t)C;
+                if (CT > 0) {
+#pragma unroll
+                    for (int c = 0; c < CT; c++) dst[c] = ld_table(src + c);
+                } else {
+                    for (int c = 0; c < C; c++) dst[c] = ld_table(src + c);
+                }
+                dst[C] = e;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace wk
