@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -769,7 +770,8 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     CUDA_TRY(cudaMalloc((void **)&e->buf[0], e->cap_words * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&e->buf[1], e->cap_words * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc((void **)&e->d_ctl, sizeof(CtlBlock)));
-    e->hq_cap = 8192;
+    // one descriptor (4 KB) per 256-row tile that may turn out heavy: sized for 64 M-row frontiers at most
+    e->hq_cap = (uint32_t)std::min<uint64_t>(262144, std::max<uint64_t>(8192, e->cap_words / 16384));
     CUDA_TRY(cudaMalloc((void **)&e->d_hq, (size_t)e->hq_cap * sizeof(HeavyTile)));
     CUDA_TRY(cudaHostAlloc((void **)&e->h_rec, sizeof(HostRec), cudaHostAllocMapped));
     memset((void *)e->h_rec, 0, sizeof(HostRec));

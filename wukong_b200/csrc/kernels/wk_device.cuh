@@ -925,15 +925,29 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
                 woffs[lane] = off;
                 __syncwarp();
                 uint32_t *dst0 = p.out + (base + woff) * (uint64_t)Cout;
-                for (uint64_t o = lane; o < wtotal; o += 32) {
-                    int r = 0;
+                for (uint64_t o0 = lane; o0 < wtotal; o0 += 64) {   // two independent outputs per lane in flight
+                    int r[2];
+                    uint32_t e[2];
 #pragma unroll
-                    for (int st = 16; st > 0; st >>= 1)
-                        if (wpre[r + st] <= o) r += st;
-                    const uint32_t e = ld_edge(p.edges + woffs[r] + (o - wpre[r]));
-                    uint32_t *dst = dst0 + o * (uint64_t)Cout;
-                    copy_row<CT>(dst, rows + r * C, C);
-                    dst[C] = e;
+                    for (int u = 0; u < 2; u++) {
+                        const uint64_t o = o0 + 32 * u;
+                        r[u] = 0;
+                        if (o < wtotal) {
+#pragma unroll
+                            for (int st = 16; st > 0; st >>= 1)
+                                if (wpre[r[u] + st] <= o) r[u] += st;
+                            e[u] = ld_edge(p.edges + woffs[r[u]] + (o - wpre[r[u]]));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const uint64_t o = o0 + 32 * u;
+                        if (o < wtotal) {
+                            uint32_t *dst = dst0 + o * (uint64_t)Cout;
+                            copy_row<CT>(dst, rows + r[u] * C, C);
+                            dst[C] = e[u];
+                        }
+                    }
                 }
             }
         }
@@ -992,21 +1006,36 @@ __device__ __forceinline__ void expand_heavy_body(const StepParam &p) {
             __syncthreads();
             const uint64_t row0 = ht->row0, base = ht->base, total = ht->total;
             const uint64_t o_end = (chunk + 1) * HEAVY_CHUNK < total ? (chunk + 1) * HEAVY_CHUNK : total;
-            for (uint64_t o = chunk * HEAVY_CHUNK + tid; o < o_end; o += CTA_THREADS) {
-                int r = 0;
+            // 4 independent (search, edge load, row load) per thread in flight, then the stores
+            for (uint64_t o0 = chunk * HEAVY_CHUNK + tid; o0 < o_end; o0 += 4 * CTA_THREADS) {
+                int r[4];
+                uint32_t e[4];
 #pragma unroll
-                for (int st = TILE_ROWS / 2; st > 0; st >>= 1)
-                    if (s_pre[r + st] <= o) r += st;
-                const uint32_t e = ld_edge(p.edges + s_off[r] + (o - s_pre[r]));
-                uint32_t *dst = p.out + (base + o) * (uint64_t)Cout;
-                const uint32_t *src = p.in + (row0 + r) * (uint64_t)C;
-                if (CT > 0) {
+                for (int u = 0; u < 4; u++) {
+                    const uint64_t o = o0 + (uint64_t)u * CTA_THREADS;
+                    r[u] = 0;
+                    if (o < o_end) {
 #pragma unroll
-                    for (int c = 0; c < CT; c++) dst[c] = ld_table(src + c);
-                } else {
-                    for (int c = 0; c < C; c++) dst[c] = ld_table(src + c);
+                        for (int st = TILE_ROWS / 2; st > 0; st >>= 1)
+                            if (s_pre[r[u] + st] <= o) r[u] += st;
+                        e[u] = ld_edge(p.edges + s_off[r[u]] + (o - s_pre[r[u]]));
+                    }
                 }
-                dst[C] = e;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint64_t o = o0 + (uint64_t)u * CTA_THREADS;
+                    if (o < o_end) {
+                        uint32_t *dst = p.out + (base + o) * (uint64_t)Cout;
+                        const uint32_t *src = p.in + (row0 + r[u]) * (uint64_t)C;   // read-only here: L1-cacheable
+                        if (CT > 0) {
+#pragma unroll
+                            for (int c = 0; c < CT; c++) dst[c] = __ldg(src + c);
+                        } else {
+                            for (int c = 0; c < C; c++) dst[c] = __ldg(src + c);
+                        }
+                        dst[C] = e[u];
+                    }
+                }
             }
         }
         __syncthreads();
