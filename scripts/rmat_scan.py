@@ -43,7 +43,12 @@ eng = capi.Engine(gst, rbuf_bytes=args.rbuf_gb << 30)
 eng.set_profiling(2)
 cap_rows_3col = (args.rbuf_gb << 30) // 12
 F = 1024
-while F <= min(args.max_frontier, subjects.shape[0]):
+sizes = []
+while F < min(args.max_frontier, subjects.shape[0]):
+    sizes.append(F)
+    F *= 4
+sizes.append(min(args.max_frontier, subjects.shape[0]))
+for F in sizes:
     frontier = subjects[perm[:F]].reshape(-1, 1)
     res = {}
     for rep in range(args.reps):
@@ -71,4 +76,3 @@ while F <= min(args.max_frontier, subjects.shape[0]):
         print(json.dumps({"frontier": F, "hop": hop, "in_rows": s["in_rows"], "out_rows": s["out_rows"], "buckets": s["buckets_visited"],
                           "algo_bytes": s["algo_bytes"], "us": round(us, 2), "gbs": round(s["algo_bytes"] / us / 1e3, 1),
                           "pct_of_peak": round(100 * s["algo_bytes"] / us / 1e3 / peak, 1)}), flush=True)
-    F *= 4

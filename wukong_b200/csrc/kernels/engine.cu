@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v5(const StepPa
 }
 
 template <int CT>
-__global__ void __launch_bounds__(CTA_THREADS) expand_heavy_kernel(const StepParam p) {
+__global__ void __launch_bounds__(CTA_THREADS, 8) expand_heavy_kernel(const StepParam p) {
     if (__ldcg(p.status) != 0) return;
     expand_heavy_body<CT>(p);
 }
@@ -495,7 +495,7 @@ static int launch_step(wk_engine *e, const StepParam &p) {
     fn<<<grid, CTA_THREADS, smem, e->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     if (MODE == MODE_K2U && p.hq_cap) {   // spreads queued heavy tiles over the grid; returns at once when there are none
-        const int g2 = e->num_sms * 4;
+        const int g2 = e->num_sms * 8;
         switch (p.C) {
         case 1: expand_heavy_kernel<1><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
         case 2: expand_heavy_kernel<2><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;

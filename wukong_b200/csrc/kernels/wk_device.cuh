@@ -143,7 +143,7 @@ struct StepParam {
 
 // A tile with a large total fan-out is not expanded in place: it only claims its output range and leaves
 // this descriptor; expand_heavy_kernel then spreads its output rows over the whole grid in equal chunks.
-enum { HEAVY_TILE_MIN = 4096, HEAVY_CHUNK = 2048 };
+enum { HEAVY_TILE_MIN = 4096, HEAVY_CHUNK = 8192 };
 struct HeavyTile {
     uint64_t row0, base, total, chunk_base;
     uint32_t nrows, _pad;

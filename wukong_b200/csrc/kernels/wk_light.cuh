@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
     int s = 0;
     bool spilled = false;
     uint32_t status = 0;
+    uint32_t shadowed = 0;   // steps whose lines were already pulled into L2 by a shadow probe
     for (; s < plan.nsteps; s++) {
         const LightStep &ls = plan.steps[s];
         const int nxt = cur ^ 1;
@@ -228,8 +229,26 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
             const int Cin = ls.C;
             const int Cout = (ls.kind == LKIND_K2U) ? Cin + 1 : Cin;
             const uint32_t *tin = sm.tab[cur];
-            // phase 1: all probes of the step in flight at once (thread per row)
-            for (uint32_t r = tid; r < N; r += CTA_THREADS) {
+            // phase 1: all probes of the step in flight at once (thread per row).  Later steps that start
+            // from a column which already exists ("star" plans: several patterns on the same variable) are
+            // shadow-probed at the same time: their bucket and edge lines are pulled into L2 now, so that
+            // those steps later see L2 hits instead of a chain of cold DRAM + page-walk latencies.
+            int sh[3], nsh = 0;
+            for (int s2 = s + 1; s2 < plan.nsteps && nsh < 3; s2++) {
+                const LightStep &l2 = plan.steps[s2];
+                if (l2.kind >= LKIND_K2U && l2.col_start < Cin && !((shadowed >> s2) & 1u)) { sh[nsh++] = s2; shadowed |= 1u << s2; }
+            }
+            if ((uint64_t)N * (uint64_t)(1 + nsh) > 2048) nsh = 0;
+            for (uint32_t item = tid; item < N * (uint32_t)(1 + nsh); item += CTA_THREADS) {
+                const uint32_t r = item % N, j = item / N;
+                if (j != 0) {
+                    const LightStep &l2 = plan.steps[sh[j - 1]];
+                    const uint64_t key2 = step_key(l2.seg, tin[r * Cin + l2.col_start]);
+                    uint32_t v2;
+                    const uint64_t ptr2 = probe_thread(plan.vertices, key2, l2.seg.bucket_start + fastmod(hash_u64(key2), l2.seg.fm), v2);
+                    if (ptr2) asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.edges + ptr_off(ptr2)));
+                    continue;
+                }
                 const uint32_t c0 = tin[r * Cin + ls.col_start];
                 const uint64_t key = step_key(ls.seg, c0);
                 const uint64_t bucket = ls.seg.bucket_start + fastmod(hash_u64(key), ls.seg.fm);
