@@ -221,7 +221,7 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": "LUBM-%d Q1-Q7 (%s), store sharded by vid %% %d" % (args.scale, args.plan, world),
                            "parallelism": "sharded x%d, NCCL all-to-all(v) before non-local steps" % world,
-                           "l2": "flushed (384 MB memset) before every timed query", "value_mode": "blind, device-resident"},
+                           "l2": "flushed before every timed query (384 MB memset + 256 MB read-back, outside the timed region)", "value_mode": "blind, device-resident"},
                 "e2e": {"value": geomean(1e6 / wall_mean), "unit": "queries/s", "h2d_bytes_per_step": 584, "d2h_bytes_per_step": 56},
                 "gpu_launches": int(rr[8]), "clocks": clocks,
                 "latency_us": {"device": {"q%d" % q: round(float(dev_mean[i]), 2) for i, q in enumerate(QUERIES)},
@@ -380,7 +380,7 @@ def main():
             "config": {"workload": "LUBM-%d Q1-Q7 (%s), seeded LUBM-shaped generator" % (args.scale, args.plan),
                        "triples": info["triples"], "keys": info["keys"], "store_mb": info["header_mb"] + info["edges_mb"],
                        "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
-                       "l2": "flushed (384 MB memset) before every timed query",
+                       "l2": "flushed before every timed query (384 MB memset + 256 MB read-back, outside the timed region)",
                        "value_mode": "blind (row count only), device-resident", "e2e_mode": "non-blind, table D2H into pinned memory"},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

@@ -54,6 +54,7 @@ struct LightPlan {
     uint64_t cap_words;         // per result buffer
     uint64_t seq;
     int32_t do_project, proj_n;
+    int32_t collect_stats, _pad1;   // per-step counters cost two block reductions per step: only when profiling
     int8_t proj_cols[MAX_COLS];
     LightStep steps[MAX_LIGHT_STEPS];
 };
@@ -299,13 +300,12 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
             C = Cout;
         }
         // per-step statistics (algorithmic-bytes accounting)
-        const uint64_t v = block_sum_u64(st_visited, sm, tid);
-        const uint64_t e = block_sum_u64(st_edges, sm, tid);
-        if (tid == 0) {
-            plan.stats[2 * s] = v;
-            plan.stats[2 * s + 1] = e;
-            plan.counts[s + 1] = N;
+        if (plan.collect_stats) {
+            const uint64_t v = block_sum_u64(st_visited, sm, tid);
+            const uint64_t e = block_sum_u64(st_edges, sm, tid);
+            if (tid == 0) { plan.stats[2 * s] = v; plan.stats[2 * s + 1] = e; }
         }
+        if (tid == 0) plan.counts[s + 1] = N;
         cur = nxt;
         __syncthreads();
     }
