@@ -799,8 +799,12 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
         const int v = atoi(ev);
         if (v >= 0 && v < WK_NUM_VARIANTS) e->variant = v;
     }
-    for (int m = 0; m < 3; m++)
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], step_kernel_fn(m, e->variant, 3), CTA_THREADS, step_smem(e, 3)));
+    for (int m = 0; m < 3; m++) {
+        StepKernelFn fn = step_kernel_fn(m, e->variant, 3);
+        const size_t smem = step_smem(e, 3);
+        if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], fn, CTA_THREADS, smem));
+    }
     if (getenv("WK_VERBOSE"))
         fprintf(stderr, "[wukong_b200] variant %d: CTAs/SM k2u=%d k2k=%d k2c=%d, %d SMs\n", e->variant, e->occ[0], e->occ[1], e->occ[2], e->num_sms);
     for (int i = 0; i < 3; i++)
