@@ -149,6 +149,12 @@ int wk_project(wk_engine_t *engine, const int32_t *cols, int ncols_out, uint64_t
 int wk_query_execute(wk_engine_t *engine, const wk_pattern_t *patterns, int npatterns, int nvars,
                      const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor,
                      int blind, wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols);
+/* Throughput path for light queries (the reference's emulator, Proxy::run_query_emu, proxy.hpp:391-545, keeps many
+ * light queries in flight): nqueries independent const-start plans are answered by ONE launch, one CTA per
+ * query; blind replies.  patterns holds all plans back to back, pat_off[q]..pat_off[q+1] delimit plan q.
+ * out_status[q] is the per-query status code (a malformed plan does not fail the batch). */
+int wk_query_execute_batch(wk_engine_t *engine, const wk_pattern_t *patterns, const int32_t *pat_off,
+                           const int32_t *nvars, int nqueries, uint64_t *out_rows, int32_t *out_status);
 /* stats of the last wk_query_execute / primitive calls since the last reset */
 int wk_engine_num_steps(wk_engine_t *engine);
 int wk_engine_step_stats(wk_engine_t *engine, int step, wk_step_stats_t *out);

@@ -84,6 +84,8 @@ def lib():
     L.wko_run_primitive.restype = C.c_int64
     L.wko_run_primitive.argtypes = [vp, C.c_int, vp, u64, C.c_int, i32, i32, C.c_int, i32, C.c_int, C.c_int,
                                     vp, u64, C.POINTER(C.c_int)]
+    L.wko_emu_run.restype = C.c_double
+    L.wko_emu_run.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
     _lib = L
     return L
 
@@ -228,3 +230,10 @@ def run_query(stores, patterns, nvars, required_vars, mt_factor=1, blind=False, 
         return QueryResult(status, rows, cols, tbl, lib().wko_result_usec(h))
     finally:
         lib().wko_result_free(h)
+
+
+def emu_run(store, pats, off, nv, nthreads):
+    """closed-loop emulator in native code: -> (seconds, rows[])"""
+    rows = np.zeros(len(nv), dtype=np.uint64)
+    sec = lib().wko_emu_run(store.h, _ptr(pats), _ptr(off), _ptr(nv), len(nv), nthreads, _ptr(rows))
+    return sec, rows

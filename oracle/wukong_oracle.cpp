@@ -1101,6 +1101,32 @@ const uint32_t *wko_result_table(wko_result *r) { return r->qo.result.result_tab
 uint64_t wko_result_table_len(wko_result *r) { return r->qo.result.result_table.size(); }
 double wko_result_usec(wko_result *r) { return r->qo.usec; }
 
+// Closed-loop "emulator" for the throughput comparison (reference proxy.hpp:391-545 runs an open loop of light
+// queries over the engine threads): nq blind queries, split statically over nthreads host threads, each thread
+// running execute_patterns back to back.  rows[q] receives each query's row count.  Returns wall seconds.
+double wko_emu_run(void *store, const int32_t *pats, const int32_t *pat_off, const int32_t *nvars, int nq, int nthreads,
+                   uint64_t *rows) {
+    Cluster cl;
+    cl.stores.push_back((Store *)store);
+    if (nthreads < 1) nthreads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) {
+        th.emplace_back([&, t]() {
+            std::vector<ssid_t> req;
+            for (int q = t; q < nq; q += nthreads) {
+                std::vector<Pattern> p;
+                for (int i = pat_off[q]; i < pat_off[q + 1]; i++) p.push_back(Pattern{pats[4 * i], pats[4 * i + 1], pats[4 * i + 2], pats[4 * i + 3]});
+                QueryOut qo;
+                run_query(cl, p, nvars[q], req, 1, true, false, qo);
+                rows[q] = (uint64_t)qo.result.row_num;
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 // Single-primitive entry points for kernel-level parity tests: run exactly one pattern function
 // on a given input table.  kind: 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c.  Returns rows; fills out.
 // For k2u `pid/dir` select the segment, col_start the probed column; k2k uses col_end, k2c end_const.

@@ -249,3 +249,20 @@ def test_query_errors(eng1):
     assert rc == 7          # OBJ_ERROR
     rc, *_ = eng1.query([(18, 1, O.IN, -1)], 1, [])
     assert rc == 5          # NO_REQUIRED_VAR
+
+
+def test_batched_light_queries(eng2, ostore2):
+    """wk_query_execute_batch (one launch, one CTA per query) against the oracle, emulator templates A1-A6"""
+    import emu_util
+    tpl = emu_util.load_templates()
+    cands = {t[4]: ostore2.get_edges(0, t[4], O.IN) for t in tpl}
+    pats, off, nv, pick = emu_util.instantiate(tpl, cands, 300, seed=5)
+    rows, st = eng2.query_batch_raw(pats, off, nv)
+    assert (st == 0).all()
+    _, want = O.emu_run(ostore2, pats, off, nv, 2)
+    assert np.array_equal(rows, want)
+    assert rows.sum() > 0 and len(set(pick.tolist())) >= 4
+    # a malformed plan inside a batch only fails itself
+    bad = np.concatenate([pats[: off[1]], np.array([[-1, 5, 1, -2]], dtype=np.int32)])
+    rows, st = eng2.query_batch_raw(bad, np.array([0, off[1], off[1] + 1], dtype=np.int32), np.array([nv[0], 2], dtype=np.int32))
+    assert st[0] == 0 and st[1] == 9 and rows[0] == want[0]

@@ -41,7 +41,7 @@ DECLARED_SYMBOLS = [
     "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_sync",
     "wk_engine_reset", "wk_table_upload", "wk_table_download", "wk_table_info", "wk_index_to_unknown",
     "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_project",
-    "wk_query_execute", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
+    "wk_query_execute", "wk_query_execute_batch", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
     "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
     "wk_comm_stats", "wk_plan_exchanges",
 ]
@@ -82,6 +82,7 @@ def lib():
     L.wk_known_to_const.argtypes = [vp, ci, u32, ci, u32, pu64]
     L.wk_project.argtypes = [vp, vp, ci, pu64]
     L.wk_query_execute.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
+    L.wk_query_execute_batch.argtypes = [vp, vp, vp, vp, ci, vp, vp]
     L.wk_engine_num_steps.argtypes = [vp]
     L.wk_engine_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
     L.wk_engine_launch_count.restype = u64
@@ -272,6 +273,21 @@ class Engine:
         if rc == 0:
             tbl = out.reshape(-1)[: n.value * c.value].reshape(n.value, c.value) if c.value else np.zeros((0, 0), np.uint32)
         return rc, n.value, c.value, tbl
+
+    def query_batch(self, plans):
+        """wk_query_execute_batch.  plans: list of (patterns, nvars).  -> (rows[], status[])"""
+        pats = np.concatenate([np.array(p, dtype=np.int32).reshape(-1, 4) for p, _ in plans])
+        off = np.zeros(len(plans) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(p) for p, _ in plans])
+        nv = np.array([n for _, n in plans], dtype=np.int32)
+        return self.query_batch_raw(pats, off, nv)
+
+    def query_batch_raw(self, pats, off, nv):
+        rows = np.zeros(len(nv), dtype=np.uint64)
+        st = np.zeros(len(nv), dtype=np.int32)
+        _check(lib().wk_query_execute_batch(self.h, _ptr(pats), _ptr(off), _ptr(nv), len(nv), _ptr(rows), _ptr(st)),
+               "wk_query_execute_batch")
+        return rows, st
 
     _out_cache = None
 

@@ -304,6 +304,9 @@ struct wk_engine {
     uint64_t launches = 0;
     uint64_t light_escalate_rows = 4096;
     struct wk_comm *comm = nullptr;      // sharded execution (wk_comm_init)
+    BatchPlan *h_bplans = nullptr, *d_bplans = nullptr;   // wk_query_execute_batch staging
+    BatchResult *h_bres = nullptr, *d_bres = nullptr;
+    int batch_cap = 0;
     HeavyTile *d_hq = nullptr;           // heavy-tile queue (skewed fan-out)
     uint32_t hq_cap = 0;
     void *d_flush = nullptr;             // > L2-sized scratch for wk_engine_flush_l2
@@ -828,6 +831,7 @@ int wk_engine_destroy(wk_engine_t *e) {
     cudaFree(e->buf[1]);
     cudaFree(e->d_ctl);
     if (e->d_hq) cudaFree(e->d_hq);
+    if (e->d_bplans) { cudaFree(e->d_bplans); cudaFree(e->d_bres); cudaFreeHost(e->h_bplans); cudaFreeHost(e->h_bres); }
     cudaFreeHost((void *)e->h_rec);
     cudaFreeHost((void *)e->h_stage);
     cudaStreamDestroy(e->stream);
@@ -1035,6 +1039,34 @@ static int plan_steps(const wk_pattern_t *pats, int npat, int nvars, std::vector
     return WK_SUCCESS;
 }
 
+// translate planned steps into the light interpreter's step descriptors
+static int fill_light_steps(wk_engine *e, const std::vector<PlannedStep> &steps, int mt_tid, int mt_factor, LightStep *out) {
+    for (size_t i = 0; i < steps.size(); i++) {
+        const PlannedStep &ps = steps[i];
+        LightStep &ls = out[i];
+        memset(&ls, 0, sizeof(ls));
+        ls.kind = ps.kind;
+        ls.C = ps.in_cols;
+        ls.col_start = ps.col_start;
+        ls.col_end = ps.col_end;
+        ls.end_const = ps.end_const;
+        ls.mt_tid = mt_tid;
+        ls.mt_factor = mt_factor < 1 ? 1 : mt_factor;
+        if (ps.kind == KIND_I2U || ps.kind == KIND_C2U) {
+            const wk_segmeta_t *m = seg_of_key(e->store, ps.vid, ps.pid, ps.dir);
+            if (!m) return WK_ERR_NO_SEGMENT;
+            ls.seg = make_segparam(m, ps.pid, ps.dir, false);
+            ls.key = make_key(ps.vid, ps.pid, (uint32_t)ps.dir);
+        } else {
+            const bool index_mode = (ps.kind == KIND_K2U && ps.pid == WK_TYPE_ID && ps.dir == WK_DIR_IN);
+            const wk_segmeta_t *m = index_mode ? find_seg(e->store, 1, WK_PREDICATE_ID, ps.dir) : find_seg(e->store, 0, ps.pid, ps.dir);
+            if (!m) return WK_ERR_NO_SEGMENT;
+            ls.seg = make_segparam(m, ps.pid, ps.dir, index_mode);
+        }
+    }
+    return WK_SUCCESS;
+}
+
 static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt_tid, int mt_factor, bool project,
                      const std::vector<int32_t> &proj_cols, RecView &rv) {
     LightPlan lp;
@@ -1057,28 +1089,8 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
     lp.collect_stats = e->profiling >= 2 ? 1 : 0;
     lp.proj_n = (int)proj_cols.size();
     for (size_t i = 0; i < proj_cols.size(); i++) lp.proj_cols[i] = (int8_t)proj_cols[i];
-    for (size_t i = 0; i < steps.size(); i++) {
-        const PlannedStep &ps = steps[i];
-        LightStep &ls = lp.steps[i];
-        ls.kind = ps.kind;
-        ls.C = ps.in_cols;
-        ls.col_start = ps.col_start;
-        ls.col_end = ps.col_end;
-        ls.end_const = ps.end_const;
-        ls.mt_tid = mt_tid;
-        ls.mt_factor = mt_factor < 1 ? 1 : mt_factor;
-        if (ps.kind == KIND_I2U || ps.kind == KIND_C2U) {
-            const wk_segmeta_t *m = seg_of_key(e->store, ps.vid, ps.pid, ps.dir);
-            if (!m) return WK_ERR_NO_SEGMENT;
-            ls.seg = make_segparam(m, ps.pid, ps.dir, false);
-            ls.key = make_key(ps.vid, ps.pid, (uint32_t)ps.dir);
-        } else {
-            const bool index_mode = (ps.kind == KIND_K2U && ps.pid == WK_TYPE_ID && ps.dir == WK_DIR_IN);
-            const wk_segmeta_t *m = index_mode ? find_seg(e->store, 1, WK_PREDICATE_ID, ps.dir) : find_seg(e->store, 0, ps.pid, ps.dir);
-            if (!m) return WK_ERR_NO_SEGMENT;
-            ls.seg = make_segparam(m, ps.pid, ps.dir, index_mode);
-        }
-    }
+    int frc = fill_light_steps(e, steps, mt_tid, mt_factor, lp.steps);
+    if (frc) return frc;
     lp.seq = ++e->seq;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->profiling >= 2) { ev0 = get_event(e); ev1 = get_event(e); if (ev0) cudaEventRecord(ev0, e->stream); }
@@ -1195,6 +1207,52 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
         } else {
             CUDA_TRY(cudaMemcpyAsync(table, e->buf[e->step & 1], words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
             CUDA_TRY(cudaStreamSynchronize(e->stream));
+        }
+    }
+    return WK_SUCCESS;
+}
+
+// Throughput path (the reference's open-loop emulator keeps many light queries in flight, proxy.hpp:391-545):
+// nqueries independent const-start plans, ONE launch, one CTA per query, blind replies.
+int wk_query_execute_batch(wk_engine_t *e, const wk_pattern_t *patterns, const int32_t *pat_off, const int32_t *nvars,
+                           int nqueries, uint64_t *out_rows, int32_t *out_status) {
+    if (!e || !patterns || !pat_off || !nvars || !out_rows || !out_status || nqueries <= 0) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (nqueries > e->batch_cap) {
+        if (e->d_bplans) { cudaFree(e->d_bplans); cudaFree(e->d_bres); cudaFreeHost(e->h_bplans); cudaFreeHost(e->h_bres); }
+        e->batch_cap = nqueries;
+        CUDA_TRY(cudaMalloc((void **)&e->d_bplans, (size_t)nqueries * sizeof(BatchPlan)));
+        CUDA_TRY(cudaMalloc((void **)&e->d_bres, (size_t)nqueries * sizeof(BatchResult)));
+        CUDA_TRY(cudaHostAlloc((void **)&e->h_bplans, (size_t)nqueries * sizeof(BatchPlan), cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc((void **)&e->h_bres, (size_t)nqueries * sizeof(BatchResult), cudaHostAllocDefault));
+    }
+    std::vector<int> v2c;
+    std::vector<PlannedStep> steps;
+    for (int q = 0; q < nqueries; q++) {
+        BatchPlan &bp = e->h_bplans[q];
+        bp.nsteps = 0;
+        steps.clear();
+        int rc = plan_steps(patterns + pat_off[q], pat_off[q + 1] - pat_off[q], nvars[q], v2c, steps);
+        if (rc == WK_SUCCESS && (steps[0].kind != KIND_C2U || (int)steps.size() > BATCH_STEPS)) rc = WK_UNKNOWN_PATTERN;
+        if (rc == WK_SUCCESS) rc = fill_light_steps(e, steps, 0, 1, bp.steps);
+        out_status[q] = rc;
+        if (rc == WK_SUCCESS) bp.nsteps = (int)steps.size();
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->d_bplans, e->h_bplans, (size_t)nqueries * sizeof(BatchPlan), cudaMemcpyHostToDevice, e->stream));
+    const int grid = std::min(nqueries, e->num_sms * 4);
+    light_batch_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->d_bplans, e->d_bres, nqueries, e->store->d_vertices, e->store->d_edges);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    CUDA_TRY(cudaMemcpyAsync(e->h_bres, e->d_bres, (size_t)nqueries * sizeof(BatchResult), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int q = 0; q < nqueries; q++) {
+        if (out_status[q] != WK_SUCCESS) { out_rows[q] = 0; continue; }
+        if (e->h_bres[q].status == 2u) {   // outgrew shared memory: the general path answers it
+            int cols = 0;
+            out_status[q] = wk_query_execute(e, patterns + pat_off[q], pat_off[q + 1] - pat_off[q], nvars[q], nullptr, 0, 0, 1, 1,
+                                             nullptr, 0, &out_rows[q], &cols);
+        } else {
+            out_rows[q] = e->h_bres[q].rows;
         }
     }
     return WK_SUCCESS;

@@ -175,21 +175,23 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, LightSmem &sm, int
     return t;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
-    __shared__ LightSmem sm;
-    const int tid = threadIdx.x;
-    // this kernel owns the control block: clear it here instead of a separate memset node
-    for (int i = tid; i < plan.ctl_nwords; i += CTA_THREADS) plan.ctl_words[i] = 0;
+// The interpreter proper: runs steps[0..nsteps) with the table in shared memory.  On return the table
+// (N x C) is in sm.tab[cur]; done = number of steps completed; spilled = the next step's output does
+// not fit shared memory (nothing of that step has been written).
+struct LightState { uint32_t N; int C, cur, done; bool spilled; };
 
+__device__ __forceinline__ LightState light_interpret(const LightStep *steps, int nsteps, const uint4 *__restrict__ vertices,
+                                                      const uint32_t *__restrict__ edges, LightSmem &sm, uint64_t *stats,
+                                                      uint64_t *counts) {
+    const int tid = threadIdx.x;
     uint32_t N = 0;          // rows of the current table (in sm.tab[cur])
     int C = 0;
     int cur = 0;
     int s = 0;
     bool spilled = false;
-    uint32_t status = 0;
     uint32_t shadowed = 0;   // steps whose lines were already pulled into L2 by a shadow probe
-    for (; s < plan.nsteps; s++) {
-        const LightStep &ls = plan.steps[s];
+    for (; s < nsteps; s++) {
+        const LightStep &ls = steps[s];
         const int nxt = cur ^ 1;
         uint64_t st_visited = 0, st_edges = 0;
         if (ls.kind == LKIND_C2U || ls.kind == LKIND_I2U) {
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
                 visited = 0;
                 while (true) {
                     uint4 v = make_uint4(0, 0, 0, 0);
-                    if (tid < 8) v = ld_slot(plan.vertices + (b * 8 + tid));
+                    if (tid < 8) v = ld_slot(vertices + (b * 8 + tid));
                     const uint64_t kk = (uint64_t)v.x | ((uint64_t)v.y << 32);
                     const uint64_t pp = (uint64_t)v.z | ((uint64_t)v.w << 32);
                     const uint32_t hit = __ballot_sync(0xFFFFFFFFu, tid < 7 && kk == ls.key && kk != 0);
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
             const uint64_t begin = start * length;
             const uint64_t len = (start == mtf - 1) ? (size - begin) : length;
             if (len > LIGHT_ROWS) { spilled = true; break; }   // nothing done yet: resume at this very step
-            for (uint32_t k = tid; k < len; k += CTA_THREADS) sm.tab[nxt][k] = ld_edge(plan.edges + off + begin + k);
+            for (uint32_t k = tid; k < len; k += CTA_THREADS) sm.tab[nxt][k] = ld_edge(edges + off + begin + k);
             if (tid == 0) st_edges = len;
             N = (uint32_t)len;
             C = 1;
@@ -235,26 +237,26 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
             // shadow-probed at the same time: their bucket and edge lines are pulled into L2 now, so that
             // those steps later see L2 hits instead of a chain of cold DRAM + page-walk latencies.
             int sh[3], nsh = 0;
-            for (int s2 = s + 1; s2 < plan.nsteps && nsh < 3; s2++) {
-                const LightStep &l2 = plan.steps[s2];
+            for (int s2 = s + 1; s2 < nsteps && nsh < 3; s2++) {
+                const LightStep &l2 = steps[s2];
                 if (l2.kind >= LKIND_K2U && l2.col_start < Cin && !((shadowed >> s2) & 1u)) { sh[nsh++] = s2; shadowed |= 1u << s2; }
             }
             if ((uint64_t)N * (uint64_t)(1 + nsh) > 2048) nsh = 0;
             for (uint32_t item = tid; item < N * (uint32_t)(1 + nsh); item += CTA_THREADS) {
                 const uint32_t r = item % N, j = item / N;
                 if (j != 0) {
-                    const LightStep &l2 = plan.steps[sh[j - 1]];
+                    const LightStep &l2 = steps[sh[j - 1]];
                     const uint64_t key2 = step_key(l2.seg, tin[r * Cin + l2.col_start]);
                     uint32_t v2;
-                    const uint64_t ptr2 = probe_thread(plan.vertices, key2, l2.seg.bucket_start + fastmod(hash_u64(key2), l2.seg.fm), v2);
-                    if (ptr2) asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.edges + ptr_off(ptr2)));
+                    const uint64_t ptr2 = probe_thread(vertices, key2, l2.seg.bucket_start + fastmod(hash_u64(key2), l2.seg.fm), v2);
+                    if (ptr2) asm volatile("prefetch.global.L2 [%0];" ::"l"(edges + ptr_off(ptr2)));
                     continue;
                 }
                 const uint32_t c0 = tin[r * Cin + ls.col_start];
                 const uint64_t key = step_key(ls.seg, c0);
                 const uint64_t bucket = ls.seg.bucket_start + fastmod(hash_u64(key), ls.seg.fm);
                 uint32_t visited;
-                const uint64_t ptr = probe_thread(plan.vertices, key, bucket, visited);
+                const uint64_t ptr = probe_thread(vertices, key, bucket, visited);
                 st_visited += visited;
                 sm.ptr[r] = ptr;
                 const uint32_t size = ptr_size(ptr);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
                 } else {
                     const uint32_t target = (ls.kind == LKIND_K2K) ? tin[r * Cin + ls.col_end] : ls.end_const;
                     uint32_t scanned;
-                    const bool hit = list_contains(plan.edges + ptr_off(ptr), size, target, scanned);
+                    const bool hit = list_contains(edges + ptr_off(ptr), size, target, scanned);
                     st_edges += scanned;
                     sm.pre[r] = hit ? 1u : 0u;
                 }
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
                         if (sm.pre[mid] <= o) lo = mid; else hi = mid;
                     }
                     const uint32_t k = o - sm.pre[lo];
-                    const uint32_t e = ld_edge(plan.edges + ptr_off(sm.ptr[lo]) + k);
+                    const uint32_t e = ld_edge(edges + ptr_off(sm.ptr[lo]) + k);
                     for (int c = 0; c < Cin; c++) tout[o * Cout + c] = tin[lo * Cin + c];
                     tout[o * Cout + Cin] = e;
                 }
@@ -300,15 +302,32 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
             C = Cout;
         }
         // per-step statistics (algorithmic-bytes accounting)
-        if (plan.collect_stats) {
+        if ((stats != nullptr)) {
             const uint64_t v = block_sum_u64(st_visited, sm, tid);
             const uint64_t e = block_sum_u64(st_edges, sm, tid);
-            if (tid == 0) { plan.stats[2 * s] = v; plan.stats[2 * s + 1] = e; }
+            if (tid == 0) { stats[2 * s] = v; stats[2 * s + 1] = e; }
         }
-        if (tid == 0) plan.counts[s + 1] = N;
+        if (tid == 0 && counts) counts[s + 1] = N;
         cur = nxt;
         __syncthreads();
     }
+    LightState st;
+    st.N = N; st.C = C; st.cur = cur; st.done = s; st.spilled = spilled;
+    return st;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
+    __shared__ LightSmem sm;
+    const int tid = threadIdx.x;
+    // this kernel owns the control block: clear it here instead of a separate memset node
+    for (int i = tid; i < plan.ctl_nwords; i += CTA_THREADS) plan.ctl_words[i] = 0;
+    __syncthreads();
+    const LightState ls_ = light_interpret(plan.steps, plan.nsteps, plan.vertices, plan.edges, sm,
+                                           plan.collect_stats ? plan.stats : nullptr, plan.counts);
+    const uint32_t N = ls_.N;
+    const int C = ls_.C, cur = ls_.cur, s = ls_.done;
+    const bool spilled = ls_.spilled;
+    uint32_t status = 0;
     const int done_steps = s;   // steps [0, done_steps) ran; the table (N x C) is in sm.tab[cur]
     uint64_t tsum = 0;
     if (spilled) {
@@ -345,6 +364,33 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
         uint64_t *rec = (uint64_t *)plan.rec;
         st_sys_v2u64(rec + 2, sr, record_check(plan.seq, rows, sr, tsum));
         st_sys_v2u64(rec, plan.seq, rows);
+    }
+}
+
+// ---- throughput path: many independent light plans in one launch, one CTA per query (blind) -------------
+enum { BATCH_STEPS = 8 };
+struct BatchPlan {
+    int32_t nsteps, _pad;
+    LightStep steps[BATCH_STEPS];
+};
+struct BatchResult {
+    uint64_t rows;
+    uint32_t status;   // 0 ok, 2 = table outgrew shared memory: run this query through wk_query_execute
+    uint32_t done;
+};
+
+__global__ void __launch_bounds__(CTA_THREADS) light_batch_kernel(const BatchPlan *plans, BatchResult *results, int nqueries,
+                                                                  const uint4 *vertices, const uint32_t *edges) {
+    __shared__ LightSmem sm;
+    for (int q = blockIdx.x; q < nqueries; q += gridDim.x) {
+        const BatchPlan *bp = plans + q;
+        const LightState st = light_interpret(bp->steps, bp->nsteps, vertices, edges, sm, nullptr, nullptr);
+        if (threadIdx.x == 0) {
+            results[q].rows = st.N;
+            results[q].status = st.spilled ? 2u : 0u;
+            results[q].done = (uint32_t)st.done;
+        }
+        __syncthreads();
     }
 }
 
