@@ -343,6 +343,10 @@ def main():
     eng.set_profiling(0)
     kern = [(k, v) for k, v in agg.items() if k[2] in ("k2u", "k2k", "k2c") and np.mean(v["us"]) > 0]
     roof = None
+    roof_expand = None
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from this round's ncu --set full capture
+    # of the same launches (profiles/README.md, LUBM-2560, osdi16 plan); only valid for that workload
+    NCU_TRAFFIC = {(1, 1): 881.1e6, (1, 2): 779.7e6, (1, 3): 111.9e6, (1, 4): 80.9e6} if (args.scale == 2560 and args.plan == "osdi16_plan") else {}
     steps_table = []
     for k, v in sorted(agg.items()):
         us = float(np.mean(v["us"])) if v["us"] else 0.0
@@ -351,13 +355,24 @@ def main():
                             "gbs": round(v["bytes"] / us / 1e3, 1) if us > 0 else None})
     if kern:
         (kq, ki, kk), v = max(kern, key=lambda kv: float(np.mean(kv[1]["us"])))
-        us = float(np.mean(v["us"]))
         peak, peak_src = peak_hbm()
-        ach = v["bytes"] / us / 1e3   # GB/s
-        roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "kernel": "step_kernel<%s> (q%d step %d: %d rows x %d cols -> %d rows)" %
-                (kk, kq, ki, v["in_rows"], v["in_cols"], v["out_rows"]),
-                "algo_bytes_per_launch": int(v["bytes"]), "us_per_launch": round(us, 2), "peak_source": peak_src}
+
+        def roof_of(kq, ki, kk, v):
+            us = float(np.mean(v["us"]))
+            ach = v["bytes"] / us / 1e3   # GB/s
+            tr_ = NCU_TRAFFIC.get((kq, ki))
+            return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                    "traffic": int(tr_) if tr_ else None,
+                    "kernel": "step_kernel_v5<%s> (q%d step %d: %d rows x %d cols -> %d rows)" % (kk, kq, ki, v["in_rows"], v["in_cols"], v["out_rows"]),
+                    "algo_bytes_per_launch": int(v["bytes"]), "us_per_launch": round(us, 2), "peak_source": peak_src}
+        roof = roof_of(kq, ki, kk, v)
+        if roof["traffic"] is not None and roof["traffic"] < 0.5 * roof["algo_bytes_per_launch"]:
+            roof["note"] = "this step probes a few thousand hot keys: most algorithmic bytes are L2 hits, not DRAM traffic"
+        # the expand (known_to_unknown) launch with the largest device time: north_star's "expand-kernel HBM GB/s"
+        k2u = [(k, v2) for k, v2 in kern if k[2] == "k2u"]
+        if k2u:
+            (eq, ei, ek), ev = max(k2u, key=lambda kv: float(np.mean(kv[1]["us"])))
+            roof_expand = roof_of(eq, ei, ek, ev)
 
     # ---- reduce over ranks (max latency), compute the metric ----------------------------------------------------
     dev_mean = np.array([np.mean(dev_us[q]) for q in QUERIES])
@@ -383,7 +398,7 @@ def main():
                        "l2": "flushed before every timed query (384 MB memset + 256 MB read-back, outside the timed region)",
                        "value_mode": "blind (row count only), device-resident", "e2e_mode": "non-blind, table D2H into pinned memory"},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_expand": roof_expand,
             "latency_us": {"device": {"q%d" % q: round(float(dev_mean[i]), 2) for i, q in enumerate(QUERIES)},
                            "e2e": {"q%d" % q: round(float(e2e_mean[i]), 2) for i, q in enumerate(QUERIES)}},
             "rows": {"q%d" % q: int(rows[q][0]) for q in QUERIES}, "steps_table": steps_table,
