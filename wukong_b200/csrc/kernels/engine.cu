@@ -90,38 +90,6 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel(const StepParam
     flush_stats(p.stats, acc_visited, acc_edges);
 }
 
-// v4: asynchronously staged tiles (see wk_device.cuh).  Dynamic smem: [bucket staging 32 KB][rows 0][rows 1]
-template <int MODE, int MINB, int CT>
-__global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v4(const StepParam p) {
-    extern __shared__ __align__(16) unsigned char dyn4[];
-    __shared__ TileSmem4 sm;
-    if (__ldcg(p.status) != 0) return;
-    const uint64_t N = ld_count(p.in_count);
-    const int C = CT > 0 ? CT : p.C;
-    unsigned char *bkt = dyn4;
-    const uint32_t rows_bytes = ((uint32_t)TILE_ROWS * (uint32_t)C * 4u + 15u) & ~15u;
-    uint32_t *rows_buf[2] = {(uint32_t *)(dyn4 + BKT_BYTES), (uint32_t *)(dyn4 + BKT_BYTES + rows_bytes)};
-    uint64_t acc_visited = 0, acc_edges = 0;
-    uint64_t tile = blockIdx.x;
-    int buf = 0;
-    if (tile * TILE_ROWS < N) {
-        const uint64_t row0 = tile * TILE_ROWS;
-        const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
-        stage_rows_async(p.in, row0, nrows, C, rows_buf[0], threadIdx.x);
-    }
-    for (; tile * TILE_ROWS < N; tile += gridDim.x, buf ^= 1) {
-        const uint64_t row0 = tile * TILE_ROWS;
-        const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
-        const uint64_t nrow0 = (tile + gridDim.x) * TILE_ROWS;
-        const bool has_next = nrow0 < N;
-        const uint32_t nnrows = has_next ? (uint32_t)((N - nrow0 < (uint64_t)TILE_ROWS) ? (N - nrow0) : (uint64_t)TILE_ROWS) : 0;
-        process_tile_v4<MODE, CT>(p, row0, nrows, has_next, nrow0, nnrows, sm, bkt, rows_buf[buf], rows_buf[buf ^ 1],
-                                  acc_visited, acc_edges);
-    }
-    cp_async_wait<0>();
-    flush_stats(p.stats, acc_visited, acc_edges);
-}
-
 // v5: warp-autonomous pipeline (see wk_device.cuh).  Dynamic smem: [bucket staging 32 KB][8 warps x 3 x rows]
 template <int MODE, int MINB, int CT>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v5(const StepParam p) {
@@ -135,14 +103,6 @@ template <int CT>
 __global__ void __launch_bounds__(CTA_THREADS, 8) expand_heavy_kernel(const StepParam p) {
     if (__ldcg(p.status) != 0) return;
     expand_heavy_body<CT>(p);
-}
-
-template <int MODE, int MINB, int CT>
-__global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v6(const StepParam p) {
-    extern __shared__ __align__(16) unsigned char dyn6[];
-    __shared__ TileSmem4 sm;
-    if (__ldcg(p.status) != 0) return;
-    step_body_v6<MODE, CT>(p, ld_count(p.in_count), sm, dyn6);
 }
 
 // ---- probe of ONE key by the first 8 lanes of a warp (seeds) ---------------------------------------
@@ -456,12 +416,11 @@ static int sync_rows(wk_engine *e, uint64_t *rows, cudaEvent_t after = nullptr) 
 }
 
 static size_t rows_smem(int C) { return (size_t)TILE_ROWS * (size_t)(C | 1) * sizeof(uint32_t); }
-// v4: bucket staging + double-buffered rows (opt-in to > 48 KB when many columns)
-static size_t rows_smem_v4(int C) { return (size_t)BKT_BYTES + 2 * (((size_t)TILE_ROWS * C * 4 + 15) & ~(size_t)15); }
 static size_t step_smem(const wk_engine *e, int C);
 
-// kernel variants (probe batch, min CTAs/SM); WK_VARIANT selects one for tuning runs
-#define WK_NUM_VARIANTS 10
+// kernel variants for A/B runs (WK_VARIANT): 0-3 register-staged probe with batch 8/4/4/2 and 1/4/5/6 CTAs per SM,
+// 6 (default) / 7 = asynchronously staged, software-pipelined v5 with 4 / 5 CTAs per SM
+#define WK_NUM_VARIANTS 8
 #define WK_DEFAULT_VARIANT 6
 typedef void (*StepKernelFn)(const StepParam);
 template <int MODE, int CT>
@@ -470,11 +429,7 @@ static StepKernelFn step_kernel_variant(int v) {
     case 0: return step_kernel<MODE, 8, 1, CT>;
     case 1: return step_kernel<MODE, 4, 4, CT>;
     case 3: return step_kernel<MODE, 2, 6, CT>;
-    case 4: return step_kernel_v4<MODE, 4, CT>;
-    case 5: return step_kernel_v4<MODE, 5, CT>;
     case 7: return step_kernel_v5<MODE, 5, CT>;
-    case 8: return step_kernel_v6<MODE, 4, CT>;
-    case 9: return step_kernel_v6<MODE, 3, CT>;
     case 2: return step_kernel<MODE, 4, 5, CT>;
     default: return step_kernel_v5<MODE, 4, CT>;
     }
@@ -495,10 +450,7 @@ static StepKernelFn step_kernel_fn(int mode, int v, int C) {
 }
 
 static size_t rows_smem_v5(int C) { return (size_t)BKT_BYTES + (size_t)(CTA_THREADS / 32) * 3 * 128 * (size_t)C; }
-static size_t rows_smem_v6(int C) { return (size_t)BKT_BYTES + (size_t)(CTA_THREADS / 32) * 4 * 128 * (size_t)C; }
-static size_t step_smem(const wk_engine *e, int C) {
-    return e->variant >= 8 ? rows_smem_v6(C) : e->variant >= 6 ? rows_smem_v5(C) : e->variant >= 4 ? rows_smem_v4(C) : rows_smem(C);
-}
+static size_t step_smem(const wk_engine *e, int C) { return e->variant >= 4 ? rows_smem_v5(C) : rows_smem(C); }
 
 template <int MODE>
 static int launch_step(wk_engine *e, const StepParam &p) {
@@ -551,7 +503,7 @@ static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, in
     p.col_end = col_end;
     p.end_const = end_const;
     p.inv_c = ((1u << 20) + (uint32_t)e->ncols - 1) / (uint32_t)e->ncols;
-    if (kind == KIND_K2U && e->variant >= 6 && e->d_hq) {
+    if (kind == KIND_K2U && e->variant >= 4 && e->d_hq) {
         p.hq = e->d_hq;
         p.hq_cap = e->hq_cap;
         p.hq_packed = &e->d_ctl->hq_packed[s];

@@ -414,9 +414,8 @@ __device__ __forceinline__ void process_tile(const StepParam &p, uint64_t row0, 
 
 
 // =============================================================================================
-// v4 tile pipeline: asynchronous staging (cp.async / LDGSTS) + owner-thread bucket scan
+// Asynchronous staging (cp.async / LDGSTS) + owner-thread bucket scan: building blocks of the v5 pipeline
 //
-//  * the tile's input rows are fetched with 16-byte cp.async into a double buffer one tile ahead,
 //  * each bucket (128 B) is fetched by 8 lanes with one 16-byte cp.async each (one L1 wavefront per
 //    probe, no registers held while the loads are in flight) into a per-warp staging area whose
 //    16-byte chunks are XOR-swizzled by the row number,
@@ -446,19 +445,6 @@ struct TileSmem4 {
 };
 enum { BKT_BYTES = TILE_ROWS * 128 };   // bucket staging area of one CTA
 
-// issue the asynchronous copy of one tile's input rows (nrows x C words, contiguous) into `dst`
-__device__ __forceinline__ void stage_rows_async(const uint32_t *__restrict__ in, uint64_t row0, uint32_t nrows, int C,
-                                                 uint32_t *dst, int tid) {
-    const uint32_t nwords = nrows * (uint32_t)C;
-    const uint32_t *src = in + row0 * (uint64_t)C;   // 16-byte aligned: row0 is a multiple of 256
-    const uint32_t nvec = nwords >> 2;
-    const uint32_t d0 = smem_u32(dst);
-    for (uint32_t i = tid; i < nvec; i += CTA_THREADS) cp_async16(d0 + i * 16, src + i * 4);
-    const uint32_t tail = nwords & 3u;
-    if ((uint32_t)tid < tail) cp_async4(d0 + (nvec * 4 + tid) * 4, src + nvec * 4 + tid);
-    cp_async_commit();
-}
-
 // thread-serial walk of a bucket chain from global memory (slow path: only rows whose first
 // bucket neither holds the key nor ends the chain)
 __device__ __noinline__ uint64_t chain_walk(const uint4 *__restrict__ vertices, uint64_t key, uint64_t bucket,
@@ -480,190 +466,6 @@ __device__ __noinline__ uint64_t chain_walk(const uint4 *__restrict__ vertices, 
         bucket = chain >> WK_KEY_VID_SHIFT;
     }
 }
-
-template <int MODE, int CT>
-__device__ __forceinline__ void process_tile_v4(const StepParam &p, uint64_t row0, uint32_t nrows, bool has_next,
-                                                uint64_t next_row0, uint32_t next_nrows, TileSmem4 &sm,
-                                                unsigned char *bkt, const uint32_t *rows, uint32_t *rows_next,
-                                                uint64_t &acc_visited, uint64_t &acc_edges) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = CT > 0 ? CT : p.C;
-    const int Cout = (MODE == MODE_K2U) ? C + 1 : C;
-
-    // A. this tile's rows were issued one iteration ago: wait for them
-    cp_async_wait<0>();
-    __syncthreads();
-
-    // B. key -> first bucket; all 8 lanes of a group fetch one bucket with one 16-byte cp.async each
-    const bool active = (uint32_t)tid < nrows;
-    const uint32_t *myrow = rows + tid * C;
-    uint64_t key = 0;
-    uint32_t bucket = BUCKET_NONE;
-    if (active) {
-        key = step_key(p.seg, myrow[p.col_start]);
-        bucket = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key), p.seg.fm));
-    }
-    {
-        const int slot = lane & 7, grp = lane >> 3;
-        const uint32_t wbase = smem_u32(bkt) + (uint32_t)warp * (32 * 128);
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int j = 4 * r + grp;
-            const uint32_t b = __shfl_sync(0xFFFFFFFFu, bucket, j);
-            if (b != BUCKET_NONE)
-                cp_async16(wbase + (uint32_t)j * 128 + (uint32_t)((slot ^ (j & 7)) << 4), p.vertices + ((uint64_t)b * 8 + slot));
-        }
-        cp_async_commit();
-    }
-    // prefetch the next tile's rows while this tile is being processed
-    if (has_next) stage_rows_async(p.in, next_row0, next_nrows, C, rows_next, tid);
-    else cp_async_commit();
-    cp_async_wait<1>();   // the bucket group (the rows group may stay in flight)
-    __syncwarp();
-
-    // C. owner thread scans its bucket in shared memory
-    uint64_t ptr = 0;
-    if (active) {
-        const unsigned char *mb = bkt + (warp * 32 + lane) * 128;
-        const int sw = lane & 7;
-        int hit = -1;
-#pragma unroll
-        for (int i = 0; i < 7; i++) {
-            const uint64_t kk = *(const uint64_t *)(mb + ((i ^ sw) << 4));
-            if (kk == key) hit = i;
-        }
-        uint32_t visited = 1;
-        if (hit >= 0) {
-            ptr = *(const uint64_t *)(mb + ((hit ^ sw) << 4) + 8);
-        } else {
-            const uint64_t chain = *(const uint64_t *)(mb + ((7 ^ sw) << 4));
-            if (chain != 0) ptr = chain_walk(p.vertices, key, chain >> WK_KEY_VID_SHIFT, visited);
-        }
-        acc_visited += visited;
-    }
-
-    // D. multiplicity of each row
-    const uint32_t size = active ? ptr_size(ptr) : 0;
-    const uint64_t off = ptr_off(ptr);
-    uint32_t mult = 0;
-    uint32_t e0 = 0;   // K2U: first edge, fetched while the tile's output space is being claimed
-    if (MODE == MODE_K2U) {
-        mult = size;
-        acc_edges += size;
-        if (size != 0 && size <= SMALL_DEG) e0 = ld_edge(p.edges + off);
-    } else {
-        const uint32_t target = (MODE == MODE_K2K) ? (active ? myrow[p.col_end] : 0) : p.end_const;
-        bool found = false;
-        if (size <= SERIAL_SCAN) {
-            uint32_t k = 0;
-            for (; k < size; k++)
-                if (ld_edge(p.edges + off + k) == target) { found = true; break; }
-            acc_edges += found ? (k + 1) : size;
-        }
-        uint32_t longmask = __ballot_sync(0xFFFFFFFFu, size > SERIAL_SCAN);
-        while (longmask) {
-            const int src = __ffs(longmask) - 1;
-            longmask &= longmask - 1;
-            const uint32_t s_size = __shfl_sync(0xFFFFFFFFu, size, src);
-            const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
-            const uint32_t s_target = __shfl_sync(0xFFFFFFFFu, target, src);
-            uint32_t scanned = s_size;
-            bool hitl = false;
-            for (uint32_t k0 = 0; k0 < s_size; k0 += 32) {
-                const uint32_t k = k0 + lane;
-                const bool eq = (k < s_size) && (ld_edge(p.edges + s_off + k) == s_target);
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
-                if (m) { hitl = true; scanned = k0 + __ffs(m); break; }
-            }
-            if (lane == src) { found = hitl; acc_edges += scanned; }
-        }
-        mult = found ? 1u : 0u;
-    }
-
-    // E. claim output space for the tile (one 64-bit atomic per tile)
-    const int widx = warp;
-    uint64_t incl;
-    if (__all_sync(0xFFFFFFFFu, mult < (1u << 26))) {
-        uint32_t x = mult;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        incl = x;
-    } else {
-        uint64_t x = mult;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        incl = x;
-    }
-    if (lane == 31) sm.wsum[widx] = incl;
-    __syncthreads();
-    uint64_t woff = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < CTA_THREADS / 32; w++) {
-        const uint64_t sx = sm.wsum[w];
-        if (w < warp) woff += sx;
-        tot += sx;
-    }
-    if (tid == 0) {
-        uint64_t b0 = 0;
-        if (tot) b0 = atomicAdd((unsigned long long *)p.out_count, (unsigned long long)tot);
-        if (b0 + tot > p.out_cap_rows) {
-            atomicOr(p.status, 1u);   // WK_ERR_RBUF_OVERFLOW
-            b0 = ~0ull;
-        }
-        sm.base = b0;
-    }
-    __syncthreads();
-    const uint64_t base = sm.base;
-    const uint64_t excl = woff + incl - mult;
-
-    // F. write the output rows
-    if (base != ~0ull && tot != 0) {
-        if (MODE != MODE_K2U) {
-            if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
-        } else {
-            if (mult != 0 && mult <= SMALL_DEG) {
-                uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
-                copy_row<CT>(dst, myrow, C);
-                dst[C] = e0;
-                for (uint32_t k = 1; k < mult; k++) {
-                    dst += Cout;
-                    const uint32_t e = ld_edge(p.edges + off + k);
-                    copy_row<CT>(dst, myrow, C);
-                    dst[C] = e;
-                }
-            }
-            uint32_t bigmask = __ballot_sync(0xFFFFFFFFu, mult > SMALL_DEG);
-            while (bigmask) {
-                const int src = __ffs(bigmask) - 1;
-                bigmask &= bigmask - 1;
-                const uint32_t s_mult = __shfl_sync(0xFFFFFFFFu, mult, src);
-                const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
-                const uint64_t s_excl = __shfl_sync(0xFFFFFFFFu, excl, src);
-                const uint32_t *srow = rows + (warp * 32 + src) * C;
-                uint32_t *dst = p.out + (base + s_excl) * (uint64_t)Cout;
-                const uint64_t nwords = (uint64_t)s_mult * (uint64_t)Cout;
-                uint32_t r = (uint32_t)lane / (uint32_t)Cout;
-                uint32_t c = (uint32_t)lane - r * (uint32_t)Cout;
-                const uint32_t dr = 32u / (uint32_t)Cout, dc = 32u - dr * (uint32_t)Cout;
-                for (uint64_t w = lane; w < nwords; w += 32) {
-                    dst[w] = (c == (uint32_t)C) ? ld_edge(p.edges + s_off + r) : srow[c];
-                    r += dr;
-                    c += dc;
-                    if (c >= (uint32_t)Cout) { c -= (uint32_t)Cout; r++; }
-                }
-            }
-        }
-    }
-    // no trailing barrier: `rows` is double-buffered, the bucket staging area is private to each
-    // warp, and wsum/base are only rewritten after the next tile's first barrier
-}
-
 
 // =============================================================================================
 // v5: warp-autonomous software pipeline.  Each warp stages only its own 32 rows of a tile (triple
@@ -954,332 +756,6 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
         __syncwarp();   // rows_buf(it) may be refilled two iterations from now; keep the warp together
         key = key_next;
         n_cur = n_next;
-    }
-    cp_async_wait<0>();
-    flush_stats(p.stats, acc_visited, acc_edges);
-}
-
-// =============================================================================================
-// v6 = v5 with the back half of a tile (multiplicity -> claim -> write) delayed by one iteration: the
-// first edges of tile t are requested right after its bucket scan and consumed while tile t+1 is in
-// its front half, so the dependent edge fetch of the filters no longer sits in front of the CTA-wide
-// claim.  Four row buffers per warp (tile t-1 is still being written while t+2 is arriving).
-// =============================================================================================
-template <int MODE, int CT>
-__device__ __forceinline__ void step_body_v6(const StepParam &p, uint64_t N, TileSmem4 &sm, unsigned char *dyn) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = CT > 0 ? CT : p.C;
-    const int Cout = (MODE == MODE_K2U) ? C + 1 : C;
-    const uint32_t rowbytes = 128u * (uint32_t)C;                    // 32 rows x C words
-    unsigned char *bkt = dyn + warp * (32 * 128);                    // this warp's bucket staging area
-    unsigned char *rows_base = dyn + BKT_BYTES + (uint32_t)warp * 4u * rowbytes;
-    const uint64_t stride = gridDim.x;
-    uint64_t tile = blockIdx.x;
-    uint64_t acc_visited = 0, acc_edges = 0;
-    if (tile * TILE_ROWS >= N) { flush_stats(p.stats, 0, 0); return; }
-
-    auto warp_n = [&](uint64_t t) -> uint32_t {
-        const uint64_t r0 = t * TILE_ROWS + (uint64_t)warp * 32;
-        return r0 >= N ? 0u : (uint32_t)((N - r0 < 32) ? (N - r0) : 32);
-    };
-    auto rows_buf = [&](uint32_t k) -> uint32_t * { return (uint32_t *)(rows_base + (k & 3u) * rowbytes); };
-    auto issue_buckets = [&](uint32_t bucket) {
-        const int slot = lane & 7, grp = lane >> 3;
-        const uint32_t wbase = smem_u32(bkt);
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int j = 4 * r + grp;
-            const uint32_t b = __shfl_sync(0xFFFFFFFFu, bucket, j);
-            if (b != BUCKET_NONE)
-                cp_async16(wbase + (uint32_t)j * 128 + (uint32_t)((slot ^ (j & 7)) << 4), p.vertices + ((uint64_t)b * 8 + slot));
-        }
-    };
-
-    // ---- prologue: rows(t0) -> keys -> B(t0); R(t0+1) ---------------------------------------------
-    uint32_t it = 0;
-    uint32_t n_cur = warp_n(tile);
-    stage_warp_rows(p.in, tile * TILE_ROWS + (uint64_t)warp * 32, n_cur, C, rows_buf(0), lane);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-    uint64_t key = 0;
-    {
-        uint32_t bucket = BUCKET_NONE;
-        if ((uint32_t)lane < n_cur) {
-            key = step_key(p.seg, rows_buf(0)[lane * C + p.col_start]);
-            bucket = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key), p.seg.fm));
-        }
-        issue_buckets(bucket);
-        cp_async_commit();
-    }
-    {
-        const uint64_t t1 = tile + stride;
-        stage_warp_rows(p.in, t1 * TILE_ROWS + (uint64_t)warp * 32, warp_n(t1), C, rows_buf(1), lane);
-        cp_async_commit();
-    }
-
-    // state of the tile whose back half (multiplicity -> claim -> write) is still pending
-    bool have_prev = false;
-    bool p_active = false;
-    uint64_t p_ptr = 0, p_tile = 0;
-    uint32_t p_x[8];
-    uint32_t p_e0 = 0;
-    const uint32_t *p_rows = nullptr;
-#pragma unroll
-    for (int j = 0; j < 8; j++) p_x[j] = 0;
-
-    for (;; tile += stride, it++) {
-        const bool have_cur = tile * TILE_ROWS < N;
-        if (!have_cur && !have_prev) break;
-        // state of the current tile's front half
-        bool c_active = false;
-        uint64_t c_ptr = 0;
-        uint32_t c_x[8];
-        uint32_t c_e0 = 0;
-        const uint32_t *c_rows = rows_buf(it);
-#pragma unroll
-        for (int j = 0; j < 8; j++) c_x[j] = 0;
-        uint64_t key_next = 0;
-        uint32_t n_next = 0;
-        if (have_cur) {
-        const bool active = (uint32_t)lane < n_cur;
-
-        // 1. buckets of this tile (issued one iteration ago)
-        cp_async_wait<1>();
-        __syncwarp();
-
-        // 2. owner thread scans its bucket in shared memory
-        uint64_t ptr = 0;
-        if (active) {
-            const unsigned char *mb = bkt + lane * 128;
-            const int sw = lane & 7;
-            int hit = -1;
-#pragma unroll
-            for (int i = 0; i < 7; i++) {
-                const uint64_t kk = *(const uint64_t *)(mb + ((i ^ sw) << 4));
-                if (kk == key) hit = i;
-            }
-            uint32_t visited = 1;
-            if (hit >= 0) {
-                ptr = *(const uint64_t *)(mb + ((hit ^ sw) << 4) + 8);
-            } else {
-                const uint64_t chain = *(const uint64_t *)(mb + ((7 ^ sw) << 4));
-                if (chain != 0) ptr = chain_walk(p.vertices, key, chain >> WK_KEY_VID_SHIFT, visited);
-            }
-            acc_visited += visited;
-        }
-        __syncwarp();   // every lane is done with the staging area before it is refilled
-        // the first edges of this tile are fetched now and consumed one iteration later (back half)
-        c_active = active;
-        c_ptr = ptr;
-        {
-            const uint32_t size = active ? ptr_size(ptr) : 0;
-            const uint32_t *ep = p.edges + ptr_off(ptr);
-            if (MODE == MODE_K2U) {
-                if (size != 0) c_e0 = ld_edge(ep);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) c_x[j] = ((uint32_t)j < size) ? ld_edge(ep + j) : 0u;
-            }
-        }
-
-        // 3./4. next tile: its rows have landed -> keys -> buckets in flight during the rest of this tile
-        cp_async_wait<0>();
-        __syncwarp();
-        const uint64_t tnext = tile + stride;
-        n_next = warp_n(tnext);
-        {
-            uint32_t bucket = BUCKET_NONE;
-            if ((uint32_t)lane < n_next) {
-                key_next = step_key(p.seg, rows_buf(it + 1)[lane * C + p.col_start]);
-                bucket = (uint32_t)(p.seg.bucket_start + fastmod(hash_u64(key_next), p.seg.fm));
-            }
-            issue_buckets(bucket);
-            cp_async_commit();
-        }
-        // 5. rows of the tile after next (its buffer was last used by the previous tile)
-        {
-            const uint64_t t2 = tnext + stride;
-            stage_warp_rows(p.in, t2 * TILE_ROWS + (uint64_t)warp * 32, warp_n(t2), C, rows_buf(it + 2), lane);
-            cp_async_commit();
-        }
-        }   // have_cur
-
-        // 6a. multiplicity of each row
-        if (have_prev) {
-        const bool active = p_active;
-        const uint64_t ptr = p_ptr;
-        const uint32_t *rows = p_rows;
-        const uint32_t *myrow = rows + lane * C;
-        const uint64_t tile = p_tile;   // shadows the loop variable: the heavy-tile descriptor needs the tile's own index
-        const uint32_t size = active ? ptr_size(ptr) : 0;
-        const uint64_t off = ptr_off(ptr);
-        uint32_t mult = 0;
-        const uint32_t e0 = p_e0;
-        if (MODE == MODE_K2U) {
-            mult = size;
-            acc_edges += size;
-        } else {
-            const uint32_t target = (MODE == MODE_K2K) ? (active ? myrow[p.col_end] : 0) : p.end_const;
-            bool found = false;
-            if (size <= SERIAL_SCAN) {
-                // the first 8 edges were fetched one iteration ago
-                uint32_t scanned = size;
-                bool hit8 = false;
-#pragma unroll
-                for (int j = 7; j >= 0; j--)
-                    if ((uint32_t)j < size && p_x[j] == target) { hit8 = true; scanned = j + 1; }
-                if (hit8) found = true;
-                else if (size > 8) {
-                    uint32_t sc2;
-                    found = list_contains8(p.edges + off + 8, size - 8, target, sc2);
-                    scanned = 8 + sc2;
-                }
-                acc_edges += scanned;
-            }
-            uint32_t longmask = __ballot_sync(0xFFFFFFFFu, size > SERIAL_SCAN);
-            while (longmask) {
-                const int src = __ffs(longmask) - 1;
-                longmask &= longmask - 1;
-                const uint32_t s_size = __shfl_sync(0xFFFFFFFFu, size, src);
-                const uint64_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
-                const uint32_t s_target = __shfl_sync(0xFFFFFFFFu, target, src);
-                uint32_t scanned = s_size;
-                bool hitl = false;
-                for (uint32_t k0 = 0; k0 < s_size; k0 += 32) {
-                    const uint32_t k = k0 + lane;
-                    const bool eq = (k < s_size) && (ld_edge(p.edges + s_off + k) == s_target);
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
-                    if (m) { hitl = true; scanned = k0 + __ffs(m); break; }
-                }
-                if (lane == src) { found = hitl; acc_edges += scanned; }
-            }
-            mult = found ? 1u : 0u;
-        }
-
-        // 6b. claim output space for the tile (one 64-bit atomic per tile; the only CTA-wide sync)
-        uint64_t incl;
-        if (__all_sync(0xFFFFFFFFu, mult < (1u << 26))) {
-            uint32_t x = mult;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-                if (lane >= o) x += y;
-            }
-            incl = x;
-        } else {
-            uint64_t x = mult;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-                if (lane >= o) x += y;
-            }
-            incl = x;
-        }
-        if (lane == 31) sm.wsum[warp] = incl;
-        __syncthreads();
-        uint64_t woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < CTA_THREADS / 32; w++) {
-            const uint64_t sx = sm.wsum[w];
-            if (w < warp) woff += sx;
-            tot += sx;
-        }
-        if (tid == 0) {
-            uint64_t b0 = 0;
-            if (tot) b0 = atomicAdd((unsigned long long *)p.out_count, (unsigned long long)tot);
-            if (b0 + tot > p.out_cap_rows) {
-                atomicOr(p.status, 1u);   // WK_ERR_RBUF_OVERFLOW
-                b0 = ~0ull;
-            }
-            sm.base = b0;
-            uint64_t q = ~0ull;
-            if (MODE == MODE_K2U && p.hq_cap && tot >= HEAVY_TILE_MIN && b0 != ~0ull) {
-                const uint64_t nchunks = (tot + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
-                const uint64_t pk = atomicAdd((unsigned long long *)p.hq_packed, (unsigned long long)((1ull << 40) + nchunks));
-                const uint64_t idx = pk >> 40;
-                if (idx < p.hq_cap) {
-                    q = idx;
-                    HeavyTile *ht = p.hq + idx;
-                    ht->row0 = tile * TILE_ROWS;
-                    ht->base = b0;
-                    ht->total = tot;
-                    ht->chunk_base = pk & ((1ull << 40) - 1);
-                    ht->nrows = TILE_ROWS;
-                }
-            }
-            sm.qidx = q;
-        }
-        __syncthreads();
-        const uint64_t base = sm.base;
-        const uint64_t excl = woff + incl - mult;
-        const uint64_t qidx = (MODE == MODE_K2U) ? sm.qidx : ~0ull;
-
-        // 6c. write the output rows
-        if (qidx != ~0ull) {
-            // skewed tile: leave the expansion to expand_heavy_kernel
-            HeavyTile *ht = p.hq + qidx;
-            ht->pre[tid] = excl;
-            ht->off[tid] = off;
-        } else if (base != ~0ull && tot != 0) {
-            if (MODE != MODE_K2U) {
-                if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
-            } else if (__all_sync(0xFFFFFFFFu, mult <= 1)) {
-                // at most one edge per row (the common case on LUBM): the owner thread writes its row
-                if (mult) {
-                    uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
-                    copy_row<CT>(dst, myrow, C);
-                    dst[C] = e0;
-                }
-            } else {
-                // load-balanced expand: every lane takes output rows o = lane, lane+32, ... of the warp's run and
-                // finds its source row by binary search in the 32 scanned multiplicities, so skewed degrees
-                // (power-law graphs, hubs) keep all lanes busy and all edge loads independent
-                const uint64_t wexcl = incl - mult;                      // prefix inside the warp
-                const uint64_t wtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                uint64_t *wpre = sm.pre[warp], *woffs = sm.off[warp];
-                wpre[lane] = wexcl;
-                woffs[lane] = off;
-                __syncwarp();
-                uint32_t *dst0 = p.out + (base + woff) * (uint64_t)Cout;
-                for (uint64_t o0 = lane; o0 < wtotal; o0 += 64) {   // two independent outputs per lane in flight
-                    int r[2];
-                    uint32_t e[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const uint64_t o = o0 + 32 * u;
-                        r[u] = 0;
-                        if (o < wtotal) {
-#pragma unroll
-                            for (int st = 16; st > 0; st >>= 1)
-                                if (wpre[r[u] + st] <= o) r[u] += st;
-                            e[u] = ld_edge(p.edges + woffs[r[u]] + (o - wpre[r[u]]));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const uint64_t o = o0 + 32 * u;
-                        if (o < wtotal) {
-                            uint32_t *dst = dst0 + o * (uint64_t)Cout;
-                            copy_row<CT>(dst, rows + r[u] * C, C);
-                            dst[C] = e[u];
-                        }
-                    }
-                }
-            }
-        }
-        }   // have_prev
-        __syncwarp();
-        // rotate: the current tile's front-half state becomes the pending back half
-        have_prev = have_cur;
-        p_active = c_active;
-        p_ptr = c_ptr;
-        p_e0 = c_e0;
-        p_rows = c_rows;
-        p_tile = tile;
-#pragma unroll
-        for (int j = 0; j < 8; j++) p_x[j] = c_x[j];
-        if (have_cur) { key = key_next; n_cur = n_next; }
     }
     cp_async_wait<0>();
     flush_stats(p.stats, acc_visited, acc_edges);
