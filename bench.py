@@ -172,9 +172,15 @@ def run_sharded(args, rank, world, local_rank, dist):
     gst = hs.upload(local_rank)
     rbuf = (args.rbuf_mb << 20) if args.rbuf_mb else max(256 << 20, min(8 << 30, int(tr.shape[0]) * 8))
     eng = capi.Engine(gst, rbuf_bytes=rbuf)
-    uid = [capi.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    eng.comm_init(world, rank, uid[0])
+    if args.exchange == "p2p":
+        allh = [None] * world
+        dist.all_gather_object(allh, eng.p2p_export(world, rank))
+        eng.p2p_import(b"".join(allh))
+        dist.barrier()
+    else:
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(world, rank, uid[0])
     plans = load_plans(args.plan)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -220,7 +226,7 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(dev_mean.sum() / 1e3), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": "LUBM-%d Q1-Q7 (%s), store sharded by vid %% %d" % (args.scale, args.plan, world),
-                           "parallelism": "sharded x%d, NCCL all-to-all(v) before non-local steps" % world,
+                           "parallelism": "sharded x%d, %s before non-local steps" % (world, "fused bucketise + peer-memory push over NVLink (CUDA IPC)" if args.exchange == "p2p" else "NCCL all-to-all(v)"),
                            "l2": "flushed before every timed query (384 MB memset + 256 MB read-back, outside the timed region)", "value_mode": "blind, device-resident"},
                 "e2e": {"value": geomean(1e6 / wall_mean), "unit": "queries/s", "h2d_bytes_per_step": 584, "d2h_bytes_per_step": 56},
                 "gpu_launches": int(rr[8]), "clocks": clocks,
@@ -246,6 +252,7 @@ def main():
     ap.add_argument("--rbuf-mb", type=int, default=0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="sharded mode: peer-memory push or NCCL all-to-all(v)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
                     help="N>1: replicas (whole store per GPU, weak scaling) or sharded (vid %% N + NCCL all-to-all)")
     args = ap.parse_args()

@@ -181,6 +181,14 @@ int wk_comm_init(wk_engine_t *engine, int nranks, int rank, const void *id128);
  * rows whose row[col_start] % nranks == rank. */
 int wk_exchange(wk_engine_t *engine, int col_start, uint64_t *out_rows);
 int wk_comm_stats(wk_engine_t *engine, uint64_t *exchanges, uint64_t *rows_sent, uint64_t *rows_recv);
+/* Peer-memory exchange over NVLink / NVSwitch instead of NCCL (one process per GPU, CUDA IPC): every rank exports a
+ * 192-byte record (handles of its two result buffers and of its exchange control block), the records of all ranks
+ * are gathered by the caller (rank order) and imported.  Afterwards wk_query_execute_sharded bucketises rows by owner
+ * and stores them straight into the owners' next-table buffers from the kernel: counts and "pushed" flags travel
+ * through peer memory too, so an exchange needs no host synchronisation at all.  Up to 16 ranks. */
+int wk_comm_p2p_export(wk_engine_t *engine, int nranks, int rank, void *out192);
+int wk_comm_p2p_import(wk_engine_t *engine, const void *all_handles);
+int wk_exchange_p2p(wk_engine_t *engine, int col_start, uint64_t *out_rows);
 /* Host-only planning helper: out[i] = -1 no exchange before step i, -2 replicate the table to every
  * shard (type-index lookup of a known variable, sparql.hpp:1091-1110), c >= 0 re-shard by column c
  * (need_fork_join with local_var, sparql.hpp:802-814).  Needs no GPU. */

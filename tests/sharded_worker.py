@@ -65,14 +65,21 @@ def run_cpu(rank, world, dist, hs, queries):
     return out
 
 
-def run_gpu(rank, world, dist, hs, queries):
+def run_gpu(rank, world, dist, hs, queries, p2p=False):
     import torch
     from wukong_b200 import capi
     gst = hs.upload(rank)
     eng = capi.Engine(gst, rbuf_bytes=128 << 20)
-    uid = [capi.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    eng.comm_init(world, rank, uid[0])
+    if p2p:      # peer-memory exchange: gather every rank's IPC handles
+        mine = eng.p2p_export(world, rank)
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        eng.p2p_import(b"".join(allh))
+        dist.barrier()
+    else:
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(world, rank, uid[0])
     out = {}
     for name, (pats, nvars, req) in queries.items():
         rc, rows, cols, tbl = eng.query_sharded(pats, nvars, req)
@@ -107,7 +114,12 @@ def main():
     for q in range(1, 8):
         for plan in PLANS:
             queries["q%d_%s" % (q, plan)] = load_query(q, plan)[:3]
-    res = (run_gpu if a.mode == "gpu" else run_cpu)(a.rank, a.world, dist, hs, queries)
+    if a.mode == "gpu":
+        res = run_gpu(a.rank, a.world, dist, hs, queries)
+    elif a.mode == "gpu_p2p":
+        res = run_gpu(a.rank, a.world, dist, hs, queries, p2p=True)
+    else:
+        res = run_cpu(a.rank, a.world, dist, hs, queries)
     np.savez(os.path.join(a.out, "rank%d.npz" % a.rank), **res)
     dist.barrier()
     dist.destroy_process_group()

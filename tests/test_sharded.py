@@ -86,3 +86,14 @@ def test_sharded_gpu_nccl(tmp_path):
     _check_against_bruteforce(res, 2, 7)
     st = res[0]["__stats__"]
     assert st[0] > 0          # exchanges happened
+
+
+@pytest.mark.gpu
+def test_sharded_gpu_peer_memory(tmp_path):
+    """same queries, exchange through CUDA-IPC peer memory (kernel stores over NVLink, no NCCL, no host sync)"""
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = min(capi.device_count(), 4)
+    res = _run_world(world, "gpu_p2p", tmp_path)
+    _check_against_bruteforce(res, 2, 7)
+    assert res[0]["__stats__"][0] > 0

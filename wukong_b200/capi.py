@@ -43,7 +43,7 @@ DECLARED_SYMBOLS = [
     "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_project",
     "wk_query_execute", "wk_query_execute_batch", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
     "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
-    "wk_comm_stats", "wk_plan_exchanges",
+    "wk_comm_stats", "wk_plan_exchanges", "wk_comm_p2p_export", "wk_comm_p2p_import", "wk_exchange_p2p",
 ]
 
 _lib = None
@@ -95,6 +95,9 @@ def lib():
     L.wk_comm_init.argtypes = [vp, ci, ci, vp]
     L.wk_exchange.argtypes = [vp, ci, pu64]
     L.wk_comm_stats.argtypes = [vp, pu64, pu64, pu64]
+    L.wk_comm_p2p_export.argtypes = [vp, ci, ci, vp]
+    L.wk_comm_p2p_import.argtypes = [vp, vp]
+    L.wk_exchange_p2p.argtypes = [vp, ci, pu64]
     L.wk_plan_exchanges.argtypes = [vp, ci, ci, vp]
     L.wk_query_execute_sharded.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
     L.wk_host_alloc.argtypes = [u64, C.POINTER(vp)]
@@ -301,6 +304,15 @@ class Engine:
     def comm_init(self, nranks, rank, unique_id_bytes):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id_bytes)
         _check(lib().wk_comm_init(self.h, nranks, rank, C.cast(buf, C.c_void_p)), "wk_comm_init")
+
+    def p2p_export(self, nranks, rank):
+        buf = (C.c_ubyte * 192)()
+        _check(lib().wk_comm_p2p_export(self.h, nranks, rank, C.cast(buf, C.c_void_p)), "wk_comm_p2p_export")
+        return bytes(buf)
+
+    def p2p_import(self, all_handles_bytes):
+        buf = (C.c_ubyte * len(all_handles_bytes)).from_buffer_copy(all_handles_bytes)
+        _check(lib().wk_comm_p2p_import(self.h, C.cast(buf, C.c_void_p)), "wk_comm_p2p_import")
 
     def partition(self, col, nparts):
         out = np.zeros(nparts, dtype=np.uint64)

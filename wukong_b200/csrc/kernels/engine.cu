@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <map>
+#include <string>
 #include <tuple>
 #include <vector>
 
@@ -411,6 +412,7 @@ static int sync_rows(wk_engine *e, uint64_t *rows, cudaEvent_t after = nullptr) 
     int rc = wait_record(e, seq, -1, 0, rv);
     if (rc) return rc;
     if (rows) *rows = rv.rows;
+    if (rv.status & 2u) return WK_ERR_COMM;          // a peer did not show up at an exchange barrier
     if (rv.status & 1u) return WK_ERR_RBUF_OVERFLOW;
     return WK_SUCCESS;
 }
@@ -1375,7 +1377,104 @@ static int exchange_table(wk_engine *e, int col, uint64_t *out_rows) {
     return WK_SUCCESS;
 }
 
+// exchange over peer memory: result in buf[(step+1)&1], step advances; no host synchronisation
+static int exchange_table_p2p(wk_engine *e, int col) {
+    wk_comm *c = e->comm;
+    if (!c || !c->p2p_ready) return WK_ERR_COMM;
+    const int n = c->nranks, s = e->step, C = e->ncols;
+    if (C <= 0) return WK_ERR_BAD_ARG;
+    const bool dup = (col == -2);
+    if (!dup && (col < 0 || col >= C)) return WK_VERTEX_INVALID;
+    const uint64_t epoch = ++c->epoch;
+    const int grid = e->num_sms * 4;
+    if (!dup) {
+        CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, MAX_PARTS * sizeof(uint64_t), e->stream));
+        part_count_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->buf[s & 1], &e->d_ctl->counts[s], C, col, (uint32_t)n, c->d_counts);
+    }
+    p2p_publish_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, c->d_counts, &e->d_ctl->counts[s], dup ? 1 : 0, epoch,
+                                                e->cap_words / (uint64_t)C, &e->d_ctl->counts[s + 1], &e->d_ctl->status);
+    p2p_scatter_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(*c->p2p, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
+                                                            dup ? 1 : 0, (s + 1) & 1, epoch);
+    p2p_wait_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, epoch, &e->d_ctl->status);
+    CUDA_TRY(cudaGetLastError());
+    e->launches += dup ? 3 : 4;
+    e->step = s + 1;
+    c->exchanges++;
+    return WK_SUCCESS;
+}
+
 extern "C" {
+
+// ---- peer-memory communicator (CUDA IPC): every rank exports 3 handles (its two result buffers and its exchange
+// control block, 64 bytes each), all ranks gather the 192-byte records and import them ------------------------------
+int wk_comm_p2p_export(wk_engine_t *e, int nranks, int rank, void *out192) {
+    if (!e || !out192) return WK_ERR_BAD_ARG;
+    if (nranks < 1 || nranks > P2P_MAX_RANKS) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    if (!e->comm) {
+        int rc = comm_alloc(e, nranks, rank);
+        if (rc) return rc;
+    }
+    wk_comm *c = e->comm;
+    c->nranks = nranks;
+    c->rank = rank;
+    if (!c->d_xctl) {
+        CUDA_TRY(cudaMalloc((void **)&c->d_xctl, sizeof(XchCtl)));
+        CUDA_TRY(cudaMemset(c->d_xctl, 0, sizeof(XchCtl)));
+        CUDA_TRY(cudaMalloc((void **)&c->d_p2p_local, sizeof(P2PLocal)));
+        CUDA_TRY(cudaMemset(c->d_p2p_local, 0, sizeof(P2PLocal)));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t *h = (cudaIpcMemHandle_t *)out192;
+    CUDA_TRY(cudaIpcGetMemHandle(&h[0], e->buf[0]));
+    CUDA_TRY(cudaIpcGetMemHandle(&h[1], e->buf[1]));
+    CUDA_TRY(cudaIpcGetMemHandle(&h[2], c->d_xctl));
+    return WK_SUCCESS;
+}
+
+int wk_comm_p2p_import(wk_engine_t *e, const void *all_handles) {
+    if (!e || !e->comm || !e->comm->d_xctl || !all_handles) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    wk_comm *c = e->comm;
+    if (!c->p2p) c->p2p = new P2PTable();
+    memset(c->p2p, 0, sizeof(P2PTable));
+    c->p2p->nranks = c->nranks;
+    c->p2p->rank = c->rank;
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handles;
+    for (int r = 0; r < c->nranks; r++) {
+        if (r == c->rank) {
+            c->p2p->buf[0][r] = e->buf[0];
+            c->p2p->buf[1][r] = e->buf[1];
+            c->p2p->ctl[r] = c->d_xctl;
+            continue;
+        }
+        void *p[3];
+        for (int k = 0; k < 3; k++) {
+            CUDA_TRY(cudaIpcOpenMemHandle(&p[k], h[3 * r + k], cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(p[k]);
+        }
+        c->p2p->buf[0][r] = (uint32_t *)p[0];
+        c->p2p->buf[1][r] = (uint32_t *)p[1];
+        c->p2p->ctl[r] = (XchCtl *)p[2];
+    }
+    c->p2p_ready = true;
+    return WK_SUCCESS;
+}
+
+// wk_exchange over peer memory instead of NCCL (same semantics; the table moves to the other buffer)
+int wk_exchange_p2p(wk_engine_t *e, int col_start, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    rc = exchange_table_p2p(e, col_start);
+    if (rc) return rc;
+    if (out_rows) {
+        rc = sync_rows(e, out_rows);
+        if (rc) return rc;
+    }
+    return WK_SUCCESS;
+}
 
 int wk_partition(wk_engine_t *e, int col_start, int nparts, uint64_t *part_rows) {
     if (!e || !part_rows) return WK_ERR_BAD_ARG;
@@ -1467,7 +1566,7 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
                              const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor, int blind,
                              wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols) {
     if (!e || !patterns) return WK_ERR_BAD_ARG;
-    if (!e->comm || !e->comm->comm) return WK_ERR_COMM;
+    if (!e->comm || (!e->comm->comm && !e->comm->p2p_ready)) return WK_ERR_COMM;
     CUDA_TRY(cudaSetDevice(e->store->device));
     if (out_rows) *out_rows = 0;
     if (out_cols) *out_cols = 0;
@@ -1498,7 +1597,7 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
     for (size_t i = 0; i < steps.size(); i++) {
         const PlannedStep &ps = steps[i];
         if (ex[i] != -1) {
-            rc = exchange_table(e, ex[i], nullptr);
+            rc = e->comm->p2p_ready ? exchange_table_p2p(e, ex[i]) : exchange_table(e, ex[i], nullptr);
             if (rc) return rc;
         }
         if (ps.kind == KIND_I2U) {

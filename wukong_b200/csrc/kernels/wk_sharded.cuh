@@ -111,6 +111,13 @@ struct wk_comm {
     uint64_t part_rows[MAX_PARTS] = {0}, part_off[MAX_PARTS] = {0};
     bool partitioned = false;
     uint64_t exchanges = 0, rows_sent = 0, rows_recv = 0;
+    // peer-memory path (CUDA IPC)
+    bool p2p_ready = false;
+    struct XchCtl *d_xctl = nullptr;
+    struct P2PLocal *d_p2p_local = nullptr;
+    struct P2PTable *p2p = nullptr;     // host copy of the peer pointer table (passed to kernels by value)
+    uint64_t epoch = 0;
+    std::vector<void *> ipc_opened;
 };
 
 // Which steps need an exchange: out[i] = -1 none, -2 replicate to every rank, c >= 0 re-shard by column c.
@@ -130,4 +137,142 @@ static void plan_exchanges(const std::vector<PlannedStep> &steps, std::vector<in
         }
         if (ps.col_start != shard_col) { out[i] = ps.col_start; shard_col = ps.col_start; }
     }
+}
+
+// =============================================================================================
+// Peer-memory exchange (NVLink / NVSwitch, no NCCL, no host synchronisation):
+//   count -> publish counts to every peer + wait for theirs (barrier 1: also proves that every peer has
+//   finished the previous step, so its next-table buffer may be overwritten) -> scatter rows STRAIGHT INTO
+//   the peers' next-table buffers with plain stores over NVLink -> "pushed" flags (barrier 2).
+// Buffers and control blocks of the peers are mapped with CUDA IPC (one process per GPU).
+// =============================================================================================
+struct XchCtl {
+    uint64_t counts[MAX_PARTS][MAX_PARTS];   // [src][dst]; row `src` is written by rank src into every peer's copy
+    uint64_t flagA[MAX_PARTS];               // epoch of the last counts publication seen from each rank
+    uint64_t flagB[MAX_PARTS];               // epoch of the last completed push seen from each rank
+};
+
+struct P2PTable {
+    uint32_t *buf[2][MAX_PARTS / 4];         // peers' result buffers (up to 16 ranks per box)
+    XchCtl *ctl[MAX_PARTS / 4];
+    int nranks, rank;
+};
+enum { P2P_MAX_RANKS = MAX_PARTS / 4 };
+
+struct P2PLocal {                            // device scratch of one rank
+    uint64_t cursor[MAX_PARTS];              // running row offset into each destination's buffer
+    uint32_t done_ctas;
+    uint32_t skip;                           // set when the exchange must not push (overflow somewhere)
+};
+
+__device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p == want; bounded (about 2 s) so that a dead peer cannot hang the GPU
+__device__ __forceinline__ bool wait_flag(const uint64_t *p, uint64_t want) {
+    for (uint32_t i = 0; i < (1u << 23); i++) {
+        if (ld_sys_u64(p) >= want) return true;
+        __nanosleep(200);
+    }
+    return false;
+}
+
+// barrier 1: publish my per-destination counts to every peer, wait for all of theirs, derive offsets
+__global__ void p2p_publish_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint64_t *my_counts, const uint64_t *in_count,
+                                   int dup, uint64_t epoch, uint64_t cap_rows, uint64_t *out_count, uint32_t *status) {
+    const int p = threadIdx.x;
+    __shared__ int ok;
+    if (p == 0) ok = 1;
+    __syncthreads();
+    if (p < t.nranks) {
+        XchCtl *peer = t.ctl[p];
+        for (int d = 0; d < t.nranks; d++) st_sys_u64(&peer->counts[t.rank][d], dup ? ld_count(in_count) : my_counts[d]);
+        __threadfence_system();
+        st_sys_u64(&peer->flagA[t.rank], epoch);
+        if (!wait_flag(&my->flagA[p], epoch)) atomicExch(&ok, 0);
+    }
+    __syncthreads();
+    if (p == 0) {
+        loc->done_ctas = 0;
+        loc->skip = 0;
+        if (!ok) { atomicOr(status, 2u); loc->skip = 1; *out_count = 0; return; }
+        // every rank sees the same matrix: offsets and overflow decisions agree everywhere
+        bool overflow = false;
+        for (int d = 0; d < t.nranks; d++) {
+            uint64_t tot = 0, before = 0;
+            for (int src = 0; src < t.nranks; src++) {
+                const uint64_t c = ld_sys_u64(&my->counts[src][d]);
+                if (src < t.rank) before += c;
+                tot += c;
+            }
+            if (tot > cap_rows) overflow = true;
+            loc->cursor[d] = before;
+            if (d == t.rank) *out_count = tot;
+        }
+        if (overflow) { atomicOr(status, 1u); loc->skip = 1; }
+    }
+}
+
+// scatter every row into its owner's next-table buffer (plain stores to peer memory); the last CTA to finish
+// publishes the "pushed" flag to every peer after a system-scope fence
+__global__ void __launch_bounds__(CTA_THREADS) p2p_scatter_kernel(P2PTable t, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
+                                                                  int C, int col, int dup, int dst_buf, uint64_t epoch) {
+    __shared__ uint32_t hist[P2P_MAX_RANKS];
+    __shared__ uint64_t base[P2P_MAX_RANKS];
+    __shared__ uint32_t last;
+    const uint32_t n = (uint32_t)t.nranks;
+    const uint64_t N = ld_count(in_count);
+    if (!__ldcg(&loc->skip)) {
+        for (uint64_t t0 = (uint64_t)blockIdx.x * CTA_THREADS; t0 < N; t0 += (uint64_t)gridDim.x * CTA_THREADS) {
+            if (threadIdx.x < P2P_MAX_RANKS) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const uint64_t r = t0 + threadIdx.x;
+            const uint32_t nrows_tile = (uint32_t)((N - t0 < CTA_THREADS) ? (N - t0) : CTA_THREADS);
+            uint32_t d = 0, local = 0;
+            if (r < N && !dup) {
+                d = ld_table(in + r * (uint64_t)C + col) % n;
+                local = atomicAdd(&hist[d], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < n) {
+                const uint32_t cnt = dup ? nrows_tile : hist[threadIdx.x];
+                if (cnt) base[threadIdx.x] = atomicAdd((unsigned long long *)&loc->cursor[threadIdx.x], (unsigned long long)cnt);
+            }
+            __syncthreads();
+            if (r < N) {
+                const uint32_t *src = in + r * (uint64_t)C;
+                if (!dup) {
+                    uint32_t *dst = t.buf[dst_buf][d] + (base[d] + local) * (uint64_t)C;
+                    for (int c = 0; c < C; c++) dst[c] = ld_table(src + c);
+                } else {
+                    for (uint32_t dd = 0; dd < n; dd++) {
+                        uint32_t *dst = t.buf[dst_buf][dd] + (base[dd] + threadIdx.x) * (uint64_t)C;
+                        for (int c = 0; c < C; c++) dst[c] = ld_table(src + c);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // completion: fence my stores system-wide, count CTAs, the last one raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&loc->done_ctas, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (last && threadIdx.x < n) {
+        __threadfence_system();
+        st_sys_u64(&t.ctl[threadIdx.x]->flagB[t.rank], epoch);
+    }
+}
+
+// barrier 2: every peer has finished pushing into my buffer
+__global__ void p2p_wait_kernel(P2PTable t, XchCtl *my, uint64_t epoch, uint32_t *status) {
+    const int p = threadIdx.x;
+    if (p < t.nranks && !wait_flag(&my->flagB[p], epoch)) atomicOr(status, 2u);
+    __threadfence_system();
 }
