@@ -74,7 +74,7 @@ typedef struct wk_engine wk_engine_t;
 
 /* per-step execution record of the last wk_query_execute (profiling mode only for device_us) */
 typedef struct {
-    int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project */
+    int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project, 6 c2k, 7 i2k */
     int32_t in_cols;
     uint64_t in_rows, out_rows;
     uint64_t buckets_visited;   /* sum over rows of L_i                      */
@@ -136,6 +136,11 @@ int wk_known_to_known(wk_engine_t *engine, int col_start, wk_sid_t pid, int dir,
                       uint64_t *out_rows);
 /* known_to_const, sparql.hpp:484-549 / gpu_engine_cuda.hpp:283-362 */
 int wk_known_to_const(wk_engine_t *engine, int col_start, wk_sid_t pid, int dir, wk_sid_t end_const,
+                      uint64_t *out_rows);
+/* const_to_known, sparql.hpp:144-186: keep the rows whose column col_end occurs in edges(vid, pid, dir) */
+int wk_const_to_known(wk_engine_t *engine, wk_sid_t vid, wk_sid_t pid, int dir, int col_end, uint64_t *out_rows);
+/* index_to_known, sparql.hpp:80-141: keep the rows whose column col_end occurs in (this mt slice of) the index list */
+int wk_index_to_known(wk_engine_t *engine, wk_sid_t tpid, int dir, int col_end, int mt_tid, int mt_factor,
                       uint64_t *out_rows);
 /* final_process projection, sparql.hpp:1507-1550: out[i][j] = in[i][cols[j]] */
 int wk_project(wk_engine_t *engine, const int32_t *cols, int ncols_out, uint64_t *out_rows);

@@ -15,6 +15,7 @@ _LIB_PATH = os.path.join(_HERE, "libwukong_oracle.so")
 IN, OUT = 0, 1
 PREDICATE_ID, TYPE_ID = 0, 1
 I2U, C2U, K2U, K2K, K2C = 0, 1, 2, 3, 4
+C2K, I2K = 6, 7
 
 
 class SegMeta(C.Structure):

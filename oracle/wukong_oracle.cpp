@@ -1128,7 +1128,7 @@ double wko_emu_run(void *store, const int32_t *pats, const int32_t *pat_off, con
 }
 
 // Single-primitive entry points for kernel-level parity tests: run exactly one pattern function
-// on a given input table.  kind: 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c.  Returns rows; fills out.
+// on a given input table.  kind: 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 6 c2k, 7 i2k.  Returns rows; fills out.
 // For k2u `pid/dir` select the segment, col_start the probed column; k2k uses col_end, k2c end_const.
 int64_t wko_run_primitive(void *store, int kind, const uint32_t *table, uint64_t nrows, int ncols,
                           int32_t a_start, int32_t pid, int dir, int32_t a_end, int mt_tid, int mt_factor,
@@ -1153,6 +1153,8 @@ int64_t wko_run_primitive(void *store, int kind, const uint32_t *table, uint64_t
         case 2: q.patterns.push_back(Pattern{-(a_start + 1), pid, dir, newvar}); eng.known_to_unknown(q); break;
         case 3: q.patterns.push_back(Pattern{-(a_start + 1), pid, dir, -(a_end + 1)}); eng.known_to_known(q); break;
         case 4: q.patterns.push_back(Pattern{-(a_start + 1), pid, dir, a_end}); eng.known_to_const(q); break;
+        case 6: q.patterns.push_back(Pattern{a_start, pid, dir, -(a_end + 1)}); eng.const_to_known(q); break;
+        case 7: q.patterns.push_back(Pattern{a_start, pid, dir, -(a_end + 1)}); eng.index_to_known(q); break;
         default: return -1;
         }
     } catch (OracleError &e) { return -(int64_t)e.code - 1000; }

@@ -155,6 +155,44 @@ def test_known_to_const_and_known(eng1, ostore1, extra_cols):
     assert rows_equal(eng1.download(), want)
 
 
+@pytest.mark.parametrize("extra_cols", [0, 3])
+def test_const_and_index_to_known(eng1, ostore1, extra_cols):
+    """sparql.hpp:80-186 — rows kept when the column occurs in one edge list (hash set on the device)"""
+    dept0 = M.lubm_str2id("<http://www.Department0.University0.edu>")
+    univ0 = M.lubm_str2id("<http://www.University0.edu>")
+    for tp, vid, p, d in [(pid("memberOf"), dept0, pid("memberOf"), O.IN),       # students: members of Department0
+                          (pid("worksFor"), dept0, pid("worksFor"), O.IN),
+                          (pid("undergraduateDegreeFrom"), univ0, pid("undergraduateDegreeFrom"), O.IN),
+                          (pid("memberOf"), univ0, pid("memberOf"), O.IN),     # empty list: nothing survives
+                          (pid("takesCourse"), dept0, pid("subOrganizationOf"), O.OUT)]:
+        tbl = _seed_table(ostore1, tp, extra_cols=extra_cols)
+        C = tbl.shape[1]
+        want = ostore1.primitive(O.C2K, tbl, C, vid, p, d, a_end=C - 1)
+        eng1.upload(tbl)
+        n = eng1.const_to_known(vid, p, d, C - 1)
+        assert n == want.shape[0], (tp, vid, p, d)
+        assert rows_equal(eng1.download(), want)
+    # index lists, whole and mt slices (type index and predicate index)
+    for tp, idx, d in [(pid("memberOf"), pid("GraduateStudent"), O.IN), (pid("takesCourse"), pid("advisor"), O.IN),
+                       (pid("advisor"), pid("FullProfessor"), O.IN), (pid("worksFor"), pid("teacherOf"), O.OUT)]:
+        tbl = _seed_table(ostore1, tp, extra_cols=extra_cols)
+        C = tbl.shape[1]
+        for mt in [(0, 1), (1, 3), (2, 3)]:
+            want = ostore1.primitive(O.I2K, tbl, C, idx, O.PREDICATE_ID, d, a_end=C - 1, mt_tid=mt[0], mt_factor=mt[1])
+            eng1.upload(tbl)
+            n = eng1.index_to_known(idx, d, C - 1, mt[0], mt[1])
+            assert n == want.shape[0], (tp, idx, d, mt)
+            assert rows_equal(eng1.download(), want)
+    # a plan whose middle pattern is CONST -> KNOWN runs through wk_query_execute
+    pats = [(pid("GraduateStudent"), O.TYPE_ID, O.IN, -1), (-1, pid("memberOf"), O.OUT, -2),
+            (univ0, pid("subOrganizationOf"), O.IN, -2), (-2, pid("name"), O.OUT, -3)]
+    want = O.run_query([ostore1], pats, 3, [-1, -3], mt_factor=1)
+    rc, rows, cols, tbl = eng1.query(pats, 3, [-1, -3])
+    assert rc == 0 and rows == want.rows and rows > 0
+    assert rows_equal(tbl, want.table)
+    assert "c2k" in [s["kind"] for s in eng1.step_stats()]
+
+
 def test_edge_cases(eng1, ostore1):
     # empty input table
     eng1.upload(np.zeros((0, 2), dtype=np.uint32), ncols=2)
@@ -266,3 +304,35 @@ def test_batched_light_queries(eng2, ostore2):
     bad = np.concatenate([pats[: off[1]], np.array([[-1, 5, 1, -2]], dtype=np.int32)])
     rows, st = eng2.query_batch_raw(bad, np.array([0, off[1], off[1] + 1], dtype=np.int32), np.array([nv[0], 2], dtype=np.int32))
     assert st[0] == 0 and st[1] == 9 and rows[0] == want[0]
+
+
+def test_concurrent_engines_share_one_store(gstore2, ostore2):
+    """any number of engines per store, one caller thread each (the emulator's concurrent queries,
+    proxy.hpp:391-545): four threads run the seven queries interleaved and must all match the oracle"""
+    import threading
+    work = []
+    for q in range(1, 8):
+        pats, nvars, req, _ = load_query(q, "osdi16_plan")
+        work.append((pats, nvars, req, O.run_query([ostore2], pats, nvars, req, mt_factor=1)))
+    errors = []
+
+    def worker(seed):
+        eng = capi.Engine(gstore2, rbuf_bytes=48 << 20)
+        try:
+            order = np.random.default_rng(seed).permutation(len(work) * 6) % len(work)
+            for i in order.tolist():
+                pats, nvars, req, want = work[i]
+                rc, rows, cols, tbl = eng.query(pats, nvars, req)
+                if rc != 0 or rows != want.rows or not rows_equal(tbl, want.table):
+                    errors.append((seed, i, rc, rows, want.rows))
+        except Exception as ex:   # noqa: BLE001 - surfaced through the assertion below
+            errors.append((seed, repr(ex)))
+        finally:
+            eng.close()
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]

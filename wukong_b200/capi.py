@@ -9,7 +9,7 @@ LIB_CUDA = os.path.join(_HERE, "libwukong_b200.so")
 
 IN, OUT = 0, 1
 PREDICATE_ID, TYPE_ID = 0, 1
-KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project"]
+KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k"]
 
 WK_SUCCESS = 0
 WK_ERR_CUDA, WK_ERR_BAD_ARG, WK_ERR_RBUF_OVERFLOW, WK_ERR_NO_SEGMENT, WK_ERR_NO_DEVICE, WK_ERR_COMM = 100, 101, 102, 103, 104, 105
@@ -40,7 +40,7 @@ DECLARED_SYMBOLS = [
     "wk_strerror", "wk_version", "wk_device_count", "wk_store_create", "wk_store_adopt", "wk_store_destroy",
     "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_sync",
     "wk_engine_reset", "wk_table_upload", "wk_table_download", "wk_table_info", "wk_index_to_unknown",
-    "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_project",
+    "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_const_to_known", "wk_index_to_known", "wk_project",
     "wk_query_execute", "wk_query_execute_batch", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
     "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
     "wk_comm_stats", "wk_plan_exchanges", "wk_comm_p2p_export", "wk_comm_p2p_import", "wk_exchange_p2p",
@@ -81,6 +81,8 @@ def lib():
     L.wk_known_to_known.argtypes = [vp, ci, u32, ci, ci, pu64]
     L.wk_known_to_const.argtypes = [vp, ci, u32, ci, u32, pu64]
     L.wk_project.argtypes = [vp, vp, ci, pu64]
+    L.wk_const_to_known.argtypes = [vp, u32, u32, ci, ci, pu64]
+    L.wk_index_to_known.argtypes = [vp, u32, ci, ci, ci, ci, pu64]
     L.wk_query_execute.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
     L.wk_query_execute_batch.argtypes = [vp, vp, vp, vp, ci, vp, vp]
     L.wk_engine_num_steps.argtypes = [vp]
@@ -251,6 +253,16 @@ class Engine:
     def known_to_const(self, col_start, pid, d, end_const, sync=True):
         n = C.c_uint64(0)
         _check(lib().wk_known_to_const(self.h, col_start, pid, d, end_const, C.byref(n) if sync else None))
+        return n.value
+
+    def const_to_known(self, vid, pid, d, col_end, sync=True):
+        n = C.c_uint64(0)
+        _check(lib().wk_const_to_known(self.h, vid, pid, d, col_end, C.byref(n) if sync else None))
+        return n.value
+
+    def index_to_known(self, tpid, d, col_end, mt_tid=0, mt_factor=1, sync=True):
+        n = C.c_uint64(0)
+        _check(lib().wk_index_to_known(self.h, tpid, d, col_end, mt_tid, mt_factor, C.byref(n) if sync else None))
         return n.value
 
     def project(self, cols, sync=True):

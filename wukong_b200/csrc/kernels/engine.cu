@@ -31,7 +31,7 @@ using namespace wk;
 // device-side control block and kernels
 // =============================================================================================
 enum { MAX_STEPS = 60 };
-enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5 };
+enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5, KIND_C2K = 6, KIND_I2K = 7 };
 
 struct CtlBlock {
     uint64_t counts[MAX_STEPS + 4];       // counts[s] = rows of the table that step s reads
@@ -194,6 +194,101 @@ __global__ void __launch_bounds__(CTA_THREADS) project_kernel(const ProjParam p)
     project_body(p, ld_count(p.in_count), blockIdx.x, gridDim.x);
 }
 
+// ---- index_to_known / const_to_known (sparql.hpp:80-186): keep the rows whose column value occurs in ONE edge list --
+// The list is hashed into an engine-owned open-addressing table (lists from a reference-built store are not
+// guaranteed to be sorted), then every row does one lookup.
+struct ListSetCtl {
+    uint64_t off, len;     // slice of the edge array that forms the set
+    uint32_t mask;         // table size - 1 (power of two >= 2 * len)
+    uint32_t visited;
+};
+static constexpr uint32_t SET_EMPTY = 0xFFFFFFFFu;   // BLANK_ID is never a vertex id (type.hpp:37)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+struct ListParam {
+    const uint4 *vertices;
+    const uint32_t *edges;
+    uint32_t *table;
+    uint64_t table_cap;          // words available in `table`
+    ListSetCtl *ctl;
+    uint32_t *status;
+    uint64_t key, bucket_start;
+    FastMod fm;
+    int32_t mt_tid, mt_factor;
+};
+
+__global__ void list_probe_kernel(const ListParam p) {
+    uint32_t visited;
+    const uint64_t bucket = p.bucket_start + fastmod(hash_u64(p.key), p.fm);
+    const uint64_t ptr = probe_single(p.vertices, p.key, bucket, threadIdx.x, visited);
+    if (threadIdx.x == 0) {
+        const uint64_t size = ptr_size(ptr);
+        const uint64_t mtf = (uint64_t)(p.mt_factor < 1 ? 1 : p.mt_factor), start = (uint64_t)p.mt_tid % mtf, length = size / mtf;
+        const uint64_t begin = start * length;
+        const uint64_t len = (start == mtf - 1) ? (size - begin) : length;   // same slicing as index_to_unknown
+        uint64_t ts = 16;
+        while (ts < 2 * len) ts <<= 1;
+        if (ts > p.table_cap) { atomicOr(p.status, 1u); ts = 16; p.ctl->len = 0; }
+        else p.ctl->len = len;
+        p.ctl->off = ptr_off(ptr) + begin;
+        p.ctl->mask = (uint32_t)(ts - 1);
+        p.ctl->visited = visited;
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) list_clear_kernel(const ListParam p) {
+    const uint64_t n = (uint64_t)__ldcg(&p.ctl->mask) + 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * CTA_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * CTA_THREADS) p.table[i] = SET_EMPTY;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) list_insert_kernel(const ListParam p) {
+    const uint64_t len = ld_count(&p.ctl->len), off = ld_count(&p.ctl->off);
+    const uint32_t mask = __ldcg(&p.ctl->mask);
+    for (uint64_t i = (uint64_t)blockIdx.x * CTA_THREADS + threadIdx.x; i < len; i += (uint64_t)gridDim.x * CTA_THREADS) {
+        const uint32_t v = ld_edge(p.edges + off + i);
+        uint32_t h = mix32(v) & mask;
+        while (true) {
+            const uint32_t old = atomicCAS(&p.table[h], SET_EMPTY, v);
+            if (old == SET_EMPTY || old == v) break;
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) list_filter_kernel(const StepParam p, const uint32_t *table, const ListSetCtl *ctl) {
+    extern __shared__ uint32_t dyn_rows[];
+    __shared__ TileSmem sm;
+    if (__ldcg(p.status) != 0) return;
+    const uint64_t N = ld_count(p.in_count);
+    const uint32_t mask = __ldcg(&ctl->mask);
+    const int C = p.C, tid = threadIdx.x;
+    for (uint64_t tile = blockIdx.x; tile * TILE_ROWS < N; tile += gridDim.x) {
+        const uint64_t row0 = tile * TILE_ROWS;
+        const uint32_t nrows = (uint32_t)((N - row0 < (uint64_t)TILE_ROWS) ? (N - row0) : (uint64_t)TILE_ROWS);
+        const bool active = (uint32_t)tid < nrows;
+        uint32_t mult = 0;
+        if (active) {
+            const uint32_t *src = p.in + (row0 + tid) * (uint64_t)C;
+            for (int c = 0; c < C; c++) dyn_rows[tid * C + c] = ld_table(src + c);
+            const uint32_t v = dyn_rows[tid * C + p.col_end];
+            uint32_t h = mix32(v) & mask;
+            while (true) {
+                const uint32_t x = __ldcg(table + h);
+                if (x == v) { mult = 1; break; }
+                if (x == SET_EMPTY) break;
+                h = (h + 1) & mask;
+            }
+        }
+        const uint64_t excl = tile_scan_and_claim(mult, sm, tid, p);
+        const uint64_t base = sm.base;
+        if (base != ~0ull && mult) copy_row<0>(p.out + (base + excl) * (uint64_t)C, dyn_rows + tid * C, C);
+        __syncthreads();
+    }
+}
+
 // ---- bookkeeping kernels -------------------------------------------------------------------------
 __global__ void set_count_kernel(uint64_t *dst, uint64_t v) { *dst = v; }
 
@@ -265,6 +360,9 @@ struct wk_engine {
     uint64_t launches = 0;
     uint64_t light_escalate_rows = 4096;
     struct wk_comm *comm = nullptr;      // sharded execution (wk_comm_init)
+    uint32_t *d_set = nullptr;           // hash set of index_to_known / const_to_known (lazy)
+    uint64_t set_cap = 0;
+    ListSetCtl *d_setctl = nullptr;
     BatchPlan *h_bplans = nullptr, *d_bplans = nullptr;   // wk_query_execute_batch staging
     BatchResult *h_bres = nullptr, *d_bres = nullptr;
     int batch_cap = 0;
@@ -582,6 +680,57 @@ static int enqueue_project(wk_engine *e, const int32_t *cols, int n) {
     return WK_SUCCESS;
 }
 
+// index_to_known / const_to_known: rows whose column `col_end` occurs in the edge list of key (vid, pid, dir)
+static int enqueue_to_known(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int dir, int col_end, int mt_tid, int mt_factor) {
+    if (e->ncols <= 0 || e->ncols >= MAX_COLS) return e->ncols <= 0 ? WK_VERTEX_INVALID : WK_ERR_BAD_ARG;
+    if (col_end < 0 || col_end >= e->ncols) return WK_VERTEX_INVALID;
+    if (dir != WK_DIR_IN && dir != WK_DIR_OUT) return WK_ERR_BAD_ARG;
+    const wk_segmeta_t *m = seg_of_key(e->store, vid, pid, dir);
+    if (!m) return WK_ERR_NO_SEGMENT;
+    if (!e->d_set) {
+        e->set_cap = std::min<uint64_t>(e->cap_words, 1ull << 28);
+        CUDA_TRY(cudaMalloc((void **)&e->d_set, e->set_cap * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc((void **)&e->d_setctl, sizeof(ListSetCtl)));
+    }
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    const int s = e->step;
+    ListParam lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.vertices = e->store->d_vertices;
+    lp.edges = e->store->d_edges;
+    lp.table = e->d_set;
+    lp.table_cap = e->set_cap;
+    lp.ctl = e->d_setctl;
+    lp.status = &e->d_ctl->status;
+    lp.key = make_key(vid, pid, (uint32_t)dir);
+    lp.bucket_start = m->bucket_start;
+    lp.fm = make_fastmod(m->num_buckets);
+    lp.mt_tid = mt_tid;
+    lp.mt_factor = mt_factor < 1 ? 1 : mt_factor;
+    StepParam p;
+    memset(&p, 0, sizeof(p));
+    p.in = e->buf[s & 1];
+    p.out = e->buf[(s + 1) & 1];
+    p.in_count = &e->d_ctl->counts[s];
+    p.out_count = &e->d_ctl->counts[s + 1];
+    p.out_cap_rows = e->cap_words / (uint64_t)e->ncols;
+    p.stats = &e->d_ctl->stats[2 * s];
+    p.status = &e->d_ctl->status;
+    p.C = e->ncols;
+    p.col_end = col_end;
+    StepRecord &r = begin_step(e, kind, e->ncols);
+    const int grid = e->num_sms * 4;
+    list_probe_kernel<<<1, 32, 0, e->stream>>>(lp);
+    list_clear_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(lp);
+    list_insert_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(lp);
+    list_filter_kernel<<<grid, CTA_THREADS, (size_t)TILE_ROWS * e->ncols * sizeof(uint32_t), e->stream>>>(p, e->d_set, e->d_setctl);
+    CUDA_TRY(cudaGetLastError());
+    end_step(e, r, 4);
+    e->step = s + 1;
+    return WK_SUCCESS;
+}
+
 // copy per-step counters back and derive the algorithmic bytes
 static int snapshot_stats(wk_engine *e) {
     CtlBlock h;
@@ -607,6 +756,8 @@ static int snapshot_stats(wk_engine *e) {
         case KIND_K2C: st.algo_bytes = 4 * C * N + 128 * st.buckets_visited + 4 * st.edges_touched + 4 * C * R; break;
         case KIND_I2U:
         case KIND_C2U: st.algo_bytes = 128 * st.buckets_visited + 4 * R + 4 * R; break;
+        case KIND_C2K:
+        case KIND_I2K: st.algo_bytes = 4 * C * N + 4 * C * R; break;
         default: st.algo_bytes = 4 * C * R + 4 * (uint64_t)e->ncols * R; break;
         }
         if (r.timed) {
@@ -785,6 +936,7 @@ int wk_engine_destroy(wk_engine_t *e) {
     cudaFree(e->buf[1]);
     cudaFree(e->d_ctl);
     if (e->d_hq) cudaFree(e->d_hq);
+    if (e->d_set) { cudaFree(e->d_set); cudaFree(e->d_setctl); }
     if (e->d_bplans) { cudaFree(e->d_bplans); cudaFree(e->d_bres); cudaFreeHost(e->h_bplans); cudaFreeHost(e->h_bres); }
     cudaFreeHost((void *)e->h_rec);
     cudaFreeHost((void *)e->h_stage);
@@ -896,6 +1048,18 @@ int wk_known_to_const(wk_engine_t *e, int col_start, wk_sid_t pid, int dir, wk_s
     return finish_call(e, enqueue_known(e, KIND_K2C, col_start, pid, dir, 0, end_const), out_rows);
 }
 
+int wk_const_to_known(wk_engine_t *e, wk_sid_t vid, wk_sid_t pid, int dir, int col_end, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_to_known(e, KIND_C2K, vid, pid, dir, col_end, 0, 1), out_rows);
+}
+
+int wk_index_to_known(wk_engine_t *e, wk_sid_t tpid, int dir, int col_end, int mt_tid, int mt_factor, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_to_known(e, KIND_I2K, 0, tpid, dir, col_end, mt_tid, mt_factor), out_rows);
+}
+
 int wk_project(wk_engine_t *e, const int32_t *cols, int n, uint64_t *out_rows) {
     if (!e || !cols) return WK_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(e->store->device));
@@ -982,10 +1146,14 @@ static int plan_steps(const wk_pattern_t *pats, int npat, int nvars, std::vector
             ps.col_start = v2c[-(pt.subject + 1)];
             v2c[-(pt.object + 1)] = ncols;
             ncols += 1;
+        } else if (ss == CONST && so == KNOWN) {
+            ps.kind = KIND_C2K;          // const_to_known (sparql.hpp:144-186)
+            ps.vid = (uint64_t)pt.subject;
+            ps.col_end = v2c[-(pt.object + 1)];
         } else if (ss == UNKNOWN) {
             return WK_UNKNOWN_SUB;
         } else {
-            return WK_UNKNOWN_PATTERN;   // CONST/CONST, CONST/KNOWN (const_to_known) not on the device path
+            return WK_UNKNOWN_PATTERN;   // CONST/CONST
         }
         if (ncols >= MAX_COLS) return WK_ERR_BAD_ARG;
         steps.push_back(ps);
@@ -1099,7 +1267,9 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
     }
     e->q_timed = false;
     if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
-    const bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS;
+    bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS;
+    for (const PlannedStep &ps : steps)
+        if (ps.kind == KIND_C2K) light = false;   // const_to_known runs on the multi-CTA path only
     if (light) {   // the fused kernel clears the control block itself
         e->step = 0;
         e->recs.clear();
@@ -1135,6 +1305,7 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
             const PlannedStep &ps = steps[i];
             if (ps.kind == KIND_I2U) rc = enqueue_seed(e, KIND_I2U, 0, ps.pid, ps.dir, mt_tid, mt_factor);
             else if (ps.kind == KIND_C2U) rc = enqueue_seed(e, KIND_C2U, ps.vid, ps.pid, ps.dir, 0, 1);
+            else if (ps.kind == KIND_C2K) rc = enqueue_to_known(e, KIND_C2K, ps.vid, ps.pid, ps.dir, ps.col_end, 0, 1);
             else rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const);
             if (rc) return rc;
         }
@@ -1188,6 +1359,8 @@ int wk_query_execute_batch(wk_engine_t *e, const wk_pattern_t *patterns, const i
         steps.clear();
         int rc = plan_steps(patterns + pat_off[q], pat_off[q + 1] - pat_off[q], nvars[q], v2c, steps);
         if (rc == WK_SUCCESS && (steps[0].kind != KIND_C2U || (int)steps.size() > BATCH_STEPS)) rc = WK_UNKNOWN_PATTERN;
+        for (const PlannedStep &ps : steps)
+            if (ps.kind == KIND_C2K) rc = WK_UNKNOWN_PATTERN;
         if (rc == WK_SUCCESS) rc = fill_light_steps(e, steps, 0, 1, bp.steps);
         out_status[q] = rc;
         if (rc == WK_SUCCESS) bp.nsteps = (int)steps.size();
