@@ -89,6 +89,7 @@ class ClockSampler(threading.Thread):
 
 
 def build_dataset(args):
+    """host arm: triples -> store arrays with the host builder (csrc/store/host_builder.cpp)"""
     from wukong_b200 import datagen, host
     t0 = time.time()
     tr = datagen.lubm(args.scale, seed=args.seed)
@@ -96,8 +97,38 @@ def build_dataset(args):
     hs = host.HostStore(tr)
     t2 = time.time()
     info = {"triples": int(tr.shape[0]), "keys": int(hs.num_keys), "gen_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2),
-            "header_mb": round(hs.num_slots * 16 / 1e6, 1), "edges_mb": round(hs.num_edges * 4 / 1e6, 1)}
+            "store_build": "host", "header_mb": round(hs.num_slots * 16 / 1e6, 1), "edges_mb": round(hs.num_edges * 4 / 1e6, 1)}
     return tr, hs, info
+
+
+class DeviceBuiltStore:
+    """the arrays of a device-built store copied back for the CPU baseline (same accessors as host.HostStore)"""
+
+    def __init__(self, gst):
+        self._v, self._e = gst.download()
+        self._s = gst.segs()
+
+    def vertices(self): return self._v
+    def edges(self): return self._e
+    def segs(self): return self._s
+
+
+def build_dataset_device(args, device, num_servers=1, sid=0):
+    """triples -> store directly in HBM (wk_store_build: sort / dedup / partition / insert on the GPU)"""
+    from wukong_b200 import capi, datagen
+    t0 = time.time()
+    if num_servers > 1:
+        tr = datagen.lubm_shard(args.scale, num_servers, sid, seed=args.seed)
+    else:
+        tr = datagen.lubm(args.scale, seed=args.seed)
+    t1 = time.time()
+    gst = capi.Store.build(tr, datagen.LUBM_NUM_NORMAL_PREDS, num_servers=num_servers, sid=sid, device=device)
+    t2 = time.time()
+    st = gst.build_stats
+    info = {"triples": int(tr.shape[0]), "keys": int(st["num_keys"]), "gen_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2),
+            "store_build": "device", "build_ms": {k: round(st[k], 1) for k in ("ms_upload", "ms_sort", "ms_insert", "ms_total")},
+            "header_mb": round(st["num_slots"] * 16 / 1e6, 1), "edges_mb": round(st["num_edges"] * 4 / 1e6, 1)}
+    return tr, gst, info
 
 
 def cpu_oracle_times(hs, plans, threads, heavy_reps, light_reps):
@@ -166,10 +197,12 @@ def run_sharded(args, rank, world, local_rank, dist):
     import torch
     from wukong_b200 import capi, datagen, host
     t0 = time.time()
-    tr = datagen.lubm_shard(args.scale, world, rank, seed=args.seed)
-    hs = host.HostStore(tr, num_servers=world, sid=rank)
+    if args.store_build == "device":
+        tr, gst, _ = build_dataset_device(args, local_rank, num_servers=world, sid=rank)
+    else:
+        tr = datagen.lubm_shard(args.scale, world, rank, seed=args.seed)
+        gst = host.HostStore(tr, num_servers=world, sid=rank).upload(local_rank)
     t1 = time.time()
-    gst = hs.upload(local_rank)
     rbuf = (args.rbuf_mb << 20) if args.rbuf_mb else max(256 << 20, min(8 << 30, int(tr.shape[0]) * 8))
     eng = capi.Engine(gst, rbuf_bytes=rbuf)
     if args.exchange == "p2p":
@@ -252,6 +285,8 @@ def main():
     ap.add_argument("--rbuf-mb", type=int, default=0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--store-build", default="device", choices=["device", "host"],
+                    help="build the graph store on the GPU (wk_store_build) or with the host builder + upload")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="sharded mode: peer-memory push or NCCL all-to-all(v)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
                     help="N>1: replicas (whole store per GPU, weak scaling) or sharded (vid %% N + NCCL all-to-all)")
@@ -286,9 +321,13 @@ def main():
     if world > 1 and args.mode == "sharded":
         run_sharded(args, rank, world, local_rank, dist)
         return
-    tr, hs, info = build_dataset(args)
+    hs = None
+    if args.store_build == "device":
+        tr, gst, info = build_dataset_device(args, local_rank)
+    else:
+        tr, hs, info = build_dataset(args)
+        gst = hs.upload(local_rank)
     plans = load_plans(args.plan)
-    gst = hs.upload(local_rank)
     rbuf = (args.rbuf_mb << 20) if args.rbuf_mb else max(256 << 20, min(8 << 30, int(info["triples"]) * 8))
     eng = capi.Engine(gst, rbuf_bytes=rbuf)
     out_tbl, _keep = capi.pinned_array(min(rbuf // 4, 1 << 28))
@@ -412,7 +451,7 @@ def main():
             "dataset": info, "timed_region_s": round(t_region, 2)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = args.cpu_threads or os.cpu_count()
-        res = cpu_oracle_times(hs, plans, threads, 3, 200)
+        res = cpu_oracle_times(hs if hs is not None else DeviceBuiltStore(gst), plans, threads, 3, 200)
         cq = [1e6 / res[q][0] for q in QUERIES]
         for q in QUERIES:
             assert res[q][1] == rows[q][0], "GPU and CPU oracle disagree on q%d rows" % q

@@ -46,7 +46,9 @@ enum {
     WK_ERR_RBUF_OVERFLOW = 102, /* result does not fit the result buffer (reference: ASSERT, gpu_engine_cuda.hpp:185) */
     WK_ERR_NO_SEGMENT = 103,  /* pattern names a (pid,dir) segment that is not in the store */
     WK_ERR_NO_DEVICE = 104,
-    WK_ERR_COMM = 105
+    WK_ERR_COMM = 105,
+    WK_ERR_STORE_FULL = 106   /* store build: header / ext extent / entry region too small (reference: ASSERT in
+                                 gstore.hpp:414-426, 789-856) or a key with >= 2^28 edges */
 };
 
 /* 128-bit slot of the cluster-hash header region: store/vertex.hpp:152-155 (vertex_t).
@@ -99,6 +101,28 @@ int wk_store_create(int device, const wk_vertex_t *vertices, uint64_t num_slots,
 int wk_store_adopt(int device, wk_vertex_t *d_vertices, uint64_t num_slots, wk_sid_t *d_edges,
                    uint64_t num_edges, const wk_segmeta_t *segs, int nsegs, int take_ownership,
                    wk_store_t **out);
+/* Build the store on the device from raw id triples: replaces the loader's sort/dedup/partition
+ * (loader/base_loader.hpp:308-378) + StaticGStore::init (store/static_gstore.hpp:383-454) for server `sid`
+ * of `num_servers`.  Same segment table and edge array as the CPU build; slot placement inside a bucket
+ * chain is free.  kvstore_bytes == 0 sizes the regions from the data (est_load_factor, global.hpp:99-104). */
+typedef struct {
+    int32_t num_servers, sid;
+    int32_t num_normal_preds;     /* (#lines of str_index) - 1, base_loader.hpp:409-424 */
+    int32_t est_load_factor;      /* 0 = 55 */
+    uint64_t kvstore_bytes;
+    int32_t triples_on_device;    /* `triples` is a device pointer on `device` */
+    int32_t _pad;
+} wk_build_opts_t;
+typedef struct {
+    uint64_t num_keys, num_triples_out, num_triples_in, num_buckets, num_buckets_ext, used_ext, num_slots, num_edges;
+    float ms_upload, ms_sort, ms_insert, ms_total;
+} wk_build_stats_t;
+int wk_store_build(int device, const wk_sid_t *triples, uint64_t n, const wk_build_opts_t *opts, wk_store_t **out,
+                   wk_build_stats_t *stats);
+/* shape of a store, its segment table, and a copy of its arrays back to the host (checks, CPU baseline) */
+int wk_store_info(wk_store_t *store, uint64_t *num_slots, uint64_t *num_edges, int *nsegs);
+int wk_store_segs(wk_store_t *store, wk_segmeta_t *dst, int cap);
+int wk_store_download(wk_store_t *store, wk_vertex_t *vertices, uint64_t num_slots, wk_sid_t *edges, uint64_t num_edges);
 int wk_store_destroy(wk_store_t *store);
 /* host-side probe of one key through the device arrays (debug / gsck-style checks) */
 int wk_store_get_edges(wk_store_t *store, wk_sid_t vid, wk_sid_t pid, int dir,

@@ -29,6 +29,18 @@ class SegMeta(C.Structure):
                 ("ext_num", C.c_uint64)]
 
 
+class BuildOpts(C.Structure):
+    _fields_ = [("num_servers", C.c_int32), ("sid", C.c_int32), ("num_normal_preds", C.c_int32),
+                ("est_load_factor", C.c_int32), ("kvstore_bytes", C.c_uint64), ("triples_on_device", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class BuildStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("num_keys", "num_triples_out", "num_triples_in", "num_buckets",
+                                          "num_buckets_ext", "used_ext", "num_slots", "num_edges")] + \
+               [(n, C.c_float) for n in ("ms_upload", "ms_sort", "ms_insert", "ms_total")]
+
+
 class StepStats(C.Structure):
     _fields_ = [("kind", C.c_int32), ("in_cols", C.c_int32), ("in_rows", C.c_uint64), ("out_rows", C.c_uint64),
                 ("buckets_visited", C.c_uint64), ("edges_touched", C.c_uint64), ("algo_bytes", C.c_uint64),
@@ -37,7 +49,8 @@ class StepStats(C.Structure):
 
 # every symbol include/wukong_b200.h declares (checked by tests/test_capi_symbols.py)
 DECLARED_SYMBOLS = [
-    "wk_strerror", "wk_version", "wk_device_count", "wk_store_create", "wk_store_adopt", "wk_store_destroy",
+    "wk_strerror", "wk_version", "wk_device_count", "wk_store_create", "wk_store_adopt", "wk_store_build", "wk_store_info", "wk_store_segs",
+    "wk_store_download", "wk_store_destroy",
     "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_sync",
     "wk_engine_reset", "wk_table_upload", "wk_table_download", "wk_table_info", "wk_index_to_unknown",
     "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_const_to_known", "wk_index_to_known", "wk_project",
@@ -66,6 +79,10 @@ def lib():
     L.wk_store_create.argtypes = [ci, vp, u64, vp, u64, vp, ci, C.POINTER(vp)]
     L.wk_store_adopt.argtypes = [ci, vp, u64, vp, u64, vp, ci, ci, C.POINTER(vp)]
     L.wk_store_destroy.argtypes = [vp]
+    L.wk_store_build.argtypes = [ci, vp, u64, vp, C.POINTER(vp), vp]
+    L.wk_store_info.argtypes = [vp, pu64, pu64, C.POINTER(ci)]
+    L.wk_store_segs.argtypes = [vp, vp, ci]
+    L.wk_store_download.argtypes = [vp, vp, u64, vp, u64]
     L.wk_store_get_edges.argtypes = [vp, u32, u32, ci, vp, u64, pu64]
     L.wk_engine_create.argtypes = [vp, u64, C.POINTER(vp)]
     L.wk_engine_destroy.argtypes = [vp]
@@ -155,6 +172,40 @@ class Store:
         self.h = h
         self.device = device
         return self
+
+    @classmethod
+    def build(cls, triples, num_normal_preds, num_servers=1, sid=0, est_load_factor=55, kvstore_bytes=0, device=0):
+        """wk_store_build: sort / dedup / partition + hash-table construction on the device.
+        Returns the store; .build_stats holds the counters and timings of the build."""
+        t = np.ascontiguousarray(triples, dtype=np.uint32).reshape(-1, 3)
+        o = BuildOpts(num_servers, sid, num_normal_preds, est_load_factor, kvstore_bytes, 0, 0)
+        st = BuildStats()
+        h = C.c_void_p()
+        _check(lib().wk_store_build(device, _ptr(t), t.shape[0], C.byref(o), C.byref(h), C.byref(st)), "wk_store_build")
+        self = cls.__new__(cls)
+        self.h = h
+        self.device = device
+        self.build_stats = {n: getattr(st, n) for n, _ in BuildStats._fields_}
+        return self
+
+    def info(self):
+        ns, ne, k = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        _check(lib().wk_store_info(self.h, C.byref(ns), C.byref(ne), C.byref(k)))
+        return ns.value, ne.value, k.value
+
+    def segs(self):
+        k = self.info()[2]
+        sa = (SegMeta * k)()
+        _check(lib().wk_store_segs(self.h, C.cast(sa, C.c_void_p), k))
+        return list(sa)
+
+    def download(self):
+        """-> (vertices (num_slots, 2) uint64, edges uint32) copied back from the device"""
+        ns, ne, _ = self.info()
+        v = np.empty((ns, 2), dtype=np.uint64)
+        e = np.empty(ne, dtype=np.uint32)
+        _check(lib().wk_store_download(self.h, _ptr(v), ns, _ptr(e), ne))
+        return v, e
 
     def get_edges(self, vid, pid, d, cap=1 << 20):
         out = np.empty(cap, dtype=np.uint32)

@@ -783,6 +783,7 @@ const char *wk_strerror(int code) {
     case WK_ERR_NO_SEGMENT: return "no such (pid, dir) segment in the store";
     case WK_ERR_NO_DEVICE: return "no CUDA device";
     case WK_ERR_COMM: return "communicator not initialised";
+    case WK_ERR_STORE_FULL: return "store build: header, ext extent or entry region too small (or a key with >= 2^28 edges)";
     default: return "unknown status";
     }
 }
@@ -840,6 +841,34 @@ int wk_store_adopt(int device, wk_vertex_t *d_vertices, uint64_t num_slots, wk_s
     int rc = store_set_segs(st, segs, nsegs);
     if (rc) { delete st; return rc; }
     *out = st;
+    return WK_SUCCESS;
+}
+
+int wk_store_info(wk_store_t *st, uint64_t *num_slots, uint64_t *num_edges, int *nsegs) {
+    if (!st) return WK_ERR_BAD_ARG;
+    if (num_slots) *num_slots = st->num_slots;
+    if (num_edges) *num_edges = st->num_edges;
+    if (nsegs) *nsegs = (int)st->segs.size();
+    return WK_SUCCESS;
+}
+
+int wk_store_segs(wk_store_t *st, wk_segmeta_t *dst, int cap) {
+    if (!st || !dst || cap < (int)st->segs.size()) return WK_ERR_BAD_ARG;
+    // ordered like segid_t::operator< (pid, index, dir), the order of GStore::rdf_seg_meta_map
+    std::vector<wk_segmeta_t> v;
+    for (auto &kv : st->segs) v.push_back(kv.second);
+    std::sort(v.begin(), v.end(), [](const wk_segmeta_t &a, const wk_segmeta_t &b) {
+        return std::make_tuple(a.pid, a.index, a.dir) < std::make_tuple(b.pid, b.index, b.dir);
+    });
+    memcpy(dst, v.data(), v.size() * sizeof(wk_segmeta_t));
+    return WK_SUCCESS;
+}
+
+int wk_store_download(wk_store_t *st, wk_vertex_t *vertices, uint64_t num_slots, wk_sid_t *edges, uint64_t num_edges) {
+    if (!st || (vertices && num_slots != st->num_slots) || (edges && num_edges != st->num_edges)) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(st->device));
+    if (vertices) CUDA_TRY(cudaMemcpy(vertices, st->d_vertices, num_slots * sizeof(wk_vertex_t), cudaMemcpyDeviceToHost));
+    if (edges) CUDA_TRY(cudaMemcpy(edges, st->d_edges, num_edges * sizeof(wk_sid_t), cudaMemcpyDeviceToHost));
     return WK_SUCCESS;
 }
 
