@@ -66,6 +66,11 @@ def lib():
     L.wko_hash_u64.argtypes = [u64]
     L.wko_hash_prime_u64.restype = u64
     L.wko_hash_prime_u64.argtypes = [u64]
+    L.wko_make_ptr.restype = u64
+    L.wko_make_ptr.argtypes = [u64, u64]
+    L.wko_is_tpid.argtypes = [C.c_int64]
+    L.wko_less_pso.argtypes = [vp, vp]
+    L.wko_less_pos.argtypes = [vp, vp]
     L.wko_make_key.restype = u64
     L.wko_make_key.argtypes = [u64, u64, u64]
     L.wko_set_plan.argtypes = [vp, C.c_int, C.c_char_p, vp, C.c_int]

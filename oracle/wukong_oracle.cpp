@@ -7,11 +7,16 @@
 // (wukong_b200/) never does and fails loudly when its CUDA library is missing.
 //
 // PARITY PINNING: the reference's own tests hold NO golden vectors for this path
-//  and the reference cannot be compiled here (boost/TBB/MPI/zmq absent), so
-// this oracle is pinned only by (i) the gsck structural invariants (gchecker.hpp:132-360)
-// restated in wko_store_check, (ii) an independent brute-force triple-scan joiner in
-// tests/sparql_mini.py (bruteforce_bgp), and (iii) committed golden fixtures generated from it (tests/golden/).
-// => "parity unpinned" against reference binaries; see DESIGN.md.
+//  and its store / engine cannot be compiled here (boost/TBB/MPI/zmq absent).
+// Pinned against the reference's COMPILED code: only the data-structure layer -- key / pointer bit
+// layout, ikey_t::hash / hash_u64, hash_prime_u64, is_tpid, triple sort orders -- through
+// oracle/_ref (ref_layout_shim.cpp over core/store/vertex.hpp, utils/math.hpp, core/type.hpp)
+// and the fixture tests/golden/ref_layout.json generated from it.  Everything above that layer
+// (store build, probe, pattern functions, dispatch) is pinned only by (i) the gsck structural
+// invariants (gchecker.hpp:132-360) restated in wko_store_check, (ii) an independent brute-force
+// triple-scan joiner in tests/sparql_mini.py (bruteforce_bgp), and (iii) committed golden
+// fixtures generated from it (tests/golden/).
+// => engine-level "parity unpinned" against reference binaries; see DESIGN.md §5.
 //
 // All file:line citations are relative to /root/reference/.
 // =============================================================================================
@@ -78,6 +83,10 @@ static inline uint64_t hash_u64(uint64_t key) {
 }
 
 // utils/math.hpp:105-131
+struct triple_t;
+static bool less_pso(const triple_t &a, const triple_t &b);   // type.hpp:88-99
+static bool less_pos(const triple_t &a, const triple_t &b);   // type.hpp:101-112
+
 static uint64_t hash_prime_u64(uint64_t upper) {
     static const uint64_t P[] = {1610612741ull, 805306457ull, 402653189ull, 201326611ull, 100663319ull,
                                  50331653ull, 25165843ull, 12582917ull, 6291469ull, 3145739ull, 1572869ull,
@@ -89,6 +98,16 @@ static uint64_t hash_prime_u64(uint64_t upper) {
 }
 
 struct triple_t { sid_t s, p, o; };
+static bool less_pso(const triple_t &a, const triple_t &b) {
+    if (a.p != b.p) return a.p < b.p;
+    if (a.s != b.s) return a.s < b.s;
+    return a.o < b.o;
+}
+static bool less_pos(const triple_t &a, const triple_t &b) {
+    if (a.p != b.p) return a.p < b.p;
+    if (a.o != b.o) return a.o < b.o;
+    return a.s < b.s;
+}
 
 // ---- segment metadata: store/meta.hpp:53-204 ---------------------------------------------------
 struct ext_extent_t { uint64_t num_ext_buckets, off, start; };
@@ -277,16 +296,8 @@ struct Store {
             if ((int)(o % num_servers) == sid) pos[o % num_engines].push_back(triple_t{s, p, o});
         }
         for (int t = 0; t < num_engines; t++) {
-            std::sort(pso[t].begin(), pso[t].end(), [](const triple_t &a, const triple_t &b) {  // type.hpp:86-96
-                if (a.p != b.p) return a.p < b.p;
-                if (a.s != b.s) return a.s < b.s;
-                return a.o < b.o;
-            });
-            std::sort(pos[t].begin(), pos[t].end(), [](const triple_t &a, const triple_t &b) {  // type.hpp:99-109
-                if (a.p != b.p) return a.p < b.p;
-                if (a.o != b.o) return a.o < b.o;
-                return a.s < b.s;
-            });
+            std::sort(pso[t].begin(), pso[t].end(), less_pso);
+            std::sort(pos[t].begin(), pos[t].end(), less_pos);
             dedup(pos[t]);
             dedup(pso[t]);
         }
@@ -1066,6 +1077,10 @@ uint64_t wko_get_edges(void *s, uint32_t vid, uint32_t pid, int dir, const uint3
 }
 uint64_t wko_hash_u64(uint64_t k) { return hash_u64(k); }
 uint64_t wko_hash_prime_u64(uint64_t k) { return hash_prime_u64(k); }
+uint64_t wko_make_ptr(uint64_t size, uint64_t off) { return make_ptr(size, off); }
+int wko_is_tpid(int64_t id) { return is_tpid(id) ? 1 : 0; }
+int wko_less_pso(const uint32_t *a, const uint32_t *b) { return less_pso(triple_t{a[0], a[1], a[2]}, triple_t{b[0], b[1], b[2]}) ? 1 : 0; }
+int wko_less_pos(const uint32_t *a, const uint32_t *b) { return less_pos(triple_t{a[0], a[1], a[2]}, triple_t{b[0], b[1], b[2]}) ? 1 : 0; }
 uint64_t wko_make_key(uint64_t vid, uint64_t pid, uint64_t dir) { return make_key(vid, pid, dir); }
 
 // apply a .fmt plan text to n patterns (4 int32 each: subject, predicate, direction, object);

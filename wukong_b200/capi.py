@@ -125,6 +125,10 @@ def lib():
     L.wk_selftest_hash.argtypes = [u64]
     L.wk_selftest_fastmod.restype = u64
     L.wk_selftest_fastmod.argtypes = [u64, u64]
+    L.wk_selftest_ptr_size.restype = u64
+    L.wk_selftest_ptr_size.argtypes = [u64]
+    L.wk_selftest_ptr_off.restype = u64
+    L.wk_selftest_ptr_off.argtypes = [u64]
     L.wk_selftest_make_key.restype = u64
     L.wk_selftest_make_key.argtypes = [u64, u32, u32]
     _lib = L

@@ -1841,5 +1841,7 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
 uint64_t wk_selftest_hash(uint64_t key) { return hash_u64(key); }
 uint64_t wk_selftest_fastmod(uint64_t n, uint64_t d) { FastMod f = make_fastmod(d); return fastmod(n, f); }
 uint64_t wk_selftest_make_key(uint64_t vid, uint32_t pid, uint32_t dir) { return make_key(vid, pid, dir); }
+uint64_t wk_selftest_ptr_size(uint64_t raw) { return ptr_size(raw); }
+uint64_t wk_selftest_ptr_off(uint64_t raw) { return ptr_off(raw); }
 
 }  // extern "C"
