@@ -188,7 +188,7 @@ def run_reference(args, rank, world):
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "latency_us": {"q%d" % q: mean[q] for q in QUERIES},
             "wall_s": round(time.time() - t_start, 1)}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_sharded(args, rank, world, local_rank, dist):
@@ -268,12 +268,34 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "rows": {"q%d" % q: int(rr[i]) for i, q in enumerate(QUERIES)},
                 "exchange": {"rows_sent_all_ranks": int(rr[7]), "exchanges_per_rank": stats["exchanges"]},
                 "dataset": {"shard_triples_rank0": int(tr.shape[0]), "build_s": round(t1 - t0, 1)}, "timed_region_s": round(t_region, 2)}
-        print(json.dumps(line))
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the whole run and keep the real stdout for the result line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -460,7 +482,7 @@ def main():
                                           "Q4-Q6 200x single thread; execute_patterns + projection" % threads,
                                 "latency_us": {"q%d" % q: round(res[q][0], 2) for q in QUERIES}}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -394,7 +394,11 @@ int build_side(Arena &ar, cudaStream_t st, int sms, const uint32_t *d_tr, uint64
         ar.drop(t2); ar.drop(head);
         B_TRY(ar.get(&sd.UK, sd.nk)); B_TRY(ar.get(&sd.CNT, sd.nk));
         runs_kernel<<<grid_for(sd.nk, sms), THREADS, 0, st>>>(K, POS, sd.nk, m, sd.UK, sd.CNT);
-        sd.OFF = POS;   // the run's first position is its offset in E
+        // the run's first position is its offset in E; keep an exact-size copy, release the m-sized scratch
+        B_TRY(ar.get(&sd.OFF, sd.nk));
+        B_TRY(cudaMemcpyAsync(sd.OFF, POS, sd.nk * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        B_TRY(cudaStreamSynchronize(st));
+        ar.drop(POS);
     }
     // per-predicate extents of triples and keys
     uint64_t *d_b = nullptr;
