@@ -134,8 +134,11 @@ int wk_store_get_edges(wk_store_t *store, wk_sid_t vid, wk_sid_t pid, int dir,
 int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out);
 int wk_engine_destroy(wk_engine_t *engine);
 /* 0 off; 1 = CUDA events around each wk_query_execute (device time of the whole pattern phase);
- * 2 = additionally one event pair per step (wk_step_stats_t.device_us) */
+ * 2 = additionally one event pair per step (wk_step_stats_t.device_us);
+ * 3 = additionally SM-clock stamps at the phase boundaries of the fused light-query kernel */
 int wk_engine_set_profiling(wk_engine_t *engine, int level);
+/* level 3 diagnostics: dst[0] entry, [1] control block cleared, [2+s] step s done, [26] table written, [27] record stored */
+int wk_engine_light_trace(wk_engine_t *engine, int64_t *dst, int cap);
 int wk_engine_sync(wk_engine_t *engine);                     /* CUDA_STREAM_SYNC */
 int wk_engine_reset(wk_engine_t *engine);                    /* empty table, 0 columns */
 

@@ -51,7 +51,7 @@ class StepStats(C.Structure):
 DECLARED_SYMBOLS = [
     "wk_strerror", "wk_version", "wk_device_count", "wk_store_create", "wk_store_adopt", "wk_store_build", "wk_store_info", "wk_store_segs",
     "wk_store_download", "wk_store_destroy",
-    "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_sync",
+    "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_light_trace", "wk_engine_sync",
     "wk_engine_reset", "wk_table_upload", "wk_table_download", "wk_table_info", "wk_index_to_unknown",
     "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_const_to_known", "wk_index_to_known", "wk_project",
     "wk_query_execute", "wk_query_execute_batch", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
@@ -125,6 +125,7 @@ def lib():
     L.wk_selftest_hash.argtypes = [u64]
     L.wk_selftest_fastmod.restype = u64
     L.wk_selftest_fastmod.argtypes = [u64, u64]
+    L.wk_engine_light_trace.argtypes = [vp, vp, ci]
     L.wk_selftest_ptr_size.restype = u64
     L.wk_selftest_ptr_size.argtypes = [u64]
     L.wk_selftest_ptr_off.restype = u64
@@ -251,6 +252,12 @@ class Engine:
 
     def set_profiling(self, level):
         _check(lib().wk_engine_set_profiling(self.h, int(level)))
+
+    def light_trace(self):
+        """profiling level 3: SM clocks at the fused light kernel's phase boundaries (diagnostics)"""
+        a = np.zeros(28, dtype=np.int64)
+        _check(lib().wk_engine_light_trace(self.h, _ptr(a), 28))
+        return a
 
     def last_query_device_us(self):
         us = C.c_float(0)

@@ -360,6 +360,7 @@ struct wk_engine {
     uint64_t launches = 0;
     uint64_t light_escalate_rows = 4096;
     struct wk_comm *comm = nullptr;      // sharded execution (wk_comm_init)
+    long long *d_trace = nullptr;        // light-kernel phase clocks (profiling level 3, lazy)
     uint32_t *d_set = nullptr;           // hash set of index_to_known / const_to_known (lazy)
     uint64_t set_cap = 0;
     ListSetCtl *d_setctl = nullptr;
@@ -966,6 +967,7 @@ int wk_engine_destroy(wk_engine_t *e) {
     cudaFree(e->d_ctl);
     if (e->d_hq) cudaFree(e->d_hq);
     if (e->d_set) { cudaFree(e->d_set); cudaFree(e->d_setctl); }
+    if (e->d_trace) cudaFree(e->d_trace);
     if (e->d_bplans) { cudaFree(e->d_bplans); cudaFree(e->d_bres); cudaFreeHost(e->h_bplans); cudaFreeHost(e->h_bres); }
     cudaFreeHost((void *)e->h_rec);
     cudaFreeHost((void *)e->h_stage);
@@ -1087,6 +1089,17 @@ int wk_index_to_known(wk_engine_t *e, wk_sid_t tpid, int dir, int col_end, int m
     if (!e) return WK_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(e->store->device));
     return finish_call(e, enqueue_to_known(e, KIND_I2K, 0, tpid, dir, col_end, mt_tid, mt_factor), out_rows);
+}
+
+// diagnostics: SM clocks of the fused light kernel's phase boundaries (profiling level 3):
+// [0] entry, [1] control block cleared, [2 + s] step s done, [2 + 24] table / projection written, [3 + 24] record stored
+int wk_engine_light_trace(wk_engine_t *e, int64_t *dst, int cap) {
+    if (!e || !dst || cap < MAX_LIGHT_STEPS + 4) return WK_ERR_BAD_ARG;
+    if (!e->d_trace) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaMemcpy(dst, e->d_trace, (MAX_LIGHT_STEPS + 4) * sizeof(long long), cudaMemcpyDeviceToHost));
+    return WK_SUCCESS;
 }
 
 int wk_project(wk_engine_t *e, const int32_t *cols, int n, uint64_t *out_rows) {
@@ -1243,9 +1256,14 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
     int frc = fill_light_steps(e, steps, mt_tid, mt_factor, lp.steps);
     if (frc) return frc;
     lp.seq = ++e->seq;
+    if (e->profiling >= 3) {
+        if (!e->d_trace) CUDA_TRY(cudaMalloc((void **)&e->d_trace, (MAX_LIGHT_STEPS + 4) * sizeof(long long)));
+        CUDA_TRY(cudaMemsetAsync(e->d_trace, 0, (MAX_LIGHT_STEPS + 4) * sizeof(long long), e->stream));
+        lp.trace = e->d_trace;
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->profiling >= 2) { ev0 = get_event(e); ev1 = get_event(e); if (ev0) cudaEventRecord(ev0, e->stream); }
-    light_query_kernel<<<1, CTA_THREADS, 0, e->stream>>>(lp);
+    light_query_kernel<<<1, LIGHT_THREADS, 0, e->stream>>>(lp);
     CUDA_TRY(cudaGetLastError());
     if (ev0 && ev1) cudaEventRecord(ev1, e->stream);
     if (e->profiling) { cudaEventRecord(e->q_ev1, e->stream); e->q_timed = true; }

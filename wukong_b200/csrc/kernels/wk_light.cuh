@@ -19,6 +19,8 @@
 namespace wk {
 
 enum { LIGHT_WORDS = 4096, LIGHT_ROWS = 1024, MAX_LIGHT_STEPS = 24 };
+// thread count of the single-CTA latency path (the interpreter is a template on it)
+enum { LIGHT_THREADS = 256, LIGHT_MAX_WARPS = 32 };   // measured: 1024 threads cost ~0.4 us more per step in barriers
 enum { LKIND_I2U = 0, LKIND_C2U = 1, LKIND_K2U = 2, LKIND_K2K = 3, LKIND_K2C = 4 };
 
 struct LightStep {
@@ -55,6 +57,7 @@ struct LightPlan {
     uint64_t seq;
     int32_t do_project, proj_n;
     int32_t collect_stats, _pad1;   // per-step counters cost two block reductions per step: only when profiling
+    long long *trace;               // diagnostics (profiling level 3): clock64() of thread 0 at phase boundaries
     int8_t proj_cols[MAX_COLS];
     LightStep steps[MAX_LIGHT_STEPS];
 };
@@ -82,11 +85,11 @@ struct LightSmem {
     uint32_t tab[2][LIGHT_WORDS];
     uint64_t ptr[LIGHT_ROWS];       // raw iptr_t of each row's key (0 = miss)
     uint32_t pre[LIGHT_ROWS + 4];   // multiplicities, then their exclusive prefix
-    uint32_t wsum[CTA_THREADS / 32];
+    uint32_t wsum[LIGHT_MAX_WARPS];
     uint32_t total;
     uint32_t seed_len;
     uint64_t seed_ptr;
-    uint64_t red[CTA_THREADS / 32];
+    uint64_t red[LIGHT_MAX_WARPS];
 };
 
 // probe one key, thread-serial over the bucket chain, 8 independent slot loads per bucket
@@ -128,12 +131,14 @@ __device__ __forceinline__ bool list_contains(const uint32_t *__restrict__ e, ui
 }
 
 // exclusive scan of sm.pre[0..n) in place (n <= LIGHT_ROWS), total in sm.total
+template <int NT>
 __device__ __forceinline__ void light_scan(LightSmem &sm, uint32_t n, int tid) {
+    constexpr int EPT = LIGHT_ROWS / NT;   // elements per thread
     const int lane = tid & 31, warp = tid >> 5;
-    uint32_t v[4], s = 0;
+    uint32_t v[EPT], s = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t i = (uint32_t)tid * 4 + j;
+    for (int j = 0; j < EPT; j++) {
+        const uint32_t i = (uint32_t)tid * EPT + j;
         v[j] = (i < n) ? sm.pre[i] : 0;
         s += v[j];
     }
@@ -146,16 +151,29 @@ __device__ __forceinline__ void light_scan(LightSmem &sm, uint32_t n, int tid) {
     if (lane == 31) sm.wsum[warp] = incl;
     __syncthreads();
     uint32_t woff = 0, tot = 0;
+    if (NT <= 256) {
 #pragma unroll
-    for (int w = 0; w < CTA_THREADS / 32; w++) {
-        const uint32_t x = sm.wsum[w];
-        if (w < warp) woff += x;
-        tot += x;
+        for (int w = 0; w < NT / 32; w++) {
+            const uint32_t x = sm.wsum[w];
+            if (w < warp) woff += x;
+            tot += x;
+        }
+    } else {
+        // 32 warp sums: one more warp-level scan instead of 32 serial shared-memory reads
+        const uint32_t x = sm.wsum[lane];
+        uint32_t wi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        tot = __shfl_sync(0xFFFFFFFFu, wi, 31);
+        woff = __shfl_sync(0xFFFFFFFFu, wi - x, warp);
     }
     uint32_t run = woff + incl - s;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t i = (uint32_t)tid * 4 + j;
+    for (int j = 0; j < EPT; j++) {
+        const uint32_t i = (uint32_t)tid * EPT + j;
         if (i < n) sm.pre[i] = run;
         run += v[j];
     }
@@ -163,6 +181,7 @@ __device__ __forceinline__ void light_scan(LightSmem &sm, uint32_t n, int tid) {
     __syncthreads();
 }
 
+template <int NT>
 __device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, LightSmem &sm, int tid) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
@@ -170,7 +189,7 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, LightSmem &sm, int
     __syncthreads();
     uint64_t t = 0;
 #pragma unroll
-    for (int w = 0; w < CTA_THREADS / 32; w++) t += sm.red[w];
+    for (int w = 0; w < NT / 32; w++) t += sm.red[w];
     __syncthreads();
     return t;
 }
@@ -180,9 +199,10 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, LightSmem &sm, int
 // not fit shared memory (nothing of that step has been written).
 struct LightState { uint32_t N; int C, cur, done; bool spilled; };
 
+template <int NT>
 __device__ __forceinline__ LightState light_interpret(const LightStep *steps, int nsteps, const uint4 *__restrict__ vertices,
                                                       const uint32_t *__restrict__ edges, LightSmem &sm, uint64_t *stats,
-                                                      uint64_t *counts) {
+                                                      uint64_t *counts, long long *trace = nullptr) {
     const int tid = threadIdx.x;
     uint32_t N = 0;          // rows of the current table (in sm.tab[cur])
     int C = 0;
@@ -224,7 +244,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             const uint64_t begin = start * length;
             const uint64_t len = (start == mtf - 1) ? (size - begin) : length;
             if (len > LIGHT_ROWS) { spilled = true; break; }   // nothing done yet: resume at this very step
-            for (uint32_t k = tid; k < len; k += CTA_THREADS) sm.tab[nxt][k] = ld_edge(edges + off + begin + k);
+            for (uint32_t k = tid; k < len; k += NT) sm.tab[nxt][k] = ld_edge(edges + off + begin + k);
             if (tid == 0) st_edges = len;
             N = (uint32_t)len;
             C = 1;
@@ -242,8 +262,15 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                 if (l2.kind >= LKIND_K2U && l2.col_start < Cin && !((shadowed >> s2) & 1u)) { sh[nsh++] = s2; shadowed |= 1u << s2; }
             }
             if ((uint64_t)N * (uint64_t)(1 + nsh) > 2048) nsh = 0;
-            for (uint32_t item = tid; item < N * (uint32_t)(1 + nsh); item += CTA_THREADS) {
-                const uint32_t r = item % N, j = item / N;
+            // tables taller than the CTA are walked in several rounds whose loads depend on each other through
+            // the loop; pull every later round's bucket line towards L2 first so that only round one pays DRAM
+            for (uint32_t r = tid + NT; r < N; r += NT) {
+                const uint64_t key = step_key(ls.seg, tin[r * Cin + ls.col_start]);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vertices + (ls.seg.bucket_start + fastmod(hash_u64(key), ls.seg.fm)) * 8));
+            }
+            for (uint32_t item = tid; item < N * (uint32_t)(1 + nsh); item += NT) {
+                uint32_t r = item, j = 0;   // item = j * N + r with j <= 3: no integer division on this path
+                while (r >= N) { r -= N; j++; }
                 if (j != 0) {
                     const LightStep &l2 = steps[sh[j - 1]];
                     const uint64_t key2 = step_key(l2.seg, tin[r * Cin + l2.col_start]);
@@ -273,13 +300,13 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             }
             __syncthreads();
             // phase 2: scan multiplicities
-            light_scan(sm, N, tid);
+            light_scan<NT>(sm, N, tid);
             const uint32_t total = sm.total;
             if (total > LIGHT_ROWS || (uint64_t)total * (uint64_t)Cout > LIGHT_WORDS) { spilled = true; break; }
             // phase 3: materialise (thread per OUTPUT row: every edge load of the step in flight at once)
             uint32_t *tout = sm.tab[nxt];
             if (ls.kind == LKIND_K2U) {
-                for (uint32_t o = tid; o < total; o += CTA_THREADS) {
+                for (uint32_t o = tid; o < total; o += NT) {
                     uint32_t lo = 0, hi = N;   // largest r with pre[r] <= o
                     while (hi - lo > 1) {
                         const uint32_t mid = (lo + hi) >> 1;
@@ -291,7 +318,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                     tout[o * Cout + Cin] = e;
                 }
             } else {
-                for (uint32_t r = tid; r < N; r += CTA_THREADS) {
+                for (uint32_t r = tid; r < N; r += NT) {
                     const uint32_t p0 = sm.pre[r];
                     const uint32_t p1 = (r + 1 < N) ? sm.pre[r + 1] : total;
                     if (p1 != p0)
@@ -303,11 +330,12 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
         }
         // per-step statistics (algorithmic-bytes accounting)
         if ((stats != nullptr)) {
-            const uint64_t v = block_sum_u64(st_visited, sm, tid);
-            const uint64_t e = block_sum_u64(st_edges, sm, tid);
+            const uint64_t v = block_sum_u64<NT>(st_visited, sm, tid);
+            const uint64_t e = block_sum_u64<NT>(st_edges, sm, tid);
             if (tid == 0) { stats[2 * s] = v; stats[2 * s + 1] = e; }
         }
         if (tid == 0 && counts) counts[s + 1] = N;
+        if (trace && tid == 0) trace[2 + s] = clock64();
         cur = nxt;
         __syncthreads();
     }
@@ -316,14 +344,29 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
     return st;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
+// The step descriptors are read many times and by data-dependent index.  Kernel parameters are freshly
+// written per launch (every first touch of a parameter line is a miss), so all lines are fetched at once,
+// by all threads, into shared memory instead of one by one on the interpreter's critical path.
+template <int NT>
+__device__ __forceinline__ void stage_steps(LightStep *dst, const LightStep *src, int nsteps, int tid) {
+    const uint32_t words = (uint32_t)nsteps * (uint32_t)(sizeof(LightStep) / sizeof(uint32_t));
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t i = tid; i < words; i += NT) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
     __shared__ LightSmem sm;
+    __shared__ LightStep s_steps[MAX_LIGHT_STEPS];
     const int tid = threadIdx.x;
+    stage_steps<LIGHT_THREADS>(s_steps, plan.steps, plan.nsteps, tid);
     // this kernel owns the control block: clear it here instead of a separate memset node
-    for (int i = tid; i < plan.ctl_nwords; i += CTA_THREADS) plan.ctl_words[i] = 0;
+    if (plan.trace && tid == 0) plan.trace[0] = clock64();
+    for (int i = tid; i < plan.ctl_nwords; i += LIGHT_THREADS) plan.ctl_words[i] = 0;
     __syncthreads();
-    const LightState ls_ = light_interpret(plan.steps, plan.nsteps, plan.vertices, plan.edges, sm,
-                                           plan.collect_stats ? plan.stats : nullptr, plan.counts);
+    if (plan.trace && tid == 0) plan.trace[1] = clock64();
+    const LightState ls_ = light_interpret<LIGHT_THREADS>(s_steps, plan.nsteps, plan.vertices, plan.edges, sm,
+                                           plan.collect_stats ? plan.stats : nullptr, plan.counts, plan.trace);
     const uint32_t N = ls_.N;
     const int C = ls_.C, cur = ls_.cur, s = ls_.done;
     const bool spilled = ls_.spilled;
@@ -336,7 +379,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
             uint32_t *dst = plan.buf[done_steps & 1];
             const uint32_t words = N * (uint32_t)C;
             if ((uint64_t)words <= plan.cap_words) {
-                for (uint32_t i = tid; i < words; i += CTA_THREADS) dst[i] = sm.tab[cur][i];
+                for (uint32_t i = tid; i < words; i += LIGHT_THREADS) dst[i] = sm.tab[cur][i];
             } else {
                 status = 1;
             }
@@ -346,7 +389,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
         const uint32_t words = N * (uint32_t)plan.proj_n;
         uint64_t part = 0;
         if ((uint64_t)words <= plan.host_table_words) {
-            for (uint32_t w = tid; w < words; w += CTA_THREADS) {
+            for (uint32_t w = tid; w < words; w += LIGHT_THREADS) {
                 const uint32_t r = w / (uint32_t)plan.proj_n, j = w - r * (uint32_t)plan.proj_n;
                 const uint32_t val = sm.tab[cur][r * C + plan.proj_cols[j]];
                 st_sys_u32(plan.host_table + w, val);
@@ -355,8 +398,9 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
         } else {
             status = 1;
         }
-        tsum = block_sum_u64(part, sm, tid);
+        tsum = block_sum_u64<LIGHT_THREADS>(part, sm, tid);
     }
+    if (plan.trace && tid == 0) plan.trace[2 + MAX_LIGHT_STEPS] = clock64();
     if (tid == 0) {
         if (status) *plan.status = status;
         const uint64_t rows = N;
@@ -364,6 +408,7 @@ __global__ void __launch_bounds__(CTA_THREADS) light_query_kernel(const __grid_c
         uint64_t *rec = (uint64_t *)plan.rec;
         st_sys_v2u64(rec + 2, sr, record_check(plan.seq, rows, sr, tsum));
         st_sys_v2u64(rec, plan.seq, rows);
+        if (plan.trace) plan.trace[3 + MAX_LIGHT_STEPS] = clock64();
     }
 }
 
@@ -382,9 +427,13 @@ struct BatchResult {
 __global__ void __launch_bounds__(CTA_THREADS) light_batch_kernel(const BatchPlan *plans, BatchResult *results, int nqueries,
                                                                   const uint4 *vertices, const uint32_t *edges) {
     __shared__ LightSmem sm;
+    __shared__ LightStep s_steps[BATCH_STEPS];
     for (int q = blockIdx.x; q < nqueries; q += gridDim.x) {
         const BatchPlan *bp = plans + q;
-        const LightState st = light_interpret(bp->steps, bp->nsteps, vertices, edges, sm, nullptr, nullptr);
+        const int nsteps = bp->nsteps;
+        stage_steps<CTA_THREADS>(s_steps, bp->steps, nsteps, threadIdx.x);
+        __syncthreads();
+        const LightState st = light_interpret<CTA_THREADS>(s_steps, nsteps, vertices, edges, sm, nullptr, nullptr);
         if (threadIdx.x == 0) {
             results[q].rows = st.N;
             results[q].status = st.spilled ? 2u : 0u;
