@@ -76,7 +76,7 @@ typedef struct wk_engine wk_engine_t;
 
 /* per-step execution record of the last wk_query_execute (profiling mode only for device_us) */
 typedef struct {
-    int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project, 6 c2k, 7 i2k */
+    int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project, 6 c2k, 7 i2k, 8 distinct, 9 slice */
     int32_t in_cols;
     uint64_t in_rows, out_rows;
     uint64_t buckets_visited;   /* sum over rows of L_i                      */
@@ -169,6 +169,11 @@ int wk_const_to_known(wk_engine_t *engine, wk_sid_t vid, wk_sid_t pid, int dir, 
 /* index_to_known, sparql.hpp:80-141: keep the rows whose column col_end occurs in (this mt slice of) the index list */
 int wk_index_to_known(wk_engine_t *engine, wk_sid_t tpid, int dir, int col_end, int mt_tid, int mt_factor,
                       uint64_t *out_rows);
+/* final_process DISTINCT, sparql.hpp:1428-1472: rows ordered by all columns (compared as signed ints, ReduceCmp :1406-1421),
+ * then adjacent rows that agree on `cols` (the columns of the required variables) collapse to the first */
+int wk_table_distinct(wk_engine_t *engine, const int32_t *cols, int n, uint64_t *out_rows);
+/* final_process OFFSET / LIMIT, sparql.hpp:1487-1499 (limit < 0: none) */
+int wk_table_slice(wk_engine_t *engine, uint64_t offset, int64_t limit, uint64_t *out_rows);
 /* final_process projection, sparql.hpp:1507-1550: out[i][j] = in[i][cols[j]] */
 int wk_project(wk_engine_t *engine, const int32_t *cols, int ncols_out, uint64_t *out_rows);
 
@@ -181,6 +186,19 @@ int wk_project(wk_engine_t *engine, const int32_t *cols, int ncols_out, uint64_t
 int wk_query_execute(wk_engine_t *engine, const wk_pattern_t *patterns, int npatterns, int nvars,
                      const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor,
                      int blind, wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols);
+/* The same with the query modifiers final_process applies before the projection (SPARQLQuery::distinct / offset / limit,
+ * query.hpp:560-682; sparql.hpp:1428-1499): DISTINCT, then OFFSET, then LIMIT.  A blind query skips them like the reference.
+ * ORDER BY compares string-server strings and is left to the host. */
+typedef struct {
+    int32_t mt_tid, mt_factor;
+    int32_t blind;
+    int32_t distinct;
+    int64_t offset;      /* rows to drop, <= 0: none */
+    int64_t limit;       /* rows to keep, < 0: no limit */
+} wk_query_opts_t;
+int wk_query_execute_ex(wk_engine_t *engine, const wk_pattern_t *patterns, int npatterns, int nvars,
+                        const int32_t *required_vars, int nrequired, const wk_query_opts_t *opts,
+                        wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols);
 /* Throughput path for light queries (the reference's emulator, Proxy::run_query_emu, proxy.hpp:391-545, keeps many
  * light queries in flight): nqueries independent const-start plans are answered by ONE launch, one CTA per
  * query; blind replies.  patterns holds all plans back to back, pat_off[q]..pat_off[q+1] delimit plan q.

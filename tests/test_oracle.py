@@ -143,3 +143,56 @@ def test_golden_fixture(ostore1, ostore2):
             ent = g[name]["q%d" % q]
             assert r.rows == ent["rows"] and r.cols == ent["cols"]
             assert _checksum(r.table) == ent["checksum"]
+
+
+def _py_final_process(full, req_cols, distinct, offset, limit):
+    """independent statement of final_process' modifiers (sparql.hpp:1424-1550) on a full binding table"""
+    t = np.asarray(full, dtype=np.uint32)
+    if t.shape[0] == 0:
+        return t[:, req_cols]
+    if distinct:
+        s = t.view(np.int32)
+        order = np.lexsort(tuple(s[:, c] for c in range(t.shape[1] - 1, -1, -1)))   # all columns, signed, col 0 first
+        t = t[order]
+        key = t[:, req_cols]
+        keep = np.ones(t.shape[0], dtype=bool)
+        keep[1:] = np.any(key[1:] != key[:-1], axis=1)
+        t = t[keep]
+    if offset > 0:
+        t = t[offset:]
+    if limit >= 0:
+        t = t[:limit]
+    return t[:, req_cols]
+
+
+@pytest.mark.parametrize("mods", [dict(distinct=True), dict(offset=7), dict(limit=5), dict(distinct=True, offset=3, limit=11),
+                                  dict(offset=10 ** 6), dict(limit=0)])
+def test_query_modifiers(ostore1, mods):
+    # Q7 projected on one variable has many duplicate bindings; Q2 has none
+    for q, req_sel in ((7, [0]), (7, [0, 1]), (2, None), (4, [1, 2])):
+        pats, nvars, req, _ = load_query(q, "osdi16_plan")
+        # full table: every variable required, in column order
+        allv = [-(i + 1) for i in range(nvars)]
+        full = O.run_query([ostore1], pats, nvars, allv)
+        assert full.status == 0
+        # column of variable v in the unprojected table = order of first binding; recover it from the all-vars projection
+        rq = req if req_sel is None else [req[i] for i in req_sel if i < len(req)]
+        got = O.run_query([ostore1], pats, nvars, rq, **mods)
+        assert got.status == 0
+        # the oracle's unprojected column order: run with required = variables sorted by their column (v2c) is not
+        # exposed, so rebuild it: a variable's column is the order in which the plan binds it
+        bound = []
+        for s, p, d, o in pats:
+            for v in (s, o):
+                if v < 0 and v not in bound:
+                    bound.append(v)
+        unproj = full.table[:, [allv.index(v) for v in bound]]
+        want = _py_final_process(unproj, [bound.index(v) for v in rq], mods.get("distinct", False), mods.get("offset", 0),
+                                 mods.get("limit", -1))
+        assert got.rows == want.shape[0], (q, rq, mods)
+        if want.shape[0]:
+            assert np.array_equal(got.table, want), (q, rq, mods)
+    # blind: final_process is skipped entirely, modifiers included (sparql.hpp:1425)
+    pats, nvars, req, _ = load_query(7, "osdi16_plan")
+    plain = O.run_query([ostore1], pats, nvars, req, blind=True)
+    assert O.run_query([ostore1], pats, nvars, req, blind=True, distinct=True, limit=3).rows == plain.rows

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB_CUDA = os.path.join(HERE, "libwukong_b200.so")
 LIB_HOST = os.path.join(HERE, "libwukong_host.so")
 
-CUDA_SOURCES = ["kernels/engine.cu", "kernels/store_build.cu"]
+CUDA_SOURCES = ["kernels/engine.cu", "kernels/store_build.cu", "kernels/table_ops.cu"]
 HOST_SOURCES = ["datagen/lubm_gen.cpp", "datagen/rmat_gen.cpp", "store/host_builder.cpp", "host/host_capi.cpp"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

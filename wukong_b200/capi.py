@@ -9,7 +9,7 @@ LIB_CUDA = os.path.join(_HERE, "libwukong_b200.so")
 
 IN, OUT = 0, 1
 PREDICATE_ID, TYPE_ID = 0, 1
-KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k"]
+KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k", "distinct", "slice"]
 
 WK_SUCCESS = 0
 WK_ERR_CUDA, WK_ERR_BAD_ARG, WK_ERR_RBUF_OVERFLOW, WK_ERR_NO_SEGMENT, WK_ERR_NO_DEVICE, WK_ERR_COMM = 100, 101, 102, 103, 104, 105
@@ -41,6 +41,11 @@ class BuildStats(C.Structure):
                [(n, C.c_float) for n in ("ms_upload", "ms_sort", "ms_insert", "ms_total")]
 
 
+class QueryOpts(C.Structure):
+    _fields_ = [("mt_tid", C.c_int32), ("mt_factor", C.c_int32), ("blind", C.c_int32), ("distinct", C.c_int32),
+                ("offset", C.c_int64), ("limit", C.c_int64)]
+
+
 class StepStats(C.Structure):
     _fields_ = [("kind", C.c_int32), ("in_cols", C.c_int32), ("in_rows", C.c_uint64), ("out_rows", C.c_uint64),
                 ("buckets_visited", C.c_uint64), ("edges_touched", C.c_uint64), ("algo_bytes", C.c_uint64),
@@ -53,7 +58,8 @@ DECLARED_SYMBOLS = [
     "wk_store_download", "wk_store_destroy",
     "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_light_trace", "wk_engine_sync",
     "wk_engine_reset", "wk_table_upload", "wk_table_download", "wk_table_info", "wk_index_to_unknown",
-    "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_const_to_known", "wk_index_to_known", "wk_project",
+    "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_const_to_known", "wk_index_to_known", "wk_table_distinct", "wk_table_slice", "wk_project",
+    "wk_query_execute_ex",
     "wk_query_execute", "wk_query_execute_batch", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
     "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
     "wk_comm_stats", "wk_plan_exchanges", "wk_comm_p2p_export", "wk_comm_p2p_import", "wk_exchange_p2p",
@@ -98,6 +104,9 @@ def lib():
     L.wk_known_to_known.argtypes = [vp, ci, u32, ci, ci, pu64]
     L.wk_known_to_const.argtypes = [vp, ci, u32, ci, u32, pu64]
     L.wk_project.argtypes = [vp, vp, ci, pu64]
+    L.wk_table_distinct.argtypes = [vp, vp, ci, pu64]
+    L.wk_table_slice.argtypes = [vp, u64, C.c_int64, pu64]
+    L.wk_query_execute_ex.argtypes = [vp, vp, ci, ci, vp, ci, vp, vp, u64, pu64, C.POINTER(ci)]
     L.wk_const_to_known.argtypes = [vp, u32, u32, ci, ci, pu64]
     L.wk_index_to_known.argtypes = [vp, u32, ci, ci, ci, ci, pu64]
     L.wk_query_execute.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
@@ -327,17 +336,39 @@ class Engine:
         _check(lib().wk_index_to_known(self.h, tpid, d, col_end, mt_tid, mt_factor, C.byref(n) if sync else None))
         return n.value
 
+    def distinct(self, cols):
+        a = np.array(cols, dtype=np.int32)
+        n = C.c_uint64(0)
+        _check(lib().wk_table_distinct(self.h, _ptr(a), len(a), C.byref(n)))
+        return n.value
+
+    def slice(self, offset, limit):
+        n = C.c_uint64(0)
+        _check(lib().wk_table_slice(self.h, offset, limit, C.byref(n)))
+        return n.value
+
     def project(self, cols, sync=True):
         a = np.array(cols, dtype=np.int32)
         n = C.c_uint64(0)
         _check(lib().wk_project(self.h, _ptr(a), len(cols), C.byref(n) if sync else None))
         return n.value
 
-    def query(self, patterns, nvars, required_vars, mt_tid=0, mt_factor=1, blind=False, out=None):
-        """wk_query_execute.  Returns (status, rows, cols, table-or-None)."""
+    def query(self, patterns, nvars, required_vars, mt_tid=0, mt_factor=1, blind=False, out=None,
+              distinct=False, offset=0, limit=-1):
+        """wk_query_execute (wk_query_execute_ex when a modifier is given).  Returns (status, rows, cols, table-or-None)."""
         p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
         rv = np.array(required_vars, dtype=np.int32)
         n, c = C.c_uint64(0), C.c_int(0)
+        if distinct or offset > 0 or limit >= 0:
+            o = QueryOpts(mt_tid, mt_factor, 1 if blind else 0, 1 if distinct else 0, offset, limit)
+            if out is None:
+                out = self._out_buf
+            rc = lib().wk_query_execute_ex(self.h, _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv), C.byref(o),
+                                           None if blind else _ptr(out), 0 if blind else out.size, C.byref(n), C.byref(c))
+            tbl = None
+            if rc == 0 and not blind:
+                tbl = out.reshape(-1)[: n.value * c.value].reshape(n.value, c.value) if c.value else np.zeros((0, 0), np.uint32)
+            return rc, n.value, c.value, tbl
         if blind:
             rc = lib().wk_query_execute(self.h, _ptr(p), p.shape[0], nvars, _ptr(rv), len(rv), mt_tid, mt_factor, 1,
                                         None, 0, C.byref(n), C.byref(c))

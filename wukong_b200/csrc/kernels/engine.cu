@@ -24,6 +24,7 @@
 #include "wukong_b200.h"
 #include "wk_device.cuh"
 #include "wk_light.cuh"
+#include "wk_internal.h"
 
 using namespace wk;
 
@@ -31,7 +32,7 @@ using namespace wk;
 // device-side control block and kernels
 // =============================================================================================
 enum { MAX_STEPS = 60 };
-enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5, KIND_C2K = 6, KIND_I2K = 7 };
+enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5, KIND_C2K = 6, KIND_I2K = 7, KIND_DISTINCT = 8, KIND_SLICE = 9 };
 
 struct CtlBlock {
     uint64_t counts[MAX_STEPS + 4];       // counts[s] = rows of the table that step s reads
@@ -681,6 +682,43 @@ static int enqueue_project(wk_engine *e, const int32_t *cols, int n) {
     return WK_SUCCESS;
 }
 
+// DISTINCT of final_process (sparql.hpp:1428-1472).  `rows` is the current row count, known on the host.
+static int enqueue_distinct(wk_engine *e, const int32_t *cols, int n, uint64_t rows) {
+    if (n <= 0 || n > MAX_COLS) return WK_NO_REQUIRED_VAR;
+    if (e->ncols <= 0) return WK_ERR_BAD_ARG;
+    for (int i = 0; i < n; i++)
+        if (cols[i] < 0 || cols[i] >= e->ncols) return WK_VERTEX_INVALID;
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    const int s = e->step;
+    StepRecord &r = begin_step(e, KIND_DISTINCT, e->ncols);
+    if (rows == 0) {
+        CUDA_TRY(cudaMemsetAsync(&e->d_ctl->counts[s + 1], 0, sizeof(uint64_t), e->stream));
+    } else {
+        rc = wk_internal_distinct(e->stream, e->num_sms, e->buf[s & 1], e->buf[(s + 1) & 1], rows, e->ncols, cols, n,
+                                  &e->d_ctl->counts[s + 1]);
+        if (rc) return rc;
+    }
+    end_step(e, r, 3 + 5 * e->ncols);
+    e->step = s + 1;
+    return WK_SUCCESS;
+}
+
+// OFFSET / LIMIT of final_process (sparql.hpp:1487-1499)
+static int enqueue_slice(wk_engine *e, uint64_t offset, int64_t limit, uint64_t rows_upper_bound) {
+    if (e->ncols <= 0) return WK_ERR_BAD_ARG;
+    int rc = ensure_step_room(e);
+    if (rc) return rc;
+    const int s = e->step;
+    StepRecord &r = begin_step(e, KIND_SLICE, e->ncols);
+    rc = wk_internal_slice(e->stream, e->num_sms, e->buf[s & 1], &e->d_ctl->counts[s], e->ncols, offset, limit, e->buf[(s + 1) & 1],
+                           &e->d_ctl->counts[s + 1], rows_upper_bound);
+    if (rc) return rc;
+    end_step(e, r, 1);
+    e->step = s + 1;
+    return WK_SUCCESS;
+}
+
 // index_to_known / const_to_known: rows whose column `col_end` occurs in the edge list of key (vid, pid, dir)
 static int enqueue_to_known(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int dir, int col_end, int mt_tid, int mt_factor) {
     if (e->ncols <= 0 || e->ncols >= MAX_COLS) return e->ncols <= 0 ? WK_VERTEX_INVALID : WK_ERR_BAD_ARG;
@@ -758,7 +796,9 @@ static int snapshot_stats(wk_engine *e) {
         case KIND_I2U:
         case KIND_C2U: st.algo_bytes = 128 * st.buckets_visited + 4 * R + 4 * R; break;
         case KIND_C2K:
-        case KIND_I2K: st.algo_bytes = 4 * C * N + 4 * C * R; break;
+        case KIND_I2K:
+        case KIND_DISTINCT:
+        case KIND_SLICE: st.algo_bytes = 4 * C * N + 4 * C * R; break;
         default: st.algo_bytes = 4 * C * R + 4 * (uint64_t)e->ncols * R; break;
         }
         if (r.timed) {
@@ -1102,6 +1142,21 @@ int wk_engine_light_trace(wk_engine_t *e, int64_t *dst, int cap) {
     return WK_SUCCESS;
 }
 
+int wk_table_distinct(wk_engine_t *e, const int32_t *cols, int n, uint64_t *out_rows) {
+    if (!e || !cols) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    uint64_t rows = 0;
+    int rc = sync_rows(e, &rows);
+    if (rc) return rc;
+    return finish_call(e, enqueue_distinct(e, cols, n, rows), out_rows);
+}
+
+int wk_table_slice(wk_engine_t *e, uint64_t offset, int64_t limit, uint64_t *out_rows) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    return finish_call(e, enqueue_slice(e, offset, limit, e->cap_words / (uint64_t)std::max(1, e->ncols)), out_rows);
+}
+
 int wk_project(wk_engine_t *e, const int32_t *cols, int n, uint64_t *out_rows) {
     if (!e || !cols) return WK_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(e->store->device));
@@ -1287,7 +1342,22 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
 int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns, int nvars,
                      const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor, int blind,
                      wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols) {
-    if (!e || !patterns) return WK_ERR_BAD_ARG;
+    wk_query_opts_t o;
+    memset(&o, 0, sizeof(o));
+    o.mt_tid = mt_tid;
+    o.mt_factor = mt_factor;
+    o.blind = blind;
+    o.limit = -1;
+    return wk_query_execute_ex(e, patterns, npatterns, nvars, required_vars, nrequired, &o, table, cap_words, out_rows, out_cols);
+}
+
+int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns, int nvars,
+                        const int32_t *required_vars, int nrequired, const wk_query_opts_t *opts,
+                        wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols) {
+    if (!e || !patterns || !opts) return WK_ERR_BAD_ARG;
+    const int mt_tid = opts->mt_tid, mt_factor = opts->mt_factor, blind = opts->blind;
+    // DISTINCT / OFFSET / LIMIT are part of final_process, which a blind query skips (sparql.hpp:1425-1426)
+    const bool post = !blind && (opts->distinct || opts->offset > 0 || opts->limit >= 0);
     CUDA_TRY(cudaSetDevice(e->store->device));
     if (out_rows) *out_rows = 0;
     if (out_cols) *out_cols = 0;
@@ -1314,7 +1384,7 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
     }
     e->q_timed = false;
     if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
-    bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS;
+    bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS && !post;
     for (const PlannedStep &ps : steps)
         if (ps.kind == KIND_C2K) light = false;   // const_to_known runs on the multi-CTA path only
     if (light) {   // the fused kernel clears the control block itself
@@ -1355,6 +1425,21 @@ int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns
             else if (ps.kind == KIND_C2K) rc = enqueue_to_known(e, KIND_C2K, ps.vid, ps.pid, ps.dir, ps.col_end, 0, 1);
             else rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const);
             if (rc) return rc;
+        }
+        if (want_table && post) {
+            // final_process order: DISTINCT, OFFSET, LIMIT, then the projection (sparql.hpp:1428-1550)
+            if (opts->distinct) {
+                rc = sync_rows(e, &rows);   // the sort is sized on the host
+                if (rc) return rc;
+                if (rows > 0) {
+                    rc = enqueue_distinct(e, proj_cols.data(), nrequired, rows);
+                    if (rc) return rc;
+                }
+            }
+            if (opts->offset > 0 || opts->limit >= 0) {
+                rc = enqueue_slice(e, (uint64_t)std::max<int64_t>(opts->offset, 0), opts->limit, e->cap_words / (uint64_t)std::max(1, e->ncols));
+                if (rc) return rc;
+            }
         }
         if (want_table) {
             rc = enqueue_project(e, proj_cols.data(), nrequired);
