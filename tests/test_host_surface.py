@@ -53,6 +53,9 @@ def test_config_loader_parser_planner_cpu(dataset_dir, lubm1):
     query, fmt = _text(2, "osdi16_plan")
     assert env.parse_plan(query.replace("ub:Course", "ub:NoSuchClass"), fmt)[0] == 2      # SYNTAX_ERROR: unknown IRI
     assert env.parse_plan(query.replace("SELECT", "SELEKT"), fmt)[0] == 2
+    assert env.parse_plan(query.replace("SELECT", "SELECT DISTINCT") + " LIMIT 10 OFFSET 2", fmt)[0] == 0   # solution modifiers
+    assert env.parse_plan(query + " ORDER BY ?X", fmt)[0] == 2                             # string ordering: not on this path
+    assert env.parse_plan(query + " LIMIT -3", fmt)[0] == 2
     assert env.parse_plan(query, "1 <\n")[0] == 2                                          # plan shorter than the query
     assert env.parse_plan(query, "1 <\n9 >\n")[0] == 2                                     # pattern number out of range
     env.close()
@@ -75,6 +78,17 @@ def test_run_single_query_gpu(dataset_dir, ostore1):
             if rows:
                 assert cols == want.cols and rows_equal(tbl, want.table), (q, per_pattern)
             assert lat > 0
+    # SELECT DISTINCT ... LIMIT / OFFSET: final_process modifiers through both host paths (sparql.hpp:1428-1499)
+    query, fmt = _text(7, "osdi16_plan")
+    pats, nvars, req, _ = load_query(7, "osdi16_plan")
+    assert "SELECT ?X ?Y ?Z" in query
+    q1 = query.replace("SELECT ?X ?Y ?Z", "SELECT DISTINCT ?X")
+    q1 = q1 + " LIMIT 20 OFFSET 4"
+    want = O.run_query([ostore1], pats, nvars, req[:1], distinct=True, offset=4, limit=20)
+    for per_pattern in (False, True):
+        rc, rows, cols, tbl, lat = env.run_single_query(q1, fmt, per_pattern=per_pattern)
+        assert rc == 0 and rows == want.rows == 20 and cols == 1, per_pattern
+        assert np.array_equal(tbl, want.table), per_pattern
     # silent mode: only the row count comes back (Global::silent, proxy.hpp:360-369)
     env2 = host.Env((CONFIG % dataset_dir).replace("global_silent                   0", "global_silent 1"), device=0)
     query, fmt = _text(2, "osdi16_plan")

@@ -61,6 +61,10 @@ public:
             check(wk_const_to_unknown(eng, (sid_t)start, (sid_t)predicate, d, &rows));
             after_expand(req, end, rows, true);
             break;
+        case const_pair(CONST_VAR, KNOWN_VAR):   // const_to_known, sparql.hpp:144-186
+            check(wk_const_to_known(eng, (sid_t)start, (sid_t)predicate, d, res.var2col(end), &rows));
+            after_expand(req, end, rows, false);
+            break;
         case const_pair(KNOWN_VAR, CONST_VAR):
             check(wk_known_to_const(eng, res.var2col(start), (sid_t)predicate, d, (sid_t)end, &rows));
             after_expand(req, end, rows, false);
@@ -94,6 +98,9 @@ public:
                 std::vector<int32_t> cols;
                 for (ssid_t v : res.required_vars) cols.push_back(res.var2col(v));
                 uint64_t rows = 0;
+                // final_process: DISTINCT, OFFSET, LIMIT, then the projection (sparql.hpp:1428-1550)
+                if (r.distinct) check(wk_table_distinct(eng, cols.data(), (int)cols.size(), &rows));
+                if (r.offset > 0 || r.limit >= 0) check(wk_table_slice(eng, r.offset, r.limit, &rows));
                 check(wk_project(eng, cols.data(), (int)cols.size(), &rows));
                 res.set_col_num((int)cols.size());
                 res.result_table.resize((size_t)rows * cols.size());
@@ -118,9 +125,12 @@ public:
         if (!res.blind && out_buf.size() < (size_t)1 << 20) out_buf.resize((size_t)1 << 20);
         int rc;
         while (true) {
-            rc = wk_query_execute(eng, pats.data(), (int)pats.size(), res.nvars, res.required_vars.data(),
-                                  (int)res.required_vars.size(), r.mt_tid, r.mt_factor, res.blind ? 1 : 0,
-                                  res.blind ? nullptr : out_buf.data(), out_buf.size(), &rows, &cols);
+            wk_query_opts_t o;
+            o.mt_tid = r.mt_tid; o.mt_factor = r.mt_factor; o.blind = res.blind ? 1 : 0;
+            o.distinct = r.distinct ? 1 : 0; o.offset = (int64_t)r.offset; o.limit = (int64_t)r.limit;   // final_process, sparql.hpp:1428-1499
+            rc = wk_query_execute_ex(eng, pats.data(), (int)pats.size(), res.nvars, res.required_vars.data(),
+                                     (int)res.required_vars.size(), &o,
+                                     res.blind ? nullptr : out_buf.data(), out_buf.size(), &rows, &cols);
             if (rc == WK_ERR_BAD_ARG && !res.blind && rows * (uint64_t)cols > out_buf.size()) { out_buf.resize(rows * (uint64_t)cols); continue; }
             break;
         }

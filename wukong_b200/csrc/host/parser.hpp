@@ -4,6 +4,7 @@
 // reference: -1, -2, ... in order of first appearance, the SELECT list first
 // (SPARQLParser.hpp:226-235, 1108-1135; parser.hpp:186-197).
 #pragma once
+#include <cstdlib>
 #include <istream>
 #include <map>
 #include <sstream>
@@ -65,6 +66,8 @@ public:
         }
         if (i >= toks.size() || upper(toks[i]) != "SELECT") { strerror = "SELECT expected"; return false; }
         i++;
+        bool distinct = false;
+        if (i < toks.size() && (upper(toks[i]) == "DISTINCT" || upper(toks[i]) == "REDUCED")) { distinct = true; i++; }   // SPARQLParser.hpp: both set `distinct`
         std::vector<ssid_t> required;
         while (i < toks.size() && toks[i][0] == '?') required.push_back(var_id(toks[i++].substr(1)));
         if (i >= toks.size() || upper(toks[i]) != "WHERE") { strerror = "WHERE expected"; return false; }
@@ -85,7 +88,27 @@ public:
         }
         if (i >= toks.size()) { strerror = "} expected"; return false; }
         if (pg.patterns.empty()) { strerror = "empty group"; return false; }
+        i++;
+        // solution modifiers: LIMIT n / OFFSET n in either order (ORDER BY needs string comparison on the proxy: rejected)
+        int limit = -1;
+        unsigned offset = 0;
+        while (i < toks.size()) {
+            const std::string kw = upper(toks[i]);
+            if ((kw == "LIMIT" || kw == "OFFSET") && i + 1 < toks.size()) {
+                char *end = nullptr;
+                const long v = strtol(toks[i + 1].c_str(), &end, 10);
+                if (*end != 0 || v < 0) { strerror = "bad " + kw; return false; }
+                if (kw == "LIMIT") limit = (int)v; else offset = (unsigned)v;
+                i += 2;
+            } else {
+                strerror = "unsupported solution modifier: " + toks[i];
+                return false;
+            }
+        }
         sq = SPARQLQuery(pg, (int)vars.size(), required);
+        sq.distinct = distinct;
+        sq.limit = limit;
+        sq.offset = offset;
         return true;
     }
 };
