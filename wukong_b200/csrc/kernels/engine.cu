@@ -290,6 +290,40 @@ __global__ void __launch_bounds__(CTA_THREADS) list_filter_kernel(const StepPara
     }
 }
 
+// ---- largest edge list per segment (one pass at store creation) ------------------------------------------
+// A known_to_unknown step can only produce a "heavy" tile (>= HEAVY_TILE_MIN output rows from 256 input rows) when some
+// key of its segment has at least HEAVY_TILE_MIN / TILE_ROWS edges; for all other segments the heavy-queue pass
+// (one more launch per step) is skipped.  Every warp walks contiguous chunks, so it meets few segment changes and
+// issues few atomics.
+__global__ void __launch_bounds__(CTA_THREADS) seg_maxdeg_kernel(const uint4 *__restrict__ V, uint64_t num_slots, uint32_t P,
+                                                                 uint32_t *__restrict__ tab) {
+    constexpr uint64_t CHUNK = 8192;
+    const uint64_t warps = (uint64_t)gridDim.x * (CTA_THREADS / 32);
+    const uint64_t w = (uint64_t)blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    for (uint64_t base = w * CHUNK; base < num_slots; base += warps * CHUNK) {
+        uint32_t cur_seg = ~0u, cur_max = 0;
+        const uint64_t end = base + CHUNK < num_slots ? base + CHUNK : num_slots;
+        for (uint64_t i = base + lane; i < end; i += 32) {
+            if ((i & 7) == 7) continue;   // chain pointer slot
+            const uint4 v = __ldcs(V + i);
+            const uint64_t key = (uint64_t)v.x | ((uint64_t)v.y << 32);
+            if (key == 0) continue;
+            const uint32_t pid = (uint32_t)(key >> 1) & ((1u << WK_NBITS_IDX) - 1);
+            if (pid >= P) continue;
+            const uint32_t seg = (((key >> WK_KEY_VID_SHIFT) == 0 ? 1u : 0u) * 2 + (uint32_t)(key & 1)) * P + pid;
+            const uint32_t size = ptr_size((uint64_t)v.z | ((uint64_t)v.w << 32));
+            if (seg != cur_seg) {
+                if (cur_seg != ~0u && cur_max) atomicMax(&tab[cur_seg], cur_max);
+                cur_seg = seg;
+                cur_max = 0;
+            }
+            cur_max = size > cur_max ? size : cur_max;
+        }
+        if (cur_seg != ~0u && cur_max) atomicMax(&tab[cur_seg], cur_max);
+    }
+}
+
 // ---- bookkeeping kernels -------------------------------------------------------------------------
 __global__ void set_count_kernel(uint64_t *dst, uint64_t v) { *dst = v; }
 
@@ -331,6 +365,7 @@ struct wk_store {
     uint64_t num_slots = 0, num_edges = 0;
     bool owns = true;
     std::map<SegKey, wk_segmeta_t> segs;
+    std::map<SegKey, uint32_t> maxdeg;   // largest edge list of a key of the segment (index segments: of the predicate's list)
 };
 
 struct StepRecord {
@@ -605,7 +640,13 @@ static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, in
     p.col_end = col_end;
     p.end_const = end_const;
     p.inv_c = ((1u << 20) + (uint32_t)e->ncols - 1) / (uint32_t)e->ncols;
-    if (kind == KIND_K2U && e->variant >= 4 && e->d_hq) {
+    // the heavy-tile pass is only needed where a tile of TILE_ROWS rows can reach HEAVY_TILE_MIN output rows
+    bool may_be_heavy = true;
+    {
+        auto it = e->store->maxdeg.find(SegKey(m->index, m->pid, m->dir));
+        if (it != e->store->maxdeg.end()) may_be_heavy = (uint64_t)it->second * TILE_ROWS >= HEAVY_TILE_MIN;
+    }
+    if (kind == KIND_K2U && e->variant >= 4 && e->d_hq && may_be_heavy) {
         p.hq = e->d_hq;
         p.hq_cap = e->hq_cap;
         p.hq_packed = &e->d_ctl->hq_packed[s];
@@ -847,6 +888,32 @@ static int store_set_segs(wk_store *st, const wk_segmeta_t *segs, int nsegs) {
     return WK_SUCCESS;
 }
 
+// one pass over the header: largest edge list per (index, pid, dir)
+static int store_scan_degrees(wk_store *st) {
+    const uint32_t P = 1u << WK_NBITS_IDX;   // pid field of a key: predicate / type id (2 MB of counters)
+    uint32_t *d_tab = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d_tab, 4ull * P * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(d_tab, 0, 4ull * P * sizeof(uint32_t)));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, st->device));
+    seg_maxdeg_kernel<<<prop.multiProcessorCount * 8, CTA_THREADS>>>(st->d_vertices, st->num_slots, P, d_tab);
+    std::vector<uint32_t> tab(4ull * P);
+    cudaError_t err = cudaMemcpy(tab.data(), d_tab, tab.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_tab);
+    if (err != cudaSuccess) return WK_ERR_CUDA;
+    for (auto &kv : st->segs) {
+        const wk_segmeta_t &m = kv.second;
+        uint32_t mx = 0;
+        if (m.index == 0) {
+            if (m.pid < P) mx = tab[(0 * 2 + (uint32_t)m.dir) * P + m.pid];
+        } else {
+            for (uint32_t p = 0; p < P; p++) mx = std::max(mx, tab[(1 * 2 + (uint32_t)m.dir) * P + p]);
+        }
+        st->maxdeg[kv.first] = mx;
+    }
+    return WK_SUCCESS;
+}
+
 int wk_store_create(int device, const wk_vertex_t *vertices, uint64_t num_slots, const wk_sid_t *edges,
                     uint64_t num_edges, const wk_segmeta_t *segs, int nsegs, wk_store_t **out) {
     if (!vertices || !segs || !out || num_slots == 0 || (num_slots % WK_ASSOCIATIVITY) != 0) return WK_ERR_BAD_ARG;
@@ -864,6 +931,8 @@ int wk_store_create(int device, const wk_vertex_t *vertices, uint64_t num_slots,
     CUDA_TRY(cudaMalloc((void **)&st->d_edges, (num_edges ? num_edges : 1) * sizeof(uint32_t)));
     CUDA_TRY(cudaMemcpy(st->d_vertices, vertices, num_slots * sizeof(uint4), cudaMemcpyHostToDevice));
     if (num_edges) CUDA_TRY(cudaMemcpy(st->d_edges, edges, num_edges * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    rc = store_scan_degrees(st);
+    if (rc) { wk_store_destroy(st); return rc; }
     *out = st;
     return WK_SUCCESS;
 }
@@ -880,6 +949,9 @@ int wk_store_adopt(int device, wk_vertex_t *d_vertices, uint64_t num_slots, wk_s
     st->d_edges = d_edges;
     st->owns = take_ownership != 0;
     int rc = store_set_segs(st, segs, nsegs);
+    if (rc) { delete st; return rc; }
+    if (cudaSetDevice(device) != cudaSuccess) { delete st; return WK_ERR_CUDA; }
+    rc = store_scan_degrees(st);
     if (rc) { delete st; return rc; }
     *out = st;
     return WK_SUCCESS;
