@@ -1,0 +1,62 @@
+"""NVLink roofline of the fork-join exchange (SURVEY.md §8d "shard exchange" row): R random rows x C columns per rank are
+bucketised by row[col] % n and moved to their owners, through the peer-memory push (wk_exchange_p2p) and through NCCL
+(wk_exchange).  Launch: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/exchange_bench.py
+Achieved GB/s = bytes a GPU sends to its peers (4 * C * rows not kept) / max-over-ranks wall time of the call (the call
+ends with the row-count synchronisation, microseconds against milliseconds here); peak = 900 GB/s per direction per GPU."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from wukong_b200 import capi, datagen  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+C_COLS = 3
+gst = capi.Store.build(datagen.lubm_shard(1, world, rank, seed=1), datagen.LUBM_NUM_NORMAL_PREDS, num_servers=world, sid=rank, device=local)
+eng = capi.Engine(gst, rbuf_bytes=2 << 30)
+allh = [None] * world
+dist.all_gather_object(allh, eng.p2p_export(world, rank))
+eng.p2p_import(b"".join(allh))
+uid = [capi.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+eng.comm_init(world, rank, uid[0])
+dist.barrier()
+out = []
+for rows in (1 << 20, 1 << 22, 1 << 24):
+    rng = np.random.default_rng(1000 + rank)
+    tbl = rng.integers(1 << 17, 1 << 31, (rows, C_COLS), dtype=np.uint32)
+    kept = int((tbl[:, 1] % world == rank).sum())
+    sent_bytes = 4 * C_COLS * (rows - kept)
+    for how in ("p2p", "nccl"):
+        ts = []
+        for rep in range(6):
+            eng.upload(tbl)
+            eng.sync()
+            dist.barrier()
+            t0 = time.perf_counter()
+            n = eng.exchange_p2p(1) if how == "p2p" else eng.exchange(1)
+            t1 = time.perf_counter()
+            t = torch.tensor([t1 - t0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rep:
+                ts.append(float(t.item()))
+        tot = torch.tensor([n, sent_bytes], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot[0]) == rows * world          # nothing lost, nothing duplicated
+        sec = float(np.median(ts))
+        out.append({"rows_per_gpu": rows, "cols": C_COLS, "exchange": how, "ms": round(sec * 1e3, 3),
+                    "sent_gb_per_gpu": round(sent_bytes / 1e9, 4), "achieved_gbs_per_gpu": round(sent_bytes / sec / 1e9, 1),
+                    "nvlink_peak_gbs": 900.0, "frac": round(sent_bytes / sec / 900e9, 3),
+                    "hbm_algo_gbs": round((2 * 4 * C_COLS * rows + 4 * C_COLS * n) / sec / 1e9, 1)})
+if rank == 0:
+    print(json.dumps({"n_gpus": world, "results": out}))
+dist.barrier()
+dist.destroy_process_group()

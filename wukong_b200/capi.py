@@ -429,6 +429,11 @@ class Engine:
         _check(lib().wk_exchange(self.h, col, C.byref(n)), "wk_exchange")
         return n.value
 
+    def exchange_p2p(self, col):
+        n = C.c_uint64(0)
+        _check(lib().wk_exchange_p2p(self.h, col, C.byref(n)), "wk_exchange_p2p")
+        return n.value
+
     def comm_stats(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         _check(lib().wk_comm_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))

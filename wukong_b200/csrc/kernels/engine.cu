@@ -1770,8 +1770,16 @@ static int exchange_table_p2p(wk_engine *e, int col) {
     }
     p2p_publish_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, c->d_counts, &e->d_ctl->counts[s], dup ? 1 : 0, epoch,
                                                 e->cap_words / (uint64_t)C, &e->d_ctl->counts[s + 1], &e->d_ctl->status);
-    p2p_scatter_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(*c->p2p, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
-                                                            dup ? 1 : 0, (s + 1) & 1, epoch);
+    {
+        // tile = 1024 / 512 / 256 rows so that the two staging areas stay within 32 KB of shared memory
+        const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
+        const size_t smem = 2 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
+        void (*kfn)(P2PTable, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t) =
+            rpt == 4 ? p2p_scatter_kernel<4> : (rpt == 2 ? p2p_scatter_kernel<2> : p2p_scatter_kernel<1>);
+        if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kfn<<<grid, CTA_THREADS, smem, e->stream>>>(*c->p2p, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
+                                                    dup ? 1 : 0, (s + 1) & 1, epoch);
+    }
     p2p_wait_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, epoch, &e->d_ctl->status);
     CUDA_TRY(cudaGetLastError());
     e->launches += dup ? 3 : 4;
