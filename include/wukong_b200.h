@@ -239,6 +239,14 @@ int wk_comm_stats(wk_engine_t *engine, uint64_t *exchanges, uint64_t *rows_sent,
 int wk_comm_p2p_export(wk_engine_t *engine, int nranks, int rank, void *out192);
 int wk_comm_p2p_import(wk_engine_t *engine, const void *all_handles);
 int wk_exchange_p2p(wk_engine_t *engine, int col_start, uint64_t *out_rows);
+/* In-place light queries on a sharded store -- the reference answers small tables with one-sided RDMA reads of the remote
+ * header / edge regions instead of a fork-join (sparql.hpp:802-814, Global::rdma_threshold): here every rank also maps its
+ * peers' store arrays.  export_store writes [IPC handles of the header and edge arrays][segment table] (size in *size; call
+ * with blob == NULL to learn it); import_store takes all ranks' blobs back to back, offsets[r] .. offsets[r + 1] = rank r.
+ * Afterwards wk_query_execute_sharded runs a const-start plan of <= 12 steps on the constant's owner alone, probing the
+ * other shards with loads over NVLink; a table that outgrows shared memory is redone through the exchange path. <= 8 ranks. */
+int wk_comm_p2p_export_store(wk_engine_t *engine, void *blob, uint64_t cap, uint64_t *size);
+int wk_comm_p2p_import_store(wk_engine_t *engine, const void *blobs, const uint64_t *offsets, int nranks);
 /* Host-only planning helper: out[i] = -1 no exchange before step i, -2 replicate the table to every
  * shard (type-index lookup of a known variable, sparql.hpp:1091-1110), c >= 0 re-shard by column c
  * (need_fork_join with local_var, sparql.hpp:802-814).  Needs no GPU. */

@@ -1,0 +1,10 @@
+mkdir -p gpurun_out
+N=2
+for EX in p2p nccl; do
+( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2954$N bench.py --gpus $N --steps 10 --warmup 3 --mode sharded --exchange $EX ) > gpurun_out/bench_sharded_${EX}_${N}gpu.json 2> gpurun_out/bench_sharded_${EX}_${N}gpu.err; echo "rc=$?"; tail -4 gpurun_out/bench_sharded_${EX}_${N}gpu.err | grep real
+python - <<PY
+import json
+d = json.load(open("gpurun_out/bench_sharded_${EX}_${N}gpu.json"))
+print("$EX", d["value"], d["rows"], d["latency_us"]["device"])
+PY
+done

@@ -65,7 +65,7 @@ def run_cpu(rank, world, dist, hs, queries):
     return out
 
 
-def run_gpu(rank, world, dist, hs, queries, p2p=False):
+def run_gpu(rank, world, dist, hs, queries, p2p=False, inplace=False):
     import torch
     from wukong_b200 import capi
     gst = hs.upload(rank)
@@ -75,6 +75,10 @@ def run_gpu(rank, world, dist, hs, queries, p2p=False):
         allh = [None] * world
         dist.all_gather_object(allh, mine)
         eng.p2p_import(b"".join(allh))
+        if inplace:   # ... and the peers' store arrays: const-start plans are answered in place by the constant's owner
+            blobs = [None] * world
+            dist.all_gather_object(blobs, eng.p2p_export_store())
+            eng.p2p_import_store(blobs)
         dist.barrier()
     else:
         uid = [capi.comm_unique_id() if rank == 0 else None]
@@ -118,6 +122,16 @@ def main():
         res = run_gpu(a.rank, a.world, dist, hs, queries)
     elif a.mode == "gpu_p2p":
         res = run_gpu(a.rank, a.world, dist, hs, queries, p2p=True)
+    elif a.mode == "gpu_inplace":
+        # a const-start plan whose table outgrows shared memory (members of one department x their courses):
+        # the owner's verdict sends every shard through the exchange path instead
+        import sparql_mini as M
+        from oracle import oracle as O
+        P = {n: i for i, n in enumerate(M.LUBM_INDEX)}
+        d0 = M.lubm_str2id("<http://www.Department0.University0.edu>")
+        queries["spill"] = ([(d0, P[M.UB + "memberOf>"], O.IN, -1), (-1, P[M.UB + "takesCourse>"], O.OUT, -2),
+                             (-2, P[M.UB + "teacherOf>"], O.IN, -3)], 3, [-1, -2, -3])
+        res = run_gpu(a.rank, a.world, dist, hs, queries, p2p=True, inplace=True)
     else:
         res = run_cpu(a.rank, a.world, dist, hs, queries)
     np.savez(os.path.join(a.out, "rank%d.npz" % a.rank), **res)

@@ -97,3 +97,30 @@ def test_sharded_gpu_peer_memory(tmp_path):
     res = _run_world(world, "gpu_p2p", tmp_path)
     _check_against_bruteforce(res, 2, 7)
     assert res[0]["__stats__"][0] > 0
+
+
+@pytest.mark.gpu
+def test_sharded_gpu_in_place_light_queries(tmp_path):
+    """const-start plans answered by the constant's owner alone, probing the other shards through peer memory (the
+    reference's in-place mode with one-sided reads); a table that outgrows shared memory falls back to the exchange path"""
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = min(capi.device_count(), 4)
+    res = _run_world(world, "gpu_inplace", tmp_path)
+    _check_against_bruteforce(res, 2, 7)
+    # light queries no longer exchange: fewer exchanges than the all-collective run of the same workload would need,
+    # and every row of a light answer sits on ONE rank (the owner of Department0 / University0)
+    for q in (4, 5, 6):
+        name = "q%d_%s" % (q, PLANS[0])
+        holders = [r for r in range(world) if res[r][name].size]
+        assert len(holders) <= 1, (name, holders)
+    tr = datagen.lubm(2, seed=7)
+    d0 = M.lubm_str2id("<http://www.Department0.University0.edu>")
+    P = {n: i for i, n in enumerate(M.LUBM_INDEX)}
+    t = np.unique(tr, axis=0)
+    mem = t[(t[:, 1] == P[M.UB + "memberOf>"]) & (t[:, 2] == d0)][:, 0]
+    tc = t[(t[:, 1] == P[M.UB + "takesCourse>"]) & np.isin(t[:, 0], mem)]
+    to = t[t[:, 1] == P[M.UB + "teacherOf>"]]
+    want = np.array([(x, c, y) for x, _, c in tc.tolist() for y, _, c2 in to[to[:, 2] == c].tolist()], dtype=np.uint32).reshape(-1, 3)
+    got = np.concatenate([r["spill"].reshape(-1, 3) for r in res])
+    assert want.shape[0] > 1024 and rows_equal(got, want)

@@ -63,6 +63,7 @@ DECLARED_SYMBOLS = [
     "wk_query_execute", "wk_query_execute_batch", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
     "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
     "wk_comm_stats", "wk_plan_exchanges", "wk_comm_p2p_export", "wk_comm_p2p_import", "wk_exchange_p2p",
+    "wk_comm_p2p_export_store", "wk_comm_p2p_import_store",
 ]
 
 _lib = None
@@ -126,6 +127,8 @@ def lib():
     L.wk_comm_p2p_export.argtypes = [vp, ci, ci, vp]
     L.wk_comm_p2p_import.argtypes = [vp, vp]
     L.wk_exchange_p2p.argtypes = [vp, ci, pu64]
+    L.wk_comm_p2p_export_store.argtypes = [vp, vp, u64, pu64]
+    L.wk_comm_p2p_import_store.argtypes = [vp, vp, vp, ci]
     L.wk_plan_exchanges.argtypes = [vp, ci, ci, vp]
     L.wk_query_execute_sharded.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
     L.wk_host_alloc.argtypes = [u64, C.POINTER(vp)]
@@ -418,6 +421,21 @@ class Engine:
     def p2p_import(self, all_handles_bytes):
         buf = (C.c_ubyte * len(all_handles_bytes)).from_buffer_copy(all_handles_bytes)
         _check(lib().wk_comm_p2p_import(self.h, C.cast(buf, C.c_void_p)), "wk_comm_p2p_import")
+
+    def p2p_export_store(self):
+        """handles of this rank's store arrays + its segment table (in-place light queries on a sharded store)"""
+        n = C.c_uint64(0)
+        lib().wk_comm_p2p_export_store(self.h, None, 0, C.byref(n))
+        buf = (C.c_ubyte * n.value)()
+        _check(lib().wk_comm_p2p_export_store(self.h, C.cast(buf, C.c_void_p), n.value, C.byref(n)), "wk_comm_p2p_export_store")
+        return bytes(buf)
+
+    def p2p_import_store(self, blobs):
+        off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        allb = b"".join(blobs)
+        buf = (C.c_ubyte * len(allb)).from_buffer_copy(allb)
+        _check(lib().wk_comm_p2p_import_store(self.h, C.cast(buf, C.c_void_p), _ptr(off), len(blobs)), "wk_comm_p2p_import_store")
 
     def partition(self, col, nparts):
         out = np.zeros(nparts, dtype=np.uint64)

@@ -1846,6 +1846,63 @@ int wk_comm_p2p_import(wk_engine_t *e, const void *all_handles) {
     return WK_SUCCESS;
 }
 
+// ---- peers' stores for in-place light queries: every rank exports the IPC handles of its header and edge arrays plus
+// its segment table (each shard sizes its segments on its own); blob = [2 x 64-byte handles][int32 nsegs][pad][segs] --------
+int wk_comm_p2p_export_store(wk_engine_t *e, void *blob, uint64_t cap, uint64_t *size) {
+    if (!e || !size) return WK_ERR_BAD_ARG;
+    const uint64_t need = 2 * sizeof(cudaIpcMemHandle_t) + 8 + e->store->segs.size() * sizeof(wk_segmeta_t);
+    *size = need;
+    if (!blob || cap < need) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    uint8_t *p = (uint8_t *)blob;
+    cudaIpcMemHandle_t h[2];
+    CUDA_TRY(cudaIpcGetMemHandle(&h[0], e->store->d_vertices));
+    CUDA_TRY(cudaIpcGetMemHandle(&h[1], e->store->d_edges));
+    memcpy(p, h, sizeof(h));
+    const int32_t ns = (int32_t)e->store->segs.size();
+    memcpy(p + sizeof(h), &ns, 4);
+    memset(p + sizeof(h) + 4, 0, 4);
+    wk_segmeta_t *dst = (wk_segmeta_t *)(p + sizeof(h) + 8);
+    int i = 0;
+    for (auto &kv : e->store->segs) dst[i++] = kv.second;
+    return WK_SUCCESS;
+}
+
+// blobs: the nranks exported blobs back to back, offsets[r] .. offsets[r + 1] delimit rank r's
+int wk_comm_p2p_import_store(wk_engine_t *e, const void *blobs, const uint64_t *offsets, int nranks) {
+    if (!e || !e->comm || !e->comm->p2p_ready || !blobs || !offsets) return WK_ERR_BAD_ARG;
+    wk_comm *c = e->comm;
+    if (nranks != c->nranks || nranks > LIGHT_PEERS) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    c->peer_segs.assign(nranks, {});
+    for (int r = 0; r < nranks; r++) {
+        const uint8_t *p = (const uint8_t *)blobs + offsets[r];
+        const uint64_t len = offsets[r + 1] - offsets[r];
+        if (len < 2 * sizeof(cudaIpcMemHandle_t) + 8) return WK_ERR_BAD_ARG;
+        int32_t ns = 0;
+        memcpy(&ns, p + 2 * sizeof(cudaIpcMemHandle_t), 4);
+        if (ns < 0 || len < 2 * sizeof(cudaIpcMemHandle_t) + 8 + (uint64_t)ns * sizeof(wk_segmeta_t)) return WK_ERR_BAD_ARG;
+        const wk_segmeta_t *sg = (const wk_segmeta_t *)(p + 2 * sizeof(cudaIpcMemHandle_t) + 8);
+        for (int i = 0; i < ns; i++) c->peer_segs[r][SegKey(sg[i].index, sg[i].pid, sg[i].dir)] = sg[i];
+        if (r == c->rank) {
+            c->peer_v[r] = e->store->d_vertices;
+            c->peer_e[r] = e->store->d_edges;
+            continue;
+        }
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, p, sizeof(h));
+        void *q[2];
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaIpcOpenMemHandle(&q[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(q[k]);
+        }
+        c->peer_v[r] = (const uint4 *)q[0];
+        c->peer_e[r] = (const uint32_t *)q[1];
+    }
+    c->peer_stores = true;
+    return WK_SUCCESS;
+}
+
 // wk_exchange over peer memory instead of NCCL (same semantics; the table moves to the other buffer)
 int wk_exchange_p2p(wk_engine_t *e, int col_start, uint64_t *out_rows) {
     if (!e) return WK_ERR_BAD_ARG;
@@ -1975,10 +2032,118 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
     }
     e->q_timed = false;
     if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
+    const int n = e->comm->nranks, me = e->comm->rank;
+    // In-place execution of a light query (the reference answers small tables with one-sided remote reads instead of a
+    // fork-join, sparql.hpp:802-814): the constant's owner walks the other shards through peer memory, nobody exchanges.
+    // Every rank takes the same decision from the plan alone; the owner's verdict (answered / outgrew shared memory)
+    // reaches the peers through a flag, and an outgrown query is redone by all shards together below.
+    bool in_place = e->comm->peer_stores && e->comm->p2p_ready && steps[0].kind == KIND_C2U &&
+                    (int)steps.size() <= LIGHT_SHARDED_STEPS && n <= LIGHT_PEERS && getenv("WK_NO_INPLACE") == nullptr;
+    for (const PlannedStep &ps : steps)
+        if (ps.kind == KIND_C2K || (ps.kind == KIND_K2U && ps.pid == WK_TYPE_ID && ps.dir == WK_DIR_IN)) in_place = false;
+    if (in_place) {
+        const int owner = (int)(steps[0].vid % (uint64_t)n);
+        const uint64_t epoch = ++e->comm->epoch;
+        if (me == owner) {
+            LightPlanSharded sp;
+            memset(&sp, 0, sizeof(sp));
+            LightPlan &lp = sp.lp;
+            lp.vertices = e->store->d_vertices;
+            lp.edges = e->store->d_edges;
+            lp.buf[0] = e->buf[0];
+            lp.buf[1] = e->buf[1];
+            lp.counts = e->d_ctl->counts;
+            lp.stats = e->d_ctl->stats;
+            lp.status = &e->d_ctl->status;
+            lp.ctl_words = (uint64_t *)e->d_ctl;
+            lp.ctl_nwords = (int)(sizeof(CtlBlock) / sizeof(uint64_t));
+            lp.rec = e->d_rec;
+            lp.host_table = e->d_stage;
+            lp.host_table_words = e->stage_words;
+            lp.cap_words = e->cap_words;
+            lp.nsteps = (int)steps.size();
+            lp.do_project = want_table ? 1 : 0;
+            lp.proj_n = (int)proj_cols.size();
+            for (size_t i = 0; i < proj_cols.size(); i++) lp.proj_cols[i] = (int8_t)proj_cols[i];
+            rc = fill_light_steps(e, steps, 0, 1, lp.steps);
+            if (rc) return rc;
+            for (int r = 0; r < n; r++) {
+                sp.pv[r] = e->comm->peer_v[r];
+                sp.pe[r] = e->comm->peer_e[r];
+                sp.peer_flag[r] = (r == me) ? nullptr : &e->comm->p2p->ctl[r]->flagL[me];
+                for (size_t i = 0; i < steps.size(); i++) {
+                    const PlannedStep &ps = steps[i];
+                    auto it = e->comm->peer_segs[r].find(SegKey(0, ps.pid, ps.dir));
+                    if (it == e->comm->peer_segs[r].end() || it->second.num_buckets == 0) {
+                        // that shard has no such segment: bucket 0 belongs to another (pid, dir), whose keys never compare
+                        // equal to this step's, so the probe walks that chain to its end and misses
+                        sp.segr[i][r].bucket_start = 0;
+                        sp.segr[i][r].fm = make_fastmod(1);
+                    } else {
+                        sp.segr[i][r].bucket_start = it->second.bucket_start;
+                        sp.segr[i][r].fm = make_fastmod(it->second.num_buckets);
+                    }
+                }
+            }
+            sp.epoch = epoch;
+            sp.nranks = (uint32_t)n;
+            if (e->profiling >= 3) {
+                if (!e->d_trace) CUDA_TRY(cudaMalloc((void **)&e->d_trace, (MAX_LIGHT_STEPS + 4) * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(e->d_trace, 0, (MAX_LIGHT_STEPS + 4) * sizeof(long long), e->stream));
+                lp.trace = e->d_trace;
+            }
+            lp.seq = ++e->seq;
+            e->step = 0;
+            e->recs.clear();
+            e->event_next = 0;
+            light_sharded_kernel<<<1, LIGHT_SHARDED_THREADS, 0, e->stream>>>(sp);
+            CUDA_TRY(cudaGetLastError());
+            if (e->profiling) { cudaEventRecord(e->q_ev1, e->stream); e->q_timed = true; }
+            e->launches++;
+            RecView rv;
+            rc = wait_record(e, lp.seq, (int)steps.size(), want_table ? (int)proj_cols.size() : 0, rv);
+            if (rc) return rc;
+            if (rv.status & 1u) return WK_ERR_RBUF_OVERFLOW;
+            if (rv.resume == (int)steps.size()) {
+                const uint64_t rows = rv.rows;
+                const int cols = (want_table && rows > 0) ? nrequired : final_cols;
+                if (out_rows) *out_rows = rows;
+                if (out_cols) *out_cols = cols;
+                if (no_required && rows > 0) return WK_NO_REQUIRED_VAR;
+                if (want_table && rows > 0 && table) {
+                    const uint64_t words = rows * (uint64_t)cols;
+                    if (words > cap_words) return WK_ERR_BAD_ARG;
+                    memcpy(table, e->h_stage, words * sizeof(uint32_t));
+                }
+                return WK_SUCCESS;
+            }
+            // outgrew shared memory: every peer has been told; fall through to the collective plan
+        } else {
+            rc = reset_ctl(e);
+            if (rc) return rc;
+            p2p_light_wait_kernel<<<1, 1, 0, e->stream>>>(e->comm->d_xctl, owner, epoch, &e->d_ctl->status);
+            CUDA_TRY(cudaGetLastError());
+            e->launches++;
+            const uint64_t seq = ++e->seq;
+            finish_kernel<<<1, 1, 0, e->stream>>>(&e->d_ctl->counts[0], &e->d_ctl->status, e->d_rec, seq, 0);
+            CUDA_TRY(cudaGetLastError());
+            if (e->profiling) { cudaEventRecord(e->q_ev1, e->stream); e->q_timed = true; }
+            e->launches++;
+            RecView rv;
+            rc = wait_record(e, seq, -1, 0, rv);
+            if (rc) return rc;
+            if (rv.status & 2u) return WK_ERR_COMM;
+            if (!(rv.status & 4u)) {   // answered by the owner: this shard contributes no rows
+                if (out_rows) *out_rows = 0;
+                if (out_cols) *out_cols = want_table ? nrequired : final_cols;
+                return WK_SUCCESS;
+            }
+        }
+        if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
+    }
     rc = reset_ctl(e);
     if (rc) return rc;
     e->ncols = 0;
-    const int n = e->comm->nranks, me = e->comm->rank;
     for (size_t i = 0; i < steps.size(); i++) {
         const PlannedStep &ps = steps[i];
         if (ex[i] != -1) {

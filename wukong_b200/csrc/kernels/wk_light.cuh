@@ -92,6 +92,34 @@ struct LightSmem {
     uint64_t red[LIGHT_MAX_WARPS];
 };
 
+// Where a key lives.  LocalView: the whole store is on this GPU.  PeerView: the store is sharded by vid % n and the
+// shards of the other GPUs are mapped into this address space (CUDA IPC): a probe is a load over NVLink from the
+// owner's header and edge arrays -- the reference's in-place execution with one-sided RDMA reads for small tables
+// (core/engine/sparql.hpp:802-814 need_fork_join, rdma_threshold), without the RDMA.
+enum { LIGHT_PEERS = 8, LIGHT_SHARDED_STEPS = 12 };
+struct SegLite { uint64_t bucket_start; FastMod fm; };
+struct LocalView {
+    const uint4 *v;
+    const uint32_t *e;
+    __device__ __forceinline__ const uint4 *vertices(uint32_t) const { return v; }
+    __device__ __forceinline__ const uint32_t *edges(uint32_t) const { return e; }
+    __device__ __forceinline__ uint64_t bucket(const LightStep &ls, int, uint64_t key, uint32_t) const {
+        return ls.seg.bucket_start + fastmod(hash_u64(key), ls.seg.fm);
+    }
+};
+struct PeerView {
+    const uint4 *const *v;                       // [rank]
+    const uint32_t *const *e;                    // [rank]
+    const SegLite (*segr)[LIGHT_PEERS];          // [step][rank]: every shard sizes its segments on its own
+    uint32_t n;
+    __device__ __forceinline__ const uint4 *vertices(uint32_t vid) const { return v[vid % n]; }
+    __device__ __forceinline__ const uint32_t *edges(uint32_t vid) const { return e[vid % n]; }
+    __device__ __forceinline__ uint64_t bucket(const LightStep &, int s, uint64_t key, uint32_t vid) const {
+        const SegLite &sg = segr[s][vid % n];
+        return sg.bucket_start + fastmod(hash_u64(key), sg.fm);
+    }
+};
+
 // probe one key, thread-serial over the bucket chain, 8 independent slot loads per bucket
 __device__ __forceinline__ uint64_t probe_thread(const uint4 *__restrict__ vertices, uint64_t key, uint64_t bucket,
                                                  uint32_t &visited) {
@@ -199,9 +227,8 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, LightSmem &sm, int
 // not fit shared memory (nothing of that step has been written).
 struct LightState { uint32_t N; int C, cur, done; bool spilled; };
 
-template <int NT>
-__device__ __forceinline__ LightState light_interpret(const LightStep *steps, int nsteps, const uint4 *__restrict__ vertices,
-                                                      const uint32_t *__restrict__ edges, LightSmem &sm, uint64_t *stats,
+template <int NT, class SV>
+__device__ __forceinline__ LightState light_interpret(const LightStep *steps, int nsteps, const SV &sv, LightSmem &sm, uint64_t *stats,
                                                       uint64_t *counts, long long *trace = nullptr) {
     const int tid = threadIdx.x;
     uint32_t N = 0;          // rows of the current table (in sm.tab[cur])
@@ -217,7 +244,9 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
         if (ls.kind == LKIND_C2U || ls.kind == LKIND_I2U) {
             if (tid < 32) {
                 uint32_t visited;
-                const uint64_t bucket = ls.seg.bucket_start + fastmod(hash_u64(ls.key), ls.seg.fm);
+                const uint32_t seed_vid = (uint32_t)(ls.key >> WK_KEY_VID_SHIFT);
+                const uint4 *vertices = sv.vertices(seed_vid);
+                const uint64_t bucket = sv.bucket(ls, s, ls.key, seed_vid);
                 // warp-cooperative single probe (8 lanes load the bucket)
                 uint64_t result = 0, b = bucket;
                 visited = 0;
@@ -244,7 +273,8 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             const uint64_t begin = start * length;
             const uint64_t len = (start == mtf - 1) ? (size - begin) : length;
             if (len > LIGHT_ROWS) { spilled = true; break; }   // nothing done yet: resume at this very step
-            for (uint32_t k = tid; k < len; k += NT) sm.tab[nxt][k] = ld_edge(edges + off + begin + k);
+            const uint32_t *seed_edges = sv.edges((uint32_t)(ls.key >> WK_KEY_VID_SHIFT));
+            for (uint32_t k = tid; k < len; k += NT) sm.tab[nxt][k] = ld_edge(seed_edges + off + begin + k);
             if (tid == 0) st_edges = len;
             N = (uint32_t)len;
             C = 1;
@@ -265,25 +295,27 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             // tables taller than the CTA are walked in several rounds whose loads depend on each other through
             // the loop; pull every later round's bucket line towards L2 first so that only round one pays DRAM
             for (uint32_t r = tid + NT; r < N; r += NT) {
-                const uint64_t key = step_key(ls.seg, tin[r * Cin + ls.col_start]);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(vertices + (ls.seg.bucket_start + fastmod(hash_u64(key), ls.seg.fm)) * 8));
+                const uint32_t c0 = tin[r * Cin + ls.col_start];
+                const uint64_t key = step_key(ls.seg, c0);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.vertices(c0) + sv.bucket(ls, s, key, c0) * 8));
             }
             for (uint32_t item = tid; item < N * (uint32_t)(1 + nsh); item += NT) {
                 uint32_t r = item, j = 0;   // item = j * N + r with j <= 3: no integer division on this path
                 while (r >= N) { r -= N; j++; }
                 if (j != 0) {
                     const LightStep &l2 = steps[sh[j - 1]];
-                    const uint64_t key2 = step_key(l2.seg, tin[r * Cin + l2.col_start]);
+                    const uint32_t c2 = tin[r * Cin + l2.col_start];
+                    const uint64_t key2 = step_key(l2.seg, c2);
                     uint32_t v2;
-                    const uint64_t ptr2 = probe_thread(vertices, key2, l2.seg.bucket_start + fastmod(hash_u64(key2), l2.seg.fm), v2);
-                    if (ptr2) asm volatile("prefetch.global.L2 [%0];" ::"l"(edges + ptr_off(ptr2)));
+                    const uint64_t ptr2 = probe_thread(sv.vertices(c2), key2, sv.bucket(l2, sh[j - 1], key2, c2), v2);
+                    if (ptr2) asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.edges(c2) + ptr_off(ptr2)));
                     continue;
                 }
                 const uint32_t c0 = tin[r * Cin + ls.col_start];
                 const uint64_t key = step_key(ls.seg, c0);
-                const uint64_t bucket = ls.seg.bucket_start + fastmod(hash_u64(key), ls.seg.fm);
+                const uint64_t bucket = sv.bucket(ls, s, key, c0);
                 uint32_t visited;
-                const uint64_t ptr = probe_thread(vertices, key, bucket, visited);
+                const uint64_t ptr = probe_thread(sv.vertices(c0), key, bucket, visited);
                 st_visited += visited;
                 sm.ptr[r] = ptr;
                 const uint32_t size = ptr_size(ptr);
@@ -293,7 +325,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                 } else {
                     const uint32_t target = (ls.kind == LKIND_K2K) ? tin[r * Cin + ls.col_end] : ls.end_const;
                     uint32_t scanned;
-                    const bool hit = list_contains(edges + ptr_off(ptr), size, target, scanned);
+                    const bool hit = list_contains(sv.edges(c0) + ptr_off(ptr), size, target, scanned);
                     st_edges += scanned;
                     sm.pre[r] = hit ? 1u : 0u;
                 }
@@ -313,7 +345,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                         if (sm.pre[mid] <= o) lo = mid; else hi = mid;
                     }
                     const uint32_t k = o - sm.pre[lo];
-                    const uint32_t e = ld_edge(edges + ptr_off(sm.ptr[lo]) + k);
+                    const uint32_t e = ld_edge(sv.edges(tin[lo * Cin + ls.col_start]) + ptr_off(sm.ptr[lo]) + k);
                     for (int c = 0; c < Cin; c++) tout[o * Cout + c] = tin[lo * Cin + c];
                     tout[o * Cout + Cin] = e;
                 }
@@ -355,17 +387,18 @@ __device__ __forceinline__ void stage_steps(LightStep *dst, const LightStep *src
     for (uint32_t i = tid; i < words; i += NT) d[i] = s[i];
 }
 
-__global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
-    __shared__ LightSmem sm;
-    __shared__ LightStep s_steps[MAX_LIGHT_STEPS];
+// whole light query: interpret, then project into the mapped staging area (or hand the table over on a spill) and
+// store the completion record.  Returns true when the table outgrew shared memory.
+template <int NT, class SV>
+__device__ __forceinline__ bool light_query_body(const LightPlan &plan, const SV &sv, LightSmem &sm, LightStep *s_steps) {
     const int tid = threadIdx.x;
-    stage_steps<LIGHT_THREADS>(s_steps, plan.steps, plan.nsteps, tid);
+    stage_steps<NT>(s_steps, plan.steps, plan.nsteps, tid);
     // this kernel owns the control block: clear it here instead of a separate memset node
     if (plan.trace && tid == 0) plan.trace[0] = clock64();
-    for (int i = tid; i < plan.ctl_nwords; i += LIGHT_THREADS) plan.ctl_words[i] = 0;
+    for (int i = tid; i < plan.ctl_nwords; i += NT) plan.ctl_words[i] = 0;
     __syncthreads();
     if (plan.trace && tid == 0) plan.trace[1] = clock64();
-    const LightState ls_ = light_interpret<LIGHT_THREADS>(s_steps, plan.nsteps, plan.vertices, plan.edges, sm,
+    const LightState ls_ = light_interpret<NT>(s_steps, plan.nsteps, sv, sm,
                                            plan.collect_stats ? plan.stats : nullptr, plan.counts, plan.trace);
     const uint32_t N = ls_.N;
     const int C = ls_.C, cur = ls_.cur, s = ls_.done;
@@ -379,7 +412,7 @@ __global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid
             uint32_t *dst = plan.buf[done_steps & 1];
             const uint32_t words = N * (uint32_t)C;
             if ((uint64_t)words <= plan.cap_words) {
-                for (uint32_t i = tid; i < words; i += LIGHT_THREADS) dst[i] = sm.tab[cur][i];
+                for (uint32_t i = tid; i < words; i += NT) dst[i] = sm.tab[cur][i];
             } else {
                 status = 1;
             }
@@ -389,7 +422,7 @@ __global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid
         const uint32_t words = N * (uint32_t)plan.proj_n;
         uint64_t part = 0;
         if ((uint64_t)words <= plan.host_table_words) {
-            for (uint32_t w = tid; w < words; w += LIGHT_THREADS) {
+            for (uint32_t w = tid; w < words; w += NT) {
                 const uint32_t r = w / (uint32_t)plan.proj_n, j = w - r * (uint32_t)plan.proj_n;
                 const uint32_t val = sm.tab[cur][r * C + plan.proj_cols[j]];
                 st_sys_u32(plan.host_table + w, val);
@@ -398,7 +431,7 @@ __global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid
         } else {
             status = 1;
         }
-        tsum = block_sum_u64<LIGHT_THREADS>(part, sm, tid);
+        tsum = block_sum_u64<NT>(part, sm, tid);
     }
     if (plan.trace && tid == 0) plan.trace[2 + MAX_LIGHT_STEPS] = clock64();
     if (tid == 0) {
@@ -410,7 +443,51 @@ __global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid
         st_sys_v2u64(rec, plan.seq, rows);
         if (plan.trace) plan.trace[3 + MAX_LIGHT_STEPS] = clock64();
     }
+    return spilled;
 }
+
+__global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {
+    __shared__ LightSmem sm;
+    __shared__ LightStep s_steps[MAX_LIGHT_STEPS];
+    LocalView sv;
+    sv.v = plan.vertices;
+    sv.e = plan.edges;
+    light_query_body<LIGHT_THREADS>(plan, sv, sm, s_steps);
+}
+
+// The same on a sharded store: this GPU owns the query's constant and walks the other shards through peer memory.
+// When done it tells every peer whether the answer stands (flag = 2 * epoch) or the table outgrew shared memory and
+// the query has to be redone by all shards together (flag = 2 * epoch + 1).
+struct LightPlanSharded {
+    LightPlan lp;
+    const uint4 *pv[LIGHT_PEERS];
+    const uint32_t *pe[LIGHT_PEERS];
+    uint64_t *peer_flag[LIGHT_PEERS];       // &XchCtl::flagL[owner] inside every peer's control block (nullptr for myself)
+    uint64_t epoch;
+    uint32_t nranks, _pad;
+    SegLite segr[LIGHT_SHARDED_STEPS][LIGHT_PEERS];
+};
+
+__device__ __forceinline__ void st_sys_u64_light(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// 1024 threads: a remote access costs about a microsecond, so a table taller than the CTA (three dependent rounds of
+// probe + list scan with 256 threads) is worth far more than the extra barrier cost measured on the local kernel
+enum { LIGHT_SHARDED_THREADS = 1024 };
+__global__ void __launch_bounds__(LIGHT_SHARDED_THREADS) light_sharded_kernel(const __grid_constant__ LightPlanSharded plan) {
+    __shared__ LightSmem sm;
+    __shared__ LightStep s_steps[LIGHT_SHARDED_STEPS];
+    PeerView sv;
+    sv.v = plan.pv;
+    sv.e = plan.pe;
+    sv.segr = plan.segr;
+    sv.n = plan.nranks;
+    const bool spilled = light_query_body<LIGHT_SHARDED_THREADS>(plan.lp, sv, sm, s_steps);
+    if (threadIdx.x < plan.nranks && plan.peer_flag[threadIdx.x] != nullptr)
+        st_sys_u64_light(plan.peer_flag[threadIdx.x], 2 * plan.epoch + (spilled ? 1 : 0));
+}
+
 
 // ---- throughput path: many independent light plans in one launch, one CTA per query (blind) -------------
 enum { BATCH_STEPS = 8 };
@@ -428,12 +505,15 @@ __global__ void __launch_bounds__(CTA_THREADS) light_batch_kernel(const BatchPla
                                                                   const uint4 *vertices, const uint32_t *edges) {
     __shared__ LightSmem sm;
     __shared__ LightStep s_steps[BATCH_STEPS];
+    LocalView sv;
+    sv.v = vertices;
+    sv.e = edges;
     for (int q = blockIdx.x; q < nqueries; q += gridDim.x) {
         const BatchPlan *bp = plans + q;
         const int nsteps = bp->nsteps;
         stage_steps<CTA_THREADS>(s_steps, bp->steps, nsteps, threadIdx.x);
         __syncthreads();
-        const LightState st = light_interpret<CTA_THREADS>(s_steps, nsteps, vertices, edges, sm, nullptr, nullptr);
+        const LightState st = light_interpret<CTA_THREADS>(s_steps, nsteps, sv, sm, nullptr, nullptr);
         if (threadIdx.x == 0) {
             results[q].rows = st.N;
             results[q].status = st.spilled ? 2u : 0u;

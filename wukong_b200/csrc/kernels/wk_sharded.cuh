@@ -118,6 +118,11 @@ struct wk_comm {
     struct P2PTable *p2p = nullptr;     // host copy of the peer pointer table (passed to kernels by value)
     uint64_t epoch = 0;
     std::vector<void *> ipc_opened;
+    // peers' stores mapped through CUDA IPC (in-place light queries): header / edge arrays and segment tables per rank
+    bool peer_stores = false;
+    const uint4 *peer_v[8] = {nullptr};
+    const uint32_t *peer_e[8] = {nullptr};
+    std::vector<std::map<std::tuple<int, uint32_t, int>, wk_segmeta_t>> peer_segs;
 };
 
 // Which steps need an exchange: out[i] = -1 none, -2 replicate to every rank, c >= 0 re-shard by column c.
@@ -150,6 +155,7 @@ struct XchCtl {
     uint64_t counts[MAX_PARTS][MAX_PARTS];   // [src][dst]; row `src` is written by rank src into every peer's copy
     uint64_t flagA[MAX_PARTS];               // epoch of the last counts publication seen from each rank
     uint64_t flagB[MAX_PARTS];               // epoch of the last completed push seen from each rank
+    uint64_t flagL[MAX_PARTS];               // light query answered in place by rank r: 2 * epoch (+ 1: redo it collectively)
 };
 
 struct P2PTable {
@@ -295,6 +301,12 @@ __global__ void __launch_bounds__(CTA_THREADS) p2p_scatter_kernel(P2PTable t, P2
         __threadfence_system();
         st_sys_u64(&t.ctl[threadIdx.x]->flagB[t.rank], epoch);
     }
+}
+
+// a peer of an in-place light query: wait for the owner's verdict; bit 2 of the status word asks for the collective redo
+__global__ void p2p_light_wait_kernel(XchCtl *my, int owner, uint64_t epoch, uint32_t *status) {
+    if (!wait_flag(&my->flagL[owner], 2 * epoch)) { atomicOr(status, 2u); return; }
+    if (ld_sys_u64(&my->flagL[owner]) == 2 * epoch + 1) atomicOr(status, 4u);
 }
 
 // barrier 2: every peer has finished pushing into my buffer
