@@ -24,13 +24,13 @@ from oracle import oracle as O  # noqa: E402
 from wukong_b200 import capi, datagen, host  # noqa: E402
 
 tr = datagen.lubm(args.scale, seed=1)
-hs = host.HostStore(tr)
+gst = capi.Store.build(tr, datagen.LUBM_NUM_NORMAL_PREDS)      # device-side store build
 del tr
-gst = hs.upload(0)
 eng = capi.Engine(gst, rbuf_bytes=256 << 20)
-ost = O.Store.wrap(hs.vertices(), hs.edges(), hs.segs())
+_v, _e = gst.download()                                         # the same arrays for the CPU oracle arm
+ost = O.Store.wrap(_v, _e, gst.segs())
 tpl = emu_util.load_templates()
-cands = {t[4]: hs.get_edges(0, t[4], 0) for t in tpl}
+cands = {t[4]: ost.get_edges(0, t[4], 0) for t in tpl}
 pats, off, nv, pick = emu_util.instantiate(tpl, cands, args.queries, seed=11)
 
 
