@@ -97,6 +97,8 @@ def test_sharded_gpu_peer_memory(tmp_path):
     res = _run_world(world, "gpu_p2p", tmp_path)
     _check_against_bruteforce(res, 2, 7)
     assert res[0]["__stats__"][0] > 0
+    tot = sum(np.asarray(r["__stats__"], dtype=np.uint64) for r in res)      # exchanges, rows sent, rows received
+    assert tot[1] == tot[2] and tot[1] > 0                                    # every row pushed to a peer arrived
 
 
 @pytest.mark.gpu

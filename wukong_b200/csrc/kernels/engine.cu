@@ -1985,9 +1985,18 @@ int wk_exchange(wk_engine_t *e, int col_start, uint64_t *out_rows) {
 
 int wk_comm_stats(wk_engine_t *e, uint64_t *exchanges, uint64_t *rows_sent, uint64_t *rows_recv) {
     if (!e || !e->comm) return WK_ERR_COMM;
+    uint64_t sent = e->comm->rows_sent, recv = e->comm->rows_recv;
+    if (e->comm->d_p2p_local) {   // the peer-memory exchange keeps its totals on the device (no host sync per exchange)
+        CUDA_TRY(cudaSetDevice(e->store->device));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        P2PLocal loc;
+        CUDA_TRY(cudaMemcpy(&loc, e->comm->d_p2p_local, sizeof(loc), cudaMemcpyDeviceToHost));
+        sent += loc.rows_sent;
+        recv += loc.rows_recv;
+    }
     if (exchanges) *exchanges = e->comm->exchanges;
-    if (rows_sent) *rows_sent = e->comm->rows_sent;
-    if (rows_recv) *rows_recv = e->comm->rows_recv;
+    if (rows_sent) *rows_sent = sent;
+    if (rows_recv) *rows_recv = recv;
     return WK_SUCCESS;
 }
 

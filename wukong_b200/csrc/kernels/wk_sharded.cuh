@@ -169,6 +169,7 @@ struct P2PLocal {                            // device scratch of one rank
     uint64_t cursor[MAX_PARTS];              // running row offset into each destination's buffer
     uint32_t done_ctas;
     uint32_t skip;                           // set when the exchange must not push (overflow somewhere)
+    uint64_t rows_sent, rows_recv;           // running totals over all exchanges (wk_comm_stats)
 };
 
 __device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
@@ -218,7 +219,12 @@ __global__ void p2p_publish_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const 
             }
             if (tot > cap_rows) overflow = true;
             loc->cursor[d] = before;
-            if (d == t.rank) *out_count = tot;
+            if (d == t.rank) {
+                *out_count = tot;
+                loc->rows_recv += tot - ld_sys_u64(&my->counts[t.rank][d]);
+            } else {
+                loc->rows_sent += ld_sys_u64(&my->counts[t.rank][d]);
+            }
         }
         if (overflow) { atomicOr(status, 1u); loc->skip = 1; }
     }
