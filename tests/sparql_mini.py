@@ -160,3 +160,23 @@ def sort_rows(a):
         return a.reshape(0, a.shape[1] if a.ndim == 2 else 0)
     idx = np.lexsort(a.T[::-1])
     return a[idx]
+
+
+def py_final_process(full, req_cols, distinct, offset, limit):
+    """independent statement of final_process' modifiers (sparql.hpp:1424-1550) on a full binding table"""
+    t = np.asarray(full, dtype=np.uint32)
+    if t.shape[0] == 0:
+        return t[:, req_cols]
+    if distinct:
+        s = t.view(np.int32)
+        order = np.lexsort(tuple(s[:, c] for c in range(t.shape[1] - 1, -1, -1)))   # all columns, signed, col 0 first
+        t = t[order]
+        key = t[:, req_cols]
+        keep = np.ones(t.shape[0], dtype=bool)
+        keep[1:] = np.any(key[1:] != key[:-1], axis=1)
+        t = t[keep]
+    if offset > 0:
+        t = t[offset:]
+    if limit >= 0:
+        t = t[:limit]
+    return t[:, req_cols]

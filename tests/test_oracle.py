@@ -145,26 +145,6 @@ def test_golden_fixture(ostore1, ostore2):
             assert _checksum(r.table) == ent["checksum"]
 
 
-def _py_final_process(full, req_cols, distinct, offset, limit):
-    """independent statement of final_process' modifiers (sparql.hpp:1424-1550) on a full binding table"""
-    t = np.asarray(full, dtype=np.uint32)
-    if t.shape[0] == 0:
-        return t[:, req_cols]
-    if distinct:
-        s = t.view(np.int32)
-        order = np.lexsort(tuple(s[:, c] for c in range(t.shape[1] - 1, -1, -1)))   # all columns, signed, col 0 first
-        t = t[order]
-        key = t[:, req_cols]
-        keep = np.ones(t.shape[0], dtype=bool)
-        keep[1:] = np.any(key[1:] != key[:-1], axis=1)
-        t = t[keep]
-    if offset > 0:
-        t = t[offset:]
-    if limit >= 0:
-        t = t[:limit]
-    return t[:, req_cols]
-
-
 @pytest.mark.parametrize("mods", [dict(distinct=True), dict(offset=7), dict(limit=5), dict(distinct=True, offset=3, limit=11),
                                   dict(offset=10 ** 6), dict(limit=0)])
 def test_query_modifiers(ostore1, mods):
@@ -187,7 +167,7 @@ def test_query_modifiers(ostore1, mods):
                 if v < 0 and v not in bound:
                     bound.append(v)
         unproj = full.table[:, [allv.index(v) for v in bound]]
-        want = _py_final_process(unproj, [bound.index(v) for v in rq], mods.get("distinct", False), mods.get("offset", 0),
+        want = M.py_final_process(unproj, [bound.index(v) for v in rq], mods.get("distinct", False), mods.get("offset", 0),
                                  mods.get("limit", -1))
         assert got.rows == want.shape[0], (q, rq, mods)
         if want.shape[0]:
