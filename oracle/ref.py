@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to oracle/_ref/libwukong_ref.so -- the reference's OWN store (StaticGStore) and
+query engine (SPARQLEngine) compiled from /root/reference behind C shims (oracle/ref_store_shim.cpp, ref_engine_shim.cpp,
+third-party stand-ins in oracle/ref_stubs/).  Exists only where `make -C oracle ref` has run (the build container; the
+.so travels to the GPU box with the snapshot).  Used to pin the oracle; never by the product."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libwukong_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def build():
+    """(re)build oracle/_ref when the reference tree is present; returns availability"""
+    if os.path.isdir("/root/reference/core"):
+        import subprocess
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return available()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB)
+        u64, vp, ci, i64 = C.c_uint64, C.c_void_p, C.c_int, C.c_int64
+        L.refs_build.restype = vp
+        L.refs_build.argtypes = [vp, u64, ci, ci, ci, ci, ci]
+        for n in ("refs_num_slots", "refs_num_buckets", "refs_num_entries", "refs_last_ext", "refs_last_entry"):
+            getattr(L, n).restype = u64
+            getattr(L, n).argtypes = [vp]
+        L.refs_vertices.restype = vp
+        L.refs_vertices.argtypes = [vp]
+        L.refs_edges.restype = vp
+        L.refs_edges.argtypes = [vp]
+        L.refs_num_segs.argtypes = [vp]
+        L.refs_segs.restype = vp
+        L.refs_segs.argtypes = [vp]
+        L.refs_get_edges.restype = u64
+        L.refs_get_edges.argtypes = [vp, C.c_uint32, C.c_uint32, ci, C.POINTER(vp)]
+        L.refe_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, i64, i64, vp, u64, C.POINTER(u64), C.POINTER(ci)]
+        _lib = L
+    return _lib
+
+
+class RefStore:
+    """One server's store built by the reference's StaticGStore::init (CPU build: 256-bucket ext extents; 1 GiB kvstore)."""
+
+    def __init__(self, triples, num_servers=1, sid=0, num_normal_preds=31, memstore_gb=1):
+        t = np.ascontiguousarray(triples, dtype=np.uint32).reshape(-1, 3)
+        self.h = lib().refs_build(t.ctypes.data_as(C.c_void_p), t.shape[0], num_servers, sid, 1, memstore_gb, num_normal_preds)
+        self._out = np.empty(1 << 22, dtype=np.uint32)
+
+    @property
+    def num_slots(self):
+        return lib().refs_num_slots(self.h)
+
+    def vertices(self):
+        n = self.num_slots
+        return np.frombuffer((C.c_uint64 * (2 * n)).from_address(lib().refs_vertices(self.h)), dtype=np.uint64).reshape(n, 2)
+
+    def edges(self):
+        n = lib().refs_last_entry(self.h)
+        return np.frombuffer((C.c_uint32 * max(n, 1)).from_address(lib().refs_edges(self.h)), dtype=np.uint32)[:n]
+
+    def segs(self):
+        """rows of (index, dir, pid, num_keys, num_buckets, bucket_start, num_edges, edge_start, n_ext, ext0_start, ext0_num)"""
+        n = lib().refs_num_segs(self.h)
+        return np.frombuffer((C.c_uint64 * (11 * n)).from_address(lib().refs_segs(self.h)), dtype=np.uint64).reshape(n, 11).copy()
+
+    def get_edges(self, vid, pid, d):
+        """GStore::get_edges (gstore.hpp:1043-1054)"""
+        out = C.c_void_p()
+        n = lib().refs_get_edges(self.h, vid, pid, d, C.byref(out))
+        if n == 0 or not out.value:
+            return np.zeros(0, dtype=np.uint32)
+        return np.frombuffer((C.c_uint32 * n).from_address(out.value), dtype=np.uint32).copy()
+
+    def query(self, patterns, nvars, required, blind=False, mt_factor=1, distinct=False, offset=0, limit=-1):
+        """SPARQLEngine::execute_one_pattern until done, then final_process.  -> (status, rows, cols, table or None)"""
+        p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+        rq = np.array(required, dtype=np.int32)
+        while True:
+            rows, cols = C.c_uint64(0), C.c_int(0)
+            rc = lib().refe_query(self.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars,
+                                  rq.ctypes.data_as(C.c_void_p) if len(rq) else None, len(rq), 1 if blind else 0, mt_factor,
+                                  1 if distinct else 0, offset, limit, self._out.ctypes.data_as(C.c_void_p), self._out.size,
+                                  C.byref(rows), C.byref(cols))
+            if rc == -1:   # table larger than the staging buffer
+                self._out = np.empty(self._out.size * 4, dtype=np.uint32)
+                continue
+            break
+        tbl = None
+        if rc == 0 and not blind and cols.value:
+            tbl = self._out[: rows.value * cols.value].reshape(rows.value, cols.value).copy()
+        return rc, rows.value, cols.value, tbl

@@ -1,0 +1,82 @@
+// TEST INFRASTRUCTURE ONLY.  The reference's OWN query engine -- core/engine/sparql.hpp (SPARQLEngine: the dispatch switch,
+// index_to_unknown / const_to_unknown / known_to_unknown / known_to_known / known_to_const / index_to_known /
+// const_to_known, final_process) with core/query.hpp, rmap.hpp, msgr.hpp, coder.hpp -- compiled over the store of
+// ref_store_shim.cpp.  Shadowed because they only reach code off this path (ref_stubs/): dgraph.hpp (two one-line forwards to
+// the real GStore), bind.hpp, comm/adaptor.hpp, string_server.hpp.  This pins SURVEY.md §8 rows a6-a14 of the oracle against
+// compiled reference code, on a single server; the fork-join transport and the proxy are not exercised.
+//
+// Compiled with -O0 -fno-unreachable-traps: the reference has a value-returning function without a return statement
+// (core/query.hpp:450, Result::set_attr_col_num, called by final_process), which GCC >= 8 turns into a trap or a
+// fall-through when it optimises.  Built by `make -C oracle ref` into oracle/_ref/ (git-ignored).
+#define WK_REF_WITH_ENGINE 1
+#include "ref_shim.h"
+
+std::vector<std::vector<int>> core_bindings;   // bind.hpp
+
+extern "C" {
+// ---- the reference's engine over that store ---------------------------------------------------------------------
+// Runs planned patterns through SPARQLEngine::execute_one_pattern (the reference's own dispatch switch and pattern
+// functions, sparql.hpp:80-1061) until the pattern phase is done, then SPARQLEngine::final_process (:1424-1551).
+// mt_factor > 1: the index start is run once per slice (mt_tid = 0 .. mt_factor - 1) and the replies are concatenated
+// the way RMap merges them (query.hpp:536-557 append_result); the fork-join transport itself is not exercised.
+// Returns the reference's status code (utils/errors.hpp).
+int refe_query(void *h, const int32_t *pats, int npat, int nvars, const int32_t *required, int nreq, int blind, int mt_factor,
+               int distinct, int64_t offset, int64_t limit, uint32_t *out, uint64_t cap_words, uint64_t *rows, int *cols) {
+    RefStore *r = (RefStore *)h;
+    Global::num_servers = 1;
+    StringServer strs;
+    DGraph graph(0, r->g);
+    Coder coder(0, 0);
+    Adaptor adaptor(0);
+    Messenger msgr(0, 0, &adaptor);
+    SPARQLEngine eng(0, 0, &strs, &graph, &coder, &msgr);
+    SPARQLQuery::PatternGroup pg;
+    for (int i = 0; i < npat; i++)
+        pg.patterns.push_back(SPARQLQuery::Pattern((ssid_t)pats[4 * i], (ssid_t)pats[4 * i + 1], (ssid_t)pats[4 * i + 2], (ssid_t)pats[4 * i + 3]));
+    std::vector<ssid_t> req(required, required + nreq);
+    SPARQLQuery fin(pg, nvars, req);
+    fin.result.blind = blind != 0;
+    fin.distinct = distinct != 0;
+    fin.offset = (unsigned)(offset < 0 ? 0 : offset);
+    fin.limit = (int)limit;
+    *rows = 0;
+    *cols = 0;
+    try {
+        if (npat == 0) throw WukongException(SYNTAX_ERROR);
+        const int slices = (fin.start_from_index() && mt_factor > 1) ? mt_factor : 1;
+        bool first = true;
+        for (int t = 0; t < slices; t++) {
+            SPARQLQuery q(pg, nvars, req);
+            q.result.blind = blind != 0;
+            q.mt_factor = slices;
+            q.mt_tid = t;
+            while (!q.done(SPARQLQuery::SQState::SQ_PATTERN)) eng.execute_one_pattern(q);
+            q.result.update_nrows();
+            if (first) {
+                fin.result.v2c_map = q.result.v2c_map;
+                fin.result.col_num = q.result.col_num;
+                fin.result.result_table.swap(q.result.result_table);
+                fin.result.row_num = q.result.row_num;
+                first = false;
+            } else {
+                fin.result.row_num += q.result.row_num;
+                fin.result.result_table.insert(fin.result.result_table.end(), q.result.result_table.begin(), q.result.result_table.end());
+            }
+        }
+        fin.pattern_step = npat;
+        if (!fin.result.blind) {
+            fin.result.update_nrows();
+            eng.final_process(fin);
+        }
+    } catch (WukongException &ex) {
+        return ex.code();
+    }
+    *rows = fin.result.blind ? (uint64_t)fin.result.row_num : (uint64_t)fin.result.get_row_num();
+    *cols = fin.result.get_col_num();
+    const uint64_t words = fin.result.result_table.size();
+    if (!fin.result.blind && out && words <= cap_words) memcpy(out, fin.result.result_table.data(), words * sizeof(uint32_t));
+    if (!fin.result.blind && words > cap_words) return -1;
+    return SUCCESS;
+}
+
+}  // extern "C"

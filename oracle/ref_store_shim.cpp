@@ -1,0 +1,95 @@
+// TEST INFRASTRUCTURE ONLY.  The reference's OWN graph store -- core/store/static_gstore.hpp + gstore.hpp + meta.hpp
+// + vertex.hpp + mem.hpp, read in place from /root/reference, never copied -- compiled against the std-based
+// stand-ins for Boost / TBB / ZeroMQ in oracle/ref_stubs/ (those libraries are not in this image; see
+// ref_stubs/README.md), behind a small C interface: build a store from id triples exactly as the loader hands
+// them to StaticGStore::init (base_loader.hpp:308-378: partition by owner and engine, PSO / POS sort with the
+// reference's comparators, dedup), read the raw arrays and segment table back, and probe with GStore::get_edges.
+// What this pins: segment sizing, insert_key / ext-bucket chaining, edge layout, index lists and the probe --
+// i.e. SURVEY.md §8 rows a3-a5 -- of the oracle (and through it the product builders) against compiled
+// reference code.  What it does not exercise: the loader's file reading, RDMA / TCP paths, attributes.
+// Built by `make -C oracle ref` into oracle/_ref/ (git-ignored).
+#include "ref_shim.h"
+
+TCP_Adaptor *con_adaptor = nullptr;   // gstore.hpp:1057 (metadata sync between servers; never reached with one server)
+
+namespace {
+void dedup(std::vector<triple_t> &t) {   // base_loader.hpp:81-95
+    if (t.size() <= 1) return;
+    uint64_t n = 1;
+    for (uint64_t i = 1; i < t.size(); i++) {
+        if (t[i].s == t[i - 1].s && t[i].p == t[i - 1].p && t[i].o == t[i - 1].o) continue;
+        t[n++] = t[i];
+    }
+    t.resize(n);
+}
+}  // namespace
+
+extern "C" {
+
+// one server `sid` of `num_servers`; memstore_gb whole GiB (Global::memstore_size_gb is an int)
+void *refs_build(const uint32_t *tr, uint64_t n, int num_servers, int sid, int num_engines, int memstore_gb, int num_normal_preds) {
+    // One engine: the build then runs single-threaded, which keeps the std-based container stand-ins out of the reference's
+    // OpenMP loops (TBB's element locks are only approximated there).  What a probe can observe does not depend on the engine
+    // count; only the per-engine partition of the sorted triple lists does.
+    num_engines = 1;
+    Global::num_servers = num_servers;
+    Global::num_engines = num_engines;
+    Global::num_threads = num_engines + 1;
+    Global::memstore_size_gb = memstore_gb;
+    Global::use_rdma = false;
+    Global::enable_vattr = false;
+    RefStore *r = new RefStore();
+    r->mem = new Mem(num_servers, Global::num_threads);
+    r->g = new StaticGStore(sid, r->mem);
+    r->g->num_normal_preds = num_normal_preds;   // base_loader.hpp:424
+    r->g->num_attr_preds = 0;
+    std::vector<std::vector<triple_t>> pso(num_engines), pos(num_engines);
+    std::vector<std::vector<triple_attr_t>> sav(num_engines);
+    for (uint64_t i = 0; i < n; i++) {           // aggregate_data, base_loader.hpp:343-361
+        const sid_t s = tr[3 * i], p = tr[3 * i + 1], o = tr[3 * i + 2];
+        if (wukong::math::hash_mod(s, num_servers) == sid) pso[s % num_engines].push_back(triple_t(s, p, o));
+        if (wukong::math::hash_mod(o, num_servers) == sid) pos[o % num_engines].push_back(triple_t(s, p, o));
+    }
+    for (int t = 0; t < num_engines; t++) {      // base_loader.hpp:363-373
+        std::sort(pso[t].begin(), pso[t].end(), triple_sort_by_pso());
+        std::sort(pos[t].begin(), pos[t].end(), triple_sort_by_pos());
+        dedup(pos[t]);
+        dedup(pso[t]);
+    }
+    Global::num_servers = 1;   // init() ends with a metadata exchange over TCP with the other servers: none here
+    r->g->refresh();           // base_loader.hpp:468 (also the only place last_ext / last_entry get their initial value)
+    r->g->init(pso, pos, sav);
+    for (auto &kv : r->g->rdf_seg_meta_map) {
+        const segid_t &id = kv.first;
+        const rdf_seg_meta_t &m = kv.second;
+        uint64_t e0s = 0, e0n = 0;
+        if (!m.ext_bucket_list.empty()) { e0s = m.ext_bucket_list[0].start; e0n = m.ext_bucket_list[0].num_ext_buckets; }
+        const uint64_t row[11] = {(uint64_t)id.index, (uint64_t)id.dir, (uint64_t)id.pid, m.num_keys, m.num_buckets, m.bucket_start,
+                                  m.num_edges, m.edge_start, (uint64_t)m.ext_bucket_list.size(), e0s, e0n};
+        r->segs.insert(r->segs.end(), row, row + 11);
+    }
+    return r;
+}
+// releases the 1 GiB store memory; the small GStore object itself is leaked on purpose (its destructor chain is not
+// exercised by the reference either: a server never tears its store down)
+void refs_free(void *h) { RefStore *r = (RefStore *)h; delete r->mem; delete r; }
+uint64_t refs_num_slots(void *h) { return ((RefStore *)h)->g->num_slots; }
+uint64_t refs_num_buckets(void *h) { return ((RefStore *)h)->g->num_buckets; }
+uint64_t refs_num_entries(void *h) { return ((RefStore *)h)->g->num_entries; }
+uint64_t refs_last_ext(void *h) { return ((RefStore *)h)->g->last_ext; }
+uint64_t refs_last_entry(void *h) { return ((RefStore *)h)->g->last_entry; }
+const void *refs_vertices(void *h) { return ((RefStore *)h)->g->vertices; }
+const void *refs_edges(void *h) { return ((RefStore *)h)->g->edges; }
+int refs_num_segs(void *h) { return (int)(((RefStore *)h)->segs.size() / 11); }
+const uint64_t *refs_segs(void *h) { return ((RefStore *)h)->segs.data(); }
+// the reference's probe: GStore::get_edges (gstore.hpp:1043-1054)
+uint64_t refs_get_edges(void *h, uint32_t vid, uint32_t pid, int dir, const uint32_t **out) {
+    uint64_t sz = 0;
+    int type = 0;   // the default argument is a reference bound to *(int *)NULL (gstore.hpp:394): give it a real object
+    edge_t *e = ((RefStore *)h)->g->get_edges(0, vid, pid, (dir_t)dir, sz, type);
+    *out = (const uint32_t *)e;
+    return e ? sz : 0;
+}
+
+
+}  // extern "C"

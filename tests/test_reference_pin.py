@@ -1,0 +1,124 @@
+"""CPU: the oracle against the reference's OWN compiled code (oracle/_ref/libwukong_ref.so: StaticGStore + SPARQLEngine from
+/root/reference behind C shims, see oracle/Makefile).  Where that library is absent (no reference tree was ever built into
+this checkout) the live checks skip; the committed fixture tests/golden/ref_engine_lubm1.json -- produced from the same
+library by tests/golden/make_ref_engine.py -- always holds the oracle to the reference engine's answers."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import random_bgp as R
+import sparql_mini as M
+from conftest import PLANS, load_query, rows_equal
+from oracle import oracle as O
+from oracle import ref as REF
+from wukong_b200 import host
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+needs_ref = pytest.mark.skipif(not REF.available(), reason="oracle/_ref not built (needs the reference tree: make -C oracle ref)")
+
+
+def table_digest(t):
+    t = M.sort_rows(np.asarray(t, dtype=np.uint32))
+    return hashlib.sha256(t.tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ref1(lubm1):
+    return REF.RefStore(lubm1)
+
+
+@needs_ref
+def test_store_matches_reference_store(lubm1, ref1):
+    """segment table, key set and every key's edge list: the reference's StaticGStore::init + GStore::get_edges"""
+    o = O.Store.build(lubm1, kvstore_bytes=1 << 30, num_engines=1, gpu_ext_mode=False)
+    assert o.vertices().shape[0] == ref1.num_slots
+    mine = sorted((x.index, x.dir, x.pid, x.num_keys, x.num_buckets, x.bucket_start, x.num_edges, x.edge_start) for x in o.segs())
+    theirs = sorted(tuple(int(v) for v in r[:8]) for r in ref1.segs())
+    assert mine == theirs
+    ov, oe = o.vertices(), o.edges()
+    idx = np.arange(ov.shape[0])
+    occ = (idx % 8 != 7) & (ov[:, 0] != 0)
+    rv = ref1.vertices()
+    assert np.array_equal(np.sort(ov[occ, 0]), np.sort(rv[(idx % 8 != 7) & (rv[:, 0] != 0), 0]))     # same key set
+    assert oe.shape[0] == ref1.edges().shape[0]
+    n_index = 0
+    for k, p in zip(ov[occ, 0].tolist(), ov[occ, 1].tolist()):
+        d, pid, vid = k & 1, (k >> 1) & 0x1FFFF, k >> 18
+        size, off = p & ((1 << 28) - 1), (p >> 28) & ((1 << 34) - 1)
+        mine_e = oe[off:off + size]
+        ref_e = ref1.get_edges(vid, pid, d)
+        if vid == 0:          # index lists: their order follows hash-map iteration in the reference, a set is the contract
+            n_index += 1
+            assert np.array_equal(np.sort(ref_e), np.sort(mine_e)), (vid, pid, d)
+        else:                 # normal keys: the sorted run itself
+            assert np.array_equal(ref_e, mine_e), (vid, pid, d)
+    assert n_index > 30
+    # the product host builder is bit-identical to the oracle (test_host_builder.py), hence pinned through it
+    hs = host.HostStore(lubm1, kvstore_bytes=1 << 30, gpu_ext_extents=False)
+    assert np.array_equal(hs.vertices(), ov) and np.array_equal(hs.edges(), oe)
+
+
+@needs_ref
+def test_engine_matches_reference_engine(lubm1, ref1, ostore1):
+    """Q1-Q7 x 3 plan sets x mt 1/3, blind, DISTINCT / OFFSET / LIMIT, error codes: SPARQLEngine vs the oracle"""
+    for q in range(1, 8):
+        for plan in PLANS:
+            pats, nvars, req, _ = load_query(q, plan)
+            for mt in (1, 3):
+                want = O.run_query([ostore1], pats, nvars, req, mt_factor=mt)
+                rc, rows, cols, t = ref1.query(pats, nvars, req, mt_factor=mt)
+                assert rc == 0 and rows == want.rows, (q, plan, mt)
+                if rows:
+                    assert cols == want.cols and rows_equal(t, want.table), (q, plan, mt)
+            rc, rows, _, _ = ref1.query(pats, nvars, req, blind=True)
+            assert rc == 0 and rows == want.rows
+            wd = O.run_query([ostore1], pats, nvars, req, distinct=True, offset=1, limit=40)
+            rc, rows, cols, t = ref1.query(pats, nvars, req, distinct=True, offset=1, limit=40)
+            assert rc == 0 and rows == wd.rows and (rows == 0 or np.array_equal(t, wd.table)), (q, plan)
+    univ0 = M.lubm_str2id("<http://www.University0.edu>")
+    for pats, nv, req in [([(-1, 5, 1, -2)], 2, [-1]), ([(18, 1, 0, -1), (univ0, 7, 0, -2)], 2, [-1]),
+                          ([(18, 5, 0, -1)], 1, [-1]), ([(18, 1, 0, -1)], 1, [])]:
+        assert ref1.query(pats, nv, req)[0] == O.run_query([ostore1], pats, nv, req).status
+
+
+@needs_ref
+def test_random_graph_matches_reference_engine():
+    """a random graph (hubs, self loops, duplicates, multi-typed vertices) and 60 random plans, including const_to_known-free
+    chains of every primitive, through the reference engine"""
+    tr, meta = R.graph(3, nv=300, ntriples=2500)
+    npreds = meta["num_normal_preds"]
+    rs = REF.RefStore(tr, num_normal_preds=npreds)
+    ost = O.Store.build(tr, kvstore_bytes=8 << 20, num_engines=2, num_normal_preds=npreds)
+    checked = 0
+    for qseed in range(60):
+        planned, _, nvars, req = R.query(7000 + qseed, tr, meta)
+        if O.run_query([ost], planned, nvars, req, blind=True).rows > 200_000:
+            continue
+        want = O.run_query([ost], planned, nvars, req)
+        rc, rows, cols, t = rs.query(planned, nvars, req)
+        assert rc == want.status == 0 and rows == want.rows, (qseed, planned)
+        if rows:
+            assert rows_equal(t, want.table), (qseed, planned)
+        wd = O.run_query([ost], planned, nvars, req, distinct=True)
+        rc, rows, _, t = rs.query(planned, nvars, req, distinct=True)
+        assert rc == 0 and rows == wd.rows and (rows == 0 or np.array_equal(t, wd.table)), (qseed, planned)
+        checked += 1
+    assert checked >= 45
+
+
+def test_oracle_matches_reference_engine_fixture(ostore1):
+    """always runs: the reference engine's answers on LUBM-1 (seed 1), committed as row counts + digests of the sorted tables"""
+    G = json.load(open(os.path.join(HERE, "golden", "ref_engine_lubm1.json")))
+    assert G["queries"]
+    for name, e in G["queries"].items():
+        q, plan = int(name.split("_")[0][1:]), name.split("_", 1)[1]
+        pats, nvars, req, _ = load_query(q, plan)
+        got = O.run_query([ostore1], pats, nvars, req)
+        assert got.status == 0 and got.rows == e["rows"], name
+        if got.rows:
+            assert table_digest(got.table) == e["sha256"], name
+        d = O.run_query([ostore1], pats, nvars, req, distinct=True, offset=1, limit=40)
+        assert d.rows == e["distinct_rows"] and (d.rows == 0 or hashlib.sha256(d.table.tobytes()).hexdigest() == e["distinct_sha256"]), name
