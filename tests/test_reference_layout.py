@@ -66,6 +66,8 @@ def test_triple_sort_orders():
 
 
 def test_fixture_matches_live_reference_headers():
+    from oracle import ref as REF
+    REF.build()                      # builds oracle/_ref where the reference tree is present
     lib = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libwukong_ref_layout.so")
     if not os.path.exists(lib):
         pytest.skip("oracle/_ref not built (the reference tree only exists in the build container)")

@@ -17,7 +17,14 @@ from oracle import ref as REF
 from wukong_b200 import host
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-needs_ref = pytest.mark.skipif(not REF.available(), reason="oracle/_ref not built (needs the reference tree: make -C oracle ref)")
+
+
+@pytest.fixture(scope="module")
+def ref_lib():
+    """builds oracle/_ref when the reference tree is present; skips where it is neither present nor prebuilt"""
+    if not REF.build():
+        pytest.skip("oracle/_ref not built (needs the reference tree: make -C oracle ref)")
+    return REF
 
 
 def table_digest(t):
@@ -26,11 +33,10 @@ def table_digest(t):
 
 
 @pytest.fixture(scope="module")
-def ref1(lubm1):
-    return REF.RefStore(lubm1)
+def ref1(lubm1, ref_lib):
+    return ref_lib.RefStore(lubm1)
 
 
-@needs_ref
 def test_store_matches_reference_store(lubm1, ref1):
     """segment table, key set and every key's edge list: the reference's StaticGStore::init + GStore::get_edges"""
     o = O.Store.build(lubm1, kvstore_bytes=1 << 30, num_engines=1, gpu_ext_mode=False)
@@ -61,7 +67,6 @@ def test_store_matches_reference_store(lubm1, ref1):
     assert np.array_equal(hs.vertices(), ov) and np.array_equal(hs.edges(), oe)
 
 
-@needs_ref
 def test_engine_matches_reference_engine(lubm1, ref1, ostore1):
     """Q1-Q7 x 3 plan sets x mt 1/3, blind, DISTINCT / OFFSET / LIMIT, error codes: SPARQLEngine vs the oracle"""
     for q in range(1, 8):
@@ -84,8 +89,7 @@ def test_engine_matches_reference_engine(lubm1, ref1, ostore1):
         assert ref1.query(pats, nv, req)[0] == O.run_query([ostore1], pats, nv, req).status
 
 
-@needs_ref
-def test_random_graph_matches_reference_engine():
+def test_random_graph_matches_reference_engine(ref_lib):
     """a random graph (hubs, self loops, duplicates, multi-typed vertices) and 60 random plans, including const_to_known-free
     chains of every primitive, through the reference engine"""
     tr, meta = R.graph(3, nv=300, ntriples=2500)
