@@ -44,8 +44,19 @@ def lib():
         L.refs_get_edges.restype = u64
         L.refs_get_edges.argtypes = [vp, C.c_uint32, C.c_uint32, ci, C.POINTER(vp)]
         L.refe_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, i64, i64, vp, u64, C.POINTER(u64), C.POINTER(ci)]
+        L.refp_set_plan.argtypes = [vp, ci, C.c_char_p, vp, ci]
         _lib = L
     return _lib
+
+
+def set_plan(patterns, fmt_text):
+    """Planner::set_plan + set_direction (core/planner.hpp:1647-1754) -> planned patterns, or None when refused"""
+    a = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+    out = np.zeros((64, 4), dtype=np.int32)
+    n = lib().refp_set_plan(a.ctypes.data_as(C.c_void_p), a.shape[0], fmt_text.encode(), out.ctypes.data_as(C.c_void_p), 64)
+    if n < 0:
+        return None
+    return [tuple(int(x) for x in row) for row in out[:n]]
 
 
 class RefStore:

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY.  The reference's OWN query engine -- core/engine/sparql.hpp (SPARQLEngine: the dispatch switch,
 // index_to_unknown / const_to_unknown / known_to_unknown / known_to_known / known_to_const / index_to_known /
-// const_to_known, final_process) with core/query.hpp, rmap.hpp, msgr.hpp, coder.hpp -- compiled over the store of
+// const_to_known, final_process) with core/query.hpp, rmap.hpp, msgr.hpp, coder.hpp, and core/planner.hpp (set_plan /
+// set_direction only) -- compiled over the store of
 // ref_store_shim.cpp.  Shadowed because they only reach code off this path (ref_stubs/): dgraph.hpp (two one-line forwards to
 // the real GStore), bind.hpp, comm/adaptor.hpp, string_server.hpp.  This pins SURVEY.md §8 rows a6-a14 of the oracle against
 // compiled reference code, on a single server; the fork-join transport and the proxy are not exercised.
@@ -77,6 +78,29 @@ int refe_query(void *h, const int32_t *pats, int npat, int nvars, const int32_t 
     if (!fin.result.blind && out && words <= cap_words) memcpy(out, fin.result.result_table.data(), words * sizeof(uint32_t));
     if (!fin.result.blind && words > cap_words) return -1;
     return SUCCESS;
+}
+
+
+// ---- the reference's plan application: Planner::set_plan + set_direction (core/planner.hpp:1647-1754) -------------------
+// pats: npat x (subject, predicate, direction, object) as parsed (direction ignored); fmt: the text of a .fmt plan file.
+// Writes the planned patterns to out (4 ints each) and returns their number, or -1 when set_plan refuses the plan.
+int refp_set_plan(const int32_t *pats, int npat, const char *fmt, int32_t *out, int cap) {
+    Global::enable_planner = false;
+    SPARQLQuery::PatternGroup pg;
+    for (int i = 0; i < npat; i++)
+        pg.patterns.push_back(SPARQLQuery::Pattern((ssid_t)pats[4 * i], (ssid_t)pats[4 * i + 1], (ssid_t)pats[4 * i + 2], (ssid_t)pats[4 * i + 3]));
+    Planner planner(0, nullptr, nullptr);
+    std::istringstream is(std::string(fmt ? fmt : ""));
+    if (!planner.set_plan(pg, is)) return -1;
+    const int n = (int)pg.patterns.size();
+    if (n > cap) return -1;
+    for (int i = 0; i < n; i++) {
+        out[4 * i] = (int32_t)pg.patterns[i].subject;
+        out[4 * i + 1] = (int32_t)pg.patterns[i].predicate;
+        out[4 * i + 2] = (int32_t)pg.patterns[i].direction;
+        out[4 * i + 3] = (int32_t)pg.patterns[i].object;
+    }
+    return n;
 }
 
 }  // extern "C"

@@ -21,7 +21,11 @@
 #include <vector>
 // third-party stand-ins first, so that the access hack below only touches the reference's own classes
 #include <boost/archive/binary_iarchive.hpp>
+#include <boost/algorithm/string.hpp>
 #include <boost/archive/binary_oarchive.hpp>
+#include <boost/archive/text_oarchive.hpp>
+#include <boost/functional/hash.hpp>
+#include <boost/mpi.hpp>
 #include <boost/serialization/common.hpp>
 #include <boost/unordered_map.hpp>
 #include <boost/unordered_set.hpp>
@@ -40,6 +44,7 @@
 #include "store/static_gstore.hpp"
 #ifdef WK_REF_WITH_ENGINE
 #include "engine/sparql.hpp"   // the reference's SPARQLEngine; dgraph / bind / adaptor / string_server are shadowed (ref_stubs/)
+#include "planner.hpp"         // the reference's Planner (only set_plan / set_direction are exercised)
 #endif
 #undef private
 #undef protected

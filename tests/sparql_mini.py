@@ -87,8 +87,10 @@ def apply_plan(patterns, fmt_text):
     out = []
     for line in fmt_text.splitlines():
         line = line.strip()
-        if not line or line.startswith("#") or line in "{}":
+        if not line or line.startswith("#") or line == "{":
             continue
+        if line == "}":          # end of the group: whatever follows belongs to nobody (planner.hpp:1728-1729)
+            break
         parts = line.split()
         order, d = int(parts[0]), (parts[1] if len(parts) > 1 else ">")
         s, p, _, o = patterns[order - 1]

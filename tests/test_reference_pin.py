@@ -126,3 +126,23 @@ def test_oracle_matches_reference_engine_fixture(ostore1):
             assert table_digest(got.table) == e["sha256"], name
         d = O.run_query([ostore1], pats, nvars, req, distinct=True, offset=1, limit=40)
         assert d.rows == e["distinct_rows"] and (d.rows == 0 or hashlib.sha256(d.table.tobytes()).hexdigest() == e["distinct_sha256"]), name
+
+
+def test_set_plan_matches_reference_planner(ref_lib):
+    """Planner::set_plan + set_direction (core/planner.hpp:1647-1754) vs the oracle's restatement and the independent Python
+    reader (the C++ host mirror is held to the same reader in test_host_surface.py)"""
+    from conftest import WORKLOADS
+    for q in range(1, 8):
+        for plan in PLANS:
+            planned, _, _, raw = load_query(q, plan)
+            fmt = open(os.path.join(WORKLOADS, plan, "lubm_q%d.fmt" % q)).read()
+            got = ref_lib.set_plan(raw, fmt)
+            assert got == planned == O.set_plan(raw, fmt), (q, plan)
+    raw = load_query(7, "osdi16_plan")[3]
+    # comments, blank lines, braces, reordering, every direction token, more plan lines than patterns
+    fmt = "# plan\n{\n 3 <\n\n1 >>\n  2 <<\n4 >\n5 <\n6 >\n1 >\n}\n9 >\n"
+    assert ref_lib.set_plan(raw, fmt) == O.set_plan(raw, fmt) == M.apply_plan(raw, fmt)
+    for bad in ("1 <\n", "", "# nothing\n"):
+        assert ref_lib.set_plan(raw, bad) is None          # fewer plan lines than patterns: refused
+        with pytest.raises(ValueError):
+            O.set_plan(raw, bad)
