@@ -45,6 +45,8 @@ def lib():
         L.refs_get_edges.argtypes = [vp, C.c_uint32, C.c_uint32, ci, C.POINTER(vp)]
         L.refe_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, i64, i64, vp, u64, C.POINTER(u64), C.POINTER(ci)]
         L.refp_set_plan.argtypes = [vp, ci, C.c_char_p, vp, ci]
+        L.refe_fork_plan.argtypes = [vp, vp, ci, ci, ci, vp]
+        L.refe_split.argtypes = [vp, vp, u64, ci, ci, ci, vp, vp]
         _lib = L
     return _lib
 
@@ -91,6 +93,24 @@ class RefStore:
         if n == 0 or not out.value:
             return np.zeros(0, dtype=np.uint32)
         return np.frombuffer((C.c_uint32 * n).from_address(out.value), dtype=np.uint32).copy()
+
+    def fork_plan(self, patterns, nvars, n):
+        """per step: -1 no exchange, -2 replicate, c >= 0 re-shard by column c -- need_fork_join / dispatch decisions of the
+        reference engine for a store sharded over n servers (RDMA rule, threshold 0).  -> (status, list)"""
+        p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+        out = np.zeros(p.shape[0], dtype=np.int32)
+        rc = lib().refe_fork_plan(self.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars, n, out.ctypes.data_as(C.c_void_p))
+        return rc, out.tolist()
+
+    def split(self, table, col, n):
+        """SPARQLEngine::generate_sub_query: -> list of n sub-tables"""
+        t = np.ascontiguousarray(table, dtype=np.uint32)
+        out = np.empty_like(t)
+        counts = np.zeros(n, dtype=np.uint64)
+        lib().refe_split(self.h, t.ctypes.data_as(C.c_void_p), t.shape[0], t.shape[1], col, n, out.ctypes.data_as(C.c_void_p),
+                         counts.ctypes.data_as(C.c_void_p))
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        return [out[offs[i]:offs[i + 1]] for i in range(n)]
 
     def query(self, patterns, nvars, required, blind=False, mt_factor=1, distinct=False, offset=0, limit=-1):
         """SPARQLEngine::execute_one_pattern until done, then final_process.  -> (status, rows, cols, table or None)"""

@@ -81,6 +81,88 @@ int refe_query(void *h, const int32_t *pats, int npat, int nvars, const int32_t 
 }
 
 
+// ---- fork-join decisions and row split --------------------------------------------------------------
+// Which steps of a plan exchange when the store is sharded over n servers, decided by the reference's own
+// SPARQLEngine::need_fork_join (sparql.hpp:802-814, RDMA rule: fork when the next hop is not local; threshold 0) and the
+// replicate rule of dispatch(r, false) (sparql.hpp:1091-1110, restated here in one line because dispatch itself sends).
+// The plan is walked on a real single-server store so that v2c_map / local_var evolve through the reference's pattern
+// functions (index_to_unknown sets local_var, :230; sub-queries inherit local_var = start, :760).
+// out[s]: -1 no exchange before step s, -2 replicate, c >= 0 re-shard by column c.  Returns 0 or the reference's status code.
+int refe_fork_plan(void *h, const int32_t *pats, int npat, int nvars, int n, int32_t *out) {
+    RefStore *r = (RefStore *)h;
+    StringServer strs;
+    DGraph graph(0, r->g);
+    Coder coder(0, 0);
+    Adaptor adaptor(0);
+    Messenger msgr(0, 0, &adaptor);
+    SPARQLEngine eng(0, 0, &strs, &graph, &coder, &msgr);
+    SPARQLQuery::PatternGroup pg;
+    for (int i = 0; i < npat; i++)
+        pg.patterns.push_back(SPARQLQuery::Pattern((ssid_t)pats[4 * i], (ssid_t)pats[4 * i + 1], (ssid_t)pats[4 * i + 2], (ssid_t)pats[4 * i + 3]));
+    std::vector<ssid_t> req;
+    SPARQLQuery q(pg, nvars, req);
+    const bool rdma0 = Global::use_rdma;
+    const int thr0 = Global::rdma_threshold;
+    int rc = SUCCESS;
+    try {
+        for (int s = 0; s < npat; s++) {
+            out[s] = -1;
+            if (s > 0) {
+                Global::num_servers = n;
+                Global::use_rdma = true;
+                Global::rdma_threshold = 0;
+                SPARQLQuery::Pattern &pt = q.get_pattern();
+                if (pt.predicate == TYPE_ID && pt.direction == IN) {          // dispatch(r, false): replicate to every server
+                    out[s] = -2;
+                    q.local_var = pt.subject;                                 // generate_sub_query(r, false), :760
+                } else if (eng.need_fork_join(q)) {
+                    out[s] = q.result.var2col(pt.subject);
+                    q.local_var = pt.subject;                                 // generate_sub_query(r), :760
+                }
+                Global::num_servers = 1;
+            }
+            eng.execute_one_pattern(q);
+        }
+    } catch (WukongException &ex) {
+        rc = ex.code();
+    }
+    Global::num_servers = 1;
+    Global::use_rdma = rdma0;
+    Global::rdma_threshold = thr0;
+    return rc;
+}
+
+// SPARQLEngine::generate_sub_query (sparql.hpp:746-799): rows of an nrows x ncols table go to server row[col] % n.
+// out receives the n sub-tables back to back, counts[i] their row numbers.
+int refe_split(void *h, const uint32_t *table, uint64_t nrows, int ncols, int col, int n, uint32_t *out, uint64_t *counts) {
+    RefStore *r = (RefStore *)h;
+    StringServer strs;
+    DGraph graph(0, r->g);
+    Coder coder(0, 0);
+    Adaptor adaptor(0);
+    Messenger msgr(0, 0, &adaptor);
+    SPARQLEngine eng(0, 0, &strs, &graph, &coder, &msgr);
+    SPARQLQuery::PatternGroup pg;
+    pg.patterns.push_back(SPARQLQuery::Pattern((ssid_t)(-(col + 1)), (ssid_t)2, (ssid_t)OUT, (ssid_t)(-(ncols + 1))));
+    std::vector<ssid_t> req;
+    SPARQLQuery q(pg, ncols + 1, req);
+    q.result.col_num = ncols;
+    for (int c = 0; c < ncols; c++) q.result.v2c_map[c] = c;
+    q.result.result_table.assign(table, table + nrows * ncols);
+    q.result.update_nrows();
+    Global::num_servers = n;
+    std::vector<SPARQLQuery> subs = eng.generate_sub_query(q);
+    Global::num_servers = 1;
+    uint64_t off = 0;
+    for (int i = 0; i < n; i++) {
+        const std::vector<sid_t> &t = subs[i].result.result_table;
+        counts[i] = t.size() / ncols;
+        if (!t.empty()) memcpy(out + off, t.data(), t.size() * sizeof(uint32_t));
+        off += t.size();
+    }
+    return SUCCESS;
+}
+
 // ---- the reference's plan application: Planner::set_plan + set_direction (core/planner.hpp:1647-1754) -------------------
 // pats: npat x (subject, predicate, direction, object) as parsed (direction ignored); fmt: the text of a .fmt plan file.
 // Writes the planned patterns to out (4 ints each) and returns their number, or -1 when set_plan refuses the plan.

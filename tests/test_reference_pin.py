@@ -146,3 +146,24 @@ def test_set_plan_matches_reference_planner(ref_lib):
         assert ref_lib.set_plan(raw, bad) is None          # fewer plan lines than patterns: refused
         with pytest.raises(ValueError):
             O.set_plan(raw, bad)
+
+
+def test_fork_join_decisions_and_split_match_reference(ref1):
+    """row a15: which steps exchange (SPARQLEngine::need_fork_join + the replicate rule of dispatch) and how rows are split
+    (generate_sub_query), against the product's host-side exchange planner and the `row[col] % n` rule of its kernels"""
+    from wukong_b200 import capi
+    for q in range(1, 8):
+        for plan in PLANS:
+            pats, nvars, _, _ = load_query(q, plan)
+            rc, want = ref1.fork_plan(pats, nvars, 4)
+            assert rc == 0 and want == capi.plan_exchanges(pats, nvars), (q, plan, want)
+    # a type-index lookup of a bound variable is replicated
+    pats = [(18, 1, 0, -1), (-1, 5, 0, -2), (-2, 1, 1, -3), (-3, 1, 0, -4)]
+    rc, want = ref1.fork_plan(pats, 4, 3)
+    assert rc == 0 and want == capi.plan_exchanges(pats, 4) and -2 in want
+    rng = np.random.default_rng(5)
+    tbl = rng.integers(1 << 17, 1 << 31, (5000, 3), dtype=np.uint32)
+    for n, col in ((2, 0), (3, 2), (8, 1)):
+        parts = ref1.split(tbl, col, n)
+        for i in range(n):
+            assert np.array_equal(parts[i], tbl[tbl[:, col] % n == i])       # same rows, original order
