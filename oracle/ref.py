@@ -87,7 +87,7 @@ class RefStore:
         return np.frombuffer((C.c_uint64 * (11 * n)).from_address(lib().refs_segs(self.h)), dtype=np.uint64).reshape(n, 11).copy()
 
     def get_edges(self, vid, pid, d):
-        """GStore::get_edges (gstore.hpp:1043-1054)"""
+        """GStore::get_edges_local (gstore.hpp:393-410)"""
         out = C.c_void_p()
         n = lib().refs_get_edges(self.h, vid, pid, d, C.byref(out))
         if n == 0 or not out.value:

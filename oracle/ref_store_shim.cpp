@@ -40,7 +40,10 @@ void *refs_build(const uint32_t *tr, uint64_t n, int num_servers, int sid, int n
     Global::enable_vattr = false;
     RefStore *r = new RefStore();
     r->mem = new Mem(num_servers, Global::num_threads);
-    r->g = new StaticGStore(sid, r->mem);
+    // The object is created as "server 0 of 1": StaticGStore::init ends by exchanging segment metadata with every OTHER
+    // server over TCP (gstore.hpp:905-941), and there is no transport here.  Which triples this shard holds is decided
+    // below, by the loader's owner rule with the real (num_servers, sid); the store's content does not depend on its id.
+    r->g = new StaticGStore(0, r->mem);
     r->g->num_normal_preds = num_normal_preds;   // base_loader.hpp:424
     r->g->num_attr_preds = 0;
     std::vector<std::vector<triple_t>> pso(num_engines), pos(num_engines);
@@ -82,11 +85,13 @@ const void *refs_vertices(void *h) { return ((RefStore *)h)->g->vertices; }
 const void *refs_edges(void *h) { return ((RefStore *)h)->g->edges; }
 int refs_num_segs(void *h) { return (int)(((RefStore *)h)->segs.size() / 11); }
 const uint64_t *refs_segs(void *h) { return ((RefStore *)h)->segs.data(); }
-// the reference's probe: GStore::get_edges (gstore.hpp:1043-1054)
+// the reference's probe: GStore::get_edges_local (gstore.hpp:393-410; bucket_local :242-248, get_vertex_local :341-361).
+// GStore::get_edges (:1043-1054) only adds the owner test hash_mod(vid, num_servers) == sid in front of it and sends
+// foreign keys to the RDMA path; a shard store is probed for its own keys here.
 uint64_t refs_get_edges(void *h, uint32_t vid, uint32_t pid, int dir, const uint32_t **out) {
     uint64_t sz = 0;
     int type = 0;   // the default argument is a reference bound to *(int *)NULL (gstore.hpp:394): give it a real object
-    edge_t *e = ((RefStore *)h)->g->get_edges(0, vid, pid, (dir_t)dir, sz, type);
+    edge_t *e = ((RefStore *)h)->g->get_edges_local(0, vid, pid, (dir_t)dir, sz, type);
     *out = (const uint32_t *)e;
     return e ? sz : 0;
 }

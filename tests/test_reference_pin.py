@@ -167,3 +167,26 @@ def test_fork_join_decisions_and_split_match_reference(ref1):
         parts = ref1.split(tbl, col, n)
         for i in range(n):
             assert np.array_equal(parts[i], tbl[tbl[:, col] % n == i])       # same rows, original order
+
+
+def test_sharded_store_matches_reference_store(lubm1, ref_lib):
+    """server 1 of 2 (OUT edges with the subject's owner, IN edges with the object's, index lists of local vertices only):
+    the reference's partition + StaticGStore::init against the oracle's per-server build"""
+    rs = ref_lib.RefStore(lubm1, num_servers=2, sid=1)
+    o = O.Store.build(lubm1, num_servers=2, sid=1, kvstore_bytes=1 << 30, num_engines=1, gpu_ext_mode=False)
+    mine = sorted((x.index, x.dir, x.pid, x.num_keys, x.num_buckets, x.bucket_start, x.num_edges, x.edge_start) for x in o.segs())
+    assert mine == sorted(tuple(int(v) for v in r[:8]) for r in rs.segs())
+    ov, oe = o.vertices(), o.edges()
+    idx = np.arange(ov.shape[0])
+    occ = (idx % 8 != 7) & (ov[:, 0] != 0)
+    rv = rs.vertices()
+    assert np.array_equal(np.sort(ov[occ, 0]), np.sort(rv[(idx % 8 != 7) & (rv[:, 0] != 0), 0]))
+    rng = np.random.default_rng(1)
+    pick = rng.permutation(int(occ.sum()))[:20000]
+    keys, ptrs = ov[occ, 0][pick], ov[occ, 1][pick]
+    idxkeys = ov[occ][(ov[occ, 0] >> np.uint64(18)) == 0]
+    for k, p in list(zip(keys.tolist(), ptrs.tolist())) + [tuple(x) for x in idxkeys.tolist()]:
+        d, pid, vid = k & 1, (k >> 1) & 0x1FFFF, k >> 18
+        size, off = p & ((1 << 28) - 1), (p >> 28) & ((1 << 34) - 1)
+        ref_e, mine_e = rs.get_edges(vid, pid, d), oe[off:off + size]
+        assert np.array_equal(np.sort(ref_e), np.sort(mine_e)) if vid == 0 else np.array_equal(ref_e, mine_e), (vid, pid, d)
