@@ -131,11 +131,39 @@ def build_dataset_device(args, device, num_servers=1, sid=0):
     return tr, gst, info
 
 
-def cpu_oracle_times(hs, plans, threads, heavy_reps, light_reps):
-    """per-query mean latency (us) of the CPU oracle engine on the product-built store arrays"""
+def cpu_engine_kind(args):
+    """which CPU engine times the path: "reference" = the reference's OWN SPARQLEngine (core/engine/sparql.hpp), compiled in
+    oracle/_ref behind C shims (oracle/Makefile `ref`), probing the same store arrays through its own GStore code;
+    "port" = the oracle restatement (when oracle/_ref was never built, i.e. no reference tree was available)."""
+    from oracle import ref as REF
+    want = getattr(args, "cpu_engine", "auto")
+    if want == "port":
+        return "port"
+    if REF.available():
+        return "reference"
+    if want == "reference":
+        raise RuntimeError("oracle/_ref/libwukong_ref.so is missing: run `make -C oracle ref` where /root/reference exists")
+    return "port"
+
+
+def cpu_engine_times(hs, plans, threads, heavy_reps, light_reps, kind):
+    """per-query mean latency (us) of the CPU engine on the same store arrays: heavy queries as `threads` index slices on
+    host threads (the reference's mt_factor replicas, sparql.hpp:1064-1089), light queries single-threaded; the timed region
+    is the pattern phase + merge + final_process (projection), non-blind."""
+    out = {}
+    if kind == "reference":
+        from oracle import ref as REF
+        rs = REF.RefStore.adopt(hs.vertices(), hs.edges(), hs.segs(), num_normal_preds=31)
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            heavy = q in HEAVY
+            mt = threads if heavy else 1
+            rc, us, rows = rs.time_query(pats, nvars, req, reps=1 + (heavy_reps if heavy else light_reps), mt_factor=mt, threaded=heavy)
+            assert rc == 0, rc
+            out[q] = (float(np.mean(us[1:])), int(rows), mt)      # first repetition = warm-up
+        return out
     from oracle import oracle as O
     ost = O.Store.wrap(hs.vertices(), hs.edges(), hs.segs())
-    out = {}
     for q in QUERIES:
         pats, nvars, req = plans[q]
         heavy = q in HEAVY
@@ -149,6 +177,11 @@ def cpu_oracle_times(hs, plans, threads, heavy_reps, light_reps):
             us.append(r.usec)
         out[q] = (float(np.mean(us)), int(r.rows), mt)
     return out
+
+
+CPU_ENGINE_NOTE = {"reference": "the reference's own SPARQLEngine + GStore probe (core/engine/sparql.hpp, core/store/gstore.hpp) compiled "
+                                "in oracle/_ref with std-based stand-ins for Boost/TBB/ZeroMQ, over the product-built store arrays",
+                   "port": "oracle restatement of the reference engine (oracle/_ref not built)"}
 
 
 def published_baseline(args):
@@ -179,11 +212,12 @@ def run_reference(args, rank, world):
     tr, hs, info = build_dataset(args)
     plans = load_plans(args.plan)
     threads = args.cpu_threads or os.cpu_count()
+    kind = cpu_engine_kind(args)
     # each step = one bounded pass: heavy queries once with all host threads, light queries 50x
     lat = {q: [] for q in QUERIES}
     t_start = time.time()
     for it in range(args.warmup + args.steps):
-        res = cpu_oracle_times(hs, plans, threads, 1, 50)
+        res = cpu_engine_times(hs, plans, threads, 1, 50, kind)
         if it >= args.warmup:
             for q in QUERIES:
                 lat[q].append(res[q][0])
@@ -197,9 +231,9 @@ def run_reference(args, rank, world):
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": "LUBM-%d Q1-Q7 (%s), seeded LUBM-shaped generator" % (args.scale, args.plan),
                        "triples": info["triples"], "non_blind": True},
-            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": kind,
                              "sample": "per step: Q1,Q2,Q3,Q7 once with mt_factor=%d threads, Q4-Q6 50x single thread; "
-                                       "execute_patterns + projection only" % threads},
+                                       "pattern phase + final_process only; engine: %s" % (threads, CPU_ENGINE_NOTE[kind])},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "latency_us": {"q%d" % q: mean[q] for q in QUERIES},
             "wall_s": round(time.time() - t_start, 1)}
@@ -327,6 +361,8 @@ def main():
     ap.add_argument("--rbuf-mb", type=int, default=0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-engine", default="auto", choices=["auto", "reference", "port"],
+                    help="CPU arm: the reference's own engine compiled in oracle/_ref, or the oracle port (auto: reference when built)")
     ap.add_argument("--store-build", default="device", choices=["device", "host"],
                     help="build the graph store on the GPU (wk_store_build) or with the host builder + upload")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="sharded mode: peer-memory push or NCCL all-to-all(v)")
@@ -493,13 +529,14 @@ def main():
             "dataset": info, "timed_region_s": round(t_region, 2)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = args.cpu_threads or os.cpu_count()
-        res = cpu_oracle_times(hs if hs is not None else DeviceBuiltStore(gst), plans, threads, 3, 200)
+        kind = cpu_engine_kind(args)
+        res = cpu_engine_times(hs if hs is not None else DeviceBuiltStore(gst), plans, threads, 3, 200, kind)
         cq = [1e6 / res[q][0] for q in QUERIES]
         for q in QUERIES:
-            assert res[q][1] == rows[q][0], "GPU and CPU oracle disagree on q%d rows" % q
-        line["cpu_baseline"] = {"value": geomean(cq), "unit": "queries/s", "cores": threads, "kind": "port",
-                                "sample": "oracle engine on the same store arrays: Q1,Q2,Q3,Q7 3x with mt_factor=%d threads, "
-                                          "Q4-Q6 200x single thread; execute_patterns + projection" % threads,
+            assert res[q][1] == rows[q][0], "GPU and CPU engine disagree on q%d rows" % q
+        line["cpu_baseline"] = {"value": geomean(cq), "unit": "queries/s", "cores": threads, "kind": kind,
+                                "sample": "same store arrays: Q1,Q2,Q3,Q7 3x with mt_factor=%d threads, Q4-Q6 200x single thread; "
+                                          "pattern phase + final_process; engine: %s" % (threads, CPU_ENGINE_NOTE[kind]),
                                 "latency_us": {"q%d" % q: round(res[q][0], 2) for q in QUERIES}}
     if rank == 0:
         emit(line)

@@ -44,6 +44,9 @@ def lib():
         L.refs_get_edges.restype = u64
         L.refs_get_edges.argtypes = [vp, C.c_uint32, C.c_uint32, ci, C.POINTER(vp)]
         L.refe_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, i64, i64, vp, u64, C.POINTER(u64), C.POINTER(ci)]
+        L.refs_adopt.restype = vp
+        L.refs_adopt.argtypes = [vp, u64, u64, vp, u64, vp, ci, ci]
+        L.refe_time_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, ci, vp, C.POINTER(u64)]
         L.refp_set_plan.argtypes = [vp, ci, C.c_char_p, vp, ci]
         L.refe_fork_plan.argtypes = [vp, vp, ci, ci, ci, vp]
         L.refe_split.argtypes = [vp, vp, u64, ci, ci, ci, vp, vp]
@@ -68,6 +71,32 @@ class RefStore:
         t = np.ascontiguousarray(triples, dtype=np.uint32).reshape(-1, 3)
         self.h = lib().refs_build(t.ctypes.data_as(C.c_void_p), t.shape[0], num_servers, sid, 1, memstore_gb, num_normal_preds)
         self._out = np.empty(1 << 22, dtype=np.uint32)
+
+    @classmethod
+    def adopt(cls, vertices, edges, segs, num_normal_preds=31):
+        """a reference GStore over existing store arrays (e.g. the host builder's); segs: objects with the wk_segmeta_t fields"""
+        self = cls.__new__(cls)
+        v = np.ascontiguousarray(vertices, dtype=np.uint64).reshape(-1, 2)
+        e = np.ascontiguousarray(edges, dtype=np.uint32)
+        rows = np.array([[x.index, x.dir, x.pid, x.num_keys, x.num_buckets, x.bucket_start, x.num_edges, x.edge_start,
+                          x.ext_start, x.ext_num] for x in segs], dtype=np.uint64)
+        main = int(max(int(r[5]) + int(r[4]) for r in rows))
+        self._keep = (v, e, rows)
+        self.h = lib().refs_adopt(v.ctypes.data_as(C.c_void_p), v.shape[0], main, e.ctypes.data_as(C.c_void_p), e.shape[0],
+                                  rows.ctypes.data_as(C.c_void_p), rows.shape[0], num_normal_preds)
+        self._out = np.empty(1 << 22, dtype=np.uint32)
+        return self
+
+    def time_query(self, patterns, nvars, required, reps=1, mt_factor=1, threaded=True, blind=False):
+        """-> (status, usec[reps], rows): wall time of pattern phase (mt_factor slices on host threads) + merge + final_process"""
+        p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+        rq = np.array(required, dtype=np.int32)
+        us = np.zeros(reps, dtype=np.float64)
+        rows = C.c_uint64(0)
+        rc = lib().refe_time_query(self.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars,
+                                   rq.ctypes.data_as(C.c_void_p) if len(rq) else None, len(rq), 1 if blind else 0, mt_factor,
+                                   1 if threaded else 0, reps, us.ctypes.data_as(C.c_void_p), C.byref(rows))
+        return rc, us, rows.value
 
     @property
     def num_slots(self):

@@ -6,10 +6,10 @@
 // the real GStore), bind.hpp, comm/adaptor.hpp, string_server.hpp.  This pins SURVEY.md §8 rows a6-a14 of the oracle against
 // compiled reference code, on a single server; the fork-join transport and the proxy are not exercised.
 //
-// Compiled with -O0 -fno-unreachable-traps: the reference has a value-returning function without a return statement
-// (core/query.hpp:450, Result::set_attr_col_num, called by final_process), which GCC >= 8 turns into a trap or a
-// fall-through when it optimises.  Built by `make -C oracle ref` into oracle/_ref/ (git-ignored).
+// Built by `make -C oracle ref` into oracle/_ref/ (git-ignored); accommodations for current GCC are listed in the Makefile
+// and in ref_shim.h.
 #define WK_REF_WITH_ENGINE 1
+#include <thread>
 #include "ref_shim.h"
 
 std::vector<std::vector<int>> core_bindings;   // bind.hpp
@@ -80,6 +80,84 @@ int refe_query(void *h, const int32_t *pats, int npat, int nvars, const int32_t 
     return SUCCESS;
 }
 
+
+// ---- timing: the reference's own engine as the CPU arm -----------------------------------------------------------------------
+// One query, `reps` times: the pattern phase runs as mt_factor slices of the index start (sparql.hpp:1064-1089 dispatch /
+// :211-221 slicing), each slice on its own host thread with its own SPARQLEngine when `threaded`; the replies are
+// concatenated and final_process runs on the merged result, as the proxy-side engine does.  usec[i] = wall time of rep i
+// (pattern phase + merge + final_process; no Bundle serialisation, no proxy hop).  Returns the reference's status code.
+int refe_time_query(void *h, const int32_t *pats, int npat, int nvars, const int32_t *required, int nreq, int blind, int mt_factor,
+                    int threaded, int reps, double *usec, uint64_t *rows_out) {
+    RefStore *r = (RefStore *)h;
+    Global::num_servers = 1;
+    SPARQLQuery::PatternGroup pg;
+    for (int i = 0; i < npat; i++)
+        pg.patterns.push_back(SPARQLQuery::Pattern((ssid_t)pats[4 * i], (ssid_t)pats[4 * i + 1], (ssid_t)pats[4 * i + 2], (ssid_t)pats[4 * i + 3]));
+    std::vector<ssid_t> req(required, required + nreq);
+    StringServer strs;
+    DGraph graph(0, r->g);
+    int status = SUCCESS;
+    for (int rep = 0; rep < reps; rep++) {
+        const uint64_t t0 = timer::get_usec();
+        SPARQLQuery fin(pg, nvars, req);
+        fin.result.blind = blind != 0;
+        const int slices = (fin.start_from_index() && mt_factor > 1) ? mt_factor : 1;
+        std::vector<SPARQLQuery> parts(slices, SPARQLQuery(pg, nvars, req));
+        std::vector<int> codes(slices, SUCCESS);
+        auto run = [&](int t) {
+            Coder coder(0, t);
+            Adaptor adaptor(t);
+            Messenger msgr(0, t, &adaptor);
+            SPARQLEngine eng(0, t, &strs, &graph, &coder, &msgr);
+            SPARQLQuery &q = parts[t];
+            q.result.blind = blind != 0;
+            q.mt_factor = slices;
+            q.mt_tid = t;
+            try {
+                while (!q.done(SPARQLQuery::SQState::SQ_PATTERN)) eng.execute_one_pattern(q);
+                q.result.update_nrows();
+            } catch (WukongException &ex) {
+                codes[t] = ex.code();
+            }
+        };
+        if (threaded && slices > 1) {
+            std::vector<std::thread> th;
+            for (int t = 0; t < slices; t++) th.emplace_back(run, t);
+            for (auto &x : th) x.join();
+        } else {
+            for (int t = 0; t < slices; t++) run(t);
+        }
+        for (int t = 0; t < slices; t++)
+            if (codes[t] != SUCCESS) status = codes[t];
+        if (status != SUCCESS) return status;
+        fin.result.v2c_map = parts[0].result.v2c_map;
+        fin.result.col_num = parts[0].result.col_num;
+        fin.result.row_num = 0;
+        for (int t = 0; t < slices; t++) {   // append_result, query.hpp:536-557
+            fin.result.row_num += parts[t].result.row_num;
+            if (!fin.result.blind) {
+                if (t == 0) fin.result.result_table.swap(parts[t].result.result_table);
+                else fin.result.result_table.insert(fin.result.result_table.end(), parts[t].result.result_table.begin(), parts[t].result.result_table.end());
+            }
+        }
+        fin.pattern_step = npat;
+        try {
+            if (!fin.result.blind) {
+                Coder coder(0, 0);
+                Adaptor adaptor(0);
+                Messenger msgr(0, 0, &adaptor);
+                SPARQLEngine eng(0, 0, &strs, &graph, &coder, &msgr);
+                fin.result.update_nrows();
+                eng.final_process(fin);
+            }
+        } catch (WukongException &ex) {
+            return ex.code();
+        }
+        usec[rep] = (double)(timer::get_usec() - t0);
+        *rows_out = fin.result.blind ? (uint64_t)fin.result.row_num : (uint64_t)fin.result.get_row_num();
+    }
+    return status;
+}
 
 // ---- fork-join decisions and row split --------------------------------------------------------------
 // Which steps of a plan exchange when the store is sharded over n servers, decided by the reference's own

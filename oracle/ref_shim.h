@@ -43,6 +43,13 @@
 #include "mem.hpp"
 #include "store/static_gstore.hpp"
 #ifdef WK_REF_WITH_ENGINE
+// core/query.hpp:450 reads `int set_attr_col_num(int n) { attr_col_num = n; }`: a value-returning function without a return
+// statement, called by every final_process.  GCC >= 8 compiles that into a trap (-O0) or lets control run off its end (-O1+).
+// Without touching the file, give the compiler a well-formed definition: while query.hpp is being read, the declarator
+// expands to a complete function followed by the head of a never-called one that swallows the original body.
+#define set_attr_col_num(decl) set_attr_col_num(decl) { attr_col_num = n; return 0; } int wk_ref_unused_set_attr_col_num(decl)
+#include "query.hpp"
+#undef set_attr_col_num
 #include "engine/sparql.hpp"   // the reference's SPARQLEngine; dgraph / bind / adaptor / string_server are shadowed (ref_stubs/)
 #include "planner.hpp"         // the reference's Planner (only set_plan / set_direction are exercised)
 #endif

@@ -75,6 +75,42 @@ void *refs_build(const uint32_t *tr, uint64_t n, int num_servers, int sid, int n
 }
 // releases the 1 GiB store memory; the small GStore object itself is leaked on purpose (its destructor chain is not
 // exercised by the reference either: a server never tears its store down)
+// A reference GStore over EXISTING arrays (the product host builder's, which are bit-identical to what StaticGStore::init
+// lays out, see tests/test_reference_pin.py): used to time the reference's own engine on stores that would take its
+// single-threaded build here many minutes (LUBM-2560).  segs: nsegs rows of (index, dir, pid, num_keys, num_buckets,
+// bucket_start, num_edges, edge_start, ext_start, ext_num).  The arrays must outlive the handle.
+void *refs_adopt(const void *vertices, uint64_t num_slots, uint64_t num_main_buckets, const void *edges, uint64_t num_edges,
+                 const uint64_t *segs, int nsegs, int num_normal_preds) {
+    Global::num_servers = 1;
+    Global::num_engines = 1;
+    Global::num_threads = 2;
+    Global::memstore_size_gb = 1;   // Mem insists on whole GiB; its own buffer stays unused
+    Global::use_rdma = false;
+    RefStore *r = new RefStore();
+    r->mem = new Mem(1, Global::num_threads);
+    r->g = new StaticGStore(0, r->mem);
+    r->g->num_normal_preds = num_normal_preds;
+    r->g->num_attr_preds = 0;
+    r->g->vertices = (vertex_t *)vertices;
+    r->g->edges = (edge_t *)edges;
+    r->g->num_slots = num_slots;
+    r->g->num_buckets = num_main_buckets;
+    r->g->num_buckets_ext = num_slots / GStore::ASSOCIATIVITY - num_main_buckets;
+    r->g->num_entries = num_edges;
+    r->g->last_ext = 0;
+    r->g->last_entry = num_edges;
+    for (int i = 0; i < nsegs; i++) {
+        const uint64_t *x = segs + 10 * i;
+        rdf_seg_meta_t m;
+        m.num_keys = x[3]; m.num_buckets = x[4]; m.bucket_start = x[5]; m.num_edges = x[6]; m.edge_start = x[7];
+        if (x[9]) m.add_ext_buckets(ext_bucket_extent_t(x[9], x[8]));
+        r->g->rdf_seg_meta_map[segid_t((int)x[0], (sid_t)x[2], (int)x[1])] = m;
+        r->segs.insert(r->segs.end(), x, x + 8);
+        r->segs.push_back(x[9] ? 1 : 0); r->segs.push_back(x[8]); r->segs.push_back(x[9]);
+    }
+    return r;
+}
+
 void refs_free(void *h) { RefStore *r = (RefStore *)h; delete r->mem; delete r; }
 uint64_t refs_num_slots(void *h) { return ((RefStore *)h)->g->num_slots; }
 uint64_t refs_num_buckets(void *h) { return ((RefStore *)h)->g->num_buckets; }
