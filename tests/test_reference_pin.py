@@ -84,6 +84,13 @@ def test_engine_matches_reference_engine(lubm1, ref1, ostore1):
             rc, rows, cols, t = ref1.query(pats, nvars, req, distinct=True, offset=1, limit=40)
             assert rc == 0 and rows == wd.rows and (rows == 0 or np.array_equal(t, wd.table)), (q, plan)
     univ0 = M.lubm_str2id("<http://www.University0.edu>")
+    # const_to_known in the middle of a plan (sparql.hpp:144-186): departments of graduate students that belong to University0
+    P = {n: i for i, n in enumerate(M.LUBM_INDEX)}
+    pats = [(P[M.UB + "GraduateStudent>"], 1, 0, -1), (-1, P[M.UB + "memberOf>"], 1, -2),
+            (univ0, P[M.UB + "subOrganizationOf>"], 0, -2), (-2, P[M.UB + "name>"], 1, -3)]
+    want = O.run_query([ostore1], pats, 3, [-1, -3])
+    rc, rows, cols, t = ref1.query(pats, 3, [-1, -3])
+    assert rc == 0 and rows == want.rows > 0 and rows_equal(t, want.table)
     for pats, nv, req in [([(-1, 5, 1, -2)], 2, [-1]), ([(18, 1, 0, -1), (univ0, 7, 0, -2)], 2, [-1]),
                           ([(18, 5, 0, -1)], 1, [-1]), ([(18, 1, 0, -1)], 1, [])]:
         assert ref1.query(pats, nv, req)[0] == O.run_query([ostore1], pats, nv, req).status
