@@ -146,37 +146,45 @@ def cpu_engine_kind(args):
     return "port"
 
 
-def cpu_engine_times(hs, plans, threads, heavy_reps, light_reps, kind):
-    """per-query mean latency (us) of the CPU engine on the same store arrays: heavy queries as `threads` index slices on
-    host threads (the reference's mt_factor replicas, sparql.hpp:1064-1089), light queries single-threaded; the timed region
-    is the pattern phase + merge + final_process (projection), non-blind."""
-    out = {}
-    if kind == "reference":
-        from oracle import ref as REF
-        rs = REF.RefStore.adopt(hs.vertices(), hs.edges(), hs.segs(), num_normal_preds=31)
+class CpuEngine:
+    """the CPU arm over one set of store arrays (adopted once): per-query mean latency (us); heavy queries as `threads` index
+    slices on host threads (the reference's mt_factor replicas, sparql.hpp:1064-1089), light queries single-threaded; the
+    timed region is the pattern phase + merge + final_process (projection), non-blind."""
+
+    def __init__(self, hs, kind):
+        self.kind = kind
+        if kind == "reference":
+            from oracle import ref as REF
+            self.rs = REF.RefStore.adopt(hs.vertices(), hs.edges(), hs.segs(), num_normal_preds=31)
+        else:
+            from oracle import oracle as O
+            self.ost = O.Store.wrap(hs.vertices(), hs.edges(), hs.segs())
+
+    def times(self, plans, threads, heavy_reps, light_reps):
+        out = {}
         for q in QUERIES:
             pats, nvars, req = plans[q]
             heavy = q in HEAVY
+            reps = heavy_reps if heavy else light_reps
             mt = threads if heavy else 1
-            rc, us, rows = rs.time_query(pats, nvars, req, reps=1 + (heavy_reps if heavy else light_reps), mt_factor=mt, threaded=heavy)
-            assert rc == 0, rc
-            out[q] = (float(np.mean(us[1:])), int(rows), mt)      # first repetition = warm-up
+            if self.kind == "reference":
+                rc, us, rows = self.rs.time_query(pats, nvars, req, reps=1 + reps, mt_factor=mt, threaded=heavy)
+                assert rc == 0, rc
+                out[q] = (float(np.mean(us[1:])), int(rows), mt)      # first repetition = warm-up
+                continue
+            from oracle import oracle as O
+            O.run_query([self.ost], pats, nvars, req, mt_factor=mt, blind=False, threaded=heavy)   # warm
+            us = []
+            for _ in range(reps):
+                r = O.run_query([self.ost], pats, nvars, req, mt_factor=mt, blind=False, threaded=heavy)
+                assert r.status == 0
+                us.append(r.usec)
+            out[q] = (float(np.mean(us)), int(r.rows), mt)
         return out
-    from oracle import oracle as O
-    ost = O.Store.wrap(hs.vertices(), hs.edges(), hs.segs())
-    for q in QUERIES:
-        pats, nvars, req = plans[q]
-        heavy = q in HEAVY
-        reps = heavy_reps if heavy else light_reps
-        mt = threads if heavy else 1
-        O.run_query([ost], pats, nvars, req, mt_factor=mt, blind=False, threaded=heavy)   # warm
-        us = []
-        for _ in range(reps):
-            r = O.run_query([ost], pats, nvars, req, mt_factor=mt, blind=False, threaded=heavy)
-            assert r.status == 0
-            us.append(r.usec)
-        out[q] = (float(np.mean(us)), int(r.rows), mt)
-    return out
+
+
+def cpu_engine_times(hs, plans, threads, heavy_reps, light_reps, kind):
+    return CpuEngine(hs, kind).times(plans, threads, heavy_reps, light_reps)
 
 
 CPU_ENGINE_NOTE = {"reference": "the reference's own SPARQLEngine + GStore probe (core/engine/sparql.hpp, core/store/gstore.hpp) compiled "
@@ -213,11 +221,12 @@ def run_reference(args, rank, world):
     plans = load_plans(args.plan)
     threads = args.cpu_threads or os.cpu_count()
     kind = cpu_engine_kind(args)
+    cpu = CpuEngine(hs, kind)
     # each step = one bounded pass: heavy queries once with all host threads, light queries 50x
     lat = {q: [] for q in QUERIES}
     t_start = time.time()
     for it in range(args.warmup + args.steps):
-        res = cpu_engine_times(hs, plans, threads, 1, 50, kind)
+        res = cpu.times(plans, threads, 1, 50)
         if it >= args.warmup:
             for q in QUERIES:
                 lat[q].append(res[q][0])
