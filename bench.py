@@ -88,16 +88,26 @@ class ClockSampler(threading.Thread):
                 "note": "sampled every 20 ms from the start of warm-up to the end of the timed region"}
 
 
+LOAD_FACTORS = (55, 45, 35, 25)   # Global::est_load_factor (global.hpp:99-104) and its fallbacks for small datasets
+
+
 def build_dataset(args):
     """host arm: triples -> store arrays with the host builder (csrc/store/host_builder.cpp)"""
     from wukong_b200 import datagen, host
     t0 = time.time()
     tr = datagen.lubm(args.scale, seed=args.seed)
     t1 = time.time()
-    hs = host.HostStore(tr)
+    hs, lf = None, None
+    for lf in LOAD_FACTORS:      # a segment that outgrows its single 15 % ext extent (meta.hpp:38-40) needs a sparser header
+        try:
+            hs = host.HostStore(tr, est_load_factor=lf)
+            break
+        except RuntimeError:
+            if lf == LOAD_FACTORS[-1]:
+                raise
     t2 = time.time()
     info = {"triples": int(tr.shape[0]), "keys": int(hs.num_keys), "gen_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2),
-            "store_build": "host", "header_mb": round(hs.num_slots * 16 / 1e6, 1), "edges_mb": round(hs.num_edges * 4 / 1e6, 1)}
+            "store_build": "host", "est_load_factor": lf, "header_mb": round(hs.num_slots * 16 / 1e6, 1), "edges_mb": round(hs.num_edges * 4 / 1e6, 1)}
     return tr, hs, info
 
 
@@ -122,11 +132,18 @@ def build_dataset_device(args, device, num_servers=1, sid=0):
     else:
         tr = datagen.lubm(args.scale, seed=args.seed)
     t1 = time.time()
-    gst = capi.Store.build(tr, datagen.LUBM_NUM_NORMAL_PREDS, num_servers=num_servers, sid=sid, device=device)
+    gst, lf = None, None
+    for lf in LOAD_FACTORS:
+        try:
+            gst = capi.Store.build(tr, datagen.LUBM_NUM_NORMAL_PREDS, num_servers=num_servers, sid=sid, est_load_factor=lf, device=device)
+            break
+        except capi.WukongError as ex:
+            if ex.code != capi.WK_ERR_STORE_FULL or lf == LOAD_FACTORS[-1]:
+                raise
     t2 = time.time()
     st = gst.build_stats
     info = {"triples": int(tr.shape[0]), "keys": int(st["num_keys"]), "gen_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2),
-            "store_build": "device", "build_ms": {k: round(st[k], 1) for k in ("ms_upload", "ms_sort", "ms_insert", "ms_total")},
+            "store_build": "device", "est_load_factor": lf, "build_ms": {k: round(st[k], 1) for k in ("ms_upload", "ms_sort", "ms_insert", "ms_total")},
             "header_mb": round(st["num_slots"] * 16 / 1e6, 1), "edges_mb": round(st["num_edges"] * 4 / 1e6, 1)}
     return tr, gst, info
 

@@ -13,6 +13,7 @@ KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k", "disti
 
 WK_SUCCESS = 0
 WK_ERR_CUDA, WK_ERR_BAD_ARG, WK_ERR_RBUF_OVERFLOW, WK_ERR_NO_SEGMENT, WK_ERR_NO_DEVICE, WK_ERR_COMM = 100, 101, 102, 103, 104, 105
+WK_ERR_STORE_FULL = 106
 
 
 class WukongError(RuntimeError):
