@@ -372,22 +372,3 @@ def test_query_modifiers_distinct_offset_limit(eng1, ostore1):
     assert eng1.slice(1, 1) == 1 and eng1.download().tolist() == [[3, 8]]
     assert eng1.slice(5, -1) == 0
 
-
-def test_matches_reference_engine_fixture(eng1):
-    """the answers of the reference's OWN compiled engine on this dataset (tests/golden/ref_engine_lubm1.json, produced by
-    tests/golden/make_ref_engine.py from oracle/_ref): row counts and digests of the sorted tables, exact tables under DISTINCT"""
-    import hashlib
-    import json
-    import os
-    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_engine_lubm1.json")))
-    for name, e in G["queries"].items():
-        q, plan = int(name.split("_")[0][1:]), name.split("_", 1)[1]
-        pats, nvars, req, _ = load_query(q, plan)
-        rc, rows, cols, tbl = eng1.query(pats, nvars, req)
-        assert rc == 0 and rows == e["rows"], name
-        if rows:
-            assert hashlib.sha256(M.sort_rows(tbl).tobytes()).hexdigest() == e["sha256"], name
-        rc, rows, cols, tbl = eng1.query(pats, nvars, req, distinct=True, offset=1, limit=40)
-        assert rc == 0 and rows == e["distinct_rows"], name
-        if rows:
-            assert hashlib.sha256(np.ascontiguousarray(tbl).tobytes()).hexdigest() == e["distinct_sha256"], name
