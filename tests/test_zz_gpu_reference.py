@@ -75,3 +75,32 @@ def test_reference_built_store_runs_on_the_gpu(lubm1, ostore1):
     assert np.array_equal(gst.get_edges(s, p, O.OUT), rs.get_edges(s, p, O.OUT))
     eng.close()
     gst.close()
+
+
+def test_random_graph_against_live_reference_engine():
+    """a random graph (tests/random_bgp.py) answered by the GPU engine and, live, by the reference's compiled engine"""
+    import random_bgp as R
+    from oracle import ref as REF
+    try:
+        ok = REF.available()
+    except OSError:
+        ok = False
+    if not ok:
+        pytest.skip("oracle/_ref not present on this box")
+    tr, meta = R.graph(0, nv=400, ntriples=4000)
+    npreds = meta["num_normal_preds"]
+    rs = REF.RefStore(tr, num_normal_preds=npreds)
+    gst = capi.Store.build(tr, npreds)
+    eng = capi.Engine(gst, rbuf_bytes=256 << 20)
+    checked = 0
+    for qseed in range(40):
+        planned, _, nvars, req = R.query(qseed, tr, meta)
+        rc, rows, cols, tbl = eng.query(planned, nvars, req)
+        if rc == capi.WK_ERR_RBUF_OVERFLOW or rows > 300_000:
+            continue
+        rrc, rrows, _, rtbl = rs.query(planned, nvars, req)
+        assert rc == 0 and rrc == 0 and rrows == rows and (rows == 0 or rows_equal(tbl, rtbl)), (qseed, planned)
+        checked += 1
+    assert checked >= 30
+    eng.close()
+    gst.close()
