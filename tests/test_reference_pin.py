@@ -91,6 +91,12 @@ def test_engine_matches_reference_engine(lubm1, ref1, ostore1):
     want = O.run_query([ostore1], pats, 3, [-1, -3])
     rc, rows, cols, t = ref1.query(pats, 3, [-1, -3])
     assert rc == 0 and rows == want.rows > 0 and rows_equal(t, want.table)
+    # known_to_unknown through the type index (pid == TYPE_ID && d == IN, sparql.hpp:339-340): professors -> their types ->
+    # every instance of those types
+    pats = [(P[M.UB + "FullProfessor>"], 1, 0, -1), (-1, 1, 1, -2), (-2, 1, 0, -3)]
+    want = O.run_query([ostore1], pats, 3, [-1, -2, -3])
+    rc, rows, cols, t = ref1.query(pats, 3, [-1, -2, -3])
+    assert rc == 0 and rows == want.rows > 1000 and rows_equal(t, want.table)
     for pats, nv, req in [([(-1, 5, 1, -2)], 2, [-1]), ([(18, 1, 0, -1), (univ0, 7, 0, -2)], 2, [-1]),
                           ([(18, 5, 0, -1)], 1, [-1]), ([(18, 1, 0, -1)], 1, [])]:
         assert ref1.query(pats, nv, req)[0] == O.run_query([ostore1], pats, nv, req).status
