@@ -1,0 +1,54 @@
+"""CPU: the JSON line bench.py prints -- keys and types the driver reads.  The reference arm runs here (tiny scale); the
+GPU arm's line is checked on the committed output of the round's final run (profiles/r1_bench_lubm2560.json)."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric": str, "value": float, "unit": str, "n_gpus": int, "steps": int, "warmup": int, "ms_per_step": float,
+             "higher_is_better": bool, "scaling": str, "dtype": str, "data": str, "config": dict, "e2e": dict}
+
+
+def _check_base(d):
+    for k, t in BASE_KEYS.items():
+        assert k in d and isinstance(d[k], t), k
+    assert "vs_baseline" in d and (d["vs_baseline"] is None or isinstance(d["vs_baseline"], float))
+    assert d["metric"] == "lubm_q1_q7_geomean_queries_per_sec" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert "workload" in d["config"] and "model" not in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["unit"] == "queries/s" and cb["sample"]
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "1", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    lines = [l for l in out.stdout.decode().splitlines() if l.strip()]
+    assert len(lines) == 1, lines                       # ONE line on stdout; libraries' chatter goes to stderr
+    d = json.loads(lines[0])
+    _check_base(d)
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["vs_baseline"] is None                     # the published figure is for LUBM-2560 only
+
+
+def test_committed_gpu_line_has_the_contract_keys():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_lubm2560.json")))
+    _check_base(d)
+    assert "impl" not in d or d["impl"] != "reference"
+    assert d["n_gpus"] == 1 and d["dtype"] == "u32" and d["data"] == "synthetic" and d["gpu_launches"] > 0
+    assert "LUBM-2560" in d["config"]["workload"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert d["roofline_expand"]["frac"] >= 0.6          # the north-star's bar for the expand kernel
+    c = d["clocks"]
+    assert c["sm_mhz"] and c["sm_max_mhz"] and isinstance(c["reasons"], list)
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    assert d["value"] / d["cpu_baseline"]["value"] >= 10    # the north-star's throughput bar, same box
