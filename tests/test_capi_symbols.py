@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from conftest import ROOT
 from oracle import oracle as O
@@ -59,3 +60,17 @@ def test_compute_fails_loudly_without_gpu():
         assert ex.code in (capi.WK_ERR_NO_DEVICE, capi.WK_ERR_CUDA)
     else:
         raise AssertionError("store creation must fail without a device (no CPU fallback)")
+
+
+def test_header_is_plain_c():
+    """the boundary is a C ABI: the header must compile as C99 (and as C++) with no torch / C++ types in it"""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "wukong_b200.h")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not cc:
+        pytest.skip("no C compiler")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call([cc, "-std=c++11", "-fsyntax-only", "-x", "c++", hdr])
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)      # declarations only, comments stripped
+    assert "torch" not in code and "std::" not in code and "at::" not in code and "pytest" not in code
