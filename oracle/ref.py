@@ -47,11 +47,28 @@ def lib():
         L.refs_adopt.restype = vp
         L.refs_adopt.argtypes = [vp, u64, u64, vp, u64, vp, ci, ci]
         L.refe_time_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, ci, vp, C.POINTER(u64)]
+        L.refe_cluster_query.argtypes = [vp, ci, vp, ci, ci, vp, ci, ci, vp, u64, C.POINTER(u64), C.POINTER(ci)]
         L.refp_set_plan.argtypes = [vp, ci, C.c_char_p, vp, ci]
         L.refe_fork_plan.argtypes = [vp, vp, ci, ci, ci, vp]
         L.refe_split.argtypes = [vp, vp, u64, ci, ci, ci, vp, vp]
         _lib = L
     return _lib
+
+
+def cluster_query(stores, patterns, nvars, required):
+    """one query over n shard stores (RefStore(..., num_servers=n, sid=i)) driven by the reference's per-server functions:
+    execute_one_pattern, need_fork_join, generate_sub_query, final_process.  -> (status, rows, cols, table or None)"""
+    n = len(stores)
+    arr = (C.c_void_p * n)(*[s.h for s in stores])
+    p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+    rq = np.array(required, dtype=np.int32)
+    out = np.empty(1 << 24, dtype=np.uint32)
+    rows, cols = C.c_uint64(0), C.c_int(0)
+    rc = lib().refe_cluster_query(C.cast(arr, C.c_void_p), n, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars,
+                                  rq.ctypes.data_as(C.c_void_p) if len(rq) else None, len(rq), 0,
+                                  out.ctypes.data_as(C.c_void_p), out.size, C.byref(rows), C.byref(cols))
+    tbl = out[: rows.value * cols.value].reshape(rows.value, cols.value).copy() if (rc == 0 and cols.value) else None
+    return rc, rows.value, cols.value, tbl
 
 
 def set_plan(patterns, fmt_text):

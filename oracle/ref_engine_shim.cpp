@@ -159,6 +159,103 @@ int refe_time_query(void *h, const int32_t *pats, int npat, int nvars, const int
     return status;
 }
 
+// ---- a simulated cluster: n shard stores in one process, the reference's own per-server functions ----------------------------
+// Every server i has its own GStore (shard i of n, built by refs_build) and its own SPARQLEngine.  The control flow of
+// SPARQLEngine::execute_patterns (sparql.hpp:1113-1154) is followed with the transport replaced by an in-process work list:
+// run execute_one_pattern; when the plan is not done, either replicate the table to every server (the rule of
+// dispatch(r, false), :1091-1110), or split it with generate_sub_query when need_fork_join says so (:802-814; without RDMA:
+// before every step), and hand every part to its server.  Index starts go to every server (dispatch, :1064-1089), constant
+// starts to the owner (proxy.hpp:205).  Finished parts are concatenated (RMap / append_result) and final_process runs once.
+// What is the reference's: every per-server decision and every row.  What is this shim's: the work list.
+int refe_cluster_query(void **stores, int n, const int32_t *pats, int npat, int nvars, const int32_t *required, int nreq, int blind,
+                       uint32_t *out, uint64_t cap_words, uint64_t *rows, int *cols) {
+    std::vector<RefStore *> rs(n);
+    for (int i = 0; i < n; i++) { rs[i] = (RefStore *)stores[i]; rs[i]->g->sid = i; }
+    StringServer strs;
+    std::vector<DGraph *> graphs;
+    std::vector<Coder *> coders;
+    std::vector<Adaptor *> adaptors;
+    std::vector<Messenger *> msgrs;
+    std::vector<SPARQLEngine *> engs;
+    for (int i = 0; i < n; i++) {
+        graphs.push_back(new DGraph(i, rs[i]->g));
+        coders.push_back(new Coder(i, 0));
+        adaptors.push_back(new Adaptor(0));
+        msgrs.push_back(new Messenger(i, 0, adaptors[i]));
+        engs.push_back(new SPARQLEngine(i, 0, &strs, graphs[i], coders[i], msgrs[i]));
+    }
+    SPARQLQuery::PatternGroup pg;
+    for (int i = 0; i < npat; i++)
+        pg.patterns.push_back(SPARQLQuery::Pattern((ssid_t)pats[4 * i], (ssid_t)pats[4 * i + 1], (ssid_t)pats[4 * i + 2], (ssid_t)pats[4 * i + 3]));
+    std::vector<ssid_t> req(required, required + nreq);
+    SPARQLQuery fin(pg, nvars, req);
+    fin.result.blind = blind != 0;
+    const bool rdma0 = Global::use_rdma;
+    Global::num_servers = n;
+    Global::use_rdma = false;
+    int status = SUCCESS;
+    *rows = 0;
+    *cols = 0;
+    try {
+        if (npat == 0) throw WukongException(SYNTAX_ERROR);
+        std::vector<std::pair<int, SPARQLQuery>> work;
+        SPARQLQuery proto(pg, nvars, req);
+        proto.result.blind = false;   // the tables travel between the simulated servers
+        if (proto.start_from_index()) {
+            for (int i = 0; i < n; i++) work.push_back(std::make_pair(i, proto));
+        } else {
+            work.push_back(std::make_pair(wukong::math::hash_mod(pg.patterns[0].subject, n), proto));
+        }
+        bool first = true;
+        while (!work.empty()) {
+            const int sid = work.back().first;
+            SPARQLQuery q = work.back().second;
+            work.pop_back();
+            while (true) {
+                engs[sid]->execute_one_pattern(q);
+                if (q.done(SPARQLQuery::SQState::SQ_PATTERN)) {
+                    q.result.update_nrows();
+                    if (first) { fin.result.v2c_map = q.result.v2c_map; fin.result.col_num = q.result.col_num; first = false; }
+                    if (q.result.col_num == fin.result.col_num || q.result.result_table.empty())
+                        fin.result.result_table.insert(fin.result.result_table.end(), q.result.result_table.begin(), q.result.result_table.end());
+                    break;
+                }
+                SPARQLQuery::Pattern &pt = q.get_pattern();
+                if (pt.predicate == TYPE_ID && pt.direction == IN) {
+                    std::vector<SPARQLQuery> subs = engs[sid]->generate_sub_query(q, false);
+                    for (int i = 0; i < n; i++) work.push_back(std::make_pair(i, subs[i]));
+                    break;
+                }
+                if (engs[sid]->need_fork_join(q)) {
+                    std::vector<SPARQLQuery> subs = engs[sid]->generate_sub_query(q);
+                    for (int i = 0; i < n; i++)
+                        if (subs[i].result.get_row_num() > 0) work.push_back(std::make_pair(i, subs[i]));
+                    break;
+                }
+            }
+        }
+        if (first) fin.result.col_num = 0;   // every branch died before the last step: an empty answer
+        fin.pattern_step = npat;
+        fin.result.update_nrows();
+        Global::num_servers = 1;
+        if (!fin.result.blind) engs[0]->final_process(fin);
+    } catch (WukongException &ex) {
+        status = ex.code();
+    }
+    Global::num_servers = 1;
+    Global::use_rdma = rdma0;
+    for (int i = 0; i < n; i++) { rs[i]->g->sid = 0; delete engs[i]; delete msgrs[i]; delete adaptors[i]; delete coders[i]; delete graphs[i]; }
+    if (status != SUCCESS) return status;
+    *rows = (uint64_t)fin.result.get_row_num();
+    *cols = fin.result.get_col_num();
+    const uint64_t words = fin.result.result_table.size();
+    if (!fin.result.blind) {
+        if (words > cap_words) return -1;
+        if (out && words) memcpy(out, fin.result.result_table.data(), words * sizeof(uint32_t));
+    }
+    return SUCCESS;
+}
+
 // ---- fork-join decisions and row split --------------------------------------------------------------
 // Which steps of a plan exchange when the store is sharded over n servers, decided by the reference's own
 // SPARQLEngine::need_fork_join (sparql.hpp:802-814, RDMA rule: fork when the next hop is not local; threshold 0) and the

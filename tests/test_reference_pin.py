@@ -203,3 +203,22 @@ def test_sharded_store_matches_reference_store(lubm1, ref_lib):
         size, off = p & ((1 << 28) - 1), (p >> 28) & ((1 << 34) - 1)
         ref_e, mine_e = rs.get_edges(vid, pid, d), oe[off:off + size]
         assert np.array_equal(np.sort(ref_e), np.sort(mine_e)) if vid == 0 else np.array_equal(ref_e, mine_e), (vid, pid, d)
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_simulated_reference_cluster(lubm1, ref_lib, n):
+    """n shard stores built by the reference (refs_build with the loader's owner rule) and one reference engine per shard; the
+    plan is driven by execute_one_pattern / need_fork_join / generate_sub_query exactly as execute_patterns does, with an
+    in-process work list instead of the transport.  Answers must equal the brute-force joiner's and the oracle's cluster's."""
+    shards = [ref_lib.RefStore(lubm1, num_servers=n, sid=i) for i in range(n)]
+    oshards = [O.Store.build(lubm1, num_servers=n, sid=i, kvstore_bytes=32 << 20, num_engines=2) for i in range(n)]
+    for q in range(1, 8):
+        for plan in PLANS:
+            pats, nvars, req, raw = load_query(q, plan)
+            bf = M.bruteforce_bgp(lubm1, raw, req)
+            rc, rows, cols, t = ref_lib.cluster_query(shards, pats, nvars, req)
+            assert rc == 0 and rows == bf.shape[0], (n, q, plan)
+            if rows:
+                assert rows_equal(t, bf), (n, q, plan)
+            mine = O.run_query(oshards, pats, nvars, req)
+            assert mine.status == 0 and mine.rows == rows
