@@ -74,3 +74,29 @@ def test_header_is_plain_c():
     subprocess.check_call([cc, "-std=c++11", "-fsyntax-only", "-x", "c++", hdr])
     code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)      # declarations only, comments stripped
     assert "torch" not in code and "std::" not in code and "at::" not in code and "pytest" not in code
+
+
+def test_argument_checks_need_no_gpu():
+    """every entry point rejects null handles / malformed arguments before touching CUDA; without a device the store
+    constructors say so instead of falling back to anything"""
+    L = capi.lib()
+    null = C.c_void_p(None)
+    n = C.c_uint64(0)
+    assert L.wk_engine_sync(null) != 0
+    assert L.wk_table_distinct(null, null, 0, C.byref(n)) == capi.WK_ERR_BAD_ARG
+    assert L.wk_table_slice(null, 0, -1, C.byref(n)) == capi.WK_ERR_BAD_ARG
+    assert L.wk_const_to_known(null, 1, 2, 0, 0, C.byref(n)) == capi.WK_ERR_BAD_ARG
+    assert L.wk_index_to_known(null, 2, 0, 0, 0, 1, C.byref(n)) == capi.WK_ERR_BAD_ARG
+    assert L.wk_store_info(null, None, None, None) == capi.WK_ERR_BAD_ARG
+    assert L.wk_query_execute_ex(null, null, 0, 0, null, 0, null, null, 0, C.byref(n), None) == capi.WK_ERR_BAD_ARG
+    h = C.c_void_p()
+    assert L.wk_store_build(0, None, 5, None, C.byref(h), None) == capi.WK_ERR_BAD_ARG          # no options
+    o = capi.BuildOpts(2, 2, 31, 55, 0, 0, 0)                                                   # sid out of range
+    assert L.wk_store_build(0, None, 0, C.byref(o), C.byref(h), None) == capi.WK_ERR_BAD_ARG
+    if capi.device_count() == 0:
+        o = capi.BuildOpts(1, 0, 31, 55, 0, 0, 0)
+        t = np.zeros((1, 3), dtype=np.uint32)
+        assert L.wk_store_build(0, t.ctypes.data_as(C.c_void_p), 1, C.byref(o), C.byref(h), None) == capi.WK_ERR_NO_DEVICE
+        v = np.zeros((8, 2), dtype=np.uint64)
+        assert L.wk_store_create(0, v.ctypes.data_as(C.c_void_p), 8, None, 0, None, 0, C.byref(h)) != 0
+    assert b"store build" in L.wk_strerror(capi.WK_ERR_STORE_FULL)
