@@ -21,10 +21,10 @@ from oracle import ref as REF  # noqa: E402
 from wukong_b200 import datagen  # noqa: E402
 
 
-def main():
-    rs = REF.RefStore(datagen.lubm(1, seed=1))
+def make(univs, seed, fname):
+    rs = REF.RefStore(datagen.lubm(univs, seed=seed))
     out = {"source": "SPARQLEngine (core/engine/sparql.hpp) over StaticGStore, compiled by oracle/Makefile `ref`",
-           "dataset": "wukong_b200.datagen.lubm(1, seed=1)", "queries": {}}
+           "dataset": "wukong_b200.datagen.lubm(%d, seed=%d)" % (univs, seed), "queries": {}}
     for q in range(1, 8):
         for plan in PLANS:
             pats, nvars, req, _ = load_query(q, plan)
@@ -37,10 +37,11 @@ def main():
             e["distinct_rows"] = drows
             e["distinct_sha256"] = hashlib.sha256(np.ascontiguousarray(dt).tobytes()).hexdigest() if drows else None
             out["queries"]["q%d_%s" % (q, plan)] = e
-    with open(os.path.join(HERE, "ref_engine_lubm1.json"), "w") as f:
+    with open(os.path.join(HERE, fname), "w") as f:
         json.dump(out, f, indent=0)
-    print("wrote", len(out["queries"]), "entries")
+    print("wrote", fname, len(out["queries"]), "entries")
 
 
 if __name__ == "__main__":
-    main()
+    make(1, 1, "ref_engine_lubm1.json")      # the dataset of the lubm1 / ostore1 / gstore1 fixtures (tests/conftest.py)
+    make(2, 7, "ref_engine_lubm2.json")      # ... of lubm2 / ostore2 / gstore2

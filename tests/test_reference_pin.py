@@ -127,9 +127,12 @@ def test_random_graph_matches_reference_engine(ref_lib, gseed):
     assert checked >= 45
 
 
-def test_oracle_matches_reference_engine_fixture(ostore1):
-    """always runs: the reference engine's answers on LUBM-1 (seed 1), committed as row counts + digests of the sorted tables"""
-    G = json.load(open(os.path.join(HERE, "golden", "ref_engine_lubm1.json")))
+@pytest.mark.parametrize("which", [1, 2])
+def test_oracle_matches_reference_engine_fixture(ostore1, ostore2, which):
+    """always runs: the reference engine's answers on LUBM-1 (seed 1) and LUBM-2 (seed 7), committed as row counts + digests of
+    the sorted tables"""
+    G = json.load(open(os.path.join(HERE, "golden", "ref_engine_lubm%d.json" % which)))
+    ostore1 = ostore1 if which == 1 else ostore2
     assert G["queries"]
     for name, e in G["queries"].items():
         q, plan = int(name.split("_")[0][1:]), name.split("_", 1)[1]

@@ -23,13 +23,22 @@ def eng1(gstore1):
     e.close()
 
 
-def test_matches_reference_engine_fixture(eng1):
+@pytest.fixture(scope="module")
+def eng2(gstore2):
+    e = capi.Engine(gstore2, rbuf_bytes=64 << 20)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_matches_reference_engine_fixture(eng1, eng2, which):
     """the answers of the reference's OWN compiled engine on this dataset (tests/golden/ref_engine_lubm1.json, produced by
     tests/golden/make_ref_engine.py from oracle/_ref): row counts and digests of the sorted tables, exact tables under DISTINCT"""
     import hashlib
     import json
     import os
-    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_engine_lubm1.json")))
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_engine_lubm%d.json" % which)))
+    eng1 = eng1 if which == 1 else eng2
     for name, e in G["queries"].items():
         q, plan = int(name.split("_")[0][1:]), name.split("_", 1)[1]
         pats, nvars, req, _ = load_query(q, plan)
