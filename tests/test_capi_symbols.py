@@ -100,3 +100,23 @@ def test_argument_checks_need_no_gpu():
         v = np.zeros((8, 2), dtype=np.uint64)
         assert L.wk_store_create(0, v.ctypes.data_as(C.c_void_p), 8, None, 0, None, 0, C.byref(h)) != 0
     assert b"store build" in L.wk_strerror(capi.WK_ERR_STORE_FULL)
+
+
+def test_c_example_builds_against_the_abi(tmp_path):
+    """examples/query_c_abi.c: a plain C99 program that uses only include/wukong_b200.h compiles and links against the library
+    (it needs a GPU to do anything useful: without one it reports `no CUDA device` and exits 1)"""
+    import shutil
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not cc:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "query_c_abi")
+    libdir = os.path.join(ROOT, "wukong_b200")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "query_c_abi.c"), "-L", libdir, "-l:libwukong_b200.so",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    if capi.device_count() == 0:
+        f = tmp_path / "t.bin"
+        np.zeros((4, 3), dtype=np.uint32).tofile(str(f))
+        r = subprocess.run([exe, str(f), "31"], capture_output=True)
+        assert r.returncode == 1 and b"no CUDA device" in r.stderr
