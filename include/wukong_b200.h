@@ -76,7 +76,9 @@ typedef struct wk_engine wk_engine_t;
 
 /* per-step execution record of the last wk_query_execute (profiling mode only for device_us) */
 typedef struct {
-    int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project, 6 c2k, 7 i2k, 8 distinct, 9 slice */
+    int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project, 6 c2k, 7 i2k, 8 distinct, 9 slice,
+                                10 peer-memory exchange: buckets_visited = rows pushed to peers, edges_touched = rows received,
+                                algo_bytes = bytes sent over NVLink */
     int32_t in_cols;
     uint64_t in_rows, out_rows;
     uint64_t buckets_visited;   /* sum over rows of L_i                      */
@@ -137,6 +139,23 @@ int wk_engine_destroy(wk_engine_t *engine);
  * 2 = additionally one event pair per step (wk_step_stats_t.device_us);
  * 3 = additionally SM-clock stamps at the phase boundaries of the fused light-query kernel */
 int wk_engine_set_profiling(wk_engine_t *engine, int level);
+/* Engine options.
+ *  WK_OPT_RESIDENT_LIGHT (default 1; environment WK_RESIDENT=0 turns it off for a whole process, e.g. under a profiler):
+ *    const-start ("light") plans are answered by a resident single-CTA server kernel that polls a doorbell in mapped pinned
+ *    memory -- no kernel launch and no stream round trip per query, like the reference's resident engine threads
+ *    (core/engine/engine.hpp:120-221, core/proxy.hpp:298-385).  The server leaves the device when a grid-filling kernel of
+ *    this engine is about to run, when it has been idle for WK_OPT_RESIDENT_IDLE_US (default 10 000), and in
+ *    wk_engine_destroy; it is relaunched on demand.  0 = one kernel launch per light query.
+ *  WK_INFO_* are read-only (wk_engine_get_option). */
+enum { WK_OPT_RESIDENT_LIGHT = 1, WK_OPT_RESIDENT_IDLE_US = 2,
+       WK_INFO_RESIDENT_LAUNCHES = 100,   /* server instances launched so far */
+       WK_INFO_RESIDENT_REQUESTS = 101,   /* queries answered through the doorbell */
+       WK_INFO_LAST_RESIDENT = 102,       /* 1 if the last wk_query_execute was answered by the server */
+       WK_INFO_LAST_RESIDENT_NS = 103,    /* its in-kernel span: request acquired -> record stored (%globaltimer) */
+       WK_INFO_RESIDENT_RUNNING = 104,
+       WK_INFO_COMM_BYTES_PUSHED = 110 };  /* bytes this rank has stored into peers' buffers (peer-memory exchange) */
+int wk_engine_set_option(wk_engine_t *engine, int option, int64_t value);
+int wk_engine_get_option(wk_engine_t *engine, int option, int64_t *value);
 /* level 3 diagnostics: dst[0] entry, [1] control block cleared, [2+s] step s done, [26] table written, [27] record stored */
 int wk_engine_light_trace(wk_engine_t *engine, int64_t *dst, int cap);
 int wk_engine_sync(wk_engine_t *engine);                     /* CUDA_STREAM_SYNC */
@@ -234,11 +253,17 @@ int wk_comm_stats(wk_engine_t *engine, uint64_t *exchanges, uint64_t *rows_sent,
 /* Peer-memory exchange over NVLink / NVSwitch instead of NCCL (one process per GPU, CUDA IPC): every rank exports a
  * 192-byte record (handles of its two result buffers and of its exchange control block), the records of all ranks
  * are gathered by the caller (rank order) and imported.  Afterwards wk_query_execute_sharded bucketises rows by owner
- * and stores them straight into the owners' next-table buffers from the kernel: counts and "pushed" flags travel
- * through peer memory too, so an exchange needs no host synchronisation at all.  Up to 16 ranks. */
+ * and stores them straight into the owners' next-table buffers from the kernel, ONE pass over the table: space in an
+ * owner's buffer is reserved with one (remote) atomic per tile and owner, "ready" / "pushed" flags travel through peer
+ * memory too, so an exchange needs no host synchronisation at all.  Up to 16 ranks, all with the same rbuf_bytes.
+ * A barrier that times out (dead peer) returns WK_ERR_COMM and poisons the group: re-import to use it again. */
 int wk_comm_p2p_export(wk_engine_t *engine, int nranks, int rank, void *out192);
 int wk_comm_p2p_import(wk_engine_t *engine, const void *all_handles);
 int wk_exchange_p2p(wk_engine_t *engine, int col_start, uint64_t *out_rows);
+/* The same group for engines of ONE process (one caller thread per engine; several shards may share a GPU): buffers, control
+ * blocks and store arrays of the peers are wired directly, engines[r] becomes rank r.  In-place light queries are enabled too.
+ * All engines must have the same rbuf_bytes. */
+int wk_comm_local_group(wk_engine_t **engines, int n);
 /* In-place light queries on a sharded store -- the reference answers small tables with one-sided RDMA reads of the remote
  * header / edge regions instead of a fork-join (sparql.hpp:802-814, Global::rdma_threshold): here every rank also maps its
  * peers' store arrays.  export_store writes [IPC handles of the header and edge arrays][segment table] (size in *size; call

@@ -47,12 +47,30 @@ def lib():
         L.refs_adopt.restype = vp
         L.refs_adopt.argtypes = [vp, u64, u64, vp, u64, vp, ci, ci]
         L.refe_time_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, ci, vp, C.POINTER(u64)]
+        L.refe_time_query_digest.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, ci, vp, C.POINTER(u64), C.POINTER(u64)]
         L.refe_cluster_query.argtypes = [vp, ci, vp, ci, ci, vp, ci, ci, vp, u64, C.POINTER(u64), C.POINTER(ci)]
         L.refp_set_plan.argtypes = [vp, ci, C.c_char_p, vp, ci]
         L.refe_fork_plan.argtypes = [vp, vp, ci, ci, ci, vp]
         L.refe_split.argtypes = [vp, vp, u64, ci, ci, ci, vp, vp]
         _lib = L
     return _lib
+
+
+def table_digest(table):
+    """order-independent digest of a binding table (a multiset of rows): sum over rows of a 64-bit mix of the row's words,
+    modulo 2^64 -- the same function as row_digest() in ref_engine_shim.cpp"""
+    t = np.asarray(table, dtype=np.uint32)
+    if t.size == 0:
+        return 0
+    t = t.reshape(t.shape[0], -1)
+    with np.errstate(over="ignore"):
+        h = np.full(t.shape[0], 0x9E3779B97F4A7C15, dtype=np.uint64)
+        for c in range(t.shape[1]):
+            h = (h ^ t[:, c].astype(np.uint64)) * np.uint64(0xBF58476D1CE4E5B9)
+            h ^= h >> np.uint64(29)
+        h *= np.uint64(0x94D049BB133111EB)
+        h ^= h >> np.uint64(32)
+        return int(h.sum(dtype=np.uint64))
 
 
 def cluster_query(stores, patterns, nvars, required):
@@ -104,15 +122,19 @@ class RefStore:
         self._out = np.empty(1 << 22, dtype=np.uint32)
         return self
 
-    def time_query(self, patterns, nvars, required, reps=1, mt_factor=1, threaded=True, blind=False):
-        """-> (status, usec[reps], rows): wall time of pattern phase (mt_factor slices on host threads) + merge + final_process"""
+    def time_query(self, patterns, nvars, required, reps=1, mt_factor=1, threaded=True, blind=False, digest=False):
+        """-> (status, usec[reps], rows[, digest]): wall time of pattern phase (mt_factor slices on host threads) + merge +
+        final_process; digest = table_digest() of the last repetition's final table (computed outside the timed region)"""
         p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
         rq = np.array(required, dtype=np.int32)
         us = np.zeros(reps, dtype=np.float64)
-        rows = C.c_uint64(0)
-        rc = lib().refe_time_query(self.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars,
-                                   rq.ctypes.data_as(C.c_void_p) if len(rq) else None, len(rq), 1 if blind else 0, mt_factor,
-                                   1 if threaded else 0, reps, us.ctypes.data_as(C.c_void_p), C.byref(rows))
+        rows, dg = C.c_uint64(0), C.c_uint64(0)
+        rc = lib().refe_time_query_digest(self.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars,
+                                          rq.ctypes.data_as(C.c_void_p) if len(rq) else None, len(rq), 1 if blind else 0, mt_factor,
+                                          1 if threaded else 0, reps, us.ctypes.data_as(C.c_void_p), C.byref(rows),
+                                          C.byref(dg) if digest else None)
+        if digest:
+            return rc, us, rows.value, dg.value
         return rc, us, rows.value
 
     @property

@@ -86,8 +86,26 @@ int refe_query(void *h, const int32_t *pats, int npat, int nvars, const int32_t 
 // :211-221 slicing), each slice on its own host thread with its own SPARQLEngine when `threaded`; the replies are
 // concatenated and final_process runs on the merged result, as the proxy-side engine does.  usec[i] = wall time of rep i
 // (pattern phase + merge + final_process; no Bundle serialisation, no proxy hop).  Returns the reference's status code.
+// digest != NULL: an order-independent digest of the final table of the last repetition (sum over rows of a 64-bit mix of the
+// row's words, computed outside the timed region) -- bench.py compares it with the same digest of the GPU engine's table
+static uint64_t row_digest(const sid_t *row, int cols) {
+    uint64_t hh = 0x9E3779B97F4A7C15ull;
+    for (int c = 0; c < cols; c++) {
+        hh = (hh ^ (uint64_t)row[c]) * 0xBF58476D1CE4E5B9ull;
+        hh ^= hh >> 29;
+    }
+    hh *= 0x94D049BB133111EBull;
+    hh ^= hh >> 32;
+    return hh;
+}
+int refe_time_query_digest(void *h, const int32_t *pats, int npat, int nvars, const int32_t *required, int nreq, int blind, int mt_factor,
+                           int threaded, int reps, double *usec, uint64_t *rows_out, uint64_t *digest);
 int refe_time_query(void *h, const int32_t *pats, int npat, int nvars, const int32_t *required, int nreq, int blind, int mt_factor,
                     int threaded, int reps, double *usec, uint64_t *rows_out) {
+    return refe_time_query_digest(h, pats, npat, nvars, required, nreq, blind, mt_factor, threaded, reps, usec, rows_out, nullptr);
+}
+int refe_time_query_digest(void *h, const int32_t *pats, int npat, int nvars, const int32_t *required, int nreq, int blind, int mt_factor,
+                           int threaded, int reps, double *usec, uint64_t *rows_out, uint64_t *digest) {
     RefStore *r = (RefStore *)h;
     Global::num_servers = 1;
     SPARQLQuery::PatternGroup pg;
@@ -155,6 +173,15 @@ int refe_time_query(void *h, const int32_t *pats, int npat, int nvars, const int
         }
         usec[rep] = (double)(timer::get_usec() - t0);
         *rows_out = fin.result.blind ? (uint64_t)fin.result.row_num : (uint64_t)fin.result.get_row_num();
+        if (digest && rep == reps - 1) {
+            uint64_t d = 0;
+            if (!fin.result.blind && fin.result.col_num > 0) {
+                const int C = fin.result.col_num;
+                const uint64_t n = fin.result.result_table.size() / (uint64_t)C;
+                for (uint64_t i = 0; i < n; i++) d += row_digest(&fin.result.result_table[i * C], C);
+            }
+            *digest = d;
+        }
     }
     return status;
 }

@@ -116,13 +116,159 @@ def test_sharded_gpu_in_place_light_queries(tmp_path):
         name = "q%d_%s" % (q, PLANS[0])
         holders = [r for r in range(world) if res[r][name].size]
         assert len(holders) <= 1, (name, holders)
-    tr = datagen.lubm(2, seed=7)
+    want = _spill_want(datagen.lubm(2, seed=7))
+    got = np.concatenate([r["spill"].reshape(-1, 3) for r in res])
+    assert want.shape[0] > 1024 and rows_equal(got, want)
+
+
+def _spill_want(tr):
+    """members of Department0.University0 x their courses x the courses' teachers, by plain numpy joins"""
     d0 = M.lubm_str2id("<http://www.Department0.University0.edu>")
     P = {n: i for i, n in enumerate(M.LUBM_INDEX)}
     t = np.unique(tr, axis=0)
     mem = t[(t[:, 1] == P[M.UB + "memberOf>"]) & (t[:, 2] == d0)][:, 0]
     tc = t[(t[:, 1] == P[M.UB + "takesCourse>"]) & np.isin(t[:, 0], mem)]
     to = t[t[:, 1] == P[M.UB + "teacherOf>"]]
-    want = np.array([(x, c, y) for x, _, c in tc.tolist() for y, _, c2 in to[to[:, 2] == c].tolist()], dtype=np.uint32).reshape(-1, 3)
+    return np.array([(x, c, y) for x, _, c in tc.tolist() for y, _, c2 in to[to[:, 2] == c].tolist()], dtype=np.uint32).reshape(-1, 3)
+
+
+# ---- the same sharded execution with all shards on ONE GPU: engines of this process as a peer-memory group
+# (wk_comm_local_group), one host thread per rank.  Runs on the single-GPU box the driver uses for `-m gpu`. ----------
+def _local_group(world, univs=2, seed=7, rbuf=128 << 20):
+    from wukong_b200 import host
+    stores, engs = [], []
+    for r in range(world):
+        tr = datagen.lubm_shard(univs, world, r, seed=seed, chunk=1)
+        stores.append(host.HostStore(tr, num_servers=world, sid=r, kvstore_bytes=48 << 20).upload(0))
+        engs.append(capi.Engine(stores[-1], rbuf_bytes=rbuf))
+    capi.local_group(engs)
+    return stores, engs
+
+
+def _run_ranks(engs, fn):
+    """fn(rank, engine) on one thread per rank (ctypes releases the GIL: the ranks' kernels are in flight together)"""
+    import threading
+    out, errs = [None] * len(engs), []
+
+    def work(r):
+        try:
+            out[r] = fn(r, engs[r])
+        except Exception as ex:   # noqa: BLE001
+            import traceback
+            errs.append("rank %d: %s" % (r, traceback.format_exc()))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(engs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, "\n".join(errs)
+    return out
+
+
+def _spill_plan():
+    from oracle import oracle as O
+    P = {n: i for i, n in enumerate(M.LUBM_INDEX)}
+    d0 = M.lubm_str2id("<http://www.Department0.University0.edu>")
+    return ([(d0, P[M.UB + "memberOf>"], O.IN, -1), (-1, P[M.UB + "takesCourse>"], O.OUT, -2),
+             (-2, P[M.UB + "teacherOf>"], O.IN, -3)], 3, [-1, -2, -3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_local_group_single_gpu(world):
+    """Q1-Q7 x 3 plan sets + a const-start plan that outgrows shared memory, `world` shards on device 0: exchange through
+    the single-pass peer-memory push, light plans in place on the constant's owner, all against the brute-force joiner"""
+    stores, engs = _local_group(world)
+    queries = {"q%d_%s" % (q, plan): load_query(q, plan)[:3] for q in range(1, 8) for plan in PLANS}
+    queries["spill"] = _spill_plan()
+
+    def run(rank, eng):
+        res = {}
+        for name, (pats, nvars, req) in queries.items():
+            rc, rows, cols, tbl = eng.query_sharded(pats, nvars, req)
+            assert rc == 0, (name, rc)
+            res[name] = tbl.copy() if rows else np.zeros((0, len(req)), np.uint32)
+            rc, rows_b, _, _ = eng.query_sharded(pats, nvars, req, blind=True)
+            assert rc == 0 and rows_b == rows, name
+        res["__stats__"] = eng.comm_stats()
+        return res
+
+    res = _run_ranks(engs, run)
+    _check_against_bruteforce(res, 2, 7)
+    want = _spill_want(datagen.lubm(2, seed=7))
     got = np.concatenate([r["spill"].reshape(-1, 3) for r in res])
     assert want.shape[0] > 1024 and rows_equal(got, want)
+    sent = sum(r["__stats__"]["rows_sent"] for r in res)
+    recv = sum(r["__stats__"]["rows_recv"] for r in res)
+    assert sent == recv and sent > 0 and res[0]["__stats__"]["exchanges"] > 0
+    for q in (4, 5, 6):   # in place: every row of a light answer sits on the constant's owner
+        assert len([r for r in range(world) if res[r]["q%d_%s" % (q, PLANS[0])].size]) <= 1
+    for e in engs:
+        e.close()
+    for s in stores:
+        s.close()
+
+
+@pytest.mark.gpu
+def test_exchange_local_group_tables_and_overflow():
+    """wk_exchange_p2p on uploaded tables (1-9 columns, ragged tiles, replicate mode) against numpy; a receive buffer that
+    is too small fails on EVERY rank with WK_ERR_RBUF_OVERFLOW and leaves the group usable"""
+    world = 3
+    stores, engs = _local_group(world, univs=1, seed=1, rbuf=8 << 20)
+    rng = np.random.default_rng(5)
+    for C, n in ((1, 70001), (3, 50000), (5, 33333), (9, 4099), (2, 0)):
+        tabs = [rng.integers(1 << 17, 1 << 26, (n + 13 * r, C), dtype=np.uint32) for r in range(world)]
+        col = C // 2
+
+        def run(rank, eng, tabs=tabs, col=col):
+            eng.upload(tabs[rank], ncols=tabs[rank].shape[1])
+            rows = eng.exchange_p2p(col)
+            t = eng.download()
+            return t[:rows]
+
+        got = _run_ranks(engs, run)
+        allrows = np.concatenate(tabs)
+        for r in range(world):
+            want = allrows[allrows[:, col] % world == r]
+            assert got[r].shape[0] == want.shape[0], (C, n, r)
+            if want.shape[0]:
+                assert rows_equal(got[r].reshape(-1, C), want), (C, n, r)
+    # overflow: 2 M words per buffer; rank 0 would receive 3 x 300 K rows x 3 columns
+    tabs = [np.full((300000, 3), 3 * 1000 + 0, dtype=np.uint32) for _ in range(world)]   # every row is owned by rank 0
+
+    def run_ovf(rank, eng):
+        eng.upload(tabs[rank])
+        try:
+            eng.exchange_p2p(0)
+        except capi.WukongError as ex:
+            return ex.code
+        return 0
+
+    assert _run_ranks(engs, run_ovf) == [capi.WK_ERR_RBUF_OVERFLOW] * world
+    # the group is still in step: a small exchange afterwards works
+    tabs2 = [rng.integers(1 << 17, 1 << 20, (1000, 2), dtype=np.uint32) for _ in range(world)]
+
+    def run2(rank, eng):
+        eng.upload(tabs2[rank])
+        rows = eng.exchange_p2p(1)
+        return eng.download()[:rows]
+
+    got = _run_ranks(engs, run2)
+    allrows = np.concatenate(tabs2)
+    for r in range(world):
+        assert rows_equal(got[r].reshape(-1, 2), allrows[allrows[:, 1] % world == r])
+    for e in engs:
+        e.close()
+    for s in stores:
+        s.close()
+
+
+def test_sharded_refuses_const_to_known():
+    # a pattern that starts from a constant after the first step cannot be forked: OBJ_ERROR like need_fork_join (sparql.hpp:808)
+    pats = [(18, 1, 0, -1), (131072, 5, 1, -1)]
+    lib = capi.lib()
+    import ctypes as C
+    p = np.array(pats, dtype=np.int32)
+    out = np.zeros(2, dtype=np.int32)
+    assert lib.wk_plan_exchanges(p.ctypes.data_as(C.c_void_p), 2, 1, out.ctypes.data_as(C.c_void_p)) == 7   # WK_OBJ_ERROR

@@ -9,11 +9,15 @@ LIB_CUDA = os.path.join(_HERE, "libwukong_b200.so")
 
 IN, OUT = 0, 1
 PREDICATE_ID, TYPE_ID = 0, 1
-KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k", "distinct", "slice"]
+KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k", "distinct", "slice", "exchange"]
 
 WK_SUCCESS = 0
 WK_ERR_CUDA, WK_ERR_BAD_ARG, WK_ERR_RBUF_OVERFLOW, WK_ERR_NO_SEGMENT, WK_ERR_NO_DEVICE, WK_ERR_COMM = 100, 101, 102, 103, 104, 105
 WK_ERR_STORE_FULL = 106
+# wk_engine_set_option / wk_engine_get_option
+WK_OPT_RESIDENT_LIGHT, WK_OPT_RESIDENT_IDLE_US = 1, 2
+WK_INFO_RESIDENT_LAUNCHES, WK_INFO_RESIDENT_REQUESTS, WK_INFO_LAST_RESIDENT, WK_INFO_LAST_RESIDENT_NS, WK_INFO_RESIDENT_RUNNING = 100, 101, 102, 103, 104
+WK_INFO_COMM_BYTES_PUSHED = 110
 
 
 class WukongError(RuntimeError):
@@ -57,14 +61,14 @@ class StepStats(C.Structure):
 DECLARED_SYMBOLS = [
     "wk_strerror", "wk_version", "wk_device_count", "wk_store_create", "wk_store_adopt", "wk_store_build", "wk_store_info", "wk_store_segs",
     "wk_store_download", "wk_store_destroy",
-    "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_profiling", "wk_engine_light_trace", "wk_engine_sync",
+    "wk_store_get_edges", "wk_engine_create", "wk_engine_destroy", "wk_engine_set_option", "wk_engine_get_option", "wk_engine_set_profiling", "wk_engine_light_trace", "wk_engine_sync",
     "wk_engine_reset", "wk_table_upload", "wk_table_download", "wk_table_info", "wk_index_to_unknown",
     "wk_const_to_unknown", "wk_known_to_unknown", "wk_known_to_known", "wk_known_to_const", "wk_const_to_known", "wk_index_to_known", "wk_table_distinct", "wk_table_slice", "wk_project",
     "wk_query_execute_ex",
     "wk_query_execute", "wk_query_execute_batch", "wk_engine_num_steps", "wk_engine_step_stats", "wk_engine_launch_count", "wk_engine_last_query_device_us", "wk_engine_flush_l2", "wk_host_alloc", "wk_host_free", "wk_partition",
     "wk_partition_ptr", "wk_comm_unique_id", "wk_comm_init", "wk_exchange", "wk_query_execute_sharded",
     "wk_comm_stats", "wk_plan_exchanges", "wk_comm_p2p_export", "wk_comm_p2p_import", "wk_exchange_p2p",
-    "wk_comm_p2p_export_store", "wk_comm_p2p_import_store",
+    "wk_comm_p2p_export_store", "wk_comm_p2p_import_store", "wk_comm_local_group",
 ]
 
 _lib = None
@@ -95,6 +99,8 @@ def lib():
     L.wk_engine_create.argtypes = [vp, u64, C.POINTER(vp)]
     L.wk_engine_destroy.argtypes = [vp]
     L.wk_engine_set_profiling.argtypes = [vp, ci]
+    L.wk_engine_set_option.argtypes = [vp, ci, C.c_int64]
+    L.wk_engine_get_option.argtypes = [vp, ci, C.POINTER(C.c_int64)]
     L.wk_engine_sync.argtypes = [vp]
     L.wk_engine_reset.argtypes = [vp]
     L.wk_table_upload.argtypes = [vp, vp, u64, ci]
@@ -131,6 +137,7 @@ def lib():
     L.wk_comm_p2p_export_store.argtypes = [vp, vp, u64, pu64]
     L.wk_comm_p2p_import_store.argtypes = [vp, vp, vp, ci]
     L.wk_plan_exchanges.argtypes = [vp, ci, ci, vp]
+    L.wk_comm_local_group.argtypes = [vp, ci]
     L.wk_query_execute_sharded.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, pu64, C.POINTER(ci)]
     L.wk_host_alloc.argtypes = [u64, C.POINTER(vp)]
     L.wk_host_free.argtypes = [vp]
@@ -265,6 +272,18 @@ class Engine:
 
     def set_profiling(self, level):
         _check(lib().wk_engine_set_profiling(self.h, int(level)))
+
+    def set_option(self, option, value):
+        _check(lib().wk_engine_set_option(self.h, int(option), int(value)), "wk_engine_set_option")
+
+    def get_option(self, option):
+        v = C.c_int64(0)
+        _check(lib().wk_engine_get_option(self.h, int(option), C.byref(v)), "wk_engine_get_option")
+        return v.value
+
+    def set_resident(self, on):
+        """light queries through the resident server kernel (default) or one launch per query"""
+        self.set_option(WK_OPT_RESIDENT_LIGHT, 1 if on else 0)
 
     def light_trace(self):
         """profiling level 3: SM clocks at the fused light kernel's phase boundaries (diagnostics)"""
@@ -499,6 +518,12 @@ def pinned_array(nwords):
     _check(lib().wk_host_alloc(nwords * 4, C.byref(p)), "wk_host_alloc")
     arr = np.frombuffer((C.c_uint32 * nwords).from_address(p.value), dtype=np.uint32)
     return arr, p
+
+
+def local_group(engines):
+    """wk_comm_local_group: engines of this process become ranks 0..n-1 of one peer-memory group"""
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    _check(lib().wk_comm_local_group(C.cast(arr, C.c_void_p), len(engines)), "wk_comm_local_group")
 
 
 def comm_unique_id():

@@ -24,6 +24,7 @@
 #include "wukong_b200.h"
 #include "wk_device.cuh"
 #include "wk_light.cuh"
+#include "wk_server.cuh"
 #include "wk_internal.h"
 
 using namespace wk;
@@ -32,7 +33,7 @@ using namespace wk;
 // device-side control block and kernels
 // =============================================================================================
 enum { MAX_STEPS = 60 };
-enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5, KIND_C2K = 6, KIND_I2K = 7, KIND_DISTINCT = 8, KIND_SLICE = 9 };
+enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5, KIND_C2K = 6, KIND_I2K = 7, KIND_DISTINCT = 8, KIND_SLICE = 9, KIND_EXCHANGE = 10 };
 
 struct CtlBlock {
     uint64_t counts[MAX_STEPS + 4];       // counts[s] = rows of the table that step s reads
@@ -366,6 +367,9 @@ struct wk_store {
     bool owns = true;
     std::map<SegKey, wk_segmeta_t> segs;
     std::map<SegKey, uint32_t> maxdeg;   // largest edge list of a key of the segment (index segments: of the predicate's list)
+    std::map<SegKey, int> seg_slot;      // slot of every segment in d_segtab (resident light-query server, wk_server.cuh)
+    SegLite *d_segtab = nullptr;
+    int nsegslots = 0;
 };
 
 struct StepRecord {
@@ -407,12 +411,34 @@ struct wk_engine {
     uint32_t hq_cap = 0;
     void *d_flush = nullptr;             // > L2-sized scratch for wk_engine_flush_l2
     size_t flush_bytes = 0;
+    int flush_gen = 0;
+    // resident light-query server (wk_server.cuh)
+    struct {
+        bool enabled = true;             // WK_OPT_RESIDENT_LIGHT
+        uint64_t idle_ns = 10ull * 1000 * 1000;
+        cudaStream_t stream = nullptr;
+        SrvMailbox *h_box = nullptr, *d_box = nullptr;   // mapped pinned page
+        uint64_t seq = 0;                // sequence number of the last request posted (QUIT included)
+        uint64_t launch_id = 0;          // 0: never launched
+        bool quitting = false;           // a QUIT is on its way: wait for the exit word before relaunching
+        uint64_t launches = 0, requests = 0;
+        uint64_t last_ns = 0;            // in-kernel span of the last request
+    } srv;
+    bool last_resident = false;          // the last wk_query_execute was answered by the resident server
     std::vector<StepRecord> recs;        // one per step since the last reset
     std::vector<cudaEvent_t> event_pool;
     size_t event_next = 0;
     // snapshot of per-step stats taken at the last synchronising call
     std::vector<wk_step_stats_t> stats;
 };
+
+extern "C" {   // defined inside the extern "C" block below
+static void srv_park(wk_engine *e);   // resident light-query server: leave before a grid-filling kernel
+static void srv_stop(wk_engine *e);
+static bool srv_exited(const wk_engine *e);
+}
+static void comm_free(wk_engine *e);   // wk_sharded.cuh
+static uint64_t comm_bytes_pushed(const wk_engine *e);
 
 static const char *k_errs[] = {"success", "unknown error", "syntax error", "unsupported triple pattern",
                                "attribute support disabled", "no required variables", "unsupported UNION",
@@ -498,8 +524,7 @@ static int ensure_step_room(wk_engine *e) {
 // the host reads (table_cols > 0: the table in h_stage is rows x table_cols words).
 struct RecView { uint64_t rows; uint32_t status; int resume; };
 
-static bool record_valid(wk_engine *e, uint64_t seq, int nsteps_full, int table_cols, RecView &out) {
-    volatile uint64_t *r = (volatile uint64_t *)e->h_rec;
+static bool record_valid_at(const volatile uint64_t *r, wk_engine *e, uint64_t seq, int nsteps_full, int table_cols, RecView &out) {
     if (r[0] != seq) return false;
     const uint64_t rows = r[1], sr = r[2], check = r[3];
     uint64_t tsum = 0;
@@ -515,6 +540,9 @@ static bool record_valid(wk_engine *e, uint64_t seq, int nsteps_full, int table_
     out.status = (uint32_t)sr;
     out.resume = resume;
     return true;
+}
+static bool record_valid(wk_engine *e, uint64_t seq, int nsteps_full, int table_cols, RecView &out) {
+    return record_valid_at((const volatile uint64_t *)e->h_rec, e, seq, nsteps_full, table_cols, out);
 }
 
 static int wait_record(wk_engine *e, uint64_t seq, int nsteps_full, int table_cols, RecView &out) {
@@ -612,6 +640,8 @@ static int launch_step(wk_engine *e, const StepParam &p) {
 
 // ---- enqueue one known_to_* step on the multi-CTA path ------------------------------------------
 static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, int dir, int col_end, uint32_t end_const) {
+    srv_park(e);
+    if (kind != KIND_K2U && kind != KIND_K2K && kind != KIND_K2C) return WK_UNKNOWN_PATTERN;
     if (e->ncols <= 0 || e->ncols > MAX_COLS - 1) return e->ncols <= 0 ? WK_FIRST_PATTERN_ERROR : WK_ERR_BAD_ARG;
     if (col_start < 0 || col_start >= e->ncols) return WK_VERTEX_INVALID;
     if (kind == KIND_K2K && (col_end < 0 || col_end >= e->ncols)) return WK_VERTEX_INVALID;
@@ -664,6 +694,7 @@ static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, in
 }
 
 static int enqueue_seed(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int dir, int mt_tid, int mt_factor) {
+    srv_park(e);
     if (e->ncols != 0) return WK_FIRST_PATTERN_ERROR;
     if (dir != WK_DIR_IN && dir != WK_DIR_OUT) return WK_ERR_BAD_ARG;
     if (mt_factor < 1) mt_factor = 1;
@@ -696,6 +727,7 @@ static int enqueue_seed(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int 
 }
 
 static int enqueue_project(wk_engine *e, const int32_t *cols, int n) {
+    srv_park(e);
     if (n <= 0 || n > MAX_COLS) return WK_NO_REQUIRED_VAR;
     if (e->ncols <= 0) return WK_ERR_BAD_ARG;
     for (int i = 0; i < n; i++)
@@ -725,6 +757,7 @@ static int enqueue_project(wk_engine *e, const int32_t *cols, int n) {
 
 // DISTINCT of final_process (sparql.hpp:1428-1472).  `rows` is the current row count, known on the host.
 static int enqueue_distinct(wk_engine *e, const int32_t *cols, int n, uint64_t rows) {
+    srv_park(e);
     if (n <= 0 || n > MAX_COLS) return WK_NO_REQUIRED_VAR;
     if (e->ncols <= 0) return WK_ERR_BAD_ARG;
     for (int i = 0; i < n; i++)
@@ -747,6 +780,7 @@ static int enqueue_distinct(wk_engine *e, const int32_t *cols, int n, uint64_t r
 
 // OFFSET / LIMIT of final_process (sparql.hpp:1487-1499)
 static int enqueue_slice(wk_engine *e, uint64_t offset, int64_t limit, uint64_t rows_upper_bound) {
+    srv_park(e);
     if (e->ncols <= 0) return WK_ERR_BAD_ARG;
     int rc = ensure_step_room(e);
     if (rc) return rc;
@@ -762,6 +796,7 @@ static int enqueue_slice(wk_engine *e, uint64_t offset, int64_t limit, uint64_t 
 
 // index_to_known / const_to_known: rows whose column `col_end` occurs in the edge list of key (vid, pid, dir)
 static int enqueue_to_known(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int dir, int col_end, int mt_tid, int mt_factor) {
+    srv_park(e);
     if (e->ncols <= 0 || e->ncols >= MAX_COLS) return e->ncols <= 0 ? WK_VERTEX_INVALID : WK_ERR_BAD_ARG;
     if (col_end < 0 || col_end >= e->ncols) return WK_VERTEX_INVALID;
     if (dir != WK_DIR_IN && dir != WK_DIR_OUT) return WK_ERR_BAD_ARG;
@@ -836,6 +871,9 @@ static int snapshot_stats(wk_engine *e) {
         case KIND_K2C: st.algo_bytes = 4 * C * N + 128 * st.buckets_visited + 4 * st.edges_touched + 4 * C * R; break;
         case KIND_I2U:
         case KIND_C2U: st.algo_bytes = 128 * st.buckets_visited + 4 * R + 4 * R; break;
+        case KIND_EXCHANGE:   // buckets_visited = rows pushed to peers, edges_touched = rows that landed here; NVLink bytes sent
+            st.algo_bytes = 4 * C * st.buckets_visited;
+            break;
         case KIND_C2K:
         case KIND_I2K:
         case KIND_DISTINCT:
@@ -888,6 +926,26 @@ static int store_set_segs(wk_store *st, const wk_segmeta_t *segs, int nsegs) {
     return WK_SUCCESS;
 }
 
+// device copy of {bucket_start, % num_buckets} per segment, addressed by slot: requests to the resident light-query server
+// name segments by slot instead of carrying 32 bytes of modulo magic per step (the device must be current)
+static int store_upload_segtab(wk_store *st) {
+    std::vector<SegLite> tab;
+    st->seg_slot.clear();
+    for (auto &kv : st->segs) {
+        SegLite sl;
+        sl.bucket_start = kv.second.bucket_start;
+        sl.fm = make_fastmod(kv.second.num_buckets);
+        st->seg_slot[kv.first] = (int)tab.size();
+        tab.push_back(sl);
+    }
+    st->nsegslots = (int)tab.size();
+    if (st->d_segtab) { cudaFree(st->d_segtab); st->d_segtab = nullptr; }
+    if (tab.empty()) return WK_SUCCESS;
+    CUDA_TRY(cudaMalloc((void **)&st->d_segtab, tab.size() * sizeof(SegLite)));
+    CUDA_TRY(cudaMemcpy(st->d_segtab, tab.data(), tab.size() * sizeof(SegLite), cudaMemcpyHostToDevice));
+    return WK_SUCCESS;
+}
+
 // one pass over the header: largest edge list per (index, pid, dir)
 static int store_scan_degrees(wk_store *st) {
     const uint32_t P = 1u << WK_NBITS_IDX;   // pid field of a key: predicate / type id (2 MB of counters)
@@ -914,6 +972,18 @@ static int store_scan_degrees(wk_store *st) {
     return WK_SUCCESS;
 }
 
+// error paths of the create functions must not leak the half-built object
+#define STORE_TRY(x)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess) {                                                                      \
+            fprintf(stderr, "[wukong_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                    cudaGetErrorString(_e));                                                          \
+            wk_store_destroy(st);                                                                     \
+            return WK_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
 int wk_store_create(int device, const wk_vertex_t *vertices, uint64_t num_slots, const wk_sid_t *edges,
                     uint64_t num_edges, const wk_segmeta_t *segs, int nsegs, wk_store_t **out) {
     if (!vertices || !segs || !out || num_slots == 0 || (num_slots % WK_ASSOCIATIVITY) != 0) return WK_ERR_BAD_ARG;
@@ -927,11 +997,12 @@ int wk_store_create(int device, const wk_vertex_t *vertices, uint64_t num_slots,
     st->num_edges = num_edges;
     int rc = store_set_segs(st, segs, nsegs);
     if (rc) { delete st; return rc; }
-    CUDA_TRY(cudaMalloc((void **)&st->d_vertices, num_slots * sizeof(uint4)));
-    CUDA_TRY(cudaMalloc((void **)&st->d_edges, (num_edges ? num_edges : 1) * sizeof(uint32_t)));
-    CUDA_TRY(cudaMemcpy(st->d_vertices, vertices, num_slots * sizeof(uint4), cudaMemcpyHostToDevice));
-    if (num_edges) CUDA_TRY(cudaMemcpy(st->d_edges, edges, num_edges * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    STORE_TRY(cudaMalloc((void **)&st->d_vertices, num_slots * sizeof(uint4)));
+    STORE_TRY(cudaMalloc((void **)&st->d_edges, (num_edges ? num_edges : 1) * sizeof(uint32_t)));
+    STORE_TRY(cudaMemcpy(st->d_vertices, vertices, num_slots * sizeof(uint4), cudaMemcpyHostToDevice));
+    if (num_edges) STORE_TRY(cudaMemcpy(st->d_edges, edges, num_edges * sizeof(uint32_t), cudaMemcpyHostToDevice));
     rc = store_scan_degrees(st);
+    if (!rc) rc = store_upload_segtab(st);
     if (rc) { wk_store_destroy(st); return rc; }
     *out = st;
     return WK_SUCCESS;
@@ -947,12 +1018,14 @@ int wk_store_adopt(int device, wk_vertex_t *d_vertices, uint64_t num_slots, wk_s
     st->num_edges = num_edges;
     st->d_vertices = (uint4 *)d_vertices;
     st->d_edges = d_edges;
-    st->owns = take_ownership != 0;
+    st->owns = false;   // until the adoption has succeeded the arrays stay the caller's
     int rc = store_set_segs(st, segs, nsegs);
     if (rc) { delete st; return rc; }
     if (cudaSetDevice(device) != cudaSuccess) { delete st; return WK_ERR_CUDA; }
     rc = store_scan_degrees(st);
-    if (rc) { delete st; return rc; }
+    if (!rc) rc = store_upload_segtab(st);
+    if (rc) { wk_store_destroy(st); return rc; }
+    st->owns = take_ownership != 0;
     *out = st;
     return WK_SUCCESS;
 }
@@ -987,11 +1060,12 @@ int wk_store_download(wk_store_t *st, wk_vertex_t *vertices, uint64_t num_slots,
 
 int wk_store_destroy(wk_store_t *st) {
     if (!st) return WK_ERR_BAD_ARG;
+    cudaSetDevice(st->device);
     if (st->owns) {
-        cudaSetDevice(st->device);
         if (st->d_vertices) cudaFree(st->d_vertices);
         if (st->d_edges) cudaFree(st->d_edges);
     }
+    if (st->d_segtab) cudaFree(st->d_segtab);
     delete st;
     return WK_SUCCESS;
 }
@@ -1021,27 +1095,67 @@ int wk_store_get_edges(wk_store_t *st, wk_sid_t vid, wk_sid_t pid, int dir, wk_s
     }
 }
 
+// release everything an engine owns (also the error path of wk_engine_create: nothing half-built is leaked)
+static void engine_free(wk_engine *e) {
+    cudaSetDevice(e->store->device);
+    srv_stop(e);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    comm_free(e);
+    for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->d_flush) cudaFree(e->d_flush);
+    if (e->q_ev0) cudaEventDestroy(e->q_ev0);
+    if (e->q_ev1) cudaEventDestroy(e->q_ev1);
+    if (e->buf[0]) cudaFree(e->buf[0]);
+    if (e->buf[1]) cudaFree(e->buf[1]);
+    if (e->d_ctl) cudaFree(e->d_ctl);
+    if (e->d_hq) cudaFree(e->d_hq);
+    if (e->d_set) cudaFree(e->d_set);
+    if (e->d_setctl) cudaFree(e->d_setctl);
+    if (e->d_trace) cudaFree(e->d_trace);
+    if (e->d_bplans) cudaFree(e->d_bplans);
+    if (e->d_bres) cudaFree(e->d_bres);
+    if (e->h_bplans) cudaFreeHost(e->h_bplans);
+    if (e->h_bres) cudaFreeHost(e->h_bres);
+    if (e->h_rec) cudaFreeHost((void *)e->h_rec);
+    if (e->h_stage) cudaFreeHost((void *)e->h_stage);
+    if (e->srv.h_box) cudaFreeHost((void *)e->srv.h_box);
+    if (e->srv.stream) cudaStreamDestroy(e->srv.stream);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+#define ENGINE_TRY(x)                                                                                 \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess) {                                                                      \
+            fprintf(stderr, "[wukong_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                    cudaGetErrorString(_e));                                                          \
+            engine_free(e);                                                                           \
+            return WK_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
 int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) {
     if (!store || !out || rbuf_bytes < 4096) return WK_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(store->device));
     wk_engine *e = new wk_engine();
     e->store = store;
     e->cap_words = rbuf_bytes / sizeof(uint32_t);
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc((void **)&e->buf[0], e->cap_words * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc((void **)&e->buf[1], e->cap_words * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc((void **)&e->d_ctl, sizeof(CtlBlock)));
+    ENGINE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    ENGINE_TRY(cudaMalloc((void **)&e->buf[0], e->cap_words * sizeof(uint32_t)));
+    ENGINE_TRY(cudaMalloc((void **)&e->buf[1], e->cap_words * sizeof(uint32_t)));
+    ENGINE_TRY(cudaMalloc((void **)&e->d_ctl, sizeof(CtlBlock)));
     // one descriptor (4 KB) per 256-row tile that may turn out heavy: sized for 64 M-row frontiers at most
     e->hq_cap = (uint32_t)std::min<uint64_t>(262144, std::max<uint64_t>(8192, e->cap_words / 16384));
-    CUDA_TRY(cudaMalloc((void **)&e->d_hq, (size_t)e->hq_cap * sizeof(HeavyTile)));
-    CUDA_TRY(cudaHostAlloc((void **)&e->h_rec, sizeof(HostRec), cudaHostAllocMapped));
+    ENGINE_TRY(cudaMalloc((void **)&e->d_hq, (size_t)e->hq_cap * sizeof(HeavyTile)));
+    ENGINE_TRY(cudaHostAlloc((void **)&e->h_rec, sizeof(HostRec), cudaHostAllocMapped));
     memset((void *)e->h_rec, 0, sizeof(HostRec));
-    CUDA_TRY(cudaHostGetDevicePointer((void **)&e->d_rec, (void *)e->h_rec, 0));
+    ENGINE_TRY(cudaHostGetDevicePointer((void **)&e->d_rec, (void *)e->h_rec, 0));
     e->stage_words = (1u << 20) / sizeof(uint32_t);   // 1 MiB zero-copy staging for small results
-    CUDA_TRY(cudaHostAlloc((void **)&e->h_stage, e->stage_words * sizeof(uint32_t), cudaHostAllocMapped));
-    CUDA_TRY(cudaHostGetDevicePointer((void **)&e->d_stage, (void *)e->h_stage, 0));
+    ENGINE_TRY(cudaHostAlloc((void **)&e->h_stage, e->stage_words * sizeof(uint32_t), cudaHostAllocMapped));
+    ENGINE_TRY(cudaHostGetDevicePointer((void **)&e->d_stage, (void *)e->h_stage, 0));
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, store->device));
+    ENGINE_TRY(cudaGetDeviceProperties(&prop, store->device));
     e->num_sms = prop.multiProcessorCount;
     // resident CTAs per SM of each fused kernel (persistent grid = SMs x occupancy)
     e->variant = WK_DEFAULT_VARIANT;
@@ -1052,39 +1166,25 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     for (int m = 0; m < 3; m++) {
         StepKernelFn fn = step_kernel_fn(m, e->variant, 3);
         const size_t smem = step_smem(e, 3);
-        if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], fn, CTA_THREADS, smem));
+        if (smem > 40 * 1024) ENGINE_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ENGINE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ[m], fn, CTA_THREADS, smem));
     }
     if (getenv("WK_VERBOSE"))
         fprintf(stderr, "[wukong_b200] variant %d: CTAs/SM k2u=%d k2k=%d k2c=%d, %d SMs\n", e->variant, e->occ[0], e->occ[1], e->occ[2], e->num_sms);
     for (int i = 0; i < 3; i++)
         if (e->occ[i] < 1) e->occ[i] = 1;
-    int rc = reset_ctl(e);
-    if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    // resident light-query server: on unless WK_RESIDENT=0 (profilers and sanitizers serialise kernels; see wk_server.cuh)
+    if (const char *ev = getenv("WK_RESIDENT")) e->srv.enabled = atoi(ev) != 0;
+    if (const char *ev = getenv("WK_RESIDENT_IDLE_US")) e->srv.idle_ns = (uint64_t)std::max(1, atoi(ev)) * 1000ull;
+    if (reset_ctl(e) != WK_SUCCESS) { engine_free(e); return WK_ERR_CUDA; }
+    ENGINE_TRY(cudaStreamSynchronize(e->stream));
     *out = e;
     return WK_SUCCESS;
 }
 
 int wk_engine_destroy(wk_engine_t *e) {
     if (!e) return WK_ERR_BAD_ARG;
-    cudaSetDevice(e->store->device);
-    cudaStreamSynchronize(e->stream);
-    for (auto ev : e->event_pool) cudaEventDestroy(ev);
-    if (e->d_flush) cudaFree(e->d_flush);
-    if (e->q_ev0) cudaEventDestroy(e->q_ev0);
-    if (e->q_ev1) cudaEventDestroy(e->q_ev1);
-    cudaFree(e->buf[0]);
-    cudaFree(e->buf[1]);
-    cudaFree(e->d_ctl);
-    if (e->d_hq) cudaFree(e->d_hq);
-    if (e->d_set) { cudaFree(e->d_set); cudaFree(e->d_setctl); }
-    if (e->d_trace) cudaFree(e->d_trace);
-    if (e->d_bplans) { cudaFree(e->d_bplans); cudaFree(e->d_bres); cudaFreeHost(e->h_bplans); cudaFreeHost(e->h_bres); }
-    cudaFreeHost((void *)e->h_rec);
-    cudaFreeHost((void *)e->h_stage);
-    cudaStreamDestroy(e->stream);
-    delete e;
+    engine_free(e);
     return WK_SUCCESS;
 }
 
@@ -1097,6 +1197,44 @@ int wk_engine_set_profiling(wk_engine_t *e, int on) {
         CUDA_TRY(cudaEventCreate(&e->q_ev1));
     }
     return WK_SUCCESS;
+}
+
+int wk_engine_set_option(wk_engine_t *e, int option, int64_t value) {
+    if (!e) return WK_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(e->store->device));
+    switch (option) {
+    case WK_OPT_RESIDENT_LIGHT:
+        e->srv.enabled = value != 0;
+        if (!e->srv.enabled) srv_stop(e);
+        return WK_SUCCESS;
+    case WK_OPT_RESIDENT_IDLE_US:
+        if (value < 1 || value > 10 * 1000 * 1000) return WK_ERR_BAD_ARG;
+        srv_stop(e);   // the next instance picks the new value up
+        e->srv.idle_ns = (uint64_t)value * 1000ull;
+        return WK_SUCCESS;
+    default: return WK_ERR_BAD_ARG;
+    }
+}
+
+int wk_engine_get_option(wk_engine_t *e, int option, int64_t *value) {
+    if (!e || !value) return WK_ERR_BAD_ARG;
+    switch (option) {
+    case WK_OPT_RESIDENT_LIGHT: *value = e->srv.enabled ? 1 : 0; return WK_SUCCESS;
+    case WK_OPT_RESIDENT_IDLE_US: *value = (int64_t)(e->srv.idle_ns / 1000ull); return WK_SUCCESS;
+    case WK_INFO_RESIDENT_LAUNCHES: *value = (int64_t)e->srv.launches; return WK_SUCCESS;
+    case WK_INFO_RESIDENT_REQUESTS: *value = (int64_t)e->srv.requests; return WK_SUCCESS;
+    case WK_INFO_LAST_RESIDENT: *value = e->last_resident ? 1 : 0; return WK_SUCCESS;
+    case WK_INFO_LAST_RESIDENT_NS: *value = (int64_t)e->srv.last_ns; return WK_SUCCESS;
+    case WK_INFO_COMM_BYTES_PUSHED: {
+        if (!e->comm) return WK_ERR_COMM;
+        int rc = wk_comm_stats(e, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        *value = (int64_t)comm_bytes_pushed(e);
+        return WK_SUCCESS;
+    }
+    case WK_INFO_RESIDENT_RUNNING: *value = (e->srv.h_box && !e->srv.quitting && !srv_exited(e)) ? 1 : 0; return WK_SUCCESS;
+    default: return WK_ERR_BAD_ARG;
+    }
 }
 
 int wk_engine_sync(wk_engine_t *e) {
@@ -1341,8 +1479,8 @@ static int fill_light_steps(wk_engine *e, const std::vector<PlannedStep> &steps,
         ls.col_start = ps.col_start;
         ls.col_end = ps.col_end;
         ls.end_const = ps.end_const;
-        ls.mt_tid = mt_tid;
-        ls.mt_factor = mt_factor < 1 ? 1 : mt_factor;
+        ls.mt_tid = ps.kind == KIND_I2U ? mt_tid : 0;   // only index_to_unknown is sliced (sparql.hpp:211-221)
+        ls.mt_factor = (ps.kind != KIND_I2U || mt_factor < 1) ? 1 : mt_factor;
         if (ps.kind == KIND_I2U || ps.kind == KIND_C2U) {
             const wk_segmeta_t *m = seg_of_key(e->store, ps.vid, ps.pid, ps.dir);
             if (!m) return WK_ERR_NO_SEGMENT;
@@ -1354,6 +1492,183 @@ static int fill_light_steps(wk_engine *e, const std::vector<PlannedStep> &steps,
             if (!m) return WK_ERR_NO_SEGMENT;
             ls.seg = make_segparam(m, ps.pid, ps.dir, index_mode);
         }
+    }
+    return WK_SUCCESS;
+}
+
+// =============================================================================================
+// resident light-query server (wk_server.cuh): host side
+// =============================================================================================
+static int srv_init(wk_engine *e) {
+    if (e->srv.h_box) return WK_SUCCESS;
+    if (!e->srv.stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->srv.stream, cudaStreamNonBlocking));
+    SrvMailbox *box = nullptr;
+    CUDA_TRY(cudaHostAlloc((void **)&box, sizeof(SrvMailbox), cudaHostAllocMapped));
+    memset((void *)box, 0, sizeof(SrvMailbox));
+    e->srv.h_box = box;
+    CUDA_TRY(cudaHostGetDevicePointer((void **)&e->srv.d_box, (void *)box, 0));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
+    return WK_SUCCESS;
+}
+
+// no server instance is (or will stay) on the device: never launched, or the last instance has stored its exit word
+static bool srv_exited(const wk_engine *e) {
+    if (e->srv.launch_id == 0) return true;
+    return *(const volatile uint64_t *)&e->srv.h_box->exit_word == e->srv.launch_id;
+}
+
+static int srv_launch(wk_engine *e, uint64_t first_seq) {
+    SrvParams P;
+    memset(&P, 0, sizeof(P));
+    P.vertices = e->store->d_vertices;
+    P.edges = e->store->d_edges;
+    P.segtab = e->store->d_segtab;
+    P.nsegs = e->store->nsegslots;
+    P.ctl_nwords = (int)(sizeof(CtlBlock) / sizeof(uint64_t));
+    P.req = e->srv.d_box->req;
+    P.rec = &e->srv.d_box->rec;
+    P.times = e->srv.d_box->times;
+    P.exit_word = &e->srv.d_box->exit_word;
+    P.host_table = e->d_stage;
+    P.host_table_words = e->stage_words;
+    P.buf[0] = e->buf[0];
+    P.buf[1] = e->buf[1];
+    P.cap_words = e->cap_words;
+    P.counts = e->d_ctl->counts;
+    P.stats = e->d_ctl->stats;
+    P.ctl_words = (uint64_t *)e->d_ctl;
+    P.status = &e->d_ctl->status;
+    P.first_seq = first_seq;
+    P.launch_id = ++e->srv.launch_id;
+    P.idle_ns = e->srv.idle_ns;
+    light_server_kernel<<<1, LIGHT_THREADS, sizeof(SrvSmem), e->srv.stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    e->srv.launches++;
+    e->srv.quitting = false;
+    return WK_SUCCESS;
+}
+
+// wait until the current instance has left (it was told to, or it is idling out)
+static int srv_wait_exit(wk_engine *e) {
+    uint32_t spins = 0;
+    while (!srv_exited(e)) {
+        if ((++spins & 0x3FFF) == 0) {
+            cudaError_t q = cudaStreamQuery(e->srv.stream);
+            if (q == cudaSuccess) break;              // the kernel is gone (its exit word may still be in flight)
+            if (q != cudaErrorNotReady) CUDA_TRY(q);
+        }
+    }
+    return WK_SUCCESS;
+}
+
+static int srv_ensure_running(wk_engine *e, uint64_t first_seq) {
+    int rc = srv_init(e);
+    if (rc) return rc;
+    if (e->srv.quitting) {
+        rc = srv_wait_exit(e);
+        if (rc) return rc;
+        e->srv.quitting = false;
+        return srv_launch(e, first_seq);
+    }
+    if (srv_exited(e)) return srv_launch(e, first_seq);
+    return WK_SUCCESS;
+}
+
+static void srv_post(wk_engine *e, const SrvChunk *ch, uint64_t seq) {
+    volatile SrvChunk *q = e->srv.h_box->req;
+    for (int i = 0; i < SRV_CHUNKS; i++) { q[i].w0 = ch[i].w0; q[i].w1 = ch[i].w1; q[i].w2 = ch[i].w2; }
+    __atomic_thread_fence(__ATOMIC_RELEASE);   // payload words before the tags (a compiler barrier on x86)
+    for (int i = 0; i < SRV_CHUNKS; i++) q[i].tag = (uint32_t)seq;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+
+// The server occupies one CTA slot of one SM.  The fused step kernels are persistent grids that fill every slot and stride
+// statically over their tiles, so a CTA that cannot become resident would run after all the others: ask the server to
+// leave before such a kernel is launched.  It is relaunched when the heavy query is over (wk_query_execute) or on demand.
+static void srv_park(wk_engine *e) {
+    if (!e->srv.h_box || e->srv.launch_id == 0 || e->srv.quitting || srv_exited(e)) return;
+    SrvChunk ch[SRV_CHUNKS];
+    memset(ch, 0, sizeof(ch));
+    ch[0].w0 = (uint32_t)SRV_F_QUIT << 8;
+    srv_post(e, ch, ++e->srv.seq);
+    e->srv.quitting = true;
+}
+
+static void srv_stop(wk_engine *e) {
+    if (!e->srv.h_box) return;
+    srv_park(e);
+    srv_wait_exit(e);
+    e->srv.quitting = false;
+    if (e->srv.stream) cudaStreamSynchronize(e->srv.stream);
+}
+
+static bool srv_usable(const wk_engine *e) {
+    return e->srv.enabled && e->profiling < 3 && e->store->nsegslots > 0 && e->store->nsegslots < (1 << 15) && e->store->d_segtab;
+}
+
+static int run_light_resident(wk_engine *e, const std::vector<PlannedStep> &steps, bool project,
+                              const std::vector<int32_t> &proj_cols, RecView &rv) {
+    SrvChunk ch[SRV_CHUNKS];
+    memset(ch, 0, sizeof(ch));
+    const uint32_t flags = (project ? SRV_F_PROJECT : 0u) | (e->profiling >= 2 ? SRV_F_STATS : 0u);
+    ch[0].w0 = (uint32_t)steps.size() | (flags << 8) | ((uint32_t)proj_cols.size() << 16);
+    for (size_t j = 0; j < proj_cols.size(); j++) {
+        SrvChunk &c = ch[1 + j / 12];
+        uint32_t &w = (j % 12) < 4 ? c.w0 : ((j % 12) < 8 ? c.w1 : c.w2);
+        w |= ((uint32_t)proj_cols[j] & 0xFFu) << (8 * (j & 3));
+    }
+    for (size_t i = 0; i < steps.size(); i++) {
+        const PlannedStep &ps = steps[i];
+        const bool seed = ps.kind == KIND_I2U || ps.kind == KIND_C2U;
+        const bool index_mode = !seed && ps.kind == KIND_K2U && ps.pid == WK_TYPE_ID && ps.dir == WK_DIR_IN;
+        const wk_segmeta_t *m = seed ? seg_of_key(e->store, ps.vid, ps.pid, ps.dir)
+                                     : (index_mode ? find_seg(e->store, 1, WK_PREDICATE_ID, ps.dir) : find_seg(e->store, 0, ps.pid, ps.dir));
+        if (!m) return WK_ERR_NO_SEGMENT;
+        const int slot = e->store->seg_slot[SegKey(m->index, m->pid, m->dir)];
+        SrvChunk &c = ch[SRV_HDR_CHUNKS + i];
+        c.w0 = srv_pack_w0(ps.kind, ps.col_start, ps.col_end, ps.dir, index_mode ? 1 : 0, ps.in_cols);
+        c.w1 = seed ? (uint32_t)ps.vid : ps.end_const;
+        c.w2 = (ps.pid & 0x1FFFFu) | ((uint32_t)slot << 17);
+    }
+    int rc = srv_ensure_running(e, e->srv.seq + 1);
+    if (rc) return rc;
+    const uint64_t seq = ++e->srv.seq;
+    srv_post(e, ch, seq);
+    e->srv.requests++;
+    const volatile uint64_t *rec = (const volatile uint64_t *)&e->srv.h_box->rec;
+    const int table_cols = project ? (int)proj_cols.size() : 0;
+    uint32_t spins = 0;
+    while (!record_valid_at(rec, e, seq, (int)steps.size(), table_cols, rv)) {
+        if ((++spins & 0xFFF) != 0) continue;
+        if (srv_exited(e)) {
+            // the instance idled out (or was leaving) without seeing this request: a new one picks it up
+            if (record_valid_at(rec, e, seq, (int)steps.size(), table_cols, rv)) break;
+            rc = srv_launch(e, seq);
+            if (rc) return rc;
+        } else if ((spins & 0xFFFFF) == 0) {
+            cudaError_t q = cudaStreamQuery(e->srv.stream);
+            if (q == cudaSuccess) {   // the kernel is gone although its exit word never showed up
+                if (record_valid_at(rec, e, seq, (int)steps.size(), table_cols, rv)) break;
+                rc = srv_launch(e, seq);
+                if (rc) return rc;
+            } else if (q != cudaErrorNotReady) {
+                CUDA_TRY(q);
+            }
+        }
+    }
+    {
+        const volatile uint64_t *t = (const volatile uint64_t *)e->srv.h_box->times;
+        const uint64_t t0 = t[0], t1 = t[1];
+        e->srv.last_ns = t1 >= t0 ? t1 - t0 : 0;
+    }
+    for (int i = 0; i < rv.resume && i < (int)steps.size(); i++) {
+        e->recs.emplace_back();
+        StepRecord &r = e->recs.back();
+        r.kind = steps[i].kind;
+        r.in_cols = steps[i].in_cols;
+        r.s = i;
+        r.launches = 0;
     }
     return WK_SUCCESS;
 }
@@ -1459,11 +1774,14 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
     bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS && !post;
     for (const PlannedStep &ps : steps)
         if (ps.kind == KIND_C2K) light = false;   // const_to_known runs on the multi-CTA path only
+    const bool resident = light && srv_usable(e);
+    e->last_resident = false;
     if (light) {   // the fused kernel clears the control block itself
         e->step = 0;
         e->recs.clear();
         e->event_next = 0;
     } else {
+        srv_park(e);   // the persistent step kernels want every CTA slot of the device
         rc = reset_ctl(e);
         if (rc) return rc;
     }
@@ -1475,9 +1793,11 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
     size_t next = 0;
     if (light) {
         RecView rv;
-        rc = run_light(e, steps, mt_tid, mt_factor, want_table, proj_cols, rv);
+        rc = resident ? run_light_resident(e, steps, want_table, proj_cols, rv)
+                      : run_light(e, steps, mt_tid, mt_factor, want_table, proj_cols, rv);
         if (rc) return rc;
         if (rv.status & 1u) return WK_ERR_RBUF_OVERFLOW;
+        e->last_resident = resident;
         next = (size_t)rv.resume;
         e->step = (int)next;
         e->ncols = (next == steps.size()) ? final_cols : steps[next].in_cols;
@@ -1520,9 +1840,15 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
         rc = sync_rows(e, &rows, e->profiling ? e->q_ev1 : nullptr);
         if (rc) return rc;
         if (e->profiling) e->q_timed = true;
+        e->last_resident = false;
         if (want_table) {
             // final_process leaves an empty table untouched (sparql.hpp:1425-1426)
             cols = rows > 0 ? nrequired : final_cols;
+        }
+        // the device is idle again: bring the light-query server back while the result is copied out
+        if (e->srv.enabled && e->srv.launch_id != 0 && srv_usable(e)) {
+            rc = srv_ensure_running(e, e->srv.seq + 1);
+            if (rc) return rc;
         }
     }
     if (out_rows) *out_rows = rows;
@@ -1570,6 +1896,7 @@ int wk_query_execute_batch(wk_engine_t *e, const wk_pattern_t *patterns, const i
         if (rc == WK_SUCCESS) bp.nsteps = (int)steps.size();
     }
     CUDA_TRY(cudaMemcpyAsync(e->d_bplans, e->h_bplans, (size_t)nqueries * sizeof(BatchPlan), cudaMemcpyHostToDevice, e->stream));
+    srv_park(e);
     const int grid = std::min(nqueries, e->num_sms * 4);
     light_batch_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->d_bplans, e->d_bres, nqueries, e->store->d_vertices, e->store->d_edges);
     CUDA_TRY(cudaGetLastError());
@@ -1623,8 +1950,7 @@ int wk_engine_flush_l2(wk_engine_t *e) {
         e->flush_bytes = (size_t)384 << 20;
         CUDA_TRY(cudaMalloc(&e->d_flush, e->flush_bytes));
     }
-    static int v = 0;
-    CUDA_TRY(cudaMemsetAsync(e->d_flush, ++v & 0xFF, e->flush_bytes, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->d_flush, ++e->flush_gen & 0xFF, e->flush_bytes, e->stream));
     flush_read_kernel<<<e->num_sms * 8, 256, 0, e->stream>>>((const uint4 *)e->d_flush, ((size_t)256 << 20) / sizeof(uint4),
                                                           (uint32_t *)e->d_flush);
     CUDA_TRY(cudaGetLastError());
@@ -1646,6 +1972,10 @@ int wk_host_free(void *p) {
 int wk_engine_last_query_device_us(wk_engine_t *e, float *us) {
     if (!e || !us) return WK_ERR_BAD_ARG;
     *us = 0;
+    if (e->last_resident) {   // answered by the resident server: %globaltimer span inside the kernel (request acquired -> record stored)
+        *us = (float)((double)e->srv.last_ns / 1000.0);
+        return WK_SUCCESS;
+    }
     if (!e->q_timed) return WK_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(e->store->device));
     CUDA_TRY(cudaEventSynchronize(e->q_ev1));
@@ -1658,6 +1988,24 @@ int wk_engine_last_query_device_us(wk_engine_t *e, float *us) {
 }  // extern "C"
 
 #include "wk_sharded.cuh"
+
+static uint64_t comm_bytes_pushed(const wk_engine *e) { return e->comm ? e->comm->bytes_pushed : 0; }
+
+static void comm_free(wk_engine *e) {
+    wk_comm *c = e->comm;
+    if (!c) return;
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (c->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(c->comm);
+    if (c->d_counts) cudaFree(c->d_counts);
+    if (c->d_cursor) cudaFree(c->d_cursor);
+    if (c->d_matrix) cudaFree(c->d_matrix);
+    if (c->h_matrix) cudaFreeHost(c->h_matrix);
+    if (c->d_xctl) cudaFree(c->d_xctl);
+    if (c->d_p2p_local) cudaFree(c->d_p2p_local);
+    delete c->p2p;
+    delete c;
+    e->comm = nullptr;
+}
 
 static int comm_alloc(wk_engine *e, int nranks, int rank) {
     if (nranks < 1 || nranks > MAX_PARTS || rank < 0 || rank >= nranks) return WK_ERR_BAD_ARG;
@@ -1676,14 +2024,16 @@ static int comm_alloc(wk_engine *e, int nranks, int rank) {
 static int partition_table(wk_engine *e, int col, int nparts) {
     wk_comm *c = e->comm;
     if (e->ncols <= 0 || col < 0 || col >= e->ncols) return WK_VERTEX_INVALID;
-    if (nparts < 1 || nparts > MAX_PARTS) return WK_ERR_BAD_ARG;
+    if (nparts < 1 || nparts >= MAX_PARTS) return WK_ERR_BAD_ARG;   // the last counter carries the overflow verdict
+    srv_park(e);
     const int s = e->step;
     CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, MAX_PARTS * sizeof(uint64_t), e->stream));
     const int grid = e->num_sms * 4;
-    part_count_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->buf[s & 1], &e->d_ctl->counts[s], e->ncols, col, (uint32_t)nparts, c->d_counts);
+    part_count_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->buf[s & 1], &e->d_ctl->counts[s], e->ncols, col, (uint32_t)nparts, c->d_counts,
+                                                           &e->d_ctl->status);
     part_scan_kernel<<<1, 1, 0, e->stream>>>(c->d_counts, c->d_cursor, (uint32_t)nparts);
     part_scatter_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->buf[s & 1], &e->d_ctl->counts[s], e->ncols, col, (uint32_t)nparts,
-                                                             c->d_cursor, e->buf[(s + 1) & 1]);
+                                                             c->d_cursor, e->buf[(s + 1) & 1], &e->d_ctl->status);
     CUDA_TRY(cudaGetLastError());
     e->launches += 3;
     return WK_SUCCESS;
@@ -1703,16 +2053,19 @@ static int exchange_table(wk_engine *e, int col, uint64_t *out_rows) {
         if (rc) return rc;
     } else {
         // every destination gets the whole table: counts[d] = N for all d
-        CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, MAX_PARTS * sizeof(uint64_t), e->stream));
-        for (int d = 0; d < n; d++)
-            CUDA_TRY(cudaMemcpyAsync(&c->d_counts[d], &e->d_ctl->counts[s], sizeof(uint64_t), cudaMemcpyDeviceToDevice, e->stream));
+        dup_counts_kernel<<<1, MAX_PARTS, 0, e->stream>>>(c->d_counts, &e->d_ctl->counts[s], n, &e->d_ctl->status);
+        CUDA_TRY(cudaGetLastError());
+        e->launches++;
     }
     // counts: all-gather the per-destination vectors, then every rank knows the whole n x n matrix
     NCCL_TRY(nc.AllGather(c->d_counts, c->d_matrix, MAX_PARTS, ncclUint64, c->comm, e->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_matrix, c->d_matrix, (size_t)n * MAX_PARTS * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    // every rank evaluates every rank's receive total, so an overflow is seen by all of them alike
+    // every rank evaluates every rank's receive total, so an overflow is seen by all of them alike; so is an overflow
+    // that happened in the step before the exchange on any rank (its verdict travels in the last counter)
     bool overflow = false;
+    for (int r = 0; r < n; r++)
+        if (c->h_matrix[(size_t)r * MAX_PARTS + MAX_PARTS - 1] != 0) overflow = true;
     for (int r = 0; r < n; r++) {
         uint64_t tot = 0;
         for (int src = 0; src < n; src++) tot += c->h_matrix[(size_t)src * MAX_PARTS + r];
@@ -1754,35 +2107,36 @@ static int exchange_table(wk_engine *e, int col, uint64_t *out_rows) {
     return WK_SUCCESS;
 }
 
-// exchange over peer memory: result in buf[(step+1)&1], step advances; no host synchronisation
+// exchange over peer memory: result in buf[(step+1)&1], step advances; no host synchronisation, one pass over the table
 static int exchange_table_p2p(wk_engine *e, int col) {
     wk_comm *c = e->comm;
     if (!c || !c->p2p_ready) return WK_ERR_COMM;
-    const int n = c->nranks, s = e->step, C = e->ncols;
+    if (c->poisoned) return WK_ERR_COMM;
+    const int s = e->step, C = e->ncols;
     if (C <= 0) return WK_ERR_BAD_ARG;
     const bool dup = (col == -2);
     if (!dup && (col < 0 || col >= C)) return WK_VERTEX_INVALID;
+    srv_park(e);
     const uint64_t epoch = ++c->epoch;
-    const int grid = e->num_sms * 4;
-    if (!dup) {
-        CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, MAX_PARTS * sizeof(uint64_t), e->stream));
-        part_count_kernel<<<grid, CTA_THREADS, 0, e->stream>>>(e->buf[s & 1], &e->d_ctl->counts[s], C, col, (uint32_t)n, c->d_counts);
-    }
-    p2p_publish_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, c->d_counts, &e->d_ctl->counts[s], dup ? 1 : 0, epoch,
-                                                e->cap_words / (uint64_t)C, &e->d_ctl->counts[s + 1], &e->d_ctl->status);
+    const uint64_t cap_rows = e->cap_words / (uint64_t)C;
+    // single-CTA kernels do the waiting; the grid of the push kernel never spins, so several ranks may share one device
+    const int grid = c->local_group ? std::max(1, e->num_sms * 4 / std::max(1, c->nranks)) : e->num_sms * 4;
+    StepRecord &r = begin_step(e, KIND_EXCHANGE, C);
+    p2p_ready_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, &e->d_ctl->status);
     {
         // tile = 1024 / 512 / 256 rows so that the two staging areas stay within 32 KB of shared memory
         const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
         const size_t smem = 2 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
-        void (*kfn)(P2PTable, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t) =
-            rpt == 4 ? p2p_scatter_kernel<4> : (rpt == 2 ? p2p_scatter_kernel<2> : p2p_scatter_kernel<1>);
+        void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, const uint32_t *) =
+            rpt == 4 ? p2p_push_kernel<4> : (rpt == 2 ? p2p_push_kernel<2> : p2p_push_kernel<1>);
         if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kfn<<<grid, CTA_THREADS, smem, e->stream>>>(*c->p2p, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
-                                                    dup ? 1 : 0, (s + 1) & 1, epoch);
+        kfn<<<grid, CTA_THREADS, smem, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
+                                                    dup ? 1 : 0, (s + 1) & 1, epoch, cap_rows, &e->d_ctl->status);
     }
-    p2p_wait_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, epoch, &e->d_ctl->status);
+    p2p_wait_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, cap_rows, &e->d_ctl->counts[s + 1], &e->d_ctl->status,
+                                             &e->d_ctl->stats[2 * s]);
     CUDA_TRY(cudaGetLastError());
-    e->launches += dup ? 3 : 4;
+    end_step(e, r, 3);
     e->step = s + 1;
     c->exchanges++;
     return WK_SUCCESS;
@@ -1903,6 +2257,71 @@ int wk_comm_p2p_import_store(wk_engine_t *e, const void *blobs, const uint64_t *
     return WK_SUCCESS;
 }
 
+// Engines of ONE process as a group (several shards per GPU, or one thread per GPU): the peers' buffers, control blocks
+// and store arrays are wired directly instead of through CUDA IPC, which cannot open a handle in the process that made it.
+// engines[r] becomes rank r.  Every engine still needs its own caller thread: the exchange kernels of a rank wait for
+// the other ranks' kernels, so the n calls of one collective query must be in flight together.
+int wk_comm_local_group(wk_engine_t **engines, int n) {
+    if (!engines || n < 1 || n > P2P_MAX_RANKS || n > LIGHT_PEERS) return WK_ERR_BAD_ARG;
+    for (int r = 0; r < n; r++) {
+        if (!engines[r]) return WK_ERR_BAD_ARG;
+        for (int q = 0; q < r; q++)
+            if (engines[q] == engines[r]) return WK_ERR_BAD_ARG;
+        if (engines[r]->cap_words != engines[0]->cap_words) return WK_ERR_BAD_ARG;   // owners' capacities are checked by the pushers
+    }
+    for (int r = 0; r < n; r++) {
+        wk_engine *e = engines[r];
+        CUDA_TRY(cudaSetDevice(e->store->device));
+        if (!e->comm) {
+            int rc = comm_alloc(e, n, r);
+            if (rc) return rc;
+        }
+        wk_comm *c = e->comm;
+        c->nranks = n;
+        c->rank = r;
+        if (!c->d_xctl) {
+            CUDA_TRY(cudaMalloc((void **)&c->d_xctl, sizeof(XchCtl)));
+            CUDA_TRY(cudaMalloc((void **)&c->d_p2p_local, sizeof(P2PLocal)));
+        }
+        CUDA_TRY(cudaMemset(c->d_xctl, 0, sizeof(XchCtl)));
+        CUDA_TRY(cudaMemset(c->d_p2p_local, 0, sizeof(P2PLocal)));
+        for (int q = 0; q < n; q++) {
+            const int dq = engines[q]->store->device;
+            if (dq != e->store->device) {
+                int can = 0;
+                CUDA_TRY(cudaDeviceCanAccessPeer(&can, e->store->device, dq));
+                if (!can) return WK_ERR_COMM;
+                cudaError_t pe = cudaDeviceEnablePeerAccess(dq, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(pe);
+                cudaGetLastError();
+            }
+        }
+    }
+    for (int r = 0; r < n; r++) {
+        wk_engine *e = engines[r];
+        wk_comm *c = e->comm;
+        if (!c->p2p) c->p2p = new P2PTable();
+        memset(c->p2p, 0, sizeof(P2PTable));
+        c->p2p->nranks = n;
+        c->p2p->rank = r;
+        c->peer_segs.assign(n, {});
+        for (int q = 0; q < n; q++) {
+            c->p2p->buf[0][q] = engines[q]->buf[0];
+            c->p2p->buf[1][q] = engines[q]->buf[1];
+            c->p2p->ctl[q] = engines[q]->comm->d_xctl;
+            c->peer_v[q] = engines[q]->store->d_vertices;
+            c->peer_e[q] = engines[q]->store->d_edges;
+            c->peer_segs[q] = engines[q]->store->segs;
+        }
+        c->epoch = 0;
+        c->poisoned = false;
+        c->local_group = true;
+        c->p2p_ready = true;
+        c->peer_stores = true;
+    }
+    return WK_SUCCESS;
+}
+
 // wk_exchange over peer memory instead of NCCL (same semantics; the table moves to the other buffer)
 int wk_exchange_p2p(wk_engine_t *e, int col_start, uint64_t *out_rows) {
     if (!e) return WK_ERR_BAD_ARG;
@@ -1932,6 +2351,7 @@ int wk_partition(wk_engine_t *e, int col_start, int nparts, uint64_t *part_rows)
     wk_comm *c = e->comm;
     CUDA_TRY(cudaMemcpyAsync(c->h_matrix, c->d_counts, MAX_PARTS * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (c->h_matrix[MAX_PARTS - 1] != 0) return WK_ERR_RBUF_OVERFLOW;   // the table overflowed in the step before
     uint64_t acc = 0;
     for (int d = 0; d < nparts; d++) {
         c->part_rows[d] = part_rows[d] = c->h_matrix[d];
@@ -1992,7 +2412,8 @@ int wk_comm_stats(wk_engine_t *e, uint64_t *exchanges, uint64_t *rows_sent, uint
         P2PLocal loc;
         CUDA_TRY(cudaMemcpy(&loc, e->comm->d_p2p_local, sizeof(loc), cudaMemcpyDeviceToHost));
         sent += loc.rows_sent;
-        recv += loc.rows_recv;
+        recv += loc.rows_landed - loc.rows_kept;
+        e->comm->bytes_pushed = loc.bytes_pushed;
     }
     if (exchanges) *exchanges = e->comm->exchanges;
     if (rows_sent) *rows_sent = sent;
@@ -2007,6 +2428,8 @@ int wk_plan_exchanges(const wk_pattern_t *patterns, int npatterns, int nvars, in
     std::vector<PlannedStep> steps;
     int rc = plan_steps(patterns, npatterns, nvars, v2c, steps);
     if (rc) return rc;
+    for (const PlannedStep &ps : steps)
+        if (ps.kind == KIND_C2K) return WK_OBJ_ERROR;   // need_fork_join refuses a subject that is not a known variable (sparql.hpp:808)
     std::vector<int> ex;
     plan_exchanges(steps, ex);
     for (size_t i = 0; i < ex.size(); i++) out[i] = ex[i];
@@ -2026,6 +2449,11 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
     int rc = plan_steps(patterns, npatterns, nvars, v2c, steps);
     if (rc) return rc;
     if ((int)steps.size() > MAX_STEPS / 2 - 2) return WK_ERR_BAD_ARG;
+    // a pattern that starts from a constant after the first step has no owner to fork to: the reference's fork-join
+    // raises OBJ_ERROR for a subject that is not a known variable (need_fork_join, sparql.hpp:808)
+    for (const PlannedStep &ps : steps)
+        if (ps.kind == KIND_C2K) return WK_OBJ_ERROR;
+    if (e->comm->poisoned) return WK_ERR_COMM;
     std::vector<int> ex;
     plan_exchanges(steps, ex);
     const int final_cols = steps.back().in_cols + ((steps.back().kind == KIND_K2K || steps.back().kind == KIND_K2C) ? 0 : 1);
@@ -2075,7 +2503,11 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
             lp.proj_n = (int)proj_cols.size();
             for (size_t i = 0; i < proj_cols.size(); i++) lp.proj_cols[i] = (int8_t)proj_cols[i];
             rc = fill_light_steps(e, steps, 0, 1, lp.steps);
-            if (rc) return rc;
+            if (rc) {   // the peers are waiting for a verdict: "answered" (this rank alone reports the error)
+                p2p_light_verdict_kernel<<<1, 64, 0, e->stream>>>(*e->comm->p2p, 2 * epoch);
+                e->launches++;
+                return rc;
+            }
             for (int r = 0; r < n; r++) {
                 sp.pv[r] = e->comm->peer_v[r];
                 sp.pe[r] = e->comm->peer_e[r];
@@ -2141,7 +2573,7 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
             RecView rv;
             rc = wait_record(e, seq, -1, 0, rv);
             if (rc) return rc;
-            if (rv.status & 2u) return WK_ERR_COMM;
+            if (rv.status & 2u) { e->comm->poisoned = true; return WK_ERR_COMM; }
             if (!(rv.status & 4u)) {   // answered by the owner: this shard contributes no rows
                 if (out_rows) *out_rows = 0;
                 if (out_cols) *out_cols = want_table ? nrequired : final_cols;
@@ -2179,6 +2611,7 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
     }
     uint64_t rows = 0;
     rc = sync_rows(e, &rows, e->profiling ? e->q_ev1 : nullptr);
+    if (rc == WK_ERR_COMM) e->comm->poisoned = true;
     if (rc) return rc;
     if (e->profiling) e->q_timed = true;
     const int cols = want_table ? nrequired : final_cols;

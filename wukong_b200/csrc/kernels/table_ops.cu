@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(THREADS) gather_col_kernel(const uint32_t *__r
     for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * THREADS)
         keys[i] = (int32_t)in[(uint64_t)idx[i] * C + c];
 }
-struct ReqCols { int32_t n; int8_t col[16]; };
+struct ReqCols { int32_t n; int8_t col[32]; };   // 32 = MAX_COLS of the engine (wk_device.cuh)
 __global__ void __launch_bounds__(THREADS) distinct_flag_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ idx, uint64_t n,
                                                                 int C, ReqCols rq, uint8_t *__restrict__ keep) {
     for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * THREADS) {
@@ -78,7 +78,7 @@ int grid_for(uint64_t n, int sms) {
 
 int wk_internal_distinct(cudaStream_t st, int sms, const uint32_t *in, uint32_t *out, uint64_t rows, int C, const int32_t *req_cols,
                          int nreq, uint64_t *d_out_rows) {
-    if (rows >= (1ull << 32) || C <= 0 || nreq <= 0 || nreq > 16) return WK_ERR_BAD_ARG;
+    if (rows >= (1ull << 32) || C <= 0 || nreq <= 0 || nreq > 32) return WK_ERR_BAD_ARG;
     int rc = WK_SUCCESS;
     uint32_t *idx = nullptr, *idx_alt = nullptr;
     int32_t *keys = nullptr, *keys_alt = nullptr;

@@ -320,7 +320,8 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                 sm.ptr[r] = ptr;
                 const uint32_t size = ptr_size(ptr);
                 if (ls.kind == LKIND_K2U) {
-                    sm.pre[r] = size;
+                    // anything above LIGHT_ROWS spills anyway: clamp so that the 32-bit scan over <= 1024 rows cannot wrap
+                    sm.pre[r] = size > LIGHT_ROWS ? (uint32_t)LIGHT_ROWS + 1u : size;
                     st_edges += size;
                 } else {
                     const uint32_t target = (ls.kind == LKIND_K2K) ? tin[r * Cin + ls.col_end] : ls.end_const;
@@ -389,17 +390,20 @@ __device__ __forceinline__ void stage_steps(LightStep *dst, const LightStep *src
 
 // whole light query: interpret, then project into the mapped staging area (or hand the table over on a spill) and
 // store the completion record.  Returns true when the table outgrew shared memory.
+// `s_steps` are the step descriptors in shared memory.  clear_ctl: the launch-per-query kernel owns the control block and
+// clears it up front; the resident server (wk_server.cuh) only touches it when it has to (spill, per-step statistics).
 template <int NT, class SV>
-__device__ __forceinline__ bool light_query_body(const LightPlan &plan, const SV &sv, LightSmem &sm, LightStep *s_steps) {
+__device__ __forceinline__ bool light_run(const LightPlan &plan, const LightStep *s_steps, const SV &sv, LightSmem &sm, bool clear_ctl,
+                                          uint64_t *times = nullptr, uint64_t t_acquired = 0) {
     const int tid = threadIdx.x;
-    stage_steps<NT>(s_steps, plan.steps, plan.nsteps, tid);
-    // this kernel owns the control block: clear it here instead of a separate memset node
     if (plan.trace && tid == 0) plan.trace[0] = clock64();
-    for (int i = tid; i < plan.ctl_nwords; i += NT) plan.ctl_words[i] = 0;
-    __syncthreads();
+    if (clear_ctl) {
+        for (int i = tid; i < plan.ctl_nwords; i += NT) plan.ctl_words[i] = 0;
+        __syncthreads();
+    }
     if (plan.trace && tid == 0) plan.trace[1] = clock64();
-    const LightState ls_ = light_interpret<NT>(s_steps, plan.nsteps, sv, sm,
-                                           plan.collect_stats ? plan.stats : nullptr, plan.counts, plan.trace);
+    const LightState ls_ = light_interpret<NT>(s_steps, plan.nsteps, sv, sm, (clear_ctl && plan.collect_stats) ? plan.stats : nullptr,
+                                           clear_ctl ? plan.counts : nullptr, plan.trace);
     const uint32_t N = ls_.N;
     const int C = ls_.C, cur = ls_.cur, s = ls_.done;
     const bool spilled = ls_.spilled;
@@ -408,6 +412,11 @@ __device__ __forceinline__ bool light_query_body(const LightPlan &plan, const SV
     uint64_t tsum = 0;
     if (spilled) {
         // hand the table over to the multi-CTA path: buf[done_steps & 1], counts[done_steps]
+        if (!clear_ctl) {   // the control block may hold a previous query's counters and status
+            for (int i = tid; i < plan.ctl_nwords; i += NT) plan.ctl_words[i] = 0;
+            __syncthreads();
+            if (tid == 0) plan.counts[done_steps] = N;
+        }
         if (done_steps > 0) {
             uint32_t *dst = plan.buf[done_steps & 1];
             const uint32_t words = N * (uint32_t)C;
@@ -417,6 +426,7 @@ __device__ __forceinline__ bool light_query_body(const LightPlan &plan, const SV
                 status = 1;
             }
         }
+        __threadfence();   // the continuation is launched by the host once it has seen the record
     } else if (plan.do_project && N > 0) {
         // final_process projection straight into the mapped staging area
         const uint32_t words = N * (uint32_t)plan.proj_n;
@@ -433,17 +443,29 @@ __device__ __forceinline__ bool light_query_body(const LightPlan &plan, const SV
         }
         tsum = block_sum_u64<NT>(part, sm, tid);
     }
+    if (spilled) __syncthreads();
     if (plan.trace && tid == 0) plan.trace[2 + MAX_LIGHT_STEPS] = clock64();
     if (tid == 0) {
         if (status) *plan.status = status;
         const uint64_t rows = N;
         const uint64_t sr = (uint64_t)status | ((uint64_t)(uint32_t)done_steps << 32);
         uint64_t *rec = (uint64_t *)plan.rec;
+        if (times) {   // diagnostics of the resident server: in-kernel span of this request (not covered by the checksum)
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            st_sys_v2u64(times, t_acquired, now);
+        }
         st_sys_v2u64(rec + 2, sr, record_check(plan.seq, rows, sr, tsum));
         st_sys_v2u64(rec, plan.seq, rows);
         if (plan.trace) plan.trace[3 + MAX_LIGHT_STEPS] = clock64();
     }
     return spilled;
+}
+
+template <int NT, class SV>
+__device__ __forceinline__ bool light_query_body(const LightPlan &plan, const SV &sv, LightSmem &sm, LightStep *s_steps) {
+    stage_steps<NT>(s_steps, plan.steps, plan.nsteps, threadIdx.x);
+    return light_run<NT>(plan, s_steps, sv, sm, true);
 }
 
 __global__ void __launch_bounds__(LIGHT_THREADS) light_query_kernel(const __grid_constant__ LightPlan plan) {

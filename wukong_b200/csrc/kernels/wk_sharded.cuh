@@ -10,16 +10,30 @@
 // ---- bucketise-by-owner kernels -----------------------------------------------------------------
 enum { MAX_PARTS = 64 };
 
+// counts[MAX_PARTS - 1] carries this rank's overflow verdict to the other ranks (nparts < MAX_PARTS): after an overflow the
+// row count of the table is a claim, not a fill level, and the table must not be walked
 __global__ void __launch_bounds__(CTA_THREADS) part_count_kernel(const uint32_t *in, const uint64_t *in_count, int C, int col,
-                                                                 uint32_t nparts, uint64_t *counts) {
+                                                                 uint32_t nparts, uint64_t *counts, const uint32_t *status) {
     __shared__ uint32_t hist[MAX_PARTS];
     if (threadIdx.x < MAX_PARTS) hist[threadIdx.x] = 0;
     __syncthreads();
+    if (__ldcg(status) != 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) counts[MAX_PARTS - 1] = 1;
+        return;
+    }
     const uint64_t N = ld_count(in_count);
     for (uint64_t r = (uint64_t)blockIdx.x * CTA_THREADS + threadIdx.x; r < N; r += (uint64_t)gridDim.x * CTA_THREADS)
         atomicAdd(&hist[ld_table(in + r * (uint64_t)C + col) % nparts], 1u);
     __syncthreads();
     if (threadIdx.x < nparts && hist[threadIdx.x]) atomicAdd((unsigned long long *)&counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+// replicate mode of the NCCL path: every destination receives the whole table
+__global__ void dup_counts_kernel(uint64_t *counts, const uint64_t *in_count, int n, const uint32_t *status) {
+    const int d = threadIdx.x;
+    const bool bad = __ldcg(status) != 0;
+    if (d < MAX_PARTS) counts[d] = (d < n && !bad) ? ld_count(in_count) : 0;
+    if (d == MAX_PARTS - 1 && bad) counts[d] = 1;
 }
 
 __global__ void part_scan_kernel(const uint64_t *counts, uint64_t *cursor, uint32_t nparts) {
@@ -29,9 +43,10 @@ __global__ void part_scan_kernel(const uint64_t *counts, uint64_t *cursor, uint3
 
 // each tile reserves a run per destination, then places its rows (order inside a run is free)
 __global__ void __launch_bounds__(CTA_THREADS) part_scatter_kernel(const uint32_t *in, const uint64_t *in_count, int C, int col,
-                                                                   uint32_t nparts, uint64_t *cursor, uint32_t *out) {
+                                                                   uint32_t nparts, uint64_t *cursor, uint32_t *out, const uint32_t *status) {
     __shared__ uint32_t hist[MAX_PARTS];
     __shared__ uint64_t base[MAX_PARTS];
+    if (__ldcg(status) != 0) return;
     const uint64_t N = ld_count(in_count);
     for (uint64_t t0 = (uint64_t)blockIdx.x * CTA_THREADS; t0 < N; t0 += (uint64_t)gridDim.x * CTA_THREADS) {
         if (threadIdx.x < MAX_PARTS) hist[threadIdx.x] = 0;
@@ -110,13 +125,15 @@ struct wk_comm {
     uint64_t *h_matrix = nullptr;    // pinned copy
     uint64_t part_rows[MAX_PARTS] = {0}, part_off[MAX_PARTS] = {0};
     bool partitioned = false;
-    uint64_t exchanges = 0, rows_sent = 0, rows_recv = 0;
+    uint64_t exchanges = 0, rows_sent = 0, rows_recv = 0, bytes_pushed = 0;
     // peer-memory path (CUDA IPC)
     bool p2p_ready = false;
     struct XchCtl *d_xctl = nullptr;
     struct P2PLocal *d_p2p_local = nullptr;
     struct P2PTable *p2p = nullptr;     // host copy of the peer pointer table (passed to kernels by value)
     uint64_t epoch = 0;
+    bool poisoned = false;              // a barrier timed out (WK_ERR_COMM): the epochs of the ranks may be skewed, rebuild the group
+    bool local_group = false;           // peers are engines of this process (wk_comm_local_group): pointers wired directly
     std::vector<void *> ipc_opened;
     // peers' stores mapped through CUDA IPC (in-place light queries): header / edge arrays and segment tables per rank
     bool peer_stores = false;
@@ -135,6 +152,7 @@ static void plan_exchanges(const std::vector<PlannedStep> &steps, std::vector<in
         const PlannedStep &ps = steps[i];
         if (ps.kind == KIND_I2U) { shard_col = 0; continue; }     // local index slice: the new column is local
         if (ps.kind == KIND_C2U) { shard_col = -1; continue; }    // rows only on the owner of the constant
+        if (ps.kind == KIND_C2K) continue;                        // refused by the sharded executor (OBJ_ERROR, sparql.hpp:808)
         if (ps.kind == KIND_K2U && ps.pid == WK_TYPE_ID && ps.dir == WK_DIR_IN) {
             out[i] = -2;
             shard_col = ps.in_cols;   // the appended instances are local to the rank that found them
@@ -145,17 +163,25 @@ static void plan_exchanges(const std::vector<PlannedStep> &steps, std::vector<in
 }
 
 // =============================================================================================
-// Peer-memory exchange (NVLink / NVSwitch, no NCCL, no host synchronisation):
-//   count -> publish counts to every peer + wait for theirs (barrier 1: also proves that every peer has
-//   finished the previous step, so its next-table buffer may be overwritten) -> scatter rows STRAIGHT INTO
-//   the peers' next-table buffers with plain stores over NVLink -> "pushed" flags (barrier 2).
-// Buffers and control blocks of the peers are mapped with CUDA IPC (one process per GPU).
+// Peer-memory exchange (NVLink / NVSwitch, no NCCL, no host synchronisation), ONE pass over the table:
+//   ready   (1 CTA)  every rank tells every peer "all my earlier kernels are done" and waits for the same from them:
+//                    the peers' next-table buffers and receive counters may now be written;
+//   push    (grid)   a tile of rows is loaded with coalesced reads, grouped by owner in shared memory, space for every
+//                    owner's run is reserved with ONE atomic per (tile, owner) on the owner's receive counter -- a remote
+//                    atomic over NVLink for the peers -- and the runs are stored STRAIGHT INTO the owners' next-table
+//                    buffers as contiguous words; the last CTA fences system-wide and raises the "pushed" flags;
+//   wait    (1 CTA)  every peer has pushed: the receive counter is the new row count.
+// No count pass, no count matrix, no second pass over the table (round 1: count -> publish -> scatter -> wait).
+// Buffers and control blocks of the peers are mapped with CUDA IPC (one process per GPU) or wired directly for engines
+// of one process (wk_comm_local_group).
 // =============================================================================================
 struct XchCtl {
-    uint64_t counts[MAX_PARTS][MAX_PARTS];   // [src][dst]; row `src` is written by rank src into every peer's copy
-    uint64_t flagA[MAX_PARTS];               // epoch of the last counts publication seen from each rank
+    uint64_t flagA[MAX_PARTS];               // epoch of the last "ready" seen from each rank
     uint64_t flagB[MAX_PARTS];               // epoch of the last completed push seen from each rank
     uint64_t flagL[MAX_PARTS];               // light query answered in place by rank r: 2 * epoch (+ 1: redo it collectively)
+    uint64_t ovf[MAX_PARTS];                 // epoch at which rank r met a full buffer (its own or an owner's)
+    uint64_t recv_count;                     // rows reserved in my next-table buffer during the running exchange (all ranks add)
+    uint64_t poison;                         // a rank gave up waiting: nobody pushes any more until the group is rebuilt
 };
 
 struct P2PTable {
@@ -166,10 +192,11 @@ struct P2PTable {
 enum { P2P_MAX_RANKS = MAX_PARTS / 4 };
 
 struct P2PLocal {                            // device scratch of one rank
-    uint64_t cursor[MAX_PARTS];              // running row offset into each destination's buffer
     uint32_t done_ctas;
-    uint32_t skip;                           // set when the exchange must not push (overflow somewhere)
-    uint64_t rows_sent, rows_recv;           // running totals over all exchanges (wk_comm_stats)
+    uint32_t ovf;                            // some CTA of the running push met a full buffer
+    uint64_t rows_sent, rows_landed, rows_kept;   // running totals over all exchanges (wk_comm_stats): pushed to peers, arrived here (own included), own
+    uint64_t bytes_pushed;                   // bytes stored into peers' buffers (NVLink traffic of the data path)
+    uint64_t sent_mark;                      // rows_sent when the running exchange began
 };
 
 __device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
@@ -180,7 +207,7 @@ __device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t *p) {
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *p == want; bounded (about 2 s) so that a dead peer cannot hang the GPU
+// spin until *p >= want; bounded (about 2 s) so that a dead peer cannot hang the GPU
 __device__ __forceinline__ bool wait_flag(const uint64_t *p, uint64_t want) {
     for (uint32_t i = 0; i < (1u << 23); i++) {
         if (ld_sys_u64(p) >= want) return true;
@@ -189,123 +216,131 @@ __device__ __forceinline__ bool wait_flag(const uint64_t *p, uint64_t want) {
     return false;
 }
 
-// barrier 1: publish my per-destination counts to every peer, wait for all of theirs, derive offsets
-__global__ void p2p_publish_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint64_t *my_counts, const uint64_t *in_count,
-                                   int dup, uint64_t epoch, uint64_t cap_rows, uint64_t *out_count, uint32_t *status) {
+// barrier A.  A rank that gives up poisons the whole group: a late peer must not push into a buffer that may already
+// hold another query's table.
+__global__ void p2p_ready_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t epoch, uint32_t *status) {
     const int p = threadIdx.x;
     __shared__ int ok;
-    if (p == 0) ok = 1;
+    if (p == 0) { ok = 1; loc->done_ctas = 0; loc->ovf = 0; loc->sent_mark = loc->rows_sent; }
     __syncthreads();
     if (p < t.nranks) {
-        XchCtl *peer = t.ctl[p];
-        for (int d = 0; d < t.nranks; d++) st_sys_u64(&peer->counts[t.rank][d], dup ? ld_count(in_count) : my_counts[d]);
         __threadfence_system();
-        st_sys_u64(&peer->flagA[t.rank], epoch);
+        st_sys_u64(&t.ctl[p]->flagA[t.rank], epoch);
         if (!wait_flag(&my->flagA[p], epoch)) atomicExch(&ok, 0);
     }
     __syncthreads();
-    if (p == 0) {
-        loc->done_ctas = 0;
-        loc->skip = 0;
-        if (!ok) { atomicOr(status, 2u); loc->skip = 1; *out_count = 0; return; }
-        // every rank sees the same matrix: offsets and overflow decisions agree everywhere
-        bool overflow = false;
-        for (int d = 0; d < t.nranks; d++) {
-            uint64_t tot = 0, before = 0;
-            for (int src = 0; src < t.nranks; src++) {
-                const uint64_t c = ld_sys_u64(&my->counts[src][d]);
-                if (src < t.rank) before += c;
-                tot += c;
-            }
-            if (tot > cap_rows) overflow = true;
-            loc->cursor[d] = before;
-            if (d == t.rank) {
-                *out_count = tot;
-                loc->rows_recv += tot - ld_sys_u64(&my->counts[t.rank][d]);
-            } else {
-                loc->rows_sent += ld_sys_u64(&my->counts[t.rank][d]);
-            }
-        }
-        if (overflow) { atomicOr(status, 1u); loc->skip = 1; }
+    if (!ok) {
+        if (p < t.nranks) st_sys_u64(&t.ctl[p]->poison, 1);
+        if (p == 0) atomicOr(status, 2u);
     }
 }
 
-// scatter every row into its owner's next-table buffer; the last CTA to finish publishes the "pushed" flag to every
-// peer after a system-scope fence.  A tile of RPT * 256 rows is loaded with coalesced reads, grouped by destination in
-// shared memory, and every destination's run leaves as consecutive words from consecutive threads: the stores that cross
-// NVLink are full, contiguous segments instead of 4-byte pieces of 12-byte rows (2.4x on 16 M rows, 2 GPUs).
+// one pass: tile -> group by owner -> reserve -> push.  RPT rows per thread: tile = 256 * RPT rows.
 template <int RPT>
-__global__ void __launch_bounds__(CTA_THREADS) p2p_scatter_kernel(P2PTable t, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
-                                                                  int C, int col, int dup, int dst_buf, uint64_t epoch) {
+__global__ void __launch_bounds__(CTA_THREADS) p2p_push_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
+                                                               int C, int col, int dup, int dst_buf, uint64_t epoch, uint64_t cap_rows,
+                                                               const uint32_t *status) {
     extern __shared__ uint32_t p2p_dyn[];
     constexpr uint32_t TILE = CTA_THREADS * RPT;
     uint32_t *rows = p2p_dyn, *stage = p2p_dyn + (size_t)TILE * C;
     __shared__ uint32_t hist[P2P_MAX_RANKS], off[P2P_MAX_RANKS + 1];
     __shared__ uint64_t base[P2P_MAX_RANKS];
-    __shared__ uint32_t last;
+    __shared__ uint32_t last, s_ovf;
     const uint32_t n = (uint32_t)t.nranks;
-    const uint64_t N = ld_count(in_count);
     const uint32_t tid = threadIdx.x;
-    if (!__ldcg(&loc->skip)) {
-        for (uint64_t t0 = (uint64_t)blockIdx.x * TILE; t0 < N; t0 += (uint64_t)gridDim.x * TILE) {
-            const uint32_t nrows = (uint32_t)((N - t0 < TILE) ? (N - t0) : TILE);
-            const uint32_t words = nrows * (uint32_t)C;
-            if (tid < P2P_MAX_RANKS) hist[tid] = 0;
-            const uint32_t *src = in + t0 * (uint64_t)C;
-            for (uint32_t w = tid; w < words; w += CTA_THREADS) rows[w] = ld_table(src + w);
-            __syncthreads();
-            if (!dup) {
-                uint32_t d[RPT], local[RPT];
+    // an earlier step of this rank overflowed (its table is not usable), or the group is poisoned: push nothing, but
+    // still take part in the barriers so that the ranks stay in step
+    const bool bad = __ldcg(status) != 0 || ld_sys_u64(&my->poison) != 0;
+    const uint64_t N = bad ? 0 : ld_count(in_count);
+    if (tid == 0) s_ovf = (__ldcg(status) & 1u) ? 1u : 0u;
+    uint64_t sent = 0, kept = 0;
+    __syncthreads();
+    for (uint64_t t0 = (uint64_t)blockIdx.x * TILE; t0 < N; t0 += (uint64_t)gridDim.x * TILE) {
+        const uint32_t nrows = (uint32_t)((N - t0 < TILE) ? (N - t0) : TILE);
+        const uint32_t words = nrows * (uint32_t)C;
+        if (tid < P2P_MAX_RANKS) hist[tid] = 0;
+        const uint32_t *src = in + t0 * (uint64_t)C;
+        for (uint32_t w = tid; w < words; w += CTA_THREADS) rows[w] = ld_table(src + w);
+        __syncthreads();
+        if (!dup) {
+            uint32_t d[RPT], local[RPT];
 #pragma unroll
-                for (int j = 0; j < RPT; j++) {
-                    const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
-                    d[j] = 0; local[j] = 0;
-                    if (r < nrows) {
-                        d[j] = rows[r * C + col] % n;
-                        local[j] = atomicAdd(&hist[d[j]], 1u);
-                    }
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    uint32_t run = 0;
-                    for (uint32_t dd = 0; dd < n; dd++) { off[dd] = run * (uint32_t)C; run += hist[dd]; }   // in words
-                    off[n] = run * (uint32_t)C;
-                }
-                if (tid < n && hist[tid]) base[tid] = atomicAdd((unsigned long long *)&loc->cursor[tid], (unsigned long long)hist[tid]);
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < RPT; j++) {
-                    const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
-                    if (r < nrows) {
-                        uint32_t *q = stage + off[d[j]] + local[j] * (uint32_t)C;
-                        for (int c = 0; c < C; c++) q[c] = rows[r * C + c];
-                    }
-                }
-                __syncthreads();
-                for (uint32_t w = tid; w < words; w += CTA_THREADS) {
-                    uint32_t dd = 0;
-                    while (w >= off[dd + 1]) dd++;
-                    t.buf[dst_buf][dd][base[dd] * (uint64_t)C + (w - off[dd])] = stage[w];
-                }
-            } else {
-                if (tid < n) base[tid] = atomicAdd((unsigned long long *)&loc->cursor[tid], (unsigned long long)nrows);
-                __syncthreads();
-                for (uint32_t dd = 0; dd < n; dd++) {
-                    uint32_t *dst = t.buf[dst_buf][dd] + base[dd] * (uint64_t)C;
-                    for (uint32_t w = tid; w < words; w += CTA_THREADS) dst[w] = rows[w];
+            for (int j = 0; j < RPT; j++) {
+                const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
+                d[j] = 0; local[j] = 0;
+                if (r < nrows) {
+                    d[j] = rows[r * C + col] % n;
+                    local[j] = atomicAdd(&hist[d[j]], 1u);
                 }
             }
             __syncthreads();
+            if (tid == 0) {
+                uint32_t run = 0;
+                for (uint32_t dd = 0; dd < n; dd++) { off[dd] = run * (uint32_t)C; run += hist[dd]; }   // in words
+                off[n] = run * (uint32_t)C;
+            }
+            if (tid < n) {
+                uint64_t b = 0;
+                if (hist[tid]) {
+                    b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)hist[tid]);
+                    if (b + hist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }   // the owner's buffer is full: drop the run, flag it
+                    else if (tid != (uint32_t)t.rank) sent += hist[tid];
+                    else kept += hist[tid];
+                }
+                base[tid] = b;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
+                if (r < nrows) {
+                    uint32_t *q = stage + off[d[j]] + local[j] * (uint32_t)C;
+                    for (int c = 0; c < C; c++) q[c] = rows[r * C + c];
+                }
+            }
+            __syncthreads();
+            for (uint32_t w = tid; w < words; w += CTA_THREADS) {
+                uint32_t dd = 0;
+                while (w >= off[dd + 1]) dd++;
+                const uint64_t b = base[dd];
+                if (b != ~0ull) t.buf[dst_buf][dd][b * (uint64_t)C + (w - off[dd])] = stage[w];
+            }
+        } else {
+            if (tid < n) {
+                uint64_t b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)nrows);
+                if (b + nrows > cap_rows) { b = ~0ull; s_ovf = 1; }
+                else if (tid != (uint32_t)t.rank) sent += nrows;
+                else kept += nrows;
+                base[tid] = b;
+            }
+            __syncthreads();
+            for (uint32_t dd = 0; dd < n; dd++) {
+                if (base[dd] == ~0ull) continue;
+                uint32_t *dst = t.buf[dst_buf][dd] + base[dd] * (uint64_t)C;
+                for (uint32_t w = tid; w < words; w += CTA_THREADS) dst[w] = rows[w];
+            }
         }
+        __syncthreads();
     }
+    if (sent) {
+        atomicAdd((unsigned long long *)&loc->rows_sent, (unsigned long long)sent);
+        atomicAdd((unsigned long long *)&loc->bytes_pushed, (unsigned long long)(sent * (uint64_t)C * 4ull));
+    }
+    if (kept) atomicAdd((unsigned long long *)&loc->rows_kept, (unsigned long long)kept);
     // completion: fence my stores system-wide, count CTAs, the last one raises the flags
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(&loc->done_ctas, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (tid == 0) {
+        if (s_ovf) atomicOr(&loc->ovf, 1u);
+        __threadfence();
+        last = (atomicAdd(&loc->done_ctas, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
     __syncthreads();
-    if (last && threadIdx.x < n) {
+    if (last && tid < n) {
         __threadfence_system();
-        st_sys_u64(&t.ctl[threadIdx.x]->flagB[t.rank], epoch);
+        if (__ldcg(&loc->ovf)) st_sys_u64(&t.ctl[tid]->ovf[t.rank], epoch);
+        __threadfence_system();
+        st_sys_u64(&t.ctl[tid]->flagB[t.rank], epoch);
     }
 }
 
@@ -315,9 +350,35 @@ __global__ void p2p_light_wait_kernel(XchCtl *my, int owner, uint64_t epoch, uin
     if (ld_sys_u64(&my->flagL[owner]) == 2 * epoch + 1) atomicOr(status, 4u);
 }
 
-// barrier 2: every peer has finished pushing into my buffer
-__global__ void p2p_wait_kernel(P2PTable t, XchCtl *my, uint64_t epoch, uint32_t *status) {
+// the owner of an in-place light query could not run it (its shard lacks a segment, ...): tell the peers anyway,
+// or they would wait for a verdict that never comes
+__global__ void p2p_light_verdict_kernel(P2PTable t, uint64_t value) {
     const int p = threadIdx.x;
-    if (p < t.nranks && !wait_flag(&my->flagB[p], epoch)) atomicOr(status, 2u);
+    if (p < t.nranks && p != t.rank) st_sys_u64(&t.ctl[p]->flagL[t.rank], value);
+}
+
+// barrier B: every peer has finished pushing into my buffer; the receive counter is my new row count
+__global__ void p2p_wait_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t epoch, uint64_t cap_rows, uint64_t *out_count,
+                                uint32_t *status, uint64_t *stats) {
+    const int p = threadIdx.x;
+    __shared__ int ok, ovf;
+    if (p == 0) { ok = 1; ovf = 0; }
+    __syncthreads();
+    if (p < t.nranks) {
+        if (!wait_flag(&my->flagB[p], epoch)) atomicExch(&ok, 0);
+        else if (ld_sys_u64(&my->ovf[p]) == epoch) atomicExch(&ovf, 1);
+    }
     __threadfence_system();
+    __syncthreads();
+    if (!ok && p < t.nranks) st_sys_u64(&t.ctl[p]->poison, 1);
+    if (p == 0) {
+        const uint64_t cnt = ld_sys_u64(&my->recv_count);
+        st_sys_u64(&my->recv_count, 0);   // nobody adds again before my next "ready"
+        if (!ok) { atomicOr(status, 2u); *out_count = 0; return; }
+        if (ovf || cnt > cap_rows) { atomicOr(status, 1u); *out_count = 0; return; }   // the same verdict on every rank
+        *out_count = cnt;
+        loc->rows_landed += cnt;
+        stats[0] = loc->rows_sent - loc->sent_mark;   // per-exchange figures for wk_engine_step_stats (kind 10)
+        stats[1] = cnt;
+    }
 }
