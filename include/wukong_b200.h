@@ -78,7 +78,7 @@ typedef struct wk_engine wk_engine_t;
 typedef struct {
     int32_t kind;            /* 0 i2u, 1 c2u, 2 k2u, 3 k2k, 4 k2c, 5 project, 6 c2k, 7 i2k, 8 distinct, 9 slice,
                                 10 peer-memory exchange: buckets_visited = rows pushed to peers, edges_touched = rows received,
-                                algo_bytes = bytes sent over NVLink */
+                                algo_bytes = bytes sent over NVLink; 11 fused filter chain (wk_query_execute, WK_OPT_FUSE_FILTERS) */
     int32_t in_cols;
     uint64_t in_rows, out_rows;
     uint64_t buckets_visited;   /* sum over rows of L_i                      */
@@ -148,6 +148,8 @@ int wk_engine_set_profiling(wk_engine_t *engine, int level);
  *    wk_engine_destroy; it is relaunched on demand.  0 = one kernel launch per light query.
  *  WK_INFO_* are read-only (wk_engine_get_option). */
 enum { WK_OPT_RESIDENT_LIGHT = 1, WK_OPT_RESIDENT_IDLE_US = 2,
+       WK_OPT_FUSE_FILTERS = 3,           /* default 1: a run of consecutive known_to_known / known_to_const steps of a plan is ONE
+                                             launch (rows staged once, no intermediate tables); the steps are reported as kind 11 */
        WK_INFO_RESIDENT_LAUNCHES = 100,   /* server instances launched so far */
        WK_INFO_RESIDENT_REQUESTS = 101,   /* queries answered through the doorbell */
        WK_INFO_LAST_RESIDENT = 102,       /* 1 if the last wk_query_execute was answered by the server */

@@ -372,3 +372,56 @@ def test_query_modifiers_distinct_offset_limit(eng1, ostore1):
     assert eng1.slice(1, 1) == 1 and eng1.download().tolist() == [[3, 8]]
     assert eng1.slice(5, -1) == 0
 
+
+
+def test_fused_filter_chains(eng2, ostore2):
+    """runs of consecutive known_to_known / known_to_const steps are one launch (WK_OPT_FUSE_FILTERS): same tables as the
+    step-by-step execution and the oracle, for chains of 2-5 filters in every order, filters that kill every row, and
+    filters in the middle of a plan"""
+    gs, ug, univ, dept = pid("GraduateStudent"), pid("UndergraduateStudent"), pid("University"), pid("Department")
+    plans = [
+        # ?x type GraduateStudent . ?x memberOf ?z . ?x undergraduateDegreeFrom ?y . then filters on ?x ?y ?z
+        ([(gs, TYPE, O.IN, -1), (-1, pid("memberOf"), O.OUT, -3), (-1, pid("undergraduateDegreeFrom"), O.OUT, -2),
+          (-2, TYPE, O.OUT, univ), (-2, pid("subOrganizationOf"), O.IN, -3), (-3, TYPE, O.OUT, dept)], 3, [-1, -2, -3]),
+        # const filters only; the middle one removes everything (?z is a department, not a university)
+        ([(gs, TYPE, O.IN, -1), (-1, pid("memberOf"), O.OUT, -3), (-3, TYPE, O.OUT, dept), (-3, TYPE, O.OUT, univ),
+          (-1, TYPE, O.OUT, gs)], 3, [-1, -3]),
+        # five filters in a row (split into two launches), then an expansion after them
+        ([(gs, TYPE, O.IN, -1), (-1, pid("memberOf"), O.OUT, -3), (-1, pid("advisor"), O.OUT, -2),
+          (-2, pid("worksFor"), O.OUT, -3), (-1, TYPE, O.OUT, gs), (-3, TYPE, O.OUT, dept), (-1, pid("memberOf"), O.OUT, -3),
+          (-2, TYPE, O.OUT, pid("FullProfessor")), (-1, pid("takesCourse"), O.OUT, -4)], 4, [-1, -2, -4]),
+        # known_to_known in both directions on the same pair
+        ([(ug, TYPE, O.IN, -1), (-1, pid("takesCourse"), O.OUT, -2), (-2, pid("takesCourse"), O.IN, -1),
+          (-1, pid("takesCourse"), O.OUT, -2), (-1, TYPE, O.OUT, ug)], 2, [-1, -2]),
+    ]
+    for q in (1, 3, 7):
+        for plan in PLANS:
+            plans.append(load_query(q, plan)[:3])
+    for pats, nvars, req in plans:
+        want = O.run_query([ostore2], pats, nvars, req)
+        got = {}
+        for fuse in (1, 0):
+            eng2.set_option(capi.WK_OPT_FUSE_FILTERS, fuse)
+            l0 = eng2.launch_count()
+            rc, rows, cols, tbl = eng2.query(pats, nvars, req)
+            got[fuse] = eng2.launch_count() - l0
+            assert rc == 0 and rows == want.rows, (pats, fuse, rows, want.rows)
+            assert rows_equal(tbl, want.table), (pats, fuse)
+            rc, rows_b, _, _ = eng2.query(pats, nvars, req, blind=True)
+            assert rc == 0 and rows_b == want.rows
+        nfilters = sum(1 for (s, p, d, o) in pats[1:] if o >= 0 or (s < 0 and o < 0 and _bound_before(pats, o)))
+        if nfilters >= 2:
+            assert got[1] < got[0], (pats, got)     # fewer launches when fused
+    eng2.set_option(capi.WK_OPT_FUSE_FILTERS, 1)
+
+
+def _bound_before(pats, var):
+    """True when `var` is the object of a pattern only after having been bound by an earlier one (rough: bound at all)"""
+    seen = set()
+    for (s, p, d, o) in pats:
+        if o == var and var in seen:
+            return True
+        for v in (s, o):
+            if v < 0:
+                seen.add(v)
+    return False

@@ -9,13 +9,13 @@ LIB_CUDA = os.path.join(_HERE, "libwukong_b200.so")
 
 IN, OUT = 0, 1
 PREDICATE_ID, TYPE_ID = 0, 1
-KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k", "distinct", "slice", "exchange"]
+KIND_NAMES = ["i2u", "c2u", "k2u", "k2k", "k2c", "project", "c2k", "i2k", "distinct", "slice", "exchange", "filter"]
 
 WK_SUCCESS = 0
 WK_ERR_CUDA, WK_ERR_BAD_ARG, WK_ERR_RBUF_OVERFLOW, WK_ERR_NO_SEGMENT, WK_ERR_NO_DEVICE, WK_ERR_COMM = 100, 101, 102, 103, 104, 105
 WK_ERR_STORE_FULL = 106
 # wk_engine_set_option / wk_engine_get_option
-WK_OPT_RESIDENT_LIGHT, WK_OPT_RESIDENT_IDLE_US = 1, 2
+WK_OPT_RESIDENT_LIGHT, WK_OPT_RESIDENT_IDLE_US, WK_OPT_FUSE_FILTERS = 1, 2, 3
 WK_INFO_RESIDENT_LAUNCHES, WK_INFO_RESIDENT_REQUESTS, WK_INFO_LAST_RESIDENT, WK_INFO_LAST_RESIDENT_NS, WK_INFO_RESIDENT_RUNNING = 100, 101, 102, 103, 104
 WK_INFO_COMM_BYTES_PUSHED = 110
 
@@ -286,9 +286,9 @@ class Engine:
         self.set_option(WK_OPT_RESIDENT_LIGHT, 1 if on else 0)
 
     def light_trace(self):
-        """profiling level 3: SM clocks at the fused light kernel's phase boundaries (diagnostics)"""
-        a = np.zeros(28, dtype=np.int64)
-        _check(lib().wk_engine_light_trace(self.h, _ptr(a), 28))
+        """profiling level 3: SM clocks at the light interpreter's phase boundaries (diagnostics; layout in wk_light.cuh)"""
+        a = np.zeros(128, dtype=np.int64)
+        _check(lib().wk_engine_light_trace(self.h, _ptr(a), 128))
         return a
 
     def last_query_device_us(self):

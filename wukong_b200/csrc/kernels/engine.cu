@@ -33,7 +33,7 @@ using namespace wk;
 // device-side control block and kernels
 // =============================================================================================
 enum { MAX_STEPS = 60 };
-enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5, KIND_C2K = 6, KIND_I2K = 7, KIND_DISTINCT = 8, KIND_SLICE = 9, KIND_EXCHANGE = 10 };
+enum { KIND_I2U = 0, KIND_C2U = 1, KIND_K2U = 2, KIND_K2K = 3, KIND_K2C = 4, KIND_PROJECT = 5, KIND_C2K = 6, KIND_I2K = 7, KIND_DISTINCT = 8, KIND_SLICE = 9, KIND_EXCHANGE = 10, KIND_FILTER = 11 };
 
 struct CtlBlock {
     uint64_t counts[MAX_STEPS + 4];       // counts[s] = rows of the table that step s reads
@@ -174,6 +174,139 @@ __global__ void __launch_bounds__(CTA_THREADS) seed_kernel(const SeedParam p) {
     __shared__ uint64_t s_ptr;
     if (__ldcg(p.status) != 0) return;
     seed_body(p, &s_ptr, blockIdx.x, gridDim.x);
+}
+
+// ---- index_to_unknown / const_to_unknown with the copy engine (sm_90+ bulk asynchronous copies) ----------------------
+// The seed of a heavy query is a plain copy of millions of ids.  Instead of every thread issuing loads and waiting for
+// them, one elected thread per CTA asks the TMA unit for a whole 16 KB chunk (cp.async.bulk global -> shared, completion on
+// an mbarrier), three chunks in flight per CTA; the chunk leaves again as ONE bulk store (shared -> global) when source and
+// destination agree modulo 16 bytes, otherwise through 16-byte vector stores of the re-aligned words.  No registers are
+// held while the data is in flight and the SM issues two instructions per 16 KB instead of thousands.
+namespace bulk {
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void store(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace bulk
+
+enum { SEED_STAGES = 3, SEED_CHUNK_WORDS = 4096, SEED_STAGE_BYTES = SEED_CHUNK_WORDS * 4 + 128 };
+
+__global__ void __launch_bounds__(CTA_THREADS) seed_bulk_kernel(const SeedParam p) {
+    extern __shared__ __align__(128) unsigned char seed_dyn[];
+    __shared__ __align__(8) uint64_t bar[SEED_STAGES];
+    __shared__ uint64_t s_ptr;
+    if (__ldcg(p.status) != 0) return;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < SEED_STAGES; i++) bulk::mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        uint32_t visited;
+        const uint64_t bucket = p.bucket_start + fastmod(hash_u64(p.key), p.fm);
+        const uint64_t ptr = probe_single(p.vertices, p.key, bucket, tid, visited);
+        if (tid == 0) {
+            s_ptr = ptr;
+            if (blockIdx.x == 0) atomicAdd((unsigned long long *)&p.stats[0], (unsigned long long)visited);
+        }
+    }
+    __syncthreads();
+    const uint64_t ptr = s_ptr;
+    const uint64_t size = ptr_size(ptr), off = ptr_off(ptr);
+    // mt slicing exactly as sparql.hpp:211-221: length = sz / mt_factor, the last one takes the tail
+    const uint64_t start = (uint64_t)(p.mt_tid % p.mt_factor);
+    const uint64_t length = size / (uint64_t)p.mt_factor;
+    const uint64_t begin = start * length;
+    const uint64_t len = (start == (uint64_t)p.mt_factor - 1) ? (size - begin) : length;
+    if (len > p.out_cap_rows) {
+        if (blockIdx.x == 0 && tid == 0) { atomicOr(p.status, 1u); *p.out_count = len; }
+        return;
+    }
+    const uint32_t *src = p.edges + off + begin;
+    const uint32_t shw = (uint32_t)(((uintptr_t)src >> 2) & 3u);          // words by which the source is off a 16-byte boundary
+    const uint64_t nchunks = (len + SEED_CHUNK_WORDS - 1) / SEED_CHUNK_WORDS;
+    // chunk k of this CTA is chunk blockIdx.x + k * gridDim.x of the list
+    auto chunk_words = [&](uint64_t c) -> uint32_t {
+        const uint64_t w0 = c * SEED_CHUNK_WORDS;
+        return (uint32_t)((len - w0 < (uint64_t)SEED_CHUNK_WORDS) ? (len - w0) : (uint64_t)SEED_CHUNK_WORDS);
+    };
+    // bytes the copy engine moves for a chunk: whole 16-byte units inside [aligned start, end of the chunk's words)
+    auto bulk_bytes = [&](uint32_t n) -> uint32_t { return ((shw + n) * 4u) & ~15u; };
+    auto issue = [&](uint64_t c, int stage) {
+        const uint32_t n = chunk_words(c);
+        const uint32_t bytes = bulk_bytes(n);
+        if (bytes) {
+            const uint32_t *a0 = src + c * SEED_CHUNK_WORDS - shw;          // 16-byte aligned, never before the edge array
+            bulk::mbar_expect_tx(&bar[stage], bytes);
+            bulk::load(seed_dyn + (size_t)stage * SEED_STAGE_BYTES, a0, bytes, &bar[stage]);
+        }
+    };
+    uint64_t c = blockIdx.x;
+    if (tid == 0) {
+        uint64_t cc = c;
+        for (int s = 0; s < SEED_STAGES - 1 && cc < nchunks; s++, cc += gridDim.x) issue(cc, s);
+    }
+    uint32_t it = 0;
+    for (; c < nchunks; c += gridDim.x, it++) {
+        const int stage = (int)(it % SEED_STAGES);
+        if (tid == 0) {
+            // the stage this load goes to was drained by every thread (and by its bulk store) in the previous iteration
+            const uint64_t cn = c + (uint64_t)(SEED_STAGES - 1) * gridDim.x;
+            if (cn < nchunks) issue(cn, (int)((it + SEED_STAGES - 1) % SEED_STAGES));
+        }
+        const uint32_t n = chunk_words(c);
+        const uint32_t bytes = bulk_bytes(n);
+        uint32_t *dst = p.out + c * SEED_CHUNK_WORDS;
+        const uint32_t *sm = reinterpret_cast<const uint32_t *>(seed_dyn + (size_t)stage * SEED_STAGE_BYTES);
+        const uint32_t avail = bytes ? bytes / 4u - shw : 0u;    // words of this chunk that arrive through shared memory
+        if (bytes) bulk::mbar_wait(&bar[stage], (it / SEED_STAGES) & 1u);
+        if (shw == 0 && bytes) {
+            // same alignment on both sides: the chunk leaves as one bulk store
+            if (tid == 0) {
+                bulk::store(dst, sm, bytes);
+                bulk::store_commit();
+            }
+        } else {
+            const uint32_t nvec = avail >> 2;
+            for (uint32_t v = tid; v < nvec; v += CTA_THREADS) {
+                const uint32_t *q = sm + shw + 4 * v;
+                *reinterpret_cast<uint4 *>(dst + 4 * v) = make_uint4(q[0], q[1], q[2], q[3]);
+            }
+            for (uint32_t w = nvec * 4 + tid; w < avail; w += CTA_THREADS) dst[w] = sm[shw + w];
+        }
+        for (uint32_t w = avail + tid; w < n; w += CTA_THREADS) dst[w] = ld_edge(src + c * SEED_CHUNK_WORDS + w);   // ragged tail (< 4 words)
+        if (tid == 0 && shw == 0 && bytes) bulk::store_wait_read_all();   // the stage may be refilled once the store has read it
+        __syncthreads();
+    }
+    if (tid == 0) bulk::store_wait_all();
+    if (blockIdx.x == 0 && tid == 0) {
+        *p.out_count = len;
+        atomicAdd((unsigned long long *)&p.stats[1], (unsigned long long)len);
+    }
 }
 
 // ---- final_process projection -------------------------------------------------------------------
@@ -425,6 +558,8 @@ struct wk_engine {
         uint64_t last_ns = 0;            // in-kernel span of the last request
     } srv;
     bool last_resident = false;          // the last wk_query_execute was answered by the resident server
+    bool seed_bulk = true;               // seeds through cp.async.bulk (WK_SEED_BULK=0: plain loads, for A/B runs)
+    bool fuse_filters = true;            // WK_OPT_FUSE_FILTERS: runs of known_to_known / known_to_const steps as one launch
     std::vector<StepRecord> recs;        // one per step since the last reset
     std::vector<cudaEvent_t> event_pool;
     size_t event_next = 0;
@@ -439,6 +574,7 @@ static bool srv_exited(const wk_engine *e);
 }
 static void comm_free(wk_engine *e);   // wk_sharded.cuh
 static uint64_t comm_bytes_pushed(const wk_engine *e);
+static int preload_kernels(wk_engine *e);   // end of this file
 
 static const char *k_errs[] = {"success", "unknown error", "syntax error", "unsupported triple pattern",
                                "attribute support disabled", "no required variables", "unsupported UNION",
@@ -639,7 +775,11 @@ static int launch_step(wk_engine *e, const StepParam &p) {
 }
 
 // ---- enqueue one known_to_* step on the multi-CTA path ------------------------------------------
-static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, int dir, int col_end, uint32_t end_const) {
+// extra: further known_to_known / known_to_const filters fused into the same launch (StepParam::extra); record_kind is what
+// the step is reported as (KIND_FILTER for a fused chain)
+struct ChainFilter { int kind, col_start, col_end, dir; uint32_t pid, end_const; };
+static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, int dir, int col_end, uint32_t end_const,
+                         const ChainFilter *extra = nullptr, int nextra = 0) {
     srv_park(e);
     if (kind != KIND_K2U && kind != KIND_K2K && kind != KIND_K2C) return WK_UNKNOWN_PATTERN;
     if (e->ncols <= 0 || e->ncols > MAX_COLS - 1) return e->ncols <= 0 ? WK_FIRST_PATTERN_ERROR : WK_ERR_BAD_ARG;
@@ -670,6 +810,21 @@ static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, in
     p.col_end = col_end;
     p.end_const = end_const;
     p.inv_c = ((1u << 20) + (uint32_t)e->ncols - 1) / (uint32_t)e->ncols;
+    if (nextra > 0) {
+        if (kind == KIND_K2U || nextra > MAX_CHAIN - 1 || e->variant < 4) return WK_ERR_BAD_ARG;
+        for (int f = 0; f < nextra; f++) {
+            const ChainFilter &cf = extra[f];
+            if (cf.col_start < 0 || cf.col_start >= e->ncols) return WK_VERTEX_INVALID;
+            if (cf.kind == KIND_K2K && (cf.col_end < 0 || cf.col_end >= e->ncols)) return WK_VERTEX_INVALID;
+            const wk_segmeta_t *mx = find_seg(e->store, 0, cf.pid, cf.dir);
+            if (!mx) return WK_ERR_NO_SEGMENT;
+            p.extra[f].seg = make_segparam(mx, cf.pid, cf.dir, false);
+            p.extra[f].col_start = cf.col_start;
+            p.extra[f].col_end = cf.kind == KIND_K2K ? cf.col_end : -1;
+            p.extra[f].end_const = cf.end_const;
+        }
+        p.nextra = nextra;
+    }
     // the heavy-tile pass is only needed where a tile of TILE_ROWS rows can reach HEAVY_TILE_MIN output rows
     bool may_be_heavy = true;
     {
@@ -682,7 +837,7 @@ static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, in
         p.hq_packed = &e->d_ctl->hq_packed[s];
         p.hq_ticket = &e->d_ctl->hq_ticket[s];
     }
-    StepRecord &r = begin_step(e, kind, e->ncols);
+    StepRecord &r = begin_step(e, nextra > 0 ? KIND_FILTER : kind, e->ncols);
     if (kind == KIND_K2U) rc = launch_step<MODE_K2U>(e, p);
     else if (kind == KIND_K2K) rc = launch_step<MODE_K2K>(e, p);
     else rc = launch_step<MODE_K2C>(e, p);
@@ -718,7 +873,17 @@ static int enqueue_seed(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int 
     p.mt_tid = mt_tid;
     p.mt_factor = mt_factor;
     StepRecord &r = begin_step(e, kind, 0);
-    seed_kernel<<<e->num_sms * 4, CTA_THREADS, 0, e->stream>>>(p);
+    if (e->seed_bulk) {
+        const size_t smem = (size_t)SEED_STAGES * SEED_STAGE_BYTES;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute((const void *)seed_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        seed_bulk_kernel<<<e->num_sms * 4, CTA_THREADS, smem, e->stream>>>(p);
+    } else {
+        seed_kernel<<<e->num_sms * 4, CTA_THREADS, 0, e->stream>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     end_step(e, r, 1);
     e->step = s + 1;
@@ -867,6 +1032,7 @@ static int snapshot_stats(wk_engine *e) {
         const uint64_t C = (uint64_t)r.in_cols, N = st.in_rows, R = st.out_rows;
         switch (r.kind) {
         case KIND_K2U: st.algo_bytes = 4 * C * N + 128 * st.buckets_visited + 4 * st.edges_touched + 4 * (C + 1) * R; break;
+        case KIND_FILTER:
         case KIND_K2K:
         case KIND_K2C: st.algo_bytes = 4 * C * N + 128 * st.buckets_visited + 4 * st.edges_touched + 4 * C * R; break;
         case KIND_I2U:
@@ -1175,9 +1341,12 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
         if (e->occ[i] < 1) e->occ[i] = 1;
     // resident light-query server: on unless WK_RESIDENT=0 (profilers and sanitizers serialise kernels; see wk_server.cuh)
     if (const char *ev = getenv("WK_RESIDENT")) e->srv.enabled = atoi(ev) != 0;
+    if (const char *ev = getenv("WK_FUSE_FILTERS")) e->fuse_filters = atoi(ev) != 0;
+    if (const char *ev = getenv("WK_SEED_BULK")) e->seed_bulk = atoi(ev) != 0;
     if (const char *ev = getenv("WK_RESIDENT_IDLE_US")) e->srv.idle_ns = (uint64_t)std::max(1, atoi(ev)) * 1000ull;
     if (reset_ctl(e) != WK_SUCCESS) { engine_free(e); return WK_ERR_CUDA; }
     ENGINE_TRY(cudaStreamSynchronize(e->stream));
+    if (preload_kernels(e) != WK_SUCCESS) { engine_free(e); return WK_ERR_CUDA; }
     *out = e;
     return WK_SUCCESS;
 }
@@ -1207,6 +1376,9 @@ int wk_engine_set_option(wk_engine_t *e, int option, int64_t value) {
         e->srv.enabled = value != 0;
         if (!e->srv.enabled) srv_stop(e);
         return WK_SUCCESS;
+    case WK_OPT_FUSE_FILTERS:
+        e->fuse_filters = value != 0;
+        return WK_SUCCESS;
     case WK_OPT_RESIDENT_IDLE_US:
         if (value < 1 || value > 10 * 1000 * 1000) return WK_ERR_BAD_ARG;
         srv_stop(e);   // the next instance picks the new value up
@@ -1221,6 +1393,7 @@ int wk_engine_get_option(wk_engine_t *e, int option, int64_t *value) {
     switch (option) {
     case WK_OPT_RESIDENT_LIGHT: *value = e->srv.enabled ? 1 : 0; return WK_SUCCESS;
     case WK_OPT_RESIDENT_IDLE_US: *value = (int64_t)(e->srv.idle_ns / 1000ull); return WK_SUCCESS;
+    case WK_OPT_FUSE_FILTERS: *value = e->fuse_filters ? 1 : 0; return WK_SUCCESS;
     case WK_INFO_RESIDENT_LAUNCHES: *value = (int64_t)e->srv.launches; return WK_SUCCESS;
     case WK_INFO_RESIDENT_REQUESTS: *value = (int64_t)e->srv.requests; return WK_SUCCESS;
     case WK_INFO_LAST_RESIDENT: *value = e->last_resident ? 1 : 0; return WK_SUCCESS;
@@ -1348,7 +1521,9 @@ int wk_engine_light_trace(wk_engine_t *e, int64_t *dst, int cap) {
     if (!e->d_trace) return WK_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(e->store->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    CUDA_TRY(cudaMemcpy(dst, e->d_trace, (MAX_LIGHT_STEPS + 4) * sizeof(long long), cudaMemcpyDeviceToHost));
+    // a blocking copy on the legacy stream does not wait for the resident server (its stream is non-blocking)
+    const int n = cap < (int)LIGHT_TRACE_WORDS ? cap : (int)LIGHT_TRACE_WORDS;
+    CUDA_TRY(cudaMemcpy(dst, e->d_trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return WK_SUCCESS;
 }
 
@@ -1508,6 +1683,10 @@ static int srv_init(wk_engine *e) {
     e->srv.h_box = box;
     CUDA_TRY(cudaHostGetDevicePointer((void **)&e->srv.d_box, (void *)box, 0));
     CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
+    if (!e->d_trace) {
+        CUDA_TRY(cudaMalloc((void **)&e->d_trace, LIGHT_TRACE_WORDS * sizeof(long long)));
+        CUDA_TRY(cudaMemset(e->d_trace, 0, LIGHT_TRACE_WORDS * sizeof(long long)));
+    }
     return WK_SUCCESS;
 }
 
@@ -1541,6 +1720,7 @@ static int srv_launch(wk_engine *e, uint64_t first_seq) {
     P.first_seq = first_seq;
     P.launch_id = ++e->srv.launch_id;
     P.idle_ns = e->srv.idle_ns;
+    P.trace = e->d_trace;
     light_server_kernel<<<1, LIGHT_THREADS, sizeof(SrvSmem), e->srv.stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     e->launches++;
@@ -1604,14 +1784,14 @@ static void srv_stop(wk_engine *e) {
 }
 
 static bool srv_usable(const wk_engine *e) {
-    return e->srv.enabled && e->profiling < 3 && e->store->nsegslots > 0 && e->store->nsegslots < (1 << 15) && e->store->d_segtab;
+    return e->srv.enabled && e->store->nsegslots > 0 && e->store->nsegslots < (1 << 15) && e->store->d_segtab;
 }
 
 static int run_light_resident(wk_engine *e, const std::vector<PlannedStep> &steps, bool project,
                               const std::vector<int32_t> &proj_cols, RecView &rv) {
     SrvChunk ch[SRV_CHUNKS];
     memset(ch, 0, sizeof(ch));
-    const uint32_t flags = (project ? SRV_F_PROJECT : 0u) | (e->profiling >= 2 ? SRV_F_STATS : 0u);
+    const uint32_t flags = (project ? SRV_F_PROJECT : 0u) | (e->profiling >= 2 ? SRV_F_STATS : 0u) | (e->profiling >= 3 ? SRV_F_TRACE : 0u);
     ch[0].w0 = (uint32_t)steps.size() | (flags << 8) | ((uint32_t)proj_cols.size() << 16);
     for (size_t j = 0; j < proj_cols.size(); j++) {
         SrvChunk &c = ch[1 + j / 12];
@@ -1699,8 +1879,8 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
     if (frc) return frc;
     lp.seq = ++e->seq;
     if (e->profiling >= 3) {
-        if (!e->d_trace) CUDA_TRY(cudaMalloc((void **)&e->d_trace, (MAX_LIGHT_STEPS + 4) * sizeof(long long)));
-        CUDA_TRY(cudaMemsetAsync(e->d_trace, 0, (MAX_LIGHT_STEPS + 4) * sizeof(long long), e->stream));
+        if (!e->d_trace) CUDA_TRY(cudaMalloc((void **)&e->d_trace, LIGHT_TRACE_WORDS * sizeof(long long)));
+        CUDA_TRY(cudaMemsetAsync(e->d_trace, 0, LIGHT_TRACE_WORDS * sizeof(long long), e->stream));
         lp.trace = e->d_trace;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1770,10 +1950,10 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
         if (nrequired > MAX_COLS) return WK_ERR_BAD_ARG;
     }
     e->q_timed = false;
-    if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
     bool light = steps[0].kind == KIND_C2U && steps.size() <= MAX_LIGHT_STEPS && !post;
     for (const PlannedStep &ps : steps)
         if (ps.kind == KIND_C2K) light = false;   // const_to_known runs on the multi-CTA path only
+    if (e->profiling && !(light && srv_usable(e))) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
     const bool resident = light && srv_usable(e);
     e->last_resident = false;
     if (light) {   // the fused kernel clears the control block itself
@@ -1810,11 +1990,30 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
     }
     if (next < steps.size()) {
         // multi-CTA path: one fused kernel per remaining step, no host sync in between
+        if (resident && e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));   // the events then cover the continuation only
         for (size_t i = next; i < steps.size(); i++) {
             const PlannedStep &ps = steps[i];
             if (ps.kind == KIND_I2U) rc = enqueue_seed(e, KIND_I2U, 0, ps.pid, ps.dir, mt_tid, mt_factor);
             else if (ps.kind == KIND_C2U) rc = enqueue_seed(e, KIND_C2U, ps.vid, ps.pid, ps.dir, 0, 1);
             else if (ps.kind == KIND_C2K) rc = enqueue_to_known(e, KIND_C2K, ps.vid, ps.pid, ps.dir, ps.col_end, 0, 1);
+            else if ((ps.kind == KIND_K2K || ps.kind == KIND_K2C) && e->fuse_filters && e->variant >= 4) {
+                // a run of consecutive filters is one launch.  The conjunction does not depend on the order of its terms:
+                // known_to_known (a join condition, usually the selective one) goes through the pipelined probe, the
+                // others are evaluated only for the rows that survive it
+                size_t j = i + 1;
+                while (j < steps.size() && j - i < MAX_CHAIN && (steps[j].kind == KIND_K2K || steps[j].kind == KIND_K2C)) j++;
+                std::vector<size_t> order;
+                for (size_t k = i; k < j; k++) if (steps[k].kind == KIND_K2K) order.push_back(k);
+                for (size_t k = i; k < j; k++) if (steps[k].kind == KIND_K2C) order.push_back(k);
+                ChainFilter ex[MAX_CHAIN];
+                for (size_t k = 1; k < order.size(); k++) {
+                    const PlannedStep &x = steps[order[k]];
+                    ex[k - 1] = ChainFilter{x.kind, x.col_start, x.col_end, x.dir, x.pid, x.end_const};
+                }
+                const PlannedStep &p0 = steps[order[0]];
+                rc = enqueue_known(e, p0.kind, p0.col_start, p0.pid, p0.dir, p0.col_end, p0.end_const, ex, (int)order.size() - 1);
+                i = j - 1;
+            }
             else rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const);
             if (rc) return rc;
         }
@@ -2529,8 +2728,8 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
             sp.epoch = epoch;
             sp.nranks = (uint32_t)n;
             if (e->profiling >= 3) {
-                if (!e->d_trace) CUDA_TRY(cudaMalloc((void **)&e->d_trace, (MAX_LIGHT_STEPS + 4) * sizeof(long long)));
-                CUDA_TRY(cudaMemsetAsync(e->d_trace, 0, (MAX_LIGHT_STEPS + 4) * sizeof(long long), e->stream));
+                if (!e->d_trace) CUDA_TRY(cudaMalloc((void **)&e->d_trace, LIGHT_TRACE_WORDS * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(e->d_trace, 0, LIGHT_TRACE_WORDS * sizeof(long long), e->stream));
                 lp.trace = e->d_trace;
             }
             lp.seq = ++e->seq;
@@ -2635,3 +2834,36 @@ uint64_t wk_selftest_ptr_size(uint64_t raw) { return ptr_size(raw); }
 uint64_t wk_selftest_ptr_off(uint64_t raw) { return ptr_off(raw); }
 
 }  // extern "C"
+
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, and loading may wait for the device
+// to drain.  Two places cannot afford that: ranks of one process whose exchange kernels wait for each other (a rank that
+// blocks in a load while its peer's kernel spins for it is a deadlock until the barrier times out), and the resident
+// light-query server (every first launch of another kernel would wait for the server to idle out).  Touch every kernel of
+// this translation unit once per device instead.
+static int preload_kernels(wk_engine *e) {
+    static bool done[64] = {false};
+    const int dev = e->store->device;
+    if (dev >= 0 && dev < 64 && done[dev]) return WK_SUCCESS;
+    std::vector<const void *> fns;
+    for (int m = 0; m < 3; m++)
+        for (int C = 0; C <= 4; C++) fns.push_back((const void *)step_kernel_fn(m, e->variant, C == 0 ? 5 : C));
+    fns.push_back((const void *)expand_heavy_kernel<0>);
+    fns.push_back((const void *)expand_heavy_kernel<1>);
+    fns.push_back((const void *)expand_heavy_kernel<2>);
+    fns.push_back((const void *)expand_heavy_kernel<3>);
+    const void *rest[] = {(const void *)seed_kernel, (const void *)seed_bulk_kernel, (const void *)project_kernel, (const void *)list_probe_kernel,
+                          (const void *)list_clear_kernel, (const void *)list_insert_kernel, (const void *)list_filter_kernel,
+                          (const void *)set_count_kernel, (const void *)rebase_kernel, (const void *)finish_kernel, (const void *)flush_read_kernel,
+                          (const void *)part_count_kernel, (const void *)dup_counts_kernel, (const void *)part_scan_kernel,
+                          (const void *)part_scatter_kernel, (const void *)p2p_ready_kernel, (const void *)p2p_push_kernel<1>,
+                          (const void *)p2p_push_kernel<2>, (const void *)p2p_push_kernel<4>, (const void *)p2p_light_wait_kernel,
+                          (const void *)p2p_light_verdict_kernel, (const void *)p2p_wait_kernel, (const void *)light_query_kernel,
+                          (const void *)light_sharded_kernel, (const void *)light_batch_kernel, (const void *)light_server_kernel};
+    for (const void *f : rest) fns.push_back(f);
+    for (const void *f : fns) {
+        cudaFuncAttributes a;
+        CUDA_TRY(cudaFuncGetAttributes(&a, f));
+    }
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return WK_SUCCESS;
+}

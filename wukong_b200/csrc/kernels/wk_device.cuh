@@ -116,7 +116,18 @@ struct StepParam {
     struct HeavyTile *hq; // tiles whose fan-out is expanded by expand_heavy_kernel (skewed degrees)
     uint64_t *hq_packed;  // entries:24 | chunks:40, one atomic keeps both consistent
     uint64_t *hq_ticket;
+    // fused filter chain: a run of consecutive known_to_known / known_to_const steps is ONE launch.  The first filter runs
+    // through the pipelined probe; a row that passes it is tested against the others by its owner thread, so a row is
+    // staged once, the intermediate tables are never written and the tile claims its output space once.
+    int32_t nextra;
+    uint32_t _pad1;
+    struct ExtraFilter {
+        SegParam seg;
+        int32_t col_start, col_end;   // col_end < 0: known_to_const against end_const
+        uint32_t end_const, _pad;
+    } extra[3];
 };
+enum { MAX_CHAIN = 4 };   // filters per launch: the pipelined one + 3
 
 // A tile with a large total fan-out is not expanded in place: it only claims its output range and leaves
 // this descriptor; expand_heavy_kernel then spreads its output rows over the whole grid in equal chunks.
@@ -615,6 +626,18 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
                     if (m) { hitl = true; scanned = k0 + __ffs(m); break; }
                 }
                 if (lane == src) { found = hitl; acc_edges += scanned; }
+            }
+            // the other filters of a fused chain, for the rows that are still alive (probe + scan by the owner thread)
+            for (int f = 0; f < p.nextra && found; f++) {
+                const StepParam::ExtraFilter &x = p.extra[f];
+                const uint64_t k2 = step_key(x.seg, myrow[x.col_start]);
+                uint32_t visited2 = 0;
+                const uint64_t ptr2 = chain_walk(p.vertices, k2, x.seg.bucket_start + fastmod(hash_u64(k2), x.seg.fm), visited2);
+                acc_visited += visited2;
+                const uint32_t target2 = x.col_end >= 0 ? myrow[x.col_end] : x.end_const;
+                uint32_t scanned2;
+                found = list_contains8(p.edges + ptr_off(ptr2), ptr_size(ptr2), target2, scanned2);
+                acc_edges += scanned2;
             }
             mult = found ? 1u : 0u;
         }

@@ -19,6 +19,10 @@
 namespace wk {
 
 enum { LIGHT_WORDS = 4096, LIGHT_ROWS = 1024, MAX_LIGHT_STEPS = 24 };
+// diagnostics (profiling level 3): [0] entry, [1] control block cleared, [2 + s] step s done, [26] table written, [27] record
+// stored, [28] request acquired / [29] decoded (resident server), [32 + 4 s + k] inside step s: k = 0 probes issued and
+// consumed, 1 multiplicities scanned, 2 rows materialised
+enum { LIGHT_TRACE_WORDS = 32 + 4 * MAX_LIGHT_STEPS };
 // thread count of the single-CTA latency path (the interpreter is a template on it)
 enum { LIGHT_THREADS = 256, LIGHT_MAX_WARPS = 32 };   // measured: 1024 threads cost ~0.4 us more per step in barriers
 enum { LKIND_I2U = 0, LKIND_C2U = 1, LKIND_K2U = 2, LKIND_K2K = 3, LKIND_K2C = 4 };
@@ -299,6 +303,11 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                 const uint64_t key = step_key(ls.seg, c0);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.vertices(c0) + sv.bucket(ls, s, key, c0) * 8));
             }
+            // A table taller than the CTA takes several rounds per thread.  A round that probes AND reads its edge list
+            // chains two cold accesses per round; instead every round first resolves its key (the bucket line was
+            // prefetched above) and asks for the edge line, and the lists are read in a second pass: two cold latencies
+            // per step however tall the table is.  (A thread owns the same rows in both passes: no barrier in between.)
+            const bool two_pass = N > (uint32_t)NT;
             for (uint32_t item = tid; item < N * (uint32_t)(1 + nsh); item += NT) {
                 uint32_t r = item, j = 0;   // item = j * N + r with j <= 3: no integer division on this path
                 while (r >= N) { r -= N; j++; }
@@ -323,6 +332,9 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                     // anything above LIGHT_ROWS spills anyway: clamp so that the 32-bit scan over <= 1024 rows cannot wrap
                     sm.pre[r] = size > LIGHT_ROWS ? (uint32_t)LIGHT_ROWS + 1u : size;
                     st_edges += size;
+                    if (size) asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.edges(c0) + ptr_off(ptr)));   // read when the rows are materialised
+                } else if (two_pass) {
+                    if (size) asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.edges(c0) + ptr_off(ptr)));
                 } else {
                     const uint32_t target = (ls.kind == LKIND_K2K) ? tin[r * Cin + ls.col_end] : ls.end_const;
                     uint32_t scanned;
@@ -331,10 +343,23 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                     sm.pre[r] = hit ? 1u : 0u;
                 }
             }
+            if (two_pass && ls.kind != LKIND_K2U) {
+                for (uint32_t r = tid; r < N; r += NT) {
+                    const uint32_t c0 = tin[r * Cin + ls.col_start];
+                    const uint64_t ptr = sm.ptr[r];
+                    const uint32_t target = (ls.kind == LKIND_K2K) ? tin[r * Cin + ls.col_end] : ls.end_const;
+                    uint32_t scanned;
+                    const bool hit = list_contains(sv.edges(c0) + ptr_off(ptr), ptr_size(ptr), target, scanned);
+                    st_edges += scanned;
+                    sm.pre[r] = hit ? 1u : 0u;
+                }
+            }
+            if (trace && tid == 0) trace[32 + 4 * s] = clock64();
             __syncthreads();
             // phase 2: scan multiplicities
             light_scan<NT>(sm, N, tid);
             const uint32_t total = sm.total;
+            if (trace && tid == 0) trace[32 + 4 * s + 1] = clock64();
             if (total > LIGHT_ROWS || (uint64_t)total * (uint64_t)Cout > LIGHT_WORDS) { spilled = true; break; }
             // phase 3: materialise (thread per OUTPUT row: every edge load of the step in flight at once)
             uint32_t *tout = sm.tab[nxt];
@@ -360,6 +385,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             }
             N = total;
             C = Cout;
+            if (trace && tid == 0) trace[32 + 4 * s + 2] = clock64();
         }
         // per-step statistics (algorithmic-bytes accounting)
         if ((stats != nullptr)) {

@@ -21,7 +21,7 @@ namespace wk {
 
 enum { SRV_HDR_CHUNKS = 4, SRV_CHUNKS = SRV_HDR_CHUNKS + MAX_LIGHT_STEPS, SRV_SMEM_SEGS = 160 };
 static_assert(SRV_CHUNKS <= 32, "one lane of the polling warp per request chunk");
-enum { SRV_F_PROJECT = 1, SRV_F_STATS = 2, SRV_F_QUIT = 4 };
+enum { SRV_F_PROJECT = 1, SRV_F_STATS = 2, SRV_F_QUIT = 4, SRV_F_TRACE = 8 };
 
 struct SrvChunk { uint32_t w0, w1, w2, tag; };
 
@@ -56,6 +56,7 @@ struct SrvParams {
     uint64_t first_seq;          // sequence number of the first request this instance serves
     uint64_t launch_id;
     uint64_t idle_ns;
+    long long *trace;            // device buffer of LIGHT_TRACE_WORDS phase clocks (requests with SRV_F_TRACE)
 };
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(LIGHT_THREADS) light_server_kernel(const __gri
             }
             if (lane == 0) S.ctrl = leave ? 1u : 0u;
             t_acq = globaltimer_ns();
+            if (lane == 0 && !leave && ((__shfl_sync(0x1u, v.x, 0) >> 8) & SRV_F_TRACE) && P.trace) P.trace[28] = clock64();
         }
         __syncthreads();
         if (S.ctrl != 0) {
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(LIGHT_THREADS) light_server_kernel(const __gri
             S.plan.do_project = (flags & SRV_F_PROJECT) ? 1 : 0;
             S.plan.collect_stats = (flags & SRV_F_STATS) ? 1 : 0;
             S.plan.proj_n = (int)((hdr >> 16) & 0xFF);
+            S.plan.trace = (flags & SRV_F_TRACE) ? P.trace : nullptr;
+            if (S.plan.trace) S.plan.trace[29] = clock64();
         }
         __syncthreads();
         light_run<LIGHT_THREADS>(S.plan, S.plan.steps, sv, S.light, (flags & SRV_F_STATS) != 0, P.times, t_acq);
