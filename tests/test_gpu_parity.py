@@ -425,3 +425,40 @@ def _bound_before(pats, var):
             if v < 0:
                 seen.add(v)
     return False
+
+
+def test_direct_output_into_pinned_buffer(eng2, ostore2):
+    """non-blind queries whose result buffer is pinned host memory: the last step writes the projected rows straight into it
+    (WK_OPT_DIRECT_OUT); same tables as the projection kernel + copy, also for a buffer that is too small"""
+    buf, keep = capi.pinned_array(1 << 22)
+    small, keep2 = capi.pinned_array(64)
+    for q in (1, 2, 3, 7):
+        for plan in PLANS:
+            pats, nvars, req, _ = load_query(q, plan)
+            want = O.run_query([ostore2], pats, nvars, req)
+            for direct in (1, 0):
+                eng2.set_option(capi.WK_OPT_DIRECT_OUT, direct)
+                l0 = eng2.launch_count()
+                buf[:] = 0xFFFFFFFF
+                rc, rows, cols, tbl = eng2.query(pats, nvars, req, out=buf)
+                nl = eng2.launch_count() - l0
+                assert rc == 0 and rows == want.rows and cols == want.cols, (q, plan, direct)
+                assert rows_equal(tbl, want.table), (q, plan, direct)
+                if direct == 1:
+                    n1 = nl
+                elif want.rows >= 0:
+                    assert n1 < nl, (q, plan, n1, nl)      # no projection launch when the last step writes the result
+            eng2.set_option(capi.WK_OPT_DIRECT_OUT, 1)
+            if want.rows * want.cols > small.size:
+                rc, rows, cols, _ = eng2.query(pats, nvars, req, out=small)
+                assert rc == capi.WK_ERR_BAD_ARG, (q, plan, rc)
+            # the engine stays usable, and a pageable buffer takes the copy path
+            rc, rows, cols, tbl = eng2.query(pats, nvars, req)
+            assert rc == 0 and rows == want.rows and rows_equal(tbl, want.table)
+    # a new column that is projected away, and one that is repeated
+    gs = pid("GraduateStudent")
+    pats = [(gs, TYPE, O.IN, -1), (-1, pid("memberOf"), O.OUT, -2), (-1, pid("takesCourse"), O.OUT, -3)]
+    for req in ([-1], [-3, -1, -3], [-2, -3]):
+        want = O.run_query([ostore2], pats, 3, req)
+        rc, rows, cols, tbl = eng2.query(pats, 3, req, out=buf)
+        assert rc == 0 and rows == want.rows and cols == len(req) and rows_equal(tbl, want.table), req

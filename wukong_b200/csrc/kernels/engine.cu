@@ -94,12 +94,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel(const StepParam
 }
 
 // v5: warp-autonomous pipeline (see wk_device.cuh).  Dynamic smem: [bucket staging 32 KB][8 warps x 3 x rows]
-template <int MODE, int MINB, int CT>
+template <int MODE, int MINB, int CT, bool PROJ = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v5(const StepParam p) {
     extern __shared__ __align__(16) unsigned char dyn5[];
     __shared__ TileSmem4 sm;
     if (__ldcg(p.status) != 0) return;
-    step_body_v5<MODE, CT>(p, ld_count(p.in_count), sm, dyn5);
+    step_body_v5<MODE, CT, PROJ>(p, ld_count(p.in_count), sm, dyn5);
 }
 
 template <int CT>
@@ -558,6 +558,9 @@ struct wk_engine {
         uint64_t last_ns = 0;            // in-kernel span of the last request
     } srv;
     bool last_resident = false;          // the last wk_query_execute was answered by the resident server
+    bool direct_out = true;              // WK_OPT_DIRECT_OUT: last step writes projected rows into the caller's pinned buffer
+    const void *dout_host = nullptr;     // last caller buffer examined, and its device address (nullptr: not device-accessible)
+    uint32_t *dout_dev = nullptr;
     bool seed_bulk = true;               // seeds through cp.async.bulk (WK_SEED_BULK=0: plain loads, for A/B runs)
     bool fuse_filters = true;            // WK_OPT_FUSE_FILTERS: runs of known_to_known / known_to_const steps as one launch
     std::vector<StepRecord> recs;        // one per step since the last reset
@@ -745,6 +748,16 @@ static StepKernelFn step_kernel_cols(int v, int C) {
     default: return step_kernel_variant<MODE, 0>(v);
     }
 }
+template <int MODE>
+static StepKernelFn step_kernel_proj(int C) {   // last step of a non-blind plan: projected rows straight to the caller's buffer
+    switch (C) {
+    case 1: return step_kernel_v5<MODE, 4, 1, true>;
+    case 2: return step_kernel_v5<MODE, 4, 2, true>;
+    case 3: return step_kernel_v5<MODE, 4, 3, true>;
+    case 4: return step_kernel_v5<MODE, 4, 4, true>;
+    default: return step_kernel_v5<MODE, 4, 0, true>;
+    }
+}
 static StepKernelFn step_kernel_fn(int mode, int v, int C) {
     return mode == MODE_K2U ? step_kernel_cols<MODE_K2U>(v, C)
          : mode == MODE_K2K ? step_kernel_cols<MODE_K2K>(v, C) : step_kernel_cols<MODE_K2C>(v, C);
@@ -756,7 +769,7 @@ static size_t step_smem(const wk_engine *e, int C) { return e->variant >= 4 ? ro
 template <int MODE>
 static int launch_step(wk_engine *e, const StepParam &p) {
     const int grid = e->num_sms * e->occ[MODE];
-    StepKernelFn fn = step_kernel_fn(MODE, e->variant, p.C);
+    StepKernelFn fn = p.proj_n > 0 ? step_kernel_proj<MODE>(p.C) : step_kernel_fn(MODE, e->variant, p.C);
     const size_t smem = step_smem(e, p.C);
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fn<<<grid, CTA_THREADS, smem, e->stream>>>(p);
@@ -778,8 +791,11 @@ static int launch_step(wk_engine *e, const StepParam &p) {
 // extra: further known_to_known / known_to_const filters fused into the same launch (StepParam::extra); record_kind is what
 // the step is reported as (KIND_FILTER for a fused chain)
 struct ChainFilter { int kind, col_start, col_end, dir; uint32_t pid, end_const; };
+// direct: the step is the last one of a non-blind plan and writes the projected rows straight into the caller's (pinned,
+// device-accessible) buffer
+struct DirectOut { uint32_t *dev_ptr; uint64_t cap_words; int n; const int32_t *cols; };
 static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, int dir, int col_end, uint32_t end_const,
-                         const ChainFilter *extra = nullptr, int nextra = 0) {
+                         const ChainFilter *extra = nullptr, int nextra = 0, const DirectOut *direct = nullptr) {
     srv_park(e);
     if (kind != KIND_K2U && kind != KIND_K2K && kind != KIND_K2C) return WK_UNKNOWN_PATTERN;
     if (e->ncols <= 0 || e->ncols > MAX_COLS - 1) return e->ncols <= 0 ? WK_FIRST_PATTERN_ERROR : WK_ERR_BAD_ARG;
@@ -831,7 +847,17 @@ static int enqueue_known(wk_engine *e, int kind, int col_start, uint32_t pid, in
         auto it = e->store->maxdeg.find(SegKey(m->index, m->pid, m->dir));
         if (it != e->store->maxdeg.end()) may_be_heavy = (uint64_t)it->second * TILE_ROWS >= HEAVY_TILE_MIN;
     }
-    if (kind == KIND_K2U && e->variant >= 4 && e->d_hq && may_be_heavy) {
+    if (direct) {
+        if (e->variant < 4 || direct->n <= 0 || direct->n > MAX_COLS) return WK_ERR_BAD_ARG;
+        p.out = direct->dev_ptr;
+        p.out_cap_rows = direct->cap_words / (uint64_t)direct->n;
+        p.proj_n = direct->n;
+        for (int j = 0; j < direct->n; j++) {
+            if (direct->cols[j] < 0 || direct->cols[j] >= Cout) return WK_VERTEX_INVALID;
+            p.proj_cols[j] = (int8_t)direct->cols[j];
+        }
+    }
+    if (kind == KIND_K2U && e->variant >= 4 && e->d_hq && may_be_heavy && !direct) {   // queued tiles are expanded in table layout
         p.hq = e->d_hq;
         p.hq_cap = e->hq_cap;
         p.hq_packed = &e->d_ctl->hq_packed[s];
@@ -1343,6 +1369,7 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     if (const char *ev = getenv("WK_RESIDENT")) e->srv.enabled = atoi(ev) != 0;
     if (const char *ev = getenv("WK_FUSE_FILTERS")) e->fuse_filters = atoi(ev) != 0;
     if (const char *ev = getenv("WK_SEED_BULK")) e->seed_bulk = atoi(ev) != 0;
+    if (const char *ev = getenv("WK_DIRECT_OUT")) e->direct_out = atoi(ev) != 0;
     if (const char *ev = getenv("WK_RESIDENT_IDLE_US")) e->srv.idle_ns = (uint64_t)std::max(1, atoi(ev)) * 1000ull;
     if (reset_ctl(e) != WK_SUCCESS) { engine_free(e); return WK_ERR_CUDA; }
     ENGINE_TRY(cudaStreamSynchronize(e->stream));
@@ -1379,6 +1406,9 @@ int wk_engine_set_option(wk_engine_t *e, int option, int64_t value) {
     case WK_OPT_FUSE_FILTERS:
         e->fuse_filters = value != 0;
         return WK_SUCCESS;
+    case WK_OPT_DIRECT_OUT:
+        e->direct_out = value != 0;
+        return WK_SUCCESS;
     case WK_OPT_RESIDENT_IDLE_US:
         if (value < 1 || value > 10 * 1000 * 1000) return WK_ERR_BAD_ARG;
         srv_stop(e);   // the next instance picks the new value up
@@ -1394,6 +1424,7 @@ int wk_engine_get_option(wk_engine_t *e, int option, int64_t *value) {
     case WK_OPT_RESIDENT_LIGHT: *value = e->srv.enabled ? 1 : 0; return WK_SUCCESS;
     case WK_OPT_RESIDENT_IDLE_US: *value = (int64_t)(e->srv.idle_ns / 1000ull); return WK_SUCCESS;
     case WK_OPT_FUSE_FILTERS: *value = e->fuse_filters ? 1 : 0; return WK_SUCCESS;
+    case WK_OPT_DIRECT_OUT: *value = e->direct_out ? 1 : 0; return WK_SUCCESS;
     case WK_INFO_RESIDENT_LAUNCHES: *value = (int64_t)e->srv.launches; return WK_SUCCESS;
     case WK_INFO_RESIDENT_REQUESTS: *value = (int64_t)e->srv.requests; return WK_SUCCESS;
     case WK_INFO_LAST_RESIDENT: *value = e->last_resident ? 1 : 0; return WK_SUCCESS;
@@ -1988,9 +2019,25 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
             cols = nrequired;
         }
     }
+    bool direct_done = false;
     if (next < steps.size()) {
         // multi-CTA path: one fused kernel per remaining step, no host sync in between
         if (resident && e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));   // the events then cover the continuation only
+        // final_process fused into the last step: projected rows go straight into the caller's buffer when that is pinned
+        // host memory the device can address (wk_host_alloc / cudaHostAlloc / cudaHostRegister)
+        DirectOut dout{nullptr, 0, 0, nullptr};
+        const int lk = steps.back().kind;
+        if (want_table && !post && table && e->direct_out && e->variant >= 4 && (lk == KIND_K2U || lk == KIND_K2K || lk == KIND_K2C)) {
+            if (table != e->dout_host) {
+                cudaPointerAttributes pa;
+                e->dout_host = table;
+                e->dout_dev = nullptr;
+                if (cudaPointerGetAttributes(&pa, table) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+                    e->dout_dev = (uint32_t *)pa.devicePointer;
+                cudaGetLastError();
+            }
+            if (e->dout_dev) dout = DirectOut{e->dout_dev, cap_words, nrequired, proj_cols.data()};
+        }
         for (size_t i = next; i < steps.size(); i++) {
             const PlannedStep &ps = steps[i];
             if (ps.kind == KIND_I2U) rc = enqueue_seed(e, KIND_I2U, 0, ps.pid, ps.dir, mt_tid, mt_factor);
@@ -2011,10 +2058,17 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
                     ex[k - 1] = ChainFilter{x.kind, x.col_start, x.col_end, x.dir, x.pid, x.end_const};
                 }
                 const PlannedStep &p0 = steps[order[0]];
-                rc = enqueue_known(e, p0.kind, p0.col_start, p0.pid, p0.dir, p0.col_end, p0.end_const, ex, (int)order.size() - 1);
+                const bool last = (j == steps.size()) && dout.dev_ptr;
+                rc = enqueue_known(e, p0.kind, p0.col_start, p0.pid, p0.dir, p0.col_end, p0.end_const, ex, (int)order.size() - 1,
+                                   last ? &dout : nullptr);
+                direct_done = last;
                 i = j - 1;
             }
-            else rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const);
+            else {
+                const bool last = (i + 1 == steps.size()) && dout.dev_ptr;
+                rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const, nullptr, 0, last ? &dout : nullptr);
+                direct_done = last;
+            }
             if (rc) return rc;
         }
         if (want_table && post) {
@@ -2032,11 +2086,18 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
                 if (rc) return rc;
             }
         }
-        if (want_table) {
+        if (want_table && !direct_done) {
             rc = enqueue_project(e, proj_cols.data(), nrequired);
             if (rc) return rc;
         }
         rc = sync_rows(e, &rows, e->profiling ? e->q_ev1 : nullptr);
+        if (direct_done) {
+            // the table is in the caller's buffer, not in the engine: leave an empty engine table behind
+            e->ncols = 0;
+            const uint64_t claimed = rows;
+            reset_ctl(e);
+            if (rc == WK_ERR_RBUF_OVERFLOW && claimed * (uint64_t)nrequired > cap_words) return WK_ERR_BAD_ARG;   // the caller's buffer is too small
+        }
         if (rc) return rc;
         if (e->profiling) e->q_timed = true;
         e->last_resident = false;
@@ -2053,7 +2114,7 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
     if (out_rows) *out_rows = rows;
     if (out_cols) *out_cols = cols;
     if (no_required && rows > 0) return WK_NO_REQUIRED_VAR;
-    if (want_table && rows > 0 && table) {
+    if (want_table && rows > 0 && table && !direct_done) {
         const uint64_t words = rows * (uint64_t)cols;
         if (words > cap_words) return WK_ERR_BAD_ARG;
         if (table_in_host) {
@@ -2159,7 +2220,7 @@ int wk_engine_flush_l2(wk_engine_t *e) {
 
 int wk_host_alloc(uint64_t bytes, void **out) {
     if (!out) return WK_ERR_BAD_ARG;
-    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
     return WK_SUCCESS;
 }
 

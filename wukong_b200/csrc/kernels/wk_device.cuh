@@ -120,7 +120,11 @@ struct StepParam {
     // through the pipelined probe; a row that passes it is tested against the others by its owner thread, so a row is
     // staged once, the intermediate tables are never written and the tile claims its output space once.
     int32_t nextra;
-    uint32_t _pad1;
+    // final_process fused into the LAST step of a non-blind plan: the projected row (sparql.hpp:1507-1550) is written
+    // straight to `out`, which is then the caller's pinned host buffer (zero-copy over PCIe): no separate projection pass,
+    // no device-to-host copy after the kernel.  proj_cols[j] == C names the column this step appends.
+    int32_t proj_n;                // 0: write whole rows to the device table
+    int8_t proj_cols[MAX_COLS];
     struct ExtraFilter {
         SegParam seg;
         int32_t col_start, col_end;   // col_end < 0: known_to_const against end_const
@@ -487,11 +491,26 @@ __device__ __forceinline__ bool list_contains8(const uint32_t *__restrict__ e, u
     return false;
 }
 
-template <int MODE, int CT>
+// one output row: the input row (+ the new edge for known_to_unknown), or its projection when PROJ
+template <int MODE, int CT, bool PROJ>
+__device__ __forceinline__ void emit_row(const StepParam &p, uint64_t orow, const uint32_t *srow, int C, uint32_t e) {
+    if (!PROJ) {
+        uint32_t *dst = p.out + orow * (uint64_t)(MODE == MODE_K2U ? C + 1 : C);
+        copy_row<CT>(dst, srow, C);
+        if (MODE == MODE_K2U) dst[C] = e;
+    } else {
+        uint32_t *dst = p.out + orow * (uint64_t)p.proj_n;
+        for (int j = 0; j < p.proj_n; j++) {
+            const int c = p.proj_cols[j];
+            dst[j] = (MODE == MODE_K2U && c == C) ? e : srow[c];
+        }
+    }
+}
+
+template <int MODE, int CT, bool PROJ = false>
 __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, TileSmem4 &sm, unsigned char *dyn) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = CT > 0 ? CT : p.C;
-    const int Cout = (MODE == MODE_K2U) ? C + 1 : C;
     const uint32_t rowbytes = 128u * (uint32_t)C;                    // 32 rows x C words
     unsigned char *bkt = dyn + warp * (32 * 128);                    // this warp's bucket staging area
     unsigned char *rows_base = dyn + BKT_BYTES + (uint32_t)warp * 3u * rowbytes;
@@ -708,14 +727,10 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
             ht->off[tid] = off;
         } else if (base != ~0ull && tot != 0) {
             if (MODE != MODE_K2U) {
-                if (mult) copy_row<CT>(p.out + (base + excl) * (uint64_t)Cout, myrow, C);
+                if (mult) emit_row<MODE, CT, PROJ>(p, base + excl, myrow, C, 0);
             } else if (__all_sync(0xFFFFFFFFu, mult <= 1)) {
                 // at most one edge per row (the common case on LUBM): the owner thread writes its row
-                if (mult) {
-                    uint32_t *dst = p.out + (base + excl) * (uint64_t)Cout;
-                    copy_row<CT>(dst, myrow, C);
-                    dst[C] = e0;
-                }
+                if (mult) emit_row<MODE, CT, PROJ>(p, base + excl, myrow, C, e0);
             } else {
                 // load-balanced expand: every lane takes output rows o = lane, lane+32, ... of the warp's run and
                 // finds its source row by binary search in the 32 scanned multiplicities, so skewed degrees
@@ -726,7 +741,7 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
                 wpre[lane] = wexcl;
                 woffs[lane] = off;
                 __syncwarp();
-                uint32_t *dst0 = p.out + (base + woff) * (uint64_t)Cout;
+                const uint64_t orow0 = base + woff;
                 for (uint64_t o0 = lane; o0 < wtotal; o0 += 64) {   // two independent outputs per lane in flight
                     int r[2];
                     uint32_t e[2];
@@ -744,11 +759,7 @@ __device__ __forceinline__ void step_body_v5(const StepParam &p, uint64_t N, Til
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const uint64_t o = o0 + 32 * u;
-                        if (o < wtotal) {
-                            uint32_t *dst = dst0 + o * (uint64_t)Cout;
-                            copy_row<CT>(dst, rows + r[u] * C, C);
-                            dst[C] = e[u];
-                        }
+                        if (o < wtotal) emit_row<MODE, CT, PROJ>(p, orow0 + o, rows + r[u] * C, C, e[u]);
                     }
                 }
             }
