@@ -56,6 +56,64 @@ def lib():
     return _lib
 
 
+def encode_group(group):
+    """group = (patterns, unions, optionals) with patterns a list of (s, p, d, o) and unions / optionals lists of groups
+    -> the int32 tree the shims and the host mirror exchange"""
+    pats, unions, optionals = group
+    out = [len(pats)]
+    for t in pats:
+        out += [int(x) for x in t]
+    out.append(len(unions))
+    for u in unions:
+        out += encode_group(u)
+    out.append(len(optionals))
+    for o in optionals:
+        out += encode_group(o)
+    return out
+
+
+def decode_group(a, pos=0):
+    n = a[pos]; pos += 1
+    pats = [tuple(int(x) for x in a[pos + 4 * i: pos + 4 * i + 4]) for i in range(n)]
+    pos += 4 * n
+    subs = []
+    for _ in range(2):
+        k = a[pos]; pos += 1
+        lst = []
+        for _ in range(k):
+            g, pos = decode_group(a, pos)
+            lst.append(g)
+        subs.append(lst)
+    return (pats, subs[0], subs[1]), pos
+
+
+def set_plan_tree(group, fmt_text):
+    """Planner::set_plan on a group tree (UNION / OPTIONAL blocks, core/planner.hpp:1722-1738) -> planned tree or None"""
+    a = np.array(encode_group(group), dtype=np.int32)
+    out = np.zeros(4096, dtype=np.int32)
+    L = lib()
+    L.refp_set_plan_tree.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int]
+    n = L.refp_set_plan_tree(a.ctypes.data_as(C.c_void_p), a.size, fmt_text.encode(), out.ctypes.data_as(C.c_void_p), out.size)
+    if n < 0:
+        return None
+    return decode_group(out[:n].tolist())[0]
+
+
+def load_config(fname, nsrvs, reload=""):
+    """the reference's load_config(fname, nsrvs) [+ reload_config(reload)] (core/config.hpp:160-230, non-GPU build without an
+    RDMA device) -> dict of the Global items in the order of wukong_b200.host.CONFIG_ITEMS, plus input_folder"""
+    from wukong_b200.host import CONFIG_ITEMS
+    L = lib()
+    L.refc_load_config.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+    out = np.zeros(len(CONFIG_ITEMS), dtype=np.int32)
+    folder = C.create_string_buffer(4096)
+    n = L.refc_load_config(fname.encode(), nsrvs, reload.encode(), out.ctypes.data_as(C.c_void_p), len(out), folder, 4096)
+    assert n == len(CONFIG_ITEMS), n
+    d = {k: int(v) for k, v in zip(CONFIG_ITEMS, out)}
+    d["input_folder"] = folder.value.decode()
+    return d
+
+
 def table_digest(table):
     """order-independent digest of a binding table (a multiset of rows): sum over rows of a 64-bit mix of the row's words,
     modulo 2^64 -- the same function as row_digest() in ref_engine_shim.cpp"""

@@ -387,4 +387,75 @@ int refp_set_plan(const int32_t *pats, int npat, const char *fmt, int32_t *out, 
     return n;
 }
 
+// ---- Planner::set_plan on a pattern-group TREE (UNION / OPTIONAL blocks of a .fmt file, core/planner.hpp:1722-1738) ------------
+// tree = [npat, (subject, predicate, direction, object) x npat, nunions, tree ..., noptional, tree ...]
+static bool ref_tree_read(const int32_t *&p, const int32_t *end, SPARQLQuery::PatternGroup &g, int depth) {
+    if (depth > 16 || p >= end) return false;
+    const int npat = *p++;
+    if (npat < 0 || p + 4 * (size_t)npat > end) return false;
+    for (int i = 0; i < npat; i++, p += 4)
+        g.patterns.push_back(SPARQLQuery::Pattern((ssid_t)p[0], (ssid_t)p[1], (ssid_t)p[2], (ssid_t)p[3]));
+    for (int kind = 0; kind < 2; kind++) {
+        if (p >= end) return false;
+        const int n = *p++;
+        if (n < 0 || n > 64) return false;
+        for (int i = 0; i < n; i++) {
+            SPARQLQuery::PatternGroup sub;
+            if (!ref_tree_read(p, end, sub, depth + 1)) return false;
+            (kind == 0 ? g.unions : g.optional).push_back(sub);
+        }
+    }
+    return true;
+}
+static void ref_tree_write(const SPARQLQuery::PatternGroup &g, std::vector<int32_t> &out) {
+    out.push_back((int32_t)g.patterns.size());
+    for (const auto &pt : g.patterns) { out.push_back((int32_t)pt.subject); out.push_back((int32_t)pt.predicate); out.push_back((int32_t)pt.direction); out.push_back((int32_t)pt.object); }
+    out.push_back((int32_t)g.unions.size());
+    for (const auto &u : g.unions) ref_tree_write(u, out);
+    out.push_back((int32_t)g.optional.size());
+    for (const auto &o : g.optional) ref_tree_write(o, out);
+}
+int refp_set_plan_tree(const int32_t *tree, int n, const char *fmt, int32_t *out, int cap) {
+    Global::enable_planner = false;
+    SPARQLQuery::PatternGroup g;
+    const int32_t *p = tree;
+    if (!tree || n <= 0 || !ref_tree_read(p, tree + n, g, 0)) return -2;
+    Planner planner(0, nullptr, nullptr);
+    std::istringstream is(std::string(fmt ? fmt : ""));
+    if (!planner.set_plan(g, is)) return -1;
+    std::vector<int32_t> v;
+    ref_tree_write(g, v);
+    if ((int)v.size() > cap) return -2;
+    memcpy(out, v.data(), v.size() * sizeof(int32_t));
+    return (int)v.size();
+}
+
+// ---- the reference's config loader: load_config + reload_config (core/config.hpp:160-230), non-GPU build, no RDMA device ----
+// Fills the integer items in the order of CONFIG_ITEMS (wukong_b200/host.py) and the input folder; returns their number.
+int refc_load_config(const char *fname, int nsrvs, const char *reload, int32_t *out, int cap, char *folder, int folder_cap) {
+    // the loader writes process-wide statics: start from the reference's defaults (global.hpp:28-124)
+    Global::num_servers = 1; Global::num_threads = 2; Global::num_proxies = 1; Global::num_engines = 1;
+    Global::input_folder = ""; Global::data_port_base = 5500; Global::ctrl_port_base = 9576;
+    Global::rdma_buf_size_mb = 64; Global::rdma_rbf_size_mb = 16; Global::use_rdma = true; Global::rdma_threshold = 300;
+    Global::mt_threshold = 16; Global::enable_caching = true; Global::enable_workstealing = false; Global::stealing_pattern = 0;
+    Global::silent = true; Global::enable_planner = true; Global::generate_statistics = true; Global::enable_vattr = false;
+    Global::memstore_size_gb = 20; Global::est_load_factor = 55; Global::num_gpus = 0; Global::gpu_kvcache_size_gb = 10;
+    Global::gpu_rbuf_size_mb = 32; Global::gpu_rdma_buf_size_mb = 64; Global::gpu_key_blk_size_mb = 16;
+    Global::gpu_value_blk_size_mb = 4; Global::gpu_enable_pipeline = true;
+    load_config(std::string(fname), nsrvs);
+    if (reload && reload[0]) reload_config(std::string(reload));
+    const int32_t v[] = {Global::num_servers, Global::num_threads, Global::num_proxies, Global::num_engines, Global::data_port_base,
+                         Global::ctrl_port_base, Global::rdma_buf_size_mb, Global::rdma_rbf_size_mb, Global::use_rdma,
+                         Global::rdma_threshold, Global::mt_threshold, Global::enable_caching, Global::enable_workstealing,
+                         Global::stealing_pattern, Global::silent, Global::enable_planner, Global::generate_statistics,
+                         Global::enable_vattr, Global::memstore_size_gb, Global::est_load_factor, Global::num_gpus,
+                         Global::gpu_kvcache_size_gb, Global::gpu_rbuf_size_mb, Global::gpu_rdma_buf_size_mb,
+                         Global::gpu_key_blk_size_mb, Global::gpu_value_blk_size_mb, Global::gpu_enable_pipeline};
+    const int n = (int)(sizeof(v) / sizeof(v[0]));
+    if (cap < n) return -2;
+    for (int i = 0; i < n; i++) out[i] = v[i];
+    if (folder && folder_cap > 0) snprintf(folder, (size_t)folder_cap, "%s", Global::input_folder.c_str());
+    return n;
+}
+
 }  // extern "C"

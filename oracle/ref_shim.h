@@ -52,6 +52,7 @@
 #undef set_attr_col_num
 #include "engine/sparql.hpp"   // the reference's SPARQLEngine; dgraph / bind / adaptor / string_server are shadowed (ref_stubs/)
 #include "planner.hpp"         // the reference's Planner (only set_plan / set_direction are exercised)
+#include "config.hpp"          // the reference's load_config / reload_config (ref_engine_shim.cpp: refc_load_config)
 #endif
 #undef private
 #undef protected

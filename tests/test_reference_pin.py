@@ -226,3 +226,72 @@ def test_simulated_reference_cluster(lubm1, ref_lib, n):
                 assert rows_equal(t, bf), (n, q, plan)
             mine = O.run_query(oshards, pats, nvars, req)
             assert mine.status == 0 and mine.rows == rows
+
+
+def test_config_loader_matches_reference(ref_lib, tmp_path):
+    """load_config(fname, nsrvs) + reload_config(str) of the host mirror (csrc/host/global.hpp) against the reference's own
+    (core/config.hpp:42-230, compiled in oracle/_ref; non-GPU build, no RDMA device): every Global item, for the reference's
+    sample config, for files that leave items at their defaults, repeat keys, carry unknown keys and comment lines, and for
+    reloads that try to change immutable items"""
+    from wukong_b200 import host
+    sample = ("# general\nglobal_num_proxies              4\nglobal_num_engines              16\nglobal_data_port_base           5500\n"
+              "global_ctrl_port_base           9576\nglobal_mt_threshold             8\nglobal_enable_workstealing      0\n"
+              "global_stealing_pattern         0\nglobal_enable_planner           1\nglobal_generate_statistics      1\n"
+              "global_enable_vattr             0\nglobal_silent                   1\n\n# kvstore\n"
+              "global_input_folder             /path/to/input/rdfdata/id_lubm_40/\nglobal_memstore_size_gb         40\n"
+              "global_est_load_factor          55\n\n# RDMA\nglobal_rdma_buf_size_mb         128\nglobal_rdma_rbf_size_mb         32\n"
+              "global_use_rdma                 1\nglobal_rdma_threshold           300\nglobal_enable_caching           0\n\n# GPU\n"
+              "global_num_gpus                 0\nglobal_gpu_rdma_buf_size_mb     64\nglobal_gpu_rbuf_size_mb         32\n"
+              "global_gpu_kvcache_size_gb      10\nglobal_gpu_key_blk_size_mb      16\nglobal_gpu_value_blk_size_mb    4\n"
+              "global_gpu_enable_pipeline      1\n")
+    cases = [sample,
+             sample.replace("global_mt_threshold             8", "global_mt_threshold             64"),     # clamped to num_engines
+             "global_num_engines 4\n# c\n\nglobal_input_folder /a/b\nglobal_mt_threshold 2\nglobal_silent 0\nfoo_bar 3\nglobal_num_engines 6\n",
+             "global_input_folder x/\nglobal_est_load_factor 35\nglobal_gpu_rbuf_size_mb 4096\nglobal_enable_planner 0 trailing words\n"]
+    reloads = ["", "global_silent 0 global_mt_threshold 100 global_num_engines 99 global_use_rdma 1 global_enable_planner 0",
+               "global_rdma_threshold 7\nglobal_enable_caching 1\nglobal_memstore_size_gb 1"]
+    for i, text in enumerate(cases):
+        f = tmp_path / ("c%d.cfg" % i)
+        f.write_text(text)
+        for nsrvs in (1, 3):
+            for rl in reloads:
+                want = ref_lib.load_config(str(f), nsrvs, rl)
+                got = host.load_config(str(f), nsrvs, rl)
+                assert got == want, (i, nsrvs, rl, {k: (want[k], got[k]) for k in want if want[k] != got[k]})
+    assert host.load_config(str(tmp_path / "missing.cfg"), 1) is None
+
+
+def test_set_plan_with_union_and_optional_blocks(ref_lib):
+    """.fmt plans with UNION { } / OPTIONAL { } blocks (core/planner.hpp:1722-1738): the host mirror's Planner::set_plan on
+    pattern-group trees against the reference's own, for the union / optional workloads (workloads/lubm/{union,optional}), a
+    nested block, blocks interleaved with the group's own lines, a sub-plan the block refuses, and refused plans"""
+    from conftest import ROOT
+    X, Y, S, UG, MAS, DOC = -1, -2, -1, -2, -3, -4
+    T, NAME, WORKS, UGD, MASD, DOCD = 1, 8, 9, 2, 11, 12
+    grp = lambda pats, unions=(), optionals=(): ([(s, p, 1, o) for (s, p, o) in pats], list(unions), list(optionals))   # noqa: E731
+    def fmt(rel):
+        return open(os.path.join(ROOT, "workloads", "lubm", rel)).read()
+    cases = [
+        (grp([], unions=[grp([(X, T, 20), (X, NAME, Y)]), grp([(X, T, 21), (X, NAME, Y)])]), fmt("union/manual_plan/q1.fmt")),
+        (grp([(X, WORKS, 131072 + 5)], unions=[grp([(X, T, 22), (X, NAME, Y)]), grp([(X, T, 23), (X, NAME, Y)]), grp([(X, T, 24), (X, NAME, Y)])]),
+         fmt("union/manual_plan/q4.fmt")),
+        (grp([(S, UGD, UG)], optionals=[grp([(S, DOCD, DOC)])]), fmt("optional/manual_plan/q1.fmt")),
+        (grp([(S, UGD, UG)], optionals=[grp([(S, MASD, MAS), (MAS, NAME, 131072 + 9)]), grp([(S, DOCD, DOC)])]), fmt("optional/manual_plan/q3.fmt")),
+        # own lines before, between and after the blocks; an optional nested in a union; upper / lower case keywords
+        (grp([(X, T, 20), (X, NAME, Y), (X, WORKS, -3)],
+             unions=[grp([(X, UGD, -4)], optionals=[grp([(-4, NAME, -5)])]), grp([(X, MASD, -4)])],
+             optionals=[grp([(X, DOCD, -6), (-6, NAME, -7)])]),
+         "2 <\nunion {\n 1 >\n OPTIONAL {\n  1 <\n }\n}\n1 >\nUnion{\n 1 <<\n}\n3 >\noptional {\n 2 <\n 1 >>\n}\n"),
+        # the second block lists fewer lines than it has patterns: refused for that block only
+        (grp([(X, T, 20)], unions=[grp([(X, NAME, Y)]), grp([(X, NAME, Y), (X, WORKS, -3)])]), "1 <\nUNION {\n 1 >\n}\nUNION {\n 1 >\n}\n"),
+        # the group itself lists fewer lines than it has patterns: no plan
+        (grp([(X, T, 20), (X, NAME, Y)], unions=[grp([(X, WORKS, -3)])]), "1 <\nUNION {\n 1 >\n}\n"),
+    ]
+    for group, text in cases:
+        want = ref_lib.set_plan_tree(group, text)
+        got = host.set_plan_tree(ref_lib.encode_group(group), text)
+        assert (got is None) == (want is None), (group, text)
+        if want is not None:
+            assert got == ref_lib.encode_group(want), (group, text, want, ref_lib.decode_group(got)[0])
+    # at least one of each outcome was seen
+    assert ref_lib.set_plan_tree(*cases[0]) is not None and ref_lib.set_plan_tree(*cases[-1]) is None

@@ -2,6 +2,7 @@
 // a file / string of "global_<key> <value>" lines.  Only the keys the hot path reads take effect;
 // the others are accepted and stored so an existing Wukong config file loads unchanged.
 #pragma once
+#include <algorithm>
 #include <fstream>
 #include <map>
 #include <sstream>
@@ -47,16 +48,18 @@ struct Global {
         if (k == "global_ctrl_port_base") return I(ctrl_port_base, 1);
         if (k == "global_memstore_size_gb") return I(memstore_size_gb, 1);
         if (k == "global_est_load_factor") { int x = atoi(v.c_str()); if (x <= 0 || x >= 100) return false; est_load_factor = x; return true; }
-        if (k == "global_rdma_buf_size_mb") return I(rdma_buf_size_mb, 0);
-        if (k == "global_rdma_rbf_size_mb") return I(rdma_rbf_size_mb, 0);
+        // no RDMA device in this build: the reference then stores 0 whatever the file says (config.hpp:74-85, 93-98) and
+        // refuses to switch RDMA on (:120-131); a key the file does not mention keeps its default
+        if (k == "global_rdma_buf_size_mb") { rdma_buf_size_mb = 0; return true; }
+        if (k == "global_rdma_rbf_size_mb") { rdma_rbf_size_mb = 0; return true; }
         if (k == "global_generate_statistics") return B(generate_statistics);
         if (k == "global_num_gpus") return I(num_gpus, 0);
-        if (k == "global_gpu_rdma_buf_size_mb") return I(gpu_rdma_buf_size_mb, 0);
+        if (k == "global_gpu_rdma_buf_size_mb") { gpu_rdma_buf_size_mb = 0; return true; }
         if (k == "global_gpu_rbuf_size_mb") return I(gpu_rbuf_size_mb, 1);
         if (k == "global_gpu_kvcache_size_gb") return I(gpu_kvcache_size_gb, 0);
         if (k == "global_gpu_key_blk_size_mb") return I(gpu_key_blk_size_mb, 1);
         if (k == "global_gpu_value_blk_size_mb") return I(gpu_value_blk_size_mb, 1);
-        if (k == "global_use_rdma") return B(use_rdma);
+        if (k == "global_use_rdma") { use_rdma = false; return true; }
         if (k == "global_rdma_threshold") return I(rdma_threshold, 0);
         if (k == "global_mt_threshold") return I(mt_threshold, 1);
         if (k == "global_enable_caching") return B(enable_caching);
@@ -89,6 +92,62 @@ struct Global {
         std::stringstream ss;
         ss << f.rdbuf();
         return load_str(ss.str(), bad);
+    }
+
+    // the reference's own defaults (core/global.hpp:28-124); this mirror deviates in three: enable_planner (no optimiser here),
+    // generate_statistics (nothing to collect for it) and num_gpus (the engine IS the GPU path)
+    void reference_defaults() {
+        use_rdma = true;
+        enable_planner = true;
+        generate_statistics = true;
+        num_gpus = 0;
+    }
+
+    // the items reload_config may change while the system runs (set_mutable_config, config.hpp:118-158)
+    static bool is_mutable(const std::string &k) {
+        static const char *keys[] = {"global_use_rdma", "global_rdma_threshold", "global_mt_threshold", "global_enable_caching",
+                                     "global_enable_workstealing", "global_stealing_pattern", "global_silent", "global_enable_planner",
+                                     "global_enable_vattr", "global_gpu_enable_pipeline"};
+        for (const char *x : keys)
+            if (k == x) return true;
+        return false;
+    }
+    void finish(bool gpu_build) {
+        num_threads = num_engines + num_proxies + (gpu_build ? num_gpus : 0);      // one agent thread per GPU (config.hpp:213-224)
+        mt_threshold = std::max(1, std::min(mt_threshold, num_engines));           // config.hpp:226-227
+    }
+    // load_config(fname, nsrvs), config.hpp:203-230: a config FILE -- lines starting with '#' and empty lines are skipped, the
+    // first two tokens of every other line are key and value, later lines win; unknown keys are reported, not fatal.
+    // gpu_build mirrors -DUSE_GPU (num_gpus must then be 1).  Returns false when the file cannot be read or a value is refused.
+    bool load_config(const std::string &fname, int nsrvs, bool gpu_build = false, std::string *bad = nullptr) {
+        if (nsrvs <= 0) { if (bad) *bad = "nsrvs"; return false; }
+        num_servers = nsrvs;
+        std::ifstream f(fname.c_str());
+        if (!f) { if (bad) *bad = fname; return false; }
+        std::map<std::string, std::string> items;   // the reference collects the file into a map first: iteration order = key order
+        std::string line;
+        while (std::getline(f, line)) {
+            if (line.empty() || line[0] == '#') continue;
+            std::istringstream ls(line);
+            std::string k, v;
+            ls >> k >> v;
+            items[k] = v;
+        }
+        for (auto &kv : items)
+            if (!set(kv.first, kv.second)) { if (bad) *bad = kv.first; return false; }
+        if (gpu_build && num_gpus != 1) { if (bad) *bad = "global_num_gpus"; return false; }
+        finish(gpu_build);
+        return true;
+    }
+    // reload_config(str), config.hpp:160-178: whitespace-separated "key value" pairs; only the mutable items are applied
+    void reload_config(const std::string &str) {
+        std::istringstream iss(str);
+        std::string k, v;
+        std::map<std::string, std::string> items;
+        while (iss >> k >> v) items[k] = v;
+        for (auto &kv : items)
+            if (is_mutable(kv.first)) set(kv.first, kv.second);
+        mt_threshold = std::max(1, std::min(mt_threshold, num_engines));
     }
 };
 

@@ -2,9 +2,11 @@
 // and the Wukong-surface mirror (query / planner / engine / proxy).  Everything GPU goes through
 // the C ABI in include/wukong_b200.h.
 #include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include <sstream>
 
@@ -130,6 +132,68 @@ int wkh_env_config_int(void *h, const char *key) {
     if (k == "global_enable_planner") return g.enable_planner;
     if (k == "global_num_threads") return g.num_threads;
     return -1;
+}
+
+// Planner::set_plan on a pattern-group TREE (UNION / OPTIONAL sub-groups), no string server needed.
+// tree = [npat, (subject, predicate, direction, object) x npat, nunions, tree ..., noptional, tree ...]; the planned tree comes
+// back in the same encoding.  Returns the number of ints written, -1 when set_plan refuses the plan, -2 on a malformed tree.
+static bool tree_read(const int32_t *&p, const int32_t *end, wukong::SPARQLQuery::PatternGroup &g, int depth = 0) {
+    if (depth > 16 || p >= end) return false;
+    const int npat = *p++;
+    if (npat < 0 || p + 4 * (size_t)npat > end) return false;
+    for (int i = 0; i < npat; i++, p += 4)
+        g.patterns.push_back(wukong::SPARQLQuery::Pattern(p[0], p[1], (wukong::dir_t)p[2], p[3]));
+    for (int kind = 0; kind < 2; kind++) {
+        if (p >= end) return false;
+        const int n = *p++;
+        if (n < 0 || n > 64) return false;
+        for (int i = 0; i < n; i++) {
+            wukong::SPARQLQuery::PatternGroup sub;
+            if (!tree_read(p, end, sub, depth + 1)) return false;
+            (kind == 0 ? g.unions : g.optional).push_back(sub);
+        }
+    }
+    return true;
+}
+static void tree_write(const wukong::SPARQLQuery::PatternGroup &g, std::vector<int32_t> &out) {
+    out.push_back((int32_t)g.patterns.size());
+    for (const auto &pt : g.patterns) { out.push_back(pt.subject); out.push_back(pt.predicate); out.push_back(pt.direction); out.push_back(pt.object); }
+    out.push_back((int32_t)g.unions.size());
+    for (const auto &u : g.unions) tree_write(u, out);
+    out.push_back((int32_t)g.optional.size());
+    for (const auto &o : g.optional) tree_write(o, out);
+}
+int wkh_set_plan_tree(const int32_t *tree, int n, const char *fmt, int32_t *out, int cap) {
+    wukong::SPARQLQuery::PatternGroup g;
+    const int32_t *p = tree;
+    if (!tree || n <= 0 || !tree_read(p, tree + n, g)) return -2;
+    wukong::Planner planner;
+    std::istringstream fs(std::string(fmt ? fmt : ""));
+    if (!planner.set_plan(g, fs)) return -1;
+    std::vector<int32_t> v;
+    tree_write(g, v);
+    if ((int)v.size() > cap) return -2;
+    memcpy(out, v.data(), v.size() * sizeof(int32_t));
+    return (int)v.size();
+}
+
+// load_config(fname, nsrvs) [+ reload_config(reload)] of the reference (core/config.hpp:160-230) on a fresh Global; the
+// integer items come back in the order of CONFIG_ITEMS (wukong_b200/host.py), the input folder as a string.
+int wkh_config_load(const char *fname, int nsrvs, int gpu_build, const char *reload, int32_t *out, int cap, char *folder, int folder_cap) {
+    wukong::Global g;
+    g.reference_defaults();
+    if (!g.load_config(fname ? fname : "", nsrvs, gpu_build != 0)) return -1;
+    if (reload && reload[0]) g.reload_config(reload);
+    const int32_t v[] = {g.num_servers, g.num_threads, g.num_proxies, g.num_engines, g.data_port_base, g.ctrl_port_base,
+                         g.rdma_buf_size_mb, g.rdma_rbf_size_mb, g.use_rdma, g.rdma_threshold, g.mt_threshold, g.enable_caching,
+                         g.enable_workstealing, g.stealing_pattern, g.silent, g.enable_planner, g.generate_statistics, g.enable_vattr,
+                         g.memstore_size_gb, g.est_load_factor, g.num_gpus, g.gpu_kvcache_size_gb, g.gpu_rbuf_size_mb,
+                         g.gpu_rdma_buf_size_mb, g.gpu_key_blk_size_mb, g.gpu_value_blk_size_mb, g.gpu_enable_pipeline};
+    const int n = (int)(sizeof(v) / sizeof(v[0]));
+    if (cap < n) return -2;
+    for (int i = 0; i < n; i++) out[i] = v[i];
+    if (folder && folder_cap > 0) snprintf(folder, (size_t)folder_cap, "%s", g.input_folder.c_str());
+    return n;
 }
 
 // parse + apply a user-defined plan; patterns come back as (subject, predicate, direction, object)

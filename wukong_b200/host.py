@@ -133,6 +133,39 @@ def time_query(engine, patterns, nvars, required_vars, reps, blind=True, table=N
     return wall, dev, rows.value, cols.value
 
 
+CONFIG_ITEMS = ["num_servers", "num_threads", "num_proxies", "num_engines", "data_port_base", "ctrl_port_base", "rdma_buf_size_mb",
+                "rdma_rbf_size_mb", "use_rdma", "rdma_threshold", "mt_threshold", "enable_caching", "enable_workstealing",
+                "stealing_pattern", "silent", "enable_planner", "generate_statistics", "enable_vattr", "memstore_size_gb",
+                "est_load_factor", "num_gpus", "gpu_kvcache_size_gb", "gpu_rbuf_size_mb", "gpu_rdma_buf_size_mb",
+                "gpu_key_blk_size_mb", "gpu_value_blk_size_mb", "gpu_enable_pipeline"]
+
+
+def set_plan_tree(tree_ints, fmt_text):
+    """Planner::set_plan of the C++ host mirror on a pattern-group tree ([npat, (s,p,d,o)*, nunions, tree*, noptional, tree*])
+    -> planned tree as a list of ints, or None when the plan is refused"""
+    L = lib()
+    L.wkh_set_plan_tree.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int]
+    a = np.array(tree_ints, dtype=np.int32)
+    out = np.zeros(4096, dtype=np.int32)
+    n = L.wkh_set_plan_tree(a.ctypes.data_as(C.c_void_p), a.size, fmt_text.encode(), out.ctypes.data_as(C.c_void_p), out.size)
+    return None if n < 0 else out[:n].tolist()
+
+
+def load_config(fname, nsrvs, reload="", gpu_build=False):
+    """Global::load_config(fname, nsrvs) [+ reload_config(reload)] of the C++ host mirror, starting from the reference's
+    defaults -> dict of the items (None when the file cannot be read or a value is refused)"""
+    L = lib()
+    L.wkh_config_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+    out = np.zeros(len(CONFIG_ITEMS), dtype=np.int32)
+    folder = C.create_string_buffer(4096)
+    n = L.wkh_config_load(fname.encode(), nsrvs, 1 if gpu_build else 0, reload.encode(), out.ctypes.data_as(C.c_void_p), len(out), folder, 4096)
+    if n < 0:
+        return None
+    d = {k: int(v) for k, v in zip(CONFIG_ITEMS, out)}
+    d["input_folder"] = folder.value.decode()
+    return d
+
+
 class Env:
     """One Wukong-surface server: Global config + StringServer + DGraph + GPUEngine + Proxy (C++, csrc/host/)."""
 
