@@ -737,6 +737,8 @@ def emit(line):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()     # a crash in native code leaves the Python stack on stderr
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

@@ -56,3 +56,20 @@ def test_rmat_two_hop_gpu(rmat_mid):
     assert rc == 0 and rows == want.rows and rows_equal(tbl, want.table)
     eng.close()
     gst.close()
+
+
+@pytest.mark.gpu
+def test_rmat_device_built_store(rmat_mid):
+    """the device-side store build on a skewed graph (hubs with thousands of edges): same two-hop answer as the oracle"""
+    from wukong_b200 import capi
+    hs = host.HostStore(rmat_mid, num_normal_preds=datagen.RMAT_NUM_NORMAL_PREDS)
+    ost = O.Store.wrap(hs.vertices(), hs.edges(), hs.segs())
+    gst = capi.Store.build(rmat_mid, datagen.RMAT_NUM_NORMAL_PREDS)
+    eng = capi.Engine(gst, rbuf_bytes=1 << 30)
+    want = O.run_query([ost], TWO_HOP, 3, [-1, -2, -3])
+    rc, rows, cols, tbl = eng.query(TWO_HOP, 3, [-1, -2, -3], out=np.empty(want.rows * 3 + 16, dtype=np.uint32))
+    assert rc == 0 and rows == want.rows and rows_equal(tbl, want.table)
+    subj = gst.get_edges(0, P, O.IN)
+    assert np.array_equal(np.sort(subj), np.sort(hs.get_edges(0, P, O.IN)))
+    eng.close()
+    gst.close()

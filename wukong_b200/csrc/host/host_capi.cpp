@@ -6,10 +6,12 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <sstream>
 
+#include "host/bundle.hpp"
 #include "host/dgraph.hpp"
 #include "host/global.hpp"
 #include "host/gpu_engine.hpp"
@@ -132,6 +134,140 @@ int wkh_env_config_int(void *h, const char *key) {
     if (k == "global_enable_planner") return g.enable_planner;
     if (k == "global_num_threads") return g.num_threads;
     return -1;
+}
+
+// ---- wire codec (csrc/host/bundle.hpp) through a flat int description of a query, for tests ------------------------------
+// flat = 19 scalars (qid .. distinct in save() order), group, norders, (id, descending)*, col_num, row_num, attr_col_num,
+//        status_code, blind, nvars, nreq, req*, nv2c, v2c*, nmatched, matched*, ntable, table*, gpu_nelems, gpu_col_num
+// group = npat, (s, p, d, o, pred_type)*, nnewvars, newvars*, nunions, group*, noptional, group*
+static bool flat_read_group(const int64_t *&p, const int64_t *end, wukong::WireQuery::Group &g, int depth = 0) {
+    if (depth > 16 || p >= end) return false;
+    int64_t n = *p++;
+    if (n < 0 || p + 5 * n > end) return false;
+    for (int64_t i = 0; i < n; i++, p += 5) {
+        wukong::SPARQLQuery::Pattern pt((wukong::ssid_t)p[0], (wukong::ssid_t)p[1], (wukong::dir_t)p[2], (wukong::ssid_t)p[3]);
+        pt.pred_type = (char)p[4];
+        g.patterns.push_back(pt);
+    }
+    if (p >= end) return false;
+    n = *p++;
+    if (n < 0 || p + n > end) return false;
+    for (int64_t i = 0; i < n; i++) g.optional_new_vars.insert((wukong::ssid_t)*p++);
+    for (int kind = 0; kind < 2; kind++) {
+        if (p >= end) return false;
+        n = *p++;
+        if (n < 0 || n > 64) return false;
+        for (int64_t i = 0; i < n; i++) {
+            wukong::WireQuery::Group sub;
+            if (!flat_read_group(p, end, sub, depth + 1)) return false;
+            (kind == 0 ? g.unions : g.optional).push_back(sub);
+        }
+    }
+    return true;
+}
+static void flat_write_group(const wukong::WireQuery::Group &g, std::vector<int64_t> &o) {
+    o.push_back((int64_t)g.patterns.size());
+    for (const auto &pt : g.patterns) { o.push_back(pt.subject); o.push_back(pt.predicate); o.push_back(pt.direction); o.push_back(pt.object); o.push_back(pt.pred_type); }
+    o.push_back((int64_t)g.optional_new_vars.size());
+    for (auto v : g.optional_new_vars) o.push_back(v);
+    o.push_back((int64_t)g.unions.size());
+    for (const auto &u : g.unions) flat_write_group(u, o);
+    o.push_back((int64_t)g.optional.size());
+    for (const auto &x : g.optional) flat_write_group(x, o);
+}
+static bool flat_to_wire(const int64_t *flat, int n, wukong::WireQuery &w) {
+    const int64_t *p = flat, *end = flat + n;
+    if (n < 19) return false;
+    w.qid = (int)p[0]; w.pqid = (int)p[1]; w.pg_type = (int)p[2]; w.state = (int)p[3]; w.dev_type = (int)p[4]; w.job_type = (int)p[5];
+    w.priority = (int)p[6]; w.mt_factor = (int)p[7]; w.mt_tid = (int)p[8]; w.pattern_step = (int)p[9]; w.local_var = (wukong::ssid_t)p[10];
+    w.corun_enabled = p[11] != 0; w.corun_step = (int)p[12]; w.fetch_step = (int)p[13]; w.union_done = p[14] != 0; w.optional_step = (int)p[15];
+    w.limit = (int)p[16]; w.offset = (unsigned)p[17]; w.distinct = p[18] != 0;
+    p += 19;
+    if (!flat_read_group(p, end, w.pattern_group)) return false;
+    auto need = [&](int64_t k) { return p + k <= end; };
+    if (!need(1)) return false;
+    int64_t k = *p++;
+    if (k < 0 || !need(2 * k)) return false;
+    for (int64_t i = 0; i < k; i++, p += 2) { wukong::WireQuery::Order o; o.id = (wukong::ssid_t)p[0]; o.descending = p[1] != 0; w.orders.push_back(o); }
+    if (!need(6)) return false;
+    w.col_num = (int)p[0]; w.row_num = (int)p[1]; w.attr_col_num = (int)p[2]; w.status_code = (int)p[3]; w.blind = p[4] != 0; w.nvars = (int)p[5];
+    p += 6;
+    auto vec = [&](auto &dst) { if (!need(1)) return false; int64_t m = *p++; if (m < 0 || !need(m)) return false; for (int64_t i = 0; i < m; i++) dst.push_back((typename std::remove_reference<decltype(dst)>::type::value_type)*p++); return true; };
+    if (!vec(w.required_vars) || !vec(w.v2c_map)) return false;
+    { if (!need(1)) return false; int64_t m = *p++; if (m < 0 || !need(m)) return false; for (int64_t i = 0; i < m; i++) w.optional_matched_rows.push_back(*p++ != 0); }
+    if (!vec(w.result_table)) return false;
+    if (!need(2)) return false;
+    w.gpu_result_buf_nelems = (uint64_t)p[0]; w.gpu_col_num = (int)p[1];
+    p += 2;
+    return p == end;
+}
+static void wire_to_flat(const wukong::WireQuery &w, std::vector<int64_t> &o) {
+    const int64_t sc[] = {w.qid, w.pqid, w.pg_type, w.state, w.dev_type, w.job_type, w.priority, w.mt_factor, w.mt_tid, w.pattern_step, w.local_var,
+                          w.corun_enabled, w.corun_step, w.fetch_step, w.union_done, w.optional_step, w.limit, w.offset, w.distinct};
+    o.assign(sc, sc + 19);
+    flat_write_group(w.pattern_group, o);
+    o.push_back((int64_t)w.orders.size());
+    for (const auto &x : w.orders) { o.push_back(x.id); o.push_back(x.descending); }
+    const int64_t rs[] = {w.col_num, w.row_num, w.attr_col_num, w.status_code, w.blind, w.nvars};
+    o.insert(o.end(), rs, rs + 6);
+    o.push_back((int64_t)w.required_vars.size()); for (auto v : w.required_vars) o.push_back(v);
+    o.push_back((int64_t)w.v2c_map.size()); for (auto v : w.v2c_map) o.push_back(v);
+    o.push_back((int64_t)w.optional_matched_rows.size()); for (bool v : w.optional_matched_rows) o.push_back(v);
+    o.push_back((int64_t)w.result_table.size()); for (auto v : w.result_table) o.push_back(v);
+    o.push_back((int64_t)w.gpu_result_buf_nelems); o.push_back(w.gpu_col_num);
+}
+// flat -> Bundle::to_str() bytes (req_type SPARQL_QUERY + archive).  Returns the length, -1 malformed, -2 buffer too small.
+int64_t wkh_bundle_encode(const int64_t *flat, int n, int gpu_build, uint8_t *out, int64_t cap) {
+    wukong::WireQuery w;
+    if (!flat || !flat_to_wire(flat, n, w)) return -1;
+    const std::string s = wukong::bundle_to_str(wukong::SPARQL_QUERY, wukong::encode_query(w, gpu_build != 0));
+    if ((int64_t)s.size() > cap) return -2;
+    memcpy(out, s.data(), s.size());
+    return (int64_t)s.size();
+}
+// Bundle bytes -> flat.  Returns the number of ints, -1 not a SPARQL_QUERY bundle / malformed archive, -2 buffer too small.
+int64_t wkh_bundle_decode(const uint8_t *bytes, int64_t len, int gpu_build, int64_t *flat, int64_t cap) {
+    wukong::req_type t;
+    std::string data;
+    if (!bytes || !wukong::bundle_from_str(std::string((const char *)bytes, (size_t)len), t, data) || t != wukong::SPARQL_QUERY) return -1;
+    wukong::WireQuery w;
+    if (!wukong::decode_query(data, w, gpu_build != 0)) return -1;
+    std::vector<int64_t> o;
+    wire_to_flat(w, o);
+    if ((int64_t)o.size() > cap) return -2;
+    memcpy(flat, o.data(), o.size() * sizeof(int64_t));
+    return (int64_t)o.size();
+}
+// a host-mirror SPARQLQuery through the wire and back (to_wire -> encode -> decode -> from_wire): planned patterns, required
+// variables and the result metadata survive.  Returns 0 when every carried field is equal.
+int wkh_bundle_roundtrip_query(const int32_t *pats, int npat, int nvars, const int32_t *req, int nreq, int blind, const uint32_t *table,
+                               int rows, int cols) {
+    wukong::SPARQLQuery::PatternGroup pg;
+    for (int i = 0; i < npat; i++) pg.patterns.push_back(wukong::SPARQLQuery::Pattern(pats[4 * i], pats[4 * i + 1], (wukong::dir_t)pats[4 * i + 2], pats[4 * i + 3]));
+    std::vector<wukong::ssid_t> rq(req, req + nreq);
+    wukong::SPARQLQuery q(pg, nvars, rq), r;
+    q.result.blind = blind != 0;
+    q.result.col_num = cols;
+    q.result.row_num = rows;
+    if (table && !blind) q.result.result_table.assign(table, table + (size_t)rows * cols);
+    q.qid = 77; q.pqid = 5; q.mt_factor = 3; q.mt_tid = 2; q.pattern_step = npat; q.limit = 10; q.offset = 4; q.distinct = true;
+    const std::string s = wukong::bundle_to_str(wukong::SPARQL_QUERY, wukong::encode_query(wukong::to_wire(q)));
+    wukong::req_type t;
+    std::string data;
+    wukong::WireQuery w;
+    if (!wukong::bundle_from_str(s, t, data) || t != wukong::SPARQL_QUERY || !wukong::decode_query(data, w)) return 1;
+    wukong::from_wire(w, r);
+    if (r.qid != q.qid || r.pqid != q.pqid || r.mt_factor != q.mt_factor || r.mt_tid != q.mt_tid || r.pattern_step != q.pattern_step ||
+        r.limit != q.limit || r.offset != q.offset || r.distinct != q.distinct) return 2;
+    if (r.pattern_group.patterns.size() != q.pattern_group.patterns.size()) return 3;
+    for (size_t i = 0; i < r.pattern_group.patterns.size(); i++) {
+        const auto &a = r.pattern_group.patterns[i], &b = q.pattern_group.patterns[i];
+        if (a.subject != b.subject || a.predicate != b.predicate || a.object != b.object || a.direction != b.direction || a.pred_type != b.pred_type) return 4;
+    }
+    if (r.result.required_vars != q.result.required_vars || r.result.v2c_map != q.result.v2c_map || r.result.nvars != q.result.nvars ||
+        r.result.blind != q.result.blind || r.result.col_num != q.result.col_num || r.result.row_num != q.result.row_num) return 5;
+    if (r.result.result_table != q.result.result_table) return 6;
+    return 0;
 }
 
 // Planner::set_plan on a pattern-group TREE (UNION / OPTIONAL sub-groups), no string server needed.

@@ -1755,7 +1755,7 @@ static int srv_launch(wk_engine *e, uint64_t first_seq) {
     P.launch_id = ++e->srv.launch_id;
     P.idle_ns = e->srv.idle_ns;
     P.trace = e->d_trace;
-    light_server_kernel<<<1, LIGHT_THREADS, sizeof(SrvSmem), e->srv.stream>>>(P);
+    light_server_kernel<<<1, LIGHT_SRV_THREADS, sizeof(SrvSmem), e->srv.stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     e->launches++;
     e->srv.launches++;
@@ -1940,6 +1940,20 @@ static int run_light(wk_engine *e, const std::vector<PlannedStep> &steps, int mt
     return WK_SUCCESS;
 }
 
+// steps[i..j) are consecutive known_to_known / known_to_const filters on bound columns: one launch
+static int enqueue_filter_chain(wk_engine *e, const std::vector<PlannedStep> &steps, size_t i, size_t j, const DirectOut *direct) {
+    std::vector<size_t> order;
+    for (size_t k = i; k < j; k++) if (steps[k].kind == KIND_K2K) order.push_back(k);
+    for (size_t k = i; k < j; k++) if (steps[k].kind == KIND_K2C) order.push_back(k);
+    ChainFilter ex[MAX_CHAIN];
+    for (size_t k = 1; k < order.size(); k++) {
+        const PlannedStep &x = steps[order[k]];
+        ex[k - 1] = ChainFilter{x.kind, x.col_start, x.col_end, x.dir, x.pid, x.end_const};
+    }
+    const PlannedStep &p0 = steps[order[0]];
+    return enqueue_known(e, p0.kind, p0.col_start, p0.pid, p0.dir, p0.col_end, p0.end_const, ex, (int)order.size() - 1, direct);
+}
+
 int wk_query_execute(wk_engine_t *e, const wk_pattern_t *patterns, int npatterns, int nvars,
                      const int32_t *required_vars, int nrequired, int mt_tid, int mt_factor, int blind,
                      wk_sid_t *table, uint64_t cap_words, uint64_t *out_rows, int *out_cols) {
@@ -2052,18 +2066,8 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
                 // others are evaluated only for the rows that survive it
                 size_t j = i + 1;
                 while (j < steps.size() && j - i < MAX_CHAIN && (steps[j].kind == KIND_K2K || steps[j].kind == KIND_K2C)) j++;
-                std::vector<size_t> order;
-                for (size_t k = i; k < j; k++) if (steps[k].kind == KIND_K2K) order.push_back(k);
-                for (size_t k = i; k < j; k++) if (steps[k].kind == KIND_K2C) order.push_back(k);
-                ChainFilter ex[MAX_CHAIN];
-                for (size_t k = 1; k < order.size(); k++) {
-                    const PlannedStep &x = steps[order[k]];
-                    ex[k - 1] = ChainFilter{x.kind, x.col_start, x.col_end, x.dir, x.pid, x.end_const};
-                }
-                const PlannedStep &p0 = steps[order[0]];
                 const bool last = (j == steps.size()) && dout.dev_ptr;
-                rc = enqueue_known(e, p0.kind, p0.col_start, p0.pid, p0.dir, p0.col_end, p0.end_const, ex, (int)order.size() - 1,
-                                   last ? &dout : nullptr);
+                rc = enqueue_filter_chain(e, steps, i, j, last ? &dout : nullptr);
                 direct_done = last;
                 i = j - 1;
             }
@@ -2385,24 +2389,27 @@ static int exchange_table_p2p(wk_engine *e, int col) {
     srv_park(e);
     const uint64_t epoch = ++c->epoch;
     const uint64_t cap_rows = e->cap_words / (uint64_t)C;
-    // single-CTA kernels do the waiting; the grid of the push kernel never spins, so several ranks may share one device
-    const int grid = c->local_group ? std::max(1, e->num_sms * 4 / std::max(1, c->nranks)) : e->num_sms * 4;
+    // ranks of one process may share a device: there only single-CTA kernels wait (a grid of waiting CTAs could keep a peer's
+    // kernel from becoming resident) and the grid leaves room for the peers; ranks on devices of their own take barrier A
+    // inside the push kernel (one launch less)
+    const bool ready_inside = !c->local_group;
+    // tile = 1024 / 512 / 256 rows so that the two staging areas stay within 32 KB of shared memory
+    const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
+    const size_t smem = 2 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
+    void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, uint32_t *, int) =
+        rpt == 4 ? p2p_push_kernel<4> : (rpt == 2 ? p2p_push_kernel<2> : p2p_push_kernel<1>);
+    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // many tiles in flight per SM hide the round trip of the remote reservations
+    int per_sm = (int)std::min<size_t>(6, std::max<size_t>(1, (200 * 1024) / std::max<size_t>(smem, 1)));
+    const int grid = c->local_group ? std::max(1, e->num_sms * 4 / std::max(1, c->nranks)) : e->num_sms * per_sm;
     StepRecord &r = begin_step(e, KIND_EXCHANGE, C);
-    p2p_ready_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, &e->d_ctl->status);
-    {
-        // tile = 1024 / 512 / 256 rows so that the two staging areas stay within 32 KB of shared memory
-        const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
-        const size_t smem = 2 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
-        void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, const uint32_t *) =
-            rpt == 4 ? p2p_push_kernel<4> : (rpt == 2 ? p2p_push_kernel<2> : p2p_push_kernel<1>);
-        if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kfn<<<grid, CTA_THREADS, smem, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
-                                                    dup ? 1 : 0, (s + 1) & 1, epoch, cap_rows, &e->d_ctl->status);
-    }
+    if (!ready_inside) p2p_ready_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, &e->d_ctl->status);
+    kfn<<<grid, CTA_THREADS, smem, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
+                                                dup ? 1 : 0, (s + 1) & 1, epoch, cap_rows, &e->d_ctl->status, ready_inside ? 1 : 0);
     p2p_wait_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, cap_rows, &e->d_ctl->counts[s + 1], &e->d_ctl->status,
                                              &e->d_ctl->stats[2 * s]);
     CUDA_TRY(cudaGetLastError());
-    end_step(e, r, 3);
+    end_step(e, r, ready_inside ? 2 : 3);
     e->step = s + 1;
     c->exchanges++;
     return WK_SUCCESS;
@@ -2866,6 +2873,12 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
                 rc = ensure_step_room(e);
                 if (!rc) { e->step += 1; e->ncols = 1; }
             }
+        } else if ((ps.kind == KIND_K2K || ps.kind == KIND_K2C) && e->fuse_filters && e->variant >= 4) {
+            // consecutive filters with no exchange between them start from the same (local) column: one launch
+            size_t j = i + 1;
+            while (j < steps.size() && j - i < MAX_CHAIN && (steps[j].kind == KIND_K2K || steps[j].kind == KIND_K2C) && ex[j] == -1) j++;
+            rc = enqueue_filter_chain(e, steps, i, j, nullptr);
+            i = j - 1;
         } else {
             rc = enqueue_known(e, ps.kind, ps.col_start, ps.pid, ps.dir, ps.col_end, ps.end_const);
         }

@@ -24,7 +24,10 @@ enum { LIGHT_WORDS = 4096, LIGHT_ROWS = 1024, MAX_LIGHT_STEPS = 24 };
 // consumed, 1 multiplicities scanned, 2 rows materialised
 enum { LIGHT_TRACE_WORDS = 32 + 4 * MAX_LIGHT_STEPS };
 // thread count of the single-CTA latency path (the interpreter is a template on it)
-enum { LIGHT_THREADS = 256, LIGHT_MAX_WARPS = 32 };   // measured: 1024 threads cost ~0.4 us more per step in barriers
+enum { LIGHT_THREADS = 256, LIGHT_MAX_WARPS = 32 };   // measured (round 1, block-wide steps only): 1024 threads cost ~0.4 us more per step in barriers
+// the resident server runs 1024 threads: tables of <= 32 rows are handled by one warp (one barrier per step whatever the CTA
+// size), and a table of hundreds of rows is probed in ONE round instead of three dependent ones
+enum { LIGHT_SRV_THREADS = 1024 };
 enum { LKIND_I2U = 0, LKIND_C2U = 1, LKIND_K2U = 2, LKIND_K2K = 3, LKIND_K2C = 4 };
 
 struct LightStep {
@@ -296,6 +299,96 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                 if (l2.kind >= LKIND_K2U && l2.col_start < Cin && !((shadowed >> s2) & 1u)) { sh[nsh++] = s2; shadowed |= 1u << s2; }
             }
             if ((uint64_t)N * (uint64_t)(1 + nsh) > 2048) nsh = 0;
+            uint32_t *tout = sm.tab[nxt];
+            if (N <= 32) {
+                // ---- warp mode: a table of at most 32 rows is ONE warp's business: lane = row, multiplicities are scanned
+                // with shuffles, rows are compacted straight into the next table, and the step costs one CTA barrier instead
+                // of four plus a block-wide scan.  The other warps pull the lines of later steps towards L2 meanwhile.
+                const int lane = tid & 31;
+                if (tid < 32) {
+                    const bool act = (uint32_t)lane < N;
+                    uint64_t ptr = 0;
+                    uint32_t c0 = 0, mult = 0, size = 0;
+                    if (act) {
+                        c0 = tin[lane * Cin + ls.col_start];
+                        const uint64_t key = step_key(ls.seg, c0);
+                        uint32_t visited;
+                        ptr = probe_thread(sv.vertices(c0), key, sv.bucket(ls, s, key, c0), visited);
+                        st_visited += visited;
+                        size = ptr_size(ptr);
+                        if (ls.kind == LKIND_K2U) {
+                            mult = size > LIGHT_ROWS ? (uint32_t)LIGHT_ROWS + 1u : size;
+                            st_edges += size;
+                        } else {
+                            const uint32_t target = (ls.kind == LKIND_K2K) ? tin[lane * Cin + ls.col_end] : ls.end_const;
+                            uint32_t scanned;
+                            mult = list_contains(sv.edges(c0) + ptr_off(ptr), size, target, scanned) ? 1u : 0u;
+                            st_edges += scanned;
+                        }
+                    }
+                    uint32_t incl = mult;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    const uint32_t excl = incl - mult;
+                    const bool fits = total <= LIGHT_ROWS && (uint64_t)total * (uint64_t)Cout <= LIGHT_WORDS;
+                    // 0: rows written by this warp, 1: spill, 2: known_to_unknown with a large fan-out: every thread of the CTA
+                    // takes output rows (prefix and pointers left in shared memory)
+                    uint32_t how = fits ? 0u : 1u;
+                    if (fits && ls.kind == LKIND_K2U && total > 64) how = 2u;
+                    if (how == 0) {
+                        if (ls.kind == LKIND_K2U) {
+                            const uint32_t *e = sv.edges(c0) + ptr_off(ptr);
+                            for (uint32_t k = 0; k < mult; k++) {
+                                uint32_t *dst = tout + (excl + k) * Cout;
+                                const uint32_t ev = ld_edge(e + k);
+                                for (int c = 0; c < Cin; c++) dst[c] = tin[lane * Cin + c];
+                                dst[Cin] = ev;
+                            }
+                        } else if (mult) {
+                            for (int c = 0; c < Cin; c++) tout[excl * Cout + c] = tin[lane * Cin + c];
+                        }
+                    } else if (how == 2 && act) {
+                        sm.pre[lane] = excl;
+                        sm.ptr[lane] = ptr;
+                    }
+                    if (lane == 0) { sm.total = total; sm.wsum[0] = how; }
+                } else if (nsh) {
+                    for (uint32_t item = tid - 32; item < N * (uint32_t)nsh; item += NT - 32) {
+                        uint32_t r = item, j = 0;
+                        while (r >= N) { r -= N; j++; }
+                        const LightStep &l2 = steps[sh[j]];
+                        const uint32_t c2 = tin[r * Cin + l2.col_start];
+                        const uint64_t key2 = step_key(l2.seg, c2);
+                        uint32_t v2;
+                        const uint64_t ptr2 = probe_thread(sv.vertices(c2), key2, sv.bucket(l2, sh[j], key2, c2), v2);
+                        if (ptr2) asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.edges(c2) + ptr_off(ptr2)));
+                    }
+                }
+                if (trace && tid == 0) trace[32 + 4 * s] = clock64();
+                __syncthreads();
+                const uint32_t total = sm.total, how = sm.wsum[0];
+                if (trace && tid == 0) trace[32 + 4 * s + 1] = clock64();
+                if (how == 1) { spilled = true; break; }
+                if (how == 2) {
+                    for (uint32_t o = tid; o < total; o += NT) {
+                        uint32_t lo = 0, hi = N;   // largest r with pre[r] <= o
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (sm.pre[mid] <= o) lo = mid; else hi = mid;
+                        }
+                        const uint32_t e = ld_edge(sv.edges(tin[lo * Cin + ls.col_start]) + ptr_off(sm.ptr[lo]) + (o - sm.pre[lo]));
+                        for (int c = 0; c < Cin; c++) tout[o * Cout + c] = tin[lo * Cin + c];
+                        tout[o * Cout + Cin] = e;
+                    }
+                }
+                N = total;
+                C = Cout;
+                if (trace && tid == 0) trace[32 + 4 * s + 2] = clock64();
+            } else {
             // tables taller than the CTA are walked in several rounds whose loads depend on each other through
             // the loop; pull every later round's bucket line towards L2 first so that only round one pays DRAM
             for (uint32_t r = tid + NT; r < N; r += NT) {
@@ -362,7 +455,6 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             if (trace && tid == 0) trace[32 + 4 * s + 1] = clock64();
             if (total > LIGHT_ROWS || (uint64_t)total * (uint64_t)Cout > LIGHT_WORDS) { spilled = true; break; }
             // phase 3: materialise (thread per OUTPUT row: every edge load of the step in flight at once)
-            uint32_t *tout = sm.tab[nxt];
             if (ls.kind == LKIND_K2U) {
                 for (uint32_t o = tid; o < total; o += NT) {
                     uint32_t lo = 0, hi = N;   // largest r with pre[r] <= o
@@ -386,6 +478,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             N = total;
             C = Cout;
             if (trace && tid == 0) trace[32 + 4 * s + 2] = clock64();
+            }   // block mode
         }
         // per-step statistics (algorithmic-bytes accounting)
         if ((stats != nullptr)) {

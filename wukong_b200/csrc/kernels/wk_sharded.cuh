@@ -236,18 +236,39 @@ __global__ void p2p_ready_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t
 }
 
 // one pass: tile -> group by owner -> reserve -> push.  RPT rows per thread: tile = 256 * RPT rows.
+// ready_inside: barrier A is taken inside this kernel (one launch less per exchange): CTA 0 tells every peer that this rank's
+// earlier kernels are done, and every CTA waits for all peers' word before its first store into a peer's buffer.  Only for
+// ranks on different devices: on a shared device a grid of waiting CTAs could keep a peer's kernel from becoming resident.
 template <int RPT>
-__global__ void __launch_bounds__(CTA_THREADS) p2p_push_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
-                                                               int C, int col, int dup, int dst_buf, uint64_t epoch, uint64_t cap_rows,
-                                                               const uint32_t *status) {
+__global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
+                                                                  int C, int col, int dup, int dst_buf, uint64_t epoch, uint64_t cap_rows,
+                                                                  uint32_t *status, int ready_inside) {
     extern __shared__ uint32_t p2p_dyn[];
     constexpr uint32_t TILE = CTA_THREADS * RPT;
     uint32_t *rows = p2p_dyn, *stage = p2p_dyn + (size_t)TILE * C;
     __shared__ uint32_t hist[P2P_MAX_RANKS], off[P2P_MAX_RANKS + 1];
     __shared__ uint64_t base[P2P_MAX_RANKS];
     __shared__ uint32_t last, s_ovf;
+    __shared__ int s_ok;
     const uint32_t n = (uint32_t)t.nranks;
     const uint32_t tid = threadIdx.x;
+    if (ready_inside) {
+        if (tid == 0) s_ok = 1;
+        __syncthreads();
+        if (tid < n) {
+            if (blockIdx.x == 0) {
+                __threadfence_system();
+                st_sys_u64(&t.ctl[tid]->flagA[t.rank], epoch);
+            }
+            if (!wait_flag(&my->flagA[tid], epoch)) atomicExch(&s_ok, 0);
+        }
+        __syncthreads();
+        if (!s_ok) {   // a peer never showed up: poison the group, push nothing (the flags below still go out)
+            if (tid < n) st_sys_u64(&t.ctl[tid]->poison, 1);
+            if (tid == 0) atomicOr(status, 2u);
+            __syncthreads();
+        }
+    }
     // an earlier step of this rank overflowed (its table is not usable), or the group is poisoned: push nothing, but
     // still take part in the barriers so that the ranks stay in step
     const bool bad = __ldcg(status) != 0 || ld_sys_u64(&my->poison) != 0;
@@ -374,11 +395,15 @@ __global__ void p2p_wait_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t 
     if (p == 0) {
         const uint64_t cnt = ld_sys_u64(&my->recv_count);
         st_sys_u64(&my->recv_count, 0);   // nobody adds again before my next "ready"
+        const uint64_t sent = loc->rows_sent - loc->sent_mark;
+        loc->done_ctas = 0;               // scratch of the next exchange's push kernel (my push of this one is over: stream order)
+        loc->ovf = 0;
+        loc->sent_mark = loc->rows_sent;
         if (!ok) { atomicOr(status, 2u); *out_count = 0; return; }
         if (ovf || cnt > cap_rows) { atomicOr(status, 1u); *out_count = 0; return; }   // the same verdict on every rank
         *out_count = cnt;
         loc->rows_landed += cnt;
-        stats[0] = loc->rows_sent - loc->sent_mark;   // per-exchange figures for wk_engine_step_stats (kind 10)
+        stats[0] = sent;                  // per-exchange figures for wk_engine_step_stats (kind 10)
         stats[1] = cnt;
     }
 }
