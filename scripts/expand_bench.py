@@ -29,8 +29,7 @@ from conftest import load_query  # noqa: E402
 
 t0 = time.time()
 tr = datagen.lubm(args.scale, seed=1)
-hs = host.HostStore(tr)
-gst = hs.upload(0)
+gst = capi.Store.build(tr, datagen.LUBM_NUM_NORMAL_PREDS)      # device-side store build, as in bench.py
 print("dataset ready in %.1fs: %d triples" % (time.time() - t0, tr.shape[0]), file=sys.stderr)
 pats, nvars, req, _ = load_query(args.query, args.plan)
 variants = [v for v in args.variants.split(",") if v != ""] or [os.environ.get("WK_VARIANT", "")]

@@ -2094,7 +2094,7 @@ int wk_query_execute_ex(wk_engine_t *e, const wk_pattern_t *patterns, int npatte
             }
         }
         // final_process projection -- unless the table already is the projection (SELECT lists every column in table order)
-        bool identity = (nrequired == final_cols);
+        bool identity = want_table && (nrequired == final_cols) && (int)proj_cols.size() == nrequired;
         for (int i = 0; i < nrequired && identity; i++) identity = proj_cols[i] == i;
         if (want_table && !direct_done && !identity) {
             rc = enqueue_project(e, proj_cols.data(), nrequired);
