@@ -46,6 +46,11 @@ struct CtlBlock {
 
 static_assert(sizeof(CtlBlock) % sizeof(uint64_t) == 0, "CtlBlock is cleared in 8-byte words");
 
+// Programmatic dependent launch (sm_90+): the kernels of a plan are launched with the programmatic-stream-serialization
+// attribute, so the launch of step s+1 is set up while step s still runs and only its body waits -- here, before the first
+// read of anything the previous kernel wrote.  Without the attribute the instruction is a no-op.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // completion record in mapped pinned host memory: wk::LightRecord (32 bytes, two 16-byte stores,
 // validated on the host by record_check instead of a system-scope fence on the device)
 typedef LightRecord HostRec;
@@ -82,6 +87,7 @@ template <int MODE, int BATCH, int MINB, int CT>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel(const StepParam p) {
     extern __shared__ uint32_t dyn_rows[];
     __shared__ TileSmem sm;
+    grid_dependency_wait();
     if (__ldcg(p.status) != 0) return;   // an earlier step overflowed: its output is not usable
     const uint64_t N = ld_count(p.in_count);
     uint64_t acc_visited = 0, acc_edges = 0;
@@ -98,12 +104,14 @@ template <int MODE, int MINB, int CT, bool PROJ = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB) step_kernel_v5(const StepParam p) {
     extern __shared__ __align__(16) unsigned char dyn5[];
     __shared__ TileSmem4 sm;
+    grid_dependency_wait();
     if (__ldcg(p.status) != 0) return;
     step_body_v5<MODE, CT, PROJ>(p, ld_count(p.in_count), sm, dyn5);
 }
 
 template <int CT>
 __global__ void __launch_bounds__(CTA_THREADS, 8) expand_heavy_kernel(const StepParam p) {
+    grid_dependency_wait();
     if (__ldcg(p.status) != 0) return;
     expand_heavy_body<CT>(p);
 }
@@ -172,6 +180,7 @@ __device__ __forceinline__ void seed_body(const SeedParam &p, uint64_t *s_ptr, u
 
 __global__ void __launch_bounds__(CTA_THREADS) seed_kernel(const SeedParam p) {
     __shared__ uint64_t s_ptr;
+    grid_dependency_wait();
     if (__ldcg(p.status) != 0) return;
     seed_body(p, &s_ptr, blockIdx.x, gridDim.x);
 }
@@ -219,6 +228,7 @@ __global__ void __launch_bounds__(CTA_THREADS) seed_bulk_kernel(const SeedParam 
     extern __shared__ __align__(128) unsigned char seed_dyn[];
     __shared__ __align__(8) uint64_t bar[SEED_STAGES];
     __shared__ uint64_t s_ptr;
+    grid_dependency_wait();
     if (__ldcg(p.status) != 0) return;
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -325,6 +335,7 @@ __device__ __forceinline__ void project_body(const ProjParam &p, uint64_t N, uin
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) project_kernel(const ProjParam p) {
+    grid_dependency_wait();
     if (__ldcg(p.status) != 0) return;
     project_body(p, ld_count(p.in_count), blockIdx.x, gridDim.x);
 }
@@ -470,6 +481,7 @@ __global__ void rebase_kernel(CtlBlock *ctl, int from, int to) {
 }
 
 __global__ void finish_kernel(const uint64_t *count, const uint32_t *status, HostRec *rec, uint64_t seq, int resume) {
+    grid_dependency_wait();
     const uint64_t rows = ld_count(count);
     const uint64_t sr = (uint64_t)__ldcg(status) | ((uint64_t)(uint32_t)resume << 32);
     uint64_t *r = (uint64_t *)rec;
@@ -491,6 +503,27 @@ __global__ void finish_kernel(const uint64_t *count, const uint32_t *status, Hos
     } while (0)
 
 typedef std::tuple<int, uint32_t, int> SegKey;   // (index, pid, dir)
+
+static bool g_use_pdl = true;   // WK_PDL=0: plain stream-ordered launches
+template <class... P, class... A>
+static cudaError_t launch_chained(void (*fn)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... p) {
+    if (!g_use_pdl) {
+        fn<<<grid, block, smem, st>>>(p...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fn, p...);
+}
 
 struct wk_store {
     int device = 0;
@@ -709,8 +742,8 @@ static int wait_record(wk_engine *e, uint64_t seq, int nsteps_full, int table_co
 // enqueue the completion record for the current table and wait for it
 static int sync_rows(wk_engine *e, uint64_t *rows, cudaEvent_t after = nullptr) {
     const uint64_t seq = ++e->seq;
-    finish_kernel<<<1, 1, 0, e->stream>>>(&e->d_ctl->counts[e->step], &e->d_ctl->status, e->d_rec, seq, e->step);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_chained(finish_kernel, dim3(1), dim3(1), 0, e->stream, (const uint64_t *)&e->d_ctl->counts[e->step],
+                            (const uint32_t *)&e->d_ctl->status, e->d_rec, seq, e->step));
     if (after) cudaEventRecord(after, e->stream);   // device-side end of the query, before the host waits
     e->launches++;
     RecView rv;
@@ -775,17 +808,15 @@ static int launch_step(wk_engine *e, const StepParam &p) {
     StepKernelFn fn = p.proj_n > 0 ? step_kernel_proj<MODE>(p.C) : step_kernel_fn(MODE, e->variant, p.C);
     const size_t smem = step_smem(e, p.C);
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fn<<<grid, CTA_THREADS, smem, e->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_chained(fn, dim3(grid), dim3(CTA_THREADS), smem, e->stream, p));
     if (MODE == MODE_K2U && p.hq_cap) {   // spreads queued heavy tiles over the grid; returns at once when there are none
         const int g2 = e->num_sms * 8;
         switch (p.C) {
-        case 1: expand_heavy_kernel<1><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
-        case 2: expand_heavy_kernel<2><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
-        case 3: expand_heavy_kernel<3><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
-        default: expand_heavy_kernel<0><<<g2, CTA_THREADS, 0, e->stream>>>(p); break;
+        case 1: CUDA_TRY(launch_chained(expand_heavy_kernel<1>, dim3(g2), dim3(CTA_THREADS), 0, e->stream, p)); break;
+        case 2: CUDA_TRY(launch_chained(expand_heavy_kernel<2>, dim3(g2), dim3(CTA_THREADS), 0, e->stream, p)); break;
+        case 3: CUDA_TRY(launch_chained(expand_heavy_kernel<3>, dim3(g2), dim3(CTA_THREADS), 0, e->stream, p)); break;
+        default: CUDA_TRY(launch_chained(expand_heavy_kernel<0>, dim3(g2), dim3(CTA_THREADS), 0, e->stream, p)); break;
         }
-        CUDA_TRY(cudaGetLastError());
     }
     return WK_SUCCESS;
 }
@@ -909,11 +940,10 @@ static int enqueue_seed(wk_engine *e, int kind, uint64_t vid, uint32_t pid, int 
             CUDA_TRY(cudaFuncSetAttribute((const void *)seed_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        seed_bulk_kernel<<<e->num_sms * 4, CTA_THREADS, smem, e->stream>>>(p);
+        CUDA_TRY(launch_chained(seed_bulk_kernel, dim3(e->num_sms * 4), dim3(CTA_THREADS), smem, e->stream, p));
     } else {
-        seed_kernel<<<e->num_sms * 4, CTA_THREADS, 0, e->stream>>>(p);
+        CUDA_TRY(launch_chained(seed_kernel, dim3(e->num_sms * 4), dim3(CTA_THREADS), 0, e->stream, p));
     }
-    CUDA_TRY(cudaGetLastError());
     end_step(e, r, 1);
     e->step = s + 1;
     e->ncols = 1;
@@ -941,8 +971,7 @@ static int enqueue_project(wk_engine *e, const int32_t *cols, int n) {
     p.Cn = n;
     for (int i = 0; i < n; i++) p.cols[i] = (int8_t)cols[i];
     StepRecord &r = begin_step(e, KIND_PROJECT, e->ncols);
-    project_kernel<<<e->num_sms * 4, CTA_THREADS, 0, e->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_chained(project_kernel, dim3(e->num_sms * 4), dim3(CTA_THREADS), 0, e->stream, p));
     end_step(e, r, 1);
     e->step = s + 1;
     e->ncols = n;
@@ -1372,6 +1401,7 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     if (const char *ev = getenv("WK_RESIDENT")) e->srv.enabled = atoi(ev) != 0;
     if (const char *ev = getenv("WK_FUSE_FILTERS")) e->fuse_filters = atoi(ev) != 0;
     if (const char *ev = getenv("WK_SEED_BULK")) e->seed_bulk = atoi(ev) != 0;
+    if (const char *ev = getenv("WK_PDL")) g_use_pdl = atoi(ev) != 0;
     if (const char *ev = getenv("WK_DIRECT_OUT")) e->direct_out = atoi(ev) != 0;
     if (const char *ev = getenv("WK_RESIDENT_IDLE_US")) e->srv.idle_ns = (uint64_t)std::max(1, atoi(ev)) * 1000ull;
     if (reset_ctl(e) != WK_SUCCESS) { engine_free(e); return WK_ERR_CUDA; }
