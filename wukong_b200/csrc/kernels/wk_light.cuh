@@ -269,21 +269,25 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                     if (chain == 0) break;
                     b = chain >> WK_KEY_VID_SHIFT;
                 }
-                if (tid == 0) { sm.seed_ptr = result; st_visited = visited; }
+                // the whole seed is this warp's business (the other warps only execute the barrier below: every
+                // instruction of the interpreter that all 8..32 warps run costs issue slots of the one that works)
+                const uint64_t size = ptr_size(result), off = ptr_off(result);
+                uint64_t begin = 0, len = size;
+                if (ls.mt_factor > 1) {   // mt slicing (index starts only), sparql.hpp:211-221
+                    const uint64_t mtf = (uint64_t)ls.mt_factor, start = (uint64_t)ls.mt_tid % mtf, length = size / mtf;
+                    begin = start * length;
+                    len = (start == mtf - 1) ? (size - begin) : length;
+                }
+                if (len <= LIGHT_ROWS) {
+                    const uint32_t *seed_edges = sv.edges(seed_vid) + off + begin;
+                    for (uint32_t k = tid; k < len; k += 32) sm.tab[nxt][k] = ld_edge(seed_edges + k);
+                }
+                if (tid == 0) { sm.seed_ptr = result; sm.seed_len = len > LIGHT_ROWS ? 0xFFFFFFFFu : (uint32_t)len; st_visited = visited; st_edges = len; }
             }
             __syncthreads();
-            const uint64_t ptr = sm.seed_ptr;
-            const uint64_t size = ptr_size(ptr), off = ptr_off(ptr);
-            const uint64_t mtf = (uint64_t)(ls.mt_factor < 1 ? 1 : ls.mt_factor);
-            const uint64_t start = (uint64_t)ls.mt_tid % mtf;
-            const uint64_t length = size / mtf;
-            const uint64_t begin = start * length;
-            const uint64_t len = (start == mtf - 1) ? (size - begin) : length;
-            if (len > LIGHT_ROWS) { spilled = true; break; }   // nothing done yet: resume at this very step
-            const uint32_t *seed_edges = sv.edges((uint32_t)(ls.key >> WK_KEY_VID_SHIFT));
-            for (uint32_t k = tid; k < len; k += NT) sm.tab[nxt][k] = ld_edge(seed_edges + off + begin + k);
-            if (tid == 0) st_edges = len;
-            N = (uint32_t)len;
+            const uint32_t slen = sm.seed_len;
+            if (slen == 0xFFFFFFFFu) { spilled = true; break; }   // nothing done yet: resume at this very step
+            N = slen;
             C = 1;
         } else {
             const int Cin = ls.C;
@@ -356,8 +360,8 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                         sm.ptr[lane] = ptr;
                     }
                     if (lane == 0) { sm.total = total; sm.wsum[0] = how; }
-                } else if (nsh) {
-                    for (uint32_t item = tid - 32; item < N * (uint32_t)nsh; item += NT - 32) {
+                } else if (nsh && tid < 64) {   // one more warp pulls the lines of later steps towards L2; the rest only meet at the barrier
+                    for (uint32_t item = tid - 32; item < N * (uint32_t)nsh; item += 32) {
                         uint32_t r = item, j = 0;
                         while (r >= N) { r -= N; j++; }
                         const LightStep &l2 = steps[sh[j]];
@@ -550,17 +554,32 @@ __device__ __forceinline__ bool light_run(const LightPlan &plan, const LightStep
         // final_process projection straight into the mapped staging area
         const uint32_t words = N * (uint32_t)plan.proj_n;
         uint64_t part = 0;
-        if ((uint64_t)words <= plan.host_table_words) {
-            for (uint32_t w = tid; w < words; w += NT) {
-                const uint32_t r = w / (uint32_t)plan.proj_n, j = w - r * (uint32_t)plan.proj_n;
-                const uint32_t val = sm.tab[cur][r * C + plan.proj_cols[j]];
-                st_sys_u32(plan.host_table + w, val);
-                part += table_word_mix(val, w);
+        if (words <= 128) {
+            // a handful of rows: one warp writes and sums them, nobody else executes a reduction
+            if (tid < 32) {
+                for (uint32_t w = tid; w < words; w += 32) {
+                    const uint32_t r = w / (uint32_t)plan.proj_n, j = w - r * (uint32_t)plan.proj_n;
+                    const uint32_t val = sm.tab[cur][r * C + plan.proj_cols[j]];
+                    st_sys_u32(plan.host_table + w, val);
+                    part += table_word_mix(val, w);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
+                tsum = part;   // lane 0 holds the sum; it also writes the record
             }
         } else {
-            status = 1;
+            if ((uint64_t)words <= plan.host_table_words) {
+                for (uint32_t w = tid; w < words; w += NT) {
+                    const uint32_t r = w / (uint32_t)plan.proj_n, j = w - r * (uint32_t)plan.proj_n;
+                    const uint32_t val = sm.tab[cur][r * C + plan.proj_cols[j]];
+                    st_sys_u32(plan.host_table + w, val);
+                    part += table_word_mix(val, w);
+                }
+            } else {
+                status = 1;
+            }
+            tsum = block_sum_u64<NT>(part, sm, tid);
         }
-        tsum = block_sum_u64<NT>(part, sm, tid);
     }
     if (spilled) __syncthreads();
     if (plan.trace && tid == 0) plan.trace[2 + MAX_LIGHT_STEPS] = clock64();
