@@ -329,8 +329,22 @@ def run_reference(args, rank, world):
     """the reference arm: the reference's CPU engine on the same config as the GPU arm at this N"""
     if rank != 0:
         return
-    tr, hs, info = build_dataset(args)
-    del tr
+    # the store arrays the CPU engine probes (input data, outside the timed region): built on the GPU when there is one (seconds
+    # and one copy back instead of minutes and a second copy of the triples in host memory at LUBM-10240), else by the host builder
+    hs = None
+    try:
+        from wukong_b200 import capi
+        if args.store_build == "device" and capi.device_count() > 0:
+            tr, gst, info = build_dataset_device(args, 0)
+            del tr
+            hs = DeviceBuiltStore(gst)
+            gst.close()
+    except Exception as ex:   # noqa: BLE001
+        print("device-side store build for the CPU arm failed (%r): host builder" % (ex,), file=sys.stderr)
+        hs = None
+    if hs is None:
+        tr, hs, info = build_dataset(args)
+        del tr
     plans = load_plans(args.plan)
     cpus = host_cpus()
     threads = args.cpu_threads or cpus["usable"]

@@ -151,6 +151,7 @@ enum { WK_OPT_RESIDENT_LIGHT = 1, WK_OPT_RESIDENT_IDLE_US = 2,
        WK_OPT_DIRECT_OUT = 4,             /* default 0 (pays only for results of a few thousand rows): when `table` of wk_query_execute is pinned host memory the device can address
                                              (wk_host_alloc), the last step of the plan writes the projected rows straight into it
                                              (final_process fused into the step, zero-copy over PCIe) */
+       WK_OPT_RESIDENT_VARIANT = 5,       /* shape of the server CTA, for A/B runs: 0 (default) / 1 / 2 / 3, see engine.cu */
        WK_OPT_FUSE_FILTERS = 3,           /* default 1: a run of consecutive known_to_known / known_to_const steps of a plan is ONE
                                              launch (rows staged once, no intermediate tables); the steps are reported as kind 11 */
        WK_INFO_RESIDENT_LAUNCHES = 100,   /* server instances launched so far */

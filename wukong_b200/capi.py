@@ -15,7 +15,7 @@ WK_SUCCESS = 0
 WK_ERR_CUDA, WK_ERR_BAD_ARG, WK_ERR_RBUF_OVERFLOW, WK_ERR_NO_SEGMENT, WK_ERR_NO_DEVICE, WK_ERR_COMM = 100, 101, 102, 103, 104, 105
 WK_ERR_STORE_FULL = 106
 # wk_engine_set_option / wk_engine_get_option
-WK_OPT_RESIDENT_LIGHT, WK_OPT_RESIDENT_IDLE_US, WK_OPT_FUSE_FILTERS, WK_OPT_DIRECT_OUT = 1, 2, 3, 4
+WK_OPT_RESIDENT_LIGHT, WK_OPT_RESIDENT_IDLE_US, WK_OPT_FUSE_FILTERS, WK_OPT_DIRECT_OUT, WK_OPT_RESIDENT_VARIANT = 1, 2, 3, 4, 5
 WK_INFO_RESIDENT_LAUNCHES, WK_INFO_RESIDENT_REQUESTS, WK_INFO_LAST_RESIDENT, WK_INFO_LAST_RESIDENT_NS, WK_INFO_RESIDENT_RUNNING = 100, 101, 102, 103, 104
 WK_INFO_COMM_BYTES_PUSHED = 110
 

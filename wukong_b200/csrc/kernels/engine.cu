@@ -589,6 +589,7 @@ struct wk_engine {
         bool quitting = false;           // a QUIT is on its way: wait for the exit word before relaunching
         uint64_t launches = 0, requests = 0;
         uint64_t last_ns = 0;            // in-kernel span of the last request
+        int variant = 0;                 // WK_OPT_RESIDENT_VARIANT: 0 = 1024 threads + warp mode, 1 = 256 + warp mode, 2 = 256, block steps only, 3 = 512 + warp mode
     } srv;
     bool last_resident = false;          // the last wk_query_execute was answered by the resident server
     // WK_OPT_DIRECT_OUT: last step writes projected rows into the caller's pinned buffer.  Off by default: measured on B200
@@ -1403,6 +1404,7 @@ int wk_engine_create(wk_store_t *store, uint64_t rbuf_bytes, wk_engine_t **out) 
     if (const char *ev = getenv("WK_SEED_BULK")) e->seed_bulk = atoi(ev) != 0;
     if (const char *ev = getenv("WK_PDL")) g_use_pdl = atoi(ev) != 0;
     if (const char *ev = getenv("WK_DIRECT_OUT")) e->direct_out = atoi(ev) != 0;
+    if (const char *ev = getenv("WK_SRV_VARIANT")) e->srv.variant = atoi(ev);
     if (const char *ev = getenv("WK_RESIDENT_IDLE_US")) e->srv.idle_ns = (uint64_t)std::max(1, atoi(ev)) * 1000ull;
     if (reset_ctl(e) != WK_SUCCESS) { engine_free(e); return WK_ERR_CUDA; }
     ENGINE_TRY(cudaStreamSynchronize(e->stream));
@@ -1438,6 +1440,11 @@ int wk_engine_set_option(wk_engine_t *e, int option, int64_t value) {
         return WK_SUCCESS;
     case WK_OPT_FUSE_FILTERS:
         e->fuse_filters = value != 0;
+        return WK_SUCCESS;
+    case WK_OPT_RESIDENT_VARIANT:
+        if (value < 0 || value > 3) return WK_ERR_BAD_ARG;
+        srv_stop(e);
+        e->srv.variant = (int)value;
         return WK_SUCCESS;
     case WK_OPT_DIRECT_OUT:
         e->direct_out = value != 0;
@@ -1746,7 +1753,10 @@ static int srv_init(wk_engine *e) {
     memset((void *)box, 0, sizeof(SrvMailbox));
     e->srv.h_box = box;
     CUDA_TRY(cudaHostGetDevicePointer((void **)&e->srv.d_box, (void *)box, 0));
-    CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel<LIGHT_SRV_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
     if (!e->d_trace) {
         CUDA_TRY(cudaMalloc((void **)&e->d_trace, LIGHT_TRACE_WORDS * sizeof(long long)));
         CUDA_TRY(cudaMemset(e->d_trace, 0, LIGHT_TRACE_WORDS * sizeof(long long)));
@@ -1785,7 +1795,12 @@ static int srv_launch(wk_engine *e, uint64_t first_seq) {
     P.launch_id = ++e->srv.launch_id;
     P.idle_ns = e->srv.idle_ns;
     P.trace = e->d_trace;
-    light_server_kernel<<<1, LIGHT_SRV_THREADS, sizeof(SrvSmem), e->srv.stream>>>(P);
+    switch (e->srv.variant) {   // WK_SRV_VARIANT, for A/B runs: threads of the server CTA x warp mode of the interpreter
+    case 1: light_server_kernel<256, true><<<1, 256, sizeof(SrvSmem), e->srv.stream>>>(P); break;
+    case 2: light_server_kernel<256, false><<<1, 256, sizeof(SrvSmem), e->srv.stream>>>(P); break;
+    case 3: light_server_kernel<512, true><<<1, 512, sizeof(SrvSmem), e->srv.stream>>>(P); break;
+    default: light_server_kernel<LIGHT_SRV_THREADS, true><<<1, LIGHT_SRV_THREADS, sizeof(SrvSmem), e->srv.stream>>>(P); break;
+    }
     CUDA_TRY(cudaGetLastError());
     e->launches++;
     e->srv.launches++;
@@ -2968,7 +2983,8 @@ static int preload_kernels(wk_engine *e) {
                           (const void *)part_scatter_kernel, (const void *)p2p_ready_kernel, (const void *)p2p_push_kernel<1>,
                           (const void *)p2p_push_kernel<2>, (const void *)p2p_push_kernel<4>, (const void *)p2p_light_wait_kernel,
                           (const void *)p2p_light_verdict_kernel, (const void *)p2p_wait_kernel, (const void *)light_query_kernel,
-                          (const void *)light_sharded_kernel, (const void *)light_batch_kernel, (const void *)light_server_kernel};
+                          (const void *)light_sharded_kernel, (const void *)light_batch_kernel, (const void *)light_server_kernel<LIGHT_SRV_THREADS, true>,
+                          (const void *)light_server_kernel<256, true>, (const void *)light_server_kernel<256, false>, (const void *)light_server_kernel<512, true>};
     for (const void *f : rest) fns.push_back(f);
     for (const void *f : fns) {
         cudaFuncAttributes a;

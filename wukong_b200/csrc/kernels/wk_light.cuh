@@ -234,7 +234,7 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, LightSmem &sm, int
 // not fit shared memory (nothing of that step has been written).
 struct LightState { uint32_t N; int C, cur, done; bool spilled; };
 
-template <int NT, class SV>
+template <int NT, class SV, bool WARPM = true>
 __device__ __forceinline__ LightState light_interpret(const LightStep *steps, int nsteps, const SV &sv, LightSmem &sm, uint64_t *stats,
                                                       uint64_t *counts, long long *trace = nullptr) {
     const int tid = threadIdx.x;
@@ -304,7 +304,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             }
             if ((uint64_t)N * (uint64_t)(1 + nsh) > 2048) nsh = 0;
             uint32_t *tout = sm.tab[nxt];
-            if (N <= 32) {
+            if (WARPM && N <= 32) {
                 // ---- warp mode: a table of at most 32 rows is ONE warp's business: lane = row, multiplicities are scanned
                 // with shuffles, rows are compacted straight into the next table, and the step costs one CTA barrier instead
                 // of four plus a block-wide scan.  The other warps pull the lines of later steps towards L2 meanwhile.
@@ -515,7 +515,7 @@ __device__ __forceinline__ void stage_steps(LightStep *dst, const LightStep *src
 // store the completion record.  Returns true when the table outgrew shared memory.
 // `s_steps` are the step descriptors in shared memory.  clear_ctl: the launch-per-query kernel owns the control block and
 // clears it up front; the resident server (wk_server.cuh) only touches it when it has to (spill, per-step statistics).
-template <int NT, class SV>
+template <int NT, class SV, bool WARPM = true>
 __device__ __forceinline__ bool light_run(const LightPlan &plan, const LightStep *s_steps, const SV &sv, LightSmem &sm, bool clear_ctl,
                                           uint64_t *times = nullptr, uint64_t t_acquired = 0) {
     const int tid = threadIdx.x;
@@ -525,7 +525,7 @@ __device__ __forceinline__ bool light_run(const LightPlan &plan, const LightStep
         __syncthreads();
     }
     if (plan.trace && tid == 0) plan.trace[1] = clock64();
-    const LightState ls_ = light_interpret<NT>(s_steps, plan.nsteps, sv, sm, (clear_ctl && plan.collect_stats) ? plan.stats : nullptr,
+    const LightState ls_ = light_interpret<NT, SV, WARPM>(s_steps, plan.nsteps, sv, sm, (clear_ctl && plan.collect_stats) ? plan.stats : nullptr,
                                            clear_ctl ? plan.counts : nullptr, plan.trace);
     const uint32_t N = ls_.N;
     const int C = ls_.C, cur = ls_.cur, s = ls_.done;

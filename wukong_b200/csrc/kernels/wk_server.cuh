@@ -85,12 +85,13 @@ struct SrvSmem {
     uint32_t ctrl;                  // 0 run, 1 leave
 };
 
-__global__ void __launch_bounds__(LIGHT_SRV_THREADS) light_server_kernel(const __grid_constant__ SrvParams P) {
+template <int NT, bool WARPM>
+__global__ void __launch_bounds__(NT) light_server_kernel(const __grid_constant__ SrvParams P) {
     extern __shared__ __align__(16) unsigned char srv_dyn[];
     SrvSmem &S = *reinterpret_cast<SrvSmem *>(srv_dyn);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // constant part of the plan header and the segment table
-    for (int i = tid; i < P.nsegs && i < SRV_SMEM_SEGS; i += LIGHT_SRV_THREADS) S.seg[i] = P.segtab[i];
+    for (int i = tid; i < P.nsegs && i < SRV_SMEM_SEGS; i += NT) S.seg[i] = P.segtab[i];
     if (tid == 0) {
         LightPlan &lp = S.plan;
         lp.vertices = P.vertices;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(LIGHT_SRV_THREADS) light_server_kernel(const _
             if (S.plan.trace) S.plan.trace[29] = clock64();
         }
         __syncthreads();
-        light_run<LIGHT_SRV_THREADS>(S.plan, S.plan.steps, sv, S.light, (flags & SRV_F_STATS) != 0, P.times, t_acq);
+        light_run<NT, LocalView, WARPM>(S.plan, S.plan.steps, sv, S.light, (flags & SRV_F_STATS) != 0, P.times, t_acq);
         seq++;
         t_idle0 = globaltimer_ns();
         __syncthreads();
