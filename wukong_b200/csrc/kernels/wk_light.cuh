@@ -304,6 +304,97 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             }
             if ((uint64_t)N * (uint64_t)(1 + nsh) > 2048) nsh = 0;
             uint32_t *tout = sm.tab[nxt];
+            // ---- star round: consecutive steps that only read columns which exist NOW do not depend on each other (a join is
+            // commutative): LUBM Q4 is "?X worksFor D . ?X type T . ?X name ?a . ?X email ?b . ?X phone ?c" -- four patterns on ?X.
+            // One warp per pattern probes all (<= 32) rows at the same time; a row's fan-out is the product of the patterns'
+            // multiplicities and an output row picks one edge per expanding pattern.  Four serial steps (each a chain of
+            // dependent instructions and memory round trips) become one.  Not taken when per-step statistics are collected
+            // (the round probes rows a serial execution would already have dropped) or when the result would not fit.
+            if (WARPM && N <= 32 && stats == nullptr && NT >= 128) {
+                int L = 1;
+                while (s + L < nsteps && L < 4) {
+                    const LightStep &x = steps[s + L];
+                    if (x.kind < LKIND_K2U || x.col_start >= Cin || (x.kind == LKIND_K2K && x.col_end >= Cin)) break;
+                    L++;
+                }
+                if (L >= 2) {
+                    const int w = tid >> 5, lane = tid & 31;
+                    if (w < L) {
+                        const LightStep &x = steps[s + w];
+                        uint32_t m = 0;
+                        uint64_t ptr = 0;
+                        if ((uint32_t)lane < N) {
+                            const uint32_t c0 = tin[lane * Cin + x.col_start];
+                            const uint64_t key = step_key(x.seg, c0);
+                            uint32_t visited;
+                            ptr = probe_thread(sv.vertices(c0), key, sv.bucket(x, s + w, key, c0), visited);
+                            const uint32_t size = ptr_size(ptr);
+                            if (x.kind == LKIND_K2U) {
+                                m = size > LIGHT_ROWS ? (uint32_t)LIGHT_ROWS + 1u : size;
+                                if (size) asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.edges(c0) + ptr_off(ptr)));
+                            } else {
+                                const uint32_t target = (x.kind == LKIND_K2K) ? tin[lane * Cin + x.col_end] : x.end_const;
+                                uint32_t scanned;
+                                m = list_contains(sv.edges(c0) + ptr_off(ptr), size, target, scanned) ? 1u : 0u;
+                            }
+                        }
+                        sm.pre[w * 32 + lane] = m;
+                        sm.ptr[w * 32 + lane] = ptr;
+                    }
+                    __syncthreads();
+                    int nk2u = 0;
+                    for (int j = 0; j < L; j++) nk2u += steps[s + j].kind == LKIND_K2U ? 1 : 0;
+                    const int CoutR = Cin + nk2u;
+                    if (tid < 32) {
+                        uint64_t M = (uint32_t)lane < N ? 1u : 0u;
+                        for (int j = 0; j < L; j++) {
+                            M *= sm.pre[j * 32 + lane];
+                            if (M > LIGHT_ROWS) M = (uint64_t)LIGHT_ROWS + 1;
+                        }
+                        uint32_t incl = (uint32_t)M;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                            if (lane >= o) incl += y;
+                        }
+                        sm.pre[128 + lane] = incl - (uint32_t)M;        // exclusive prefix of the rows' fan-outs
+                        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        if (lane == 0) {
+                            sm.total = total;
+                            sm.wsum[0] = (total <= LIGHT_ROWS && (uint64_t)total * (uint64_t)CoutR <= LIGHT_WORDS) ? 0u : 1u;
+                        }
+                    }
+                    __syncthreads();
+                    if (sm.wsum[0] == 0) {
+                        const uint32_t total = sm.total;
+                        for (uint32_t o = tid; o < total; o += NT) {
+                            uint32_t r = 0;
+                            while (r + 1 < N && sm.pre[128 + r + 1] <= o) r++;   // last row whose prefix is <= o (zero fan-outs share a prefix)
+                            uint32_t idx = o - sm.pre[128 + r];
+                            uint32_t *dst = tout + o * CoutR;
+                            for (int c = 0; c < Cin; c++) dst[c] = tin[r * Cin + c];
+                            int kc = Cin;
+                            for (int j = 0; j < L; j++) {
+                                const LightStep &x = steps[s + j];
+                                if (x.kind != LKIND_K2U) continue;
+                                const uint32_t sz = sm.pre[j * 32 + r];
+                                const uint32_t k = idx % sz;
+                                idx /= sz;
+                                dst[kc++] = ld_edge(sv.edges(tin[r * Cin + x.col_start]) + ptr_off(sm.ptr[j * 32 + r]) + k);
+                            }
+                        }
+                        if (tid == 0 && counts)
+                            for (int j = 0; j < L; j++) counts[s + j + 1] = total;
+                        N = total;
+                        C = CoutR;
+                        s += L - 1;
+                        cur = nxt;
+                        __syncthreads();
+                        continue;
+                    }
+                    // does not fit shared memory as a whole: take the steps one by one (nothing has been written)
+                }
+            }
             if (WARPM && N <= 32) {
                 // ---- warp mode: a table of at most 32 rows is ONE warp's business: lane = row, multiplicities are scanned
                 // with shuffles, rows are compacted straight into the next table, and the step costs one CTA barrier instead
