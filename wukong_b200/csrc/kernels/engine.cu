@@ -589,7 +589,7 @@ struct wk_engine {
         bool quitting = false;           // a QUIT is on its way: wait for the exit word before relaunching
         uint64_t launches = 0, requests = 0;
         uint64_t last_ns = 0;            // in-kernel span of the last request
-        int variant = 1;                 // WK_OPT_RESIDENT_VARIANT (default 1; measured on B200, profiles/r2_light_ab.json): 0 = 1024 threads + warp mode, 1 = 256 + warp mode, 2 = 256, block steps only, 3 = 512 + warp mode
+        int variant = 0;                 // WK_OPT_RESIDENT_VARIANT (default 0; A/B on B200 in profiles/r2_light_ab.json): 0 = 1024 threads + warp mode, 1 = 256 + warp mode, 2 = 256, block steps only, 3 = 512 + warp mode
     } srv;
     bool last_resident = false;          // the last wk_query_execute was answered by the resident server
     // WK_OPT_DIRECT_OUT: last step writes projected rows into the caller's pinned buffer.  Off by default: measured on B200

@@ -28,6 +28,7 @@ enum { LIGHT_THREADS = 256, LIGHT_MAX_WARPS = 32 };   // measured (round 1, bloc
 // the resident server runs 1024 threads: tables of <= 32 rows are handled by one warp (one barrier per step whatever the CTA
 // size), and a table of hundreds of rows is probed in ONE round instead of three dependent ones
 enum { LIGHT_SRV_THREADS = 1024 };
+enum { STAR_ROWS = 128 };   // tallest table of a star round (4 patterns x 128 rows of multiplicities and pointers in LightSmem)
 enum { LKIND_I2U = 0, LKIND_C2U = 1, LKIND_K2U = 2, LKIND_K2K = 3, LKIND_K2C = 4 };
 
 struct LightStep {
@@ -310,7 +311,7 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
             // multiplicities and an output row picks one edge per expanding pattern.  Four serial steps (each a chain of
             // dependent instructions and memory round trips) become one.  Not taken when per-step statistics are collected
             // (the round probes rows a serial execution would already have dropped) or when the result would not fit.
-            if (WARPM && N <= 32 && stats == nullptr && NT >= 128) {
+            if (WARPM && N <= STAR_ROWS && stats == nullptr && NT >= 128) {
                 int L = 1;
                 while (s + L < nsteps && L < 4) {
                     const LightStep &x = steps[s + L];
@@ -321,66 +322,79 @@ __device__ __forceinline__ LightState light_interpret(const LightStep *steps, in
                     const int w = tid >> 5, lane = tid & 31;
                     if (w < L) {
                         const LightStep &x = steps[s + w];
-                        uint32_t m = 0;
-                        uint64_t ptr = 0;
-                        if ((uint32_t)lane < N) {
-                            const uint32_t c0 = tin[lane * Cin + x.col_start];
+                        for (uint32_t r = lane; r < N; r += 32) {   // every probe of the pattern in flight before the first is consumed
+                            const uint32_t c0 = tin[r * Cin + x.col_start];
                             const uint64_t key = step_key(x.seg, c0);
-                            uint32_t visited;
-                            ptr = probe_thread(sv.vertices(c0), key, sv.bucket(x, s + w, key, c0), visited);
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.vertices(c0) + sv.bucket(x, s + w, key, c0) * 8));
+                        }
+                        for (uint32_t r = lane; r < N; r += 32) {
+                            const uint32_t c0 = tin[r * Cin + x.col_start];
+                            const uint64_t key = step_key(x.seg, c0);
+                            uint32_t visited, m;
+                            const uint64_t ptr = probe_thread(sv.vertices(c0), key, sv.bucket(x, s + w, key, c0), visited);
                             const uint32_t size = ptr_size(ptr);
                             if (x.kind == LKIND_K2U) {
                                 m = size > LIGHT_ROWS ? (uint32_t)LIGHT_ROWS + 1u : size;
                                 if (size) asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.edges(c0) + ptr_off(ptr)));
                             } else {
-                                const uint32_t target = (x.kind == LKIND_K2K) ? tin[lane * Cin + x.col_end] : x.end_const;
+                                const uint32_t target = (x.kind == LKIND_K2K) ? tin[r * Cin + x.col_end] : x.end_const;
                                 uint32_t scanned;
                                 m = list_contains(sv.edges(c0) + ptr_off(ptr), size, target, scanned) ? 1u : 0u;
                             }
+                            sm.pre[w * STAR_ROWS + r] = m;
+                            sm.ptr[w * STAR_ROWS + r] = ptr;
                         }
-                        sm.pre[w * 32 + lane] = m;
-                        sm.ptr[w * 32 + lane] = ptr;
                     }
                     __syncthreads();
                     int nk2u = 0;
                     for (int j = 0; j < L; j++) nk2u += steps[s + j].kind == LKIND_K2U ? 1 : 0;
                     const int CoutR = Cin + nk2u;
                     if (tid < 32) {
-                        uint64_t M = (uint32_t)lane < N ? 1u : 0u;
-                        for (int j = 0; j < L; j++) {
-                            M *= sm.pre[j * 32 + lane];
-                            if (M > LIGHT_ROWS) M = (uint64_t)LIGHT_ROWS + 1;
-                        }
-                        uint32_t incl = (uint32_t)M;
+                        uint32_t base = 0;
+                        for (uint32_t r0 = 0; r0 < N; r0 += 32) {      // fan-out of a row = product over the patterns; prefix over the rows
+                            const uint32_t r = r0 + lane;
+                            uint64_t M = r < N ? 1u : 0u;
+                            for (int j = 0; j < L && r < N; j++) {
+                                M *= sm.pre[j * STAR_ROWS + r];
+                                if (M > LIGHT_ROWS) M = (uint64_t)LIGHT_ROWS + 1;
+                            }
+                            uint32_t incl = (uint32_t)M;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                            if (lane >= o) incl += y;
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                                if (lane >= o) incl += y;
+                            }
+                            if (r < N) sm.pre[4 * STAR_ROWS + r] = base + incl - (uint32_t)M;
+                            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                            base = (base + tot > 2u * LIGHT_ROWS) ? 2u * LIGHT_ROWS : base + tot;   // saturate: it will not fit anyway
                         }
-                        sm.pre[128 + lane] = incl - (uint32_t)M;        // exclusive prefix of the rows' fan-outs
-                        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                         if (lane == 0) {
-                            sm.total = total;
-                            sm.wsum[0] = (total <= LIGHT_ROWS && (uint64_t)total * (uint64_t)CoutR <= LIGHT_WORDS) ? 0u : 1u;
+                            sm.total = base;
+                            sm.wsum[0] = (base <= LIGHT_ROWS && (uint64_t)base * (uint64_t)CoutR <= LIGHT_WORDS) ? 0u : 1u;
                         }
                     }
                     __syncthreads();
                     if (sm.wsum[0] == 0) {
                         const uint32_t total = sm.total;
+                        const uint32_t *rpre = sm.pre + 4 * STAR_ROWS;
                         for (uint32_t o = tid; o < total; o += NT) {
-                            uint32_t r = 0;
-                            while (r + 1 < N && sm.pre[128 + r + 1] <= o) r++;   // last row whose prefix is <= o (zero fan-outs share a prefix)
-                            uint32_t idx = o - sm.pre[128 + r];
+                            uint32_t lo = 0, hi = N;   // largest r with rpre[r] <= o (rows without fan-out share their successor's prefix)
+                            while (hi - lo > 1) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (rpre[mid] <= o) lo = mid; else hi = mid;
+                            }
+                            const uint32_t r = lo;
+                            uint32_t idx = o - rpre[r];
                             uint32_t *dst = tout + o * CoutR;
                             for (int c = 0; c < Cin; c++) dst[c] = tin[r * Cin + c];
                             int kc = Cin;
                             for (int j = 0; j < L; j++) {
                                 const LightStep &x = steps[s + j];
                                 if (x.kind != LKIND_K2U) continue;
-                                const uint32_t sz = sm.pre[j * 32 + r];
+                                const uint32_t sz = sm.pre[j * STAR_ROWS + r];
                                 const uint32_t k = idx % sz;
                                 idx /= sz;
-                                dst[kc++] = ld_edge(sv.edges(tin[r * Cin + x.col_start]) + ptr_off(sm.ptr[j * 32 + r]) + k);
+                                dst[kc++] = ld_edge(sv.edges(tin[r * Cin + x.col_start]) + ptr_off(sm.ptr[j * STAR_ROWS + r]) + k);
                             }
                         }
                         if (tid == 0 && counts)
