@@ -55,48 +55,81 @@ def load_plans(plan):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """SM clock and clock-event (throttle) reasons of one GPU sampled DURING the timed region: NVML in this process every 10 ms
+    (the counters nvidia-smi prints; a subprocess of nvidia-smi -lms needs seconds to deliver its first line on an 8-GPU
+    host, longer than a sharded run's timed region), falling back to `nvidia-smi -lms 20` when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        cvd = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(x) for x in cvd.split(",") if x.strip() != ""]
+            if ids and index < len(ids):
+                self.index = ids[index]
+        except ValueError:
+            pass
+        self.rows = []          # (time, sm MHz, max MHz, set of reasons)
         self.proc = None
         self.t_mark = None
+        self.source = None
+        self.quit = threading.Event()
+
+    def run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        get = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        while not self.quit.is_set():
+            sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+            bits = int(get(h))
+            self.rows.append((time.time(), sm, mx, {nm for nm, b in self.BITS if bits & b}))
+            self.quit.wait(0.01)
+
+    def run_smi(self):
+        self.source = "nvidia-smi"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits", "-lms", "20"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.time(), float(r[1]), float(r[2]), {nm for i, nm in enumerate(names) if r[5 + i].lower().startswith("active")}))
+            except Exception:
+                continue
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+            self.run_nvml()
         except Exception:
-            pass
+            try:
+                self.run_smi()
+            except Exception:
+                pass
 
     def stop(self):
+        self.quit.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons, timed = [], 0, set(), 0
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, r in self.rows:
-            try:
-                if self.t_mark is not None and ts >= self.t_mark:
-                    timed += 1
-                sm.append(float(r[1]))
-                mx = max(mx, float(r[2]))
-                for i, nm in enumerate(names):
-                    if r[5 + i].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": timed,
-                "note": "sampled every 20 ms from the start of warm-up to the end of the timed region"}
+        rows = list(self.rows)
+        timed = [r for r in rows if self.t_mark is not None and r[0] >= self.t_mark]
+        use = timed if timed else rows      # the statistics are those of the timed region whenever a sample fell into it
+        sm = [r[1] for r in use]
+        reasons = set()
+        for r in use:
+            reasons |= r[3]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": (max(r[2] for r in use) if use else None),
+                "reasons": sorted(reasons), "samples": len(rows), "samples_in_timed_region": len(timed), "source": self.source,
+                "note": "sampled from the start of warm-up to the end of the timed region (NVML every 10 ms); sm_mhz / reasons over the "
+                        "samples inside the timed region when there are any"}
 
 
 LOAD_FACTORS = (55, 45, 35, 25)   # Global::est_load_factor (global.hpp:99-104) and its fallbacks for small datasets
@@ -407,6 +440,42 @@ def setup_group(args, eng, rank, world, dist):
         eng.comm_init(world, rank, uid[0])
 
 
+class SpinBarrier:
+    """Host barrier with a release skew of about a microsecond: one generation counter per rank in a shared-memory file, spun
+    on.  dist.barrier() alone lets the ranks leave tens of microseconds apart, which a query of 10-20 us then absorbs as waiting
+    time on whichever rank left first (every collective query ends when its slowest rank ends)."""
+
+    def __init__(self, rank, world, dist):
+        self.rank, self.dist, self.gen, self.a = rank, dist, 0, None
+        name = [None]
+        if rank == 0:
+            try:
+                path = "/dev/shm/wk_bench_%d_%d" % (os.getpid(), time.time_ns())
+                np.zeros(world * 8, dtype=np.int64).tofile(path)
+                name[0] = path
+            except OSError:
+                name[0] = None
+        dist.broadcast_object_list(name, src=0)
+        if name[0]:
+            self.a = np.memmap(name[0], dtype=np.int64, mode="r+")
+            self.slots = self.a[::8]
+        dist.barrier()
+        if rank == 0 and name[0]:
+            os.unlink(name[0])
+
+    def wait(self):
+        self.dist.barrier()
+        if self.a is None:
+            return
+        self.gen += 1
+        g = self.gen
+        self.a[self.rank * 8] = g
+        t0 = time.monotonic()
+        while (self.slots < g).any():
+            if time.monotonic() - t0 > 120:
+                raise RuntimeError("spin barrier timed out")
+
+
 def run_sharded(args, rank, world, local_rank, dist):
     """vid % N sharded store; before every step whose start variable is not local the table is bucketised by owner and pushed
     over NVLink (or exchanged through NCCL).  Strong scaling: the dataset is fixed, every query is answered by all ranks together."""
@@ -429,15 +498,20 @@ def run_sharded(args, rank, world, local_rank, dist):
     eng = capi.Engine(gst, rbuf_bytes=rbuf)
     setup_group(args, eng, rank, world, dist)
     plans = load_plans(args.plan)
+    out_tbl, _keep = capi.pinned_array(min(rbuf // 4, 1 << 26))
+    bar = SpinBarrier(rank, world, dist)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    rows = {}
+    rows, nb_words = {}, {}
     for _ in range(args.warmup):
         for q in QUERIES:
             pats, nvars, req = plans[q]
             rc, r, c, _ = eng.query_sharded(pats, nvars, req, blind=True)
             assert rc == 0, rc
             rows[q] = r
+            rc, r2, c2, _ = eng.query_sharded(pats, nvars, req, out=out_tbl)
+            assert rc == 0 and r2 == r, (rc, r2, r)
+            nb_words[q] = r2 * c2
     launches0 = eng.launch_count()
     st0 = eng.comm_stats()
     bytes0 = eng.get_option(capi.WK_INFO_COMM_BYTES_PUSHED) if args.exchange == "p2p" else 0
@@ -447,18 +521,36 @@ def run_sharded(args, rank, world, local_rank, dist):
     eng.set_profiling(1)
     dev_us = {q: [] for q in QUERIES}
     wall_us = {q: [] for q in QUERIES}
+    e2e_us = {q: [] for q in QUERIES}
+    resident = {}
     for _ in range(args.steps):
         for q in QUERIES:
             pats, nvars, req = plans[q]
             eng.flush_l2()
             eng.sync()        # the flush must be over on EVERY rank before anyone starts: a rank still flushing would
-            dist.barrier()    # make its peers' exchange waits (and their device times) absorb its flush
+            bar.wait()        # make its peers' exchange waits (and their device times) absorb its flush
             w0 = time.perf_counter_ns()
             rc, r, c, _ = eng.query_sharded(pats, nvars, req, blind=True)
             w1 = time.perf_counter_ns()
             assert rc == 0, rc
-            dev_us[q].append(eng.last_query_device_us())
+            resident[q] = bool(eng.get_option(capi.WK_INFO_LAST_RESIDENT))
             wall_us[q].append((w1 - w0) / 1e3)
+            # a light plan answered by the resident servers has no launch to bracket with events: its term is the wall clock
+            # of the call (doorbell -> record), like at N = 1
+            dev_us[q].append((w1 - w0) / 1e3 if resident[q] else eng.last_query_device_us())
+    eng.set_profiling(0)
+    # end to end: non-blind, every rank receives its share of the projected table in pinned host memory
+    for _ in range(args.steps):
+        for q in QUERIES:
+            pats, nvars, req = plans[q]
+            eng.flush_l2()
+            eng.sync()
+            bar.wait()
+            w0 = time.perf_counter_ns()
+            rc, r, c, _ = eng.query_sharded(pats, nvars, req, out=out_tbl)
+            w1 = time.perf_counter_ns()
+            assert rc == 0 and r == rows[q], (rc, r, rows[q])
+            e2e_us[q].append((w1 - w0) / 1e3)
     eng.sync(); dist.barrier(); torch.cuda.synchronize()
     t_region = time.time() - t_region0
     clocks = sampler.stop()
@@ -508,10 +600,12 @@ def run_sharded(args, rank, world, local_rank, dist):
                     "frac": round(per_gpu / NVLINK_PEAK_GBS, 4),
                     "note": "bytes stored into peers' buffers (4*C*rows pushed, SURVEY 8d) / summed ready->push->wait time of the heavy queries' "
                             "exchanges, barriers included; peak = measured peer copy per direction (B200_PROFILING.md), 900 GB/s nominal"}
-    t = torch.tensor([np.mean(dev_us[q]) for q in QUERIES] + [np.mean(wall_us[q]) for q in QUERIES], device="cuda", dtype=torch.float64)
+    t = torch.tensor([np.mean(dev_us[q]) for q in QUERIES] + [np.mean(wall_us[q]) for q in QUERIES] + [np.mean(e2e_us[q]) for q in QUERIES] +
+                     [1.0 if resident.get(q) else 0.0 for q in QUERIES], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     lat = t.cpu().numpy()
-    rr = torch.tensor([rows[q] for q in QUERIES] + [stats["rows_sent"] - st0["rows_sent"], launches, bytes_pushed], device="cuda", dtype=torch.int64)
+    rr = torch.tensor([rows[q] for q in QUERIES] + [stats["rows_sent"] - st0["rows_sent"], launches, bytes_pushed, sum(nb_words.values()) * 4],
+                      device="cuda", dtype=torch.int64)
     dist.all_reduce(rr, op=dist.ReduceOp.SUM)
     rr = rr.cpu().numpy()
     nx = stats["exchanges"] - st0["exchanges"]
@@ -519,7 +613,7 @@ def run_sharded(args, rank, world, local_rank, dist):
     gst.close()
     line = None
     if rank == 0:
-        dev_mean, wall_mean = lat[:7], lat[7:]
+        dev_mean, wall_mean, e2e_mean, res = lat[:7], lat[7:14], lat[14:21], lat[21:28]
         value = geomean(1e6 / dev_mean)
         par = ("single-pass bucketise + peer-memory push over NVLink (CUDA IPC, remote atomic reservations); light plans in place on the "
                "constant's owner through peer loads") if args.exchange == "p2p" else "NCCL all-to-all(v)"
@@ -529,11 +623,17 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "config": {"workload": workload_name(args, world, True),
                            "parallelism": "sharded x%d, %s before non-local steps" % (world, par),
                            "l2": "flushed before every timed query (384 MB memset + 256 MB read-back, outside the timed region)",
-                           "value_mode": "blind, device-resident, CUDA events, max over ranks"},
-                "e2e": {"value": geomean(1e6 / wall_mean), "unit": "queries/s", "h2d_bytes_per_step": 584 * world, "d2h_bytes_per_step": 56 * world},
+                           "value_mode": "blind (row count only), shards resident in HBM, max over ranks; CUDA events, except light plans answered "
+                                         "in place by the resident servers (no launch on any rank: wall clock of the call, doorbell -> record)",
+                           "e2e_mode": "non-blind: every rank's share of the projected table D2H into pinned memory, host wall clock, max over ranks",
+                           "barrier": "dist.barrier + shared-memory spin barrier before every timed query"},
+                "e2e": {"value": geomean(1e6 / e2e_mean), "unit": "queries/s", "h2d_bytes_per_step": 584 * world,
+                        "d2h_bytes_per_step": int(rr[10]) + 32 * len(QUERIES) * world},
                 "gpu_launches": int(rr[8]), "clocks": clocks,
                 "latency_us": {"device": {"q%d" % q: round(float(dev_mean[i]), 2) for i, q in enumerate(QUERIES)},
-                               "wall": {"q%d" % q: round(float(wall_mean[i]), 2) for i, q in enumerate(QUERIES)}},
+                               "wall": {"q%d" % q: round(float(wall_mean[i]), 2) for i, q in enumerate(QUERIES)},
+                               "e2e": {"q%d" % q: round(float(e2e_mean[i]), 2) for i, q in enumerate(QUERIES)}},
+                "light_path": {"resident_servers": {"q%d" % q: bool(res[i] > 0) for i, q in enumerate(QUERIES)}},
                 "rows": {"q%d" % q: int(rr[i]) for i, q in enumerate(QUERIES)},
                 "comm": {"rows_pushed_all_ranks": int(rr[7]), "bytes_pushed_all_ranks": int(rr[9]),
                          "bytes_pushed_per_step_all_ranks": int(rr[9] // max(1, args.steps)),

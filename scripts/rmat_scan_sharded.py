@@ -5,7 +5,9 @@ edges, one predicate), store sharded by vid % N, 2-hop pattern ?a p ?b . ?b p ?c
 Launch:  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/rmat_scan_sharded.py
 One JSON line per frontier size: per hop the slowest rank's CUDA-event time, the algorithmic bytes of all ranks,
 aggregate and per-GPU GB/s against the measured HBM peak; for the exchange the bytes pushed over NVLink, GB/s per GPU and
-direction against the measured peer-copy peak."""
+direction against the measured peer-copy peak.  A second hop whose output does not fit the result buffers is run over
+buffer-sized chunks of the first hop's output (wk_table_slice), the first --max-chunks of them, as SURVEY.md 8d prescribes.
+Vertex labels are scrambled like Graph500's, so that vid % N shards carry equal shares of the hubs."""
 import argparse
 import json
 import os
@@ -23,7 +25,10 @@ ap.add_argument("--edges", type=int, default=1_000_000_000)
 ap.add_argument("--max-frontier", type=int, default=64 << 20)
 ap.add_argument("--rbuf-gb", type=int, default=32)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--max-chunks", type=int, default=6)
 args = ap.parse_args()
+if int(os.environ.get("WORLD_SIZE", 1)) > 1:   # torchrun pins OMP_NUM_THREADS=1; the generator is OpenMP-parallel
+    os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // int(os.environ["WORLD_SIZE"])))
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -95,47 +100,64 @@ def allsum(x):
     return float(t.item())
 
 
+def prepare(frontier):
+    """frontier -> hop 1 -> exchange by ?b; returns (rows now on this rank, hop-1 stats, exchange stats)"""
+    eng.upload(frontier)
+    eng.flush_l2()
+    eng.sync()
+    if world > 1:
+        dist.barrier()
+    eng.known_to_unknown(0, P, 1)
+    s1 = eng.step_stats()[-1]
+    sx = None
+    if world > 1:
+        eng.flush_l2(); eng.sync(); dist.barrier()
+        eng.exchange_p2p(1)
+        sx = [x for x in eng.step_stats() if x["kind"] == "exchange"][-1]
+    return eng.info()[0], s1, sx
+
+
+def timed_hop2():
+    """second hop over the current table; None when some rank's output did not fit"""
+    eng.flush_l2(); eng.sync()
+    if world > 1:
+        dist.barrier()
+    try:
+        eng.known_to_unknown(1, P, 1)
+        st, ok = eng.step_stats()[-1], 1.0
+    except capi.WukongError as ex:
+        if ex.code != capi.WK_ERR_RBUF_OVERFLOW:
+            raise
+        st, ok = None, 0.0
+    return st if allsum(ok) == world else None
+
+
+fan = 64.0          # rows out per row in of the last second hop that ran: sizes the chunks of the next one
 for F in sizes:
     mine = min(subjects.shape[0], (F + world - 1) // world)
     frontier = subjects[perm[:mine]].reshape(-1, 1)
     acc = {"hop1": [], "xchg": [], "hop2": []}
     last = {}
-    skipped = False
+    whole = True
+    n_in = 0
     for rep in range(args.reps):
-        eng.upload(frontier)
-        eng.flush_l2()
-        eng.sync()
-        if world > 1:
-            dist.barrier()
-        n1 = eng.known_to_unknown(0, P, 1)
-        s1 = eng.step_stats()[-1]
+        n_in, s1, sx = prepare(frontier)
         acc["hop1"].append(s1["device_us"]); last["hop1"] = s1
-        # hop 2 would overflow the buffer somewhere: every rank takes the same decision
-        est = allmax(n1 * max(1.0, n1 / max(1, mine)))
-        if est > cap_rows * 0.8:
-            skipped = True
-            break
-        if world > 1:
-            eng.flush_l2(); eng.sync(); dist.barrier()
-            eng.exchange_p2p(1)
-            sx = [x for x in eng.step_stats() if x["kind"] == "exchange"][-1]
+        if sx is not None:
             acc["xchg"].append(sx["device_us"]); last["xchg"] = sx
-        eng.flush_l2(); eng.sync()
-        if world > 1:
-            dist.barrier()
-        try:
-            eng.known_to_unknown(1, P, 1)
-            s2 = eng.step_stats()[-1]
-            acc["hop2"].append(s2["device_us"]); last["hop2"] = s2
-            ok = 1.0
-        except capi.WukongError as ex:
-            if ex.code != capi.WK_ERR_RBUF_OVERFLOW:
-                raise
-            ok = 0.0
-        if allsum(ok) < world:
-            skipped = True
+        if not whole:
+            continue
+        # every rank takes the same decision
+        if allmax(n_in * fan) > cap_rows * 0.7:
+            whole = False
+            continue
+        s2 = timed_hop2()
+        if s2 is None:
+            whole = False
             acc["hop2"] = []
-            break
+            continue
+        acc["hop2"].append(s2["device_us"]); last["hop2"] = s2
+        fan = max(1.0, allmax(s2["out_rows"] / max(1, s2["in_rows"])))
     line = {"frontier": F, "n_gpus": world}
     for name in ("hop1", "xchg", "hop2"):
         have = allsum(1.0 if acc[name] else 0.0)
@@ -152,8 +174,42 @@ for F in sizes:
             e.update({"gbs_all_gpus": round(by / us / 1e3, 1), "gbs_per_gpu": round(by / world / us / 1e3, 1),
                       "pct_of_hbm_peak_per_gpu": round(100 * by / world / us / 1e3 / peak, 1)})
         line[name] = e
-    if skipped:
-        line["note"] = "second hop skipped: its output would not fit the result buffers"
+    if not whole:
+        # chunked second hop: B rows of the (exchanged) first-hop output at a time, sized from the last fan-out seen and halved
+        # until every rank's output fits; the first max_chunks chunks are timed
+        nmax = int(allmax(n_in))
+        B = int(max(1024, min(nmax, cap_rows * 0.5 / fan)))
+        tries = 0
+        while True:
+            prepare(frontier)
+            eng.slice(0, B)
+            s2 = timed_hop2()
+            tries += 1
+            if s2 is not None or B <= 1024 or tries > 24:
+                break
+            B //= 2
+        if s2 is not None:
+            nchunks_all = (nmax + B - 1) // B
+            K = int(min(args.max_chunks, nchunks_all))
+            us_sum, by_sum, in_sum, out_sum = allmax(s2["device_us"]), allsum(s2["algo_bytes"]), allsum(s2["in_rows"]), allsum(s2["out_rows"])
+            done = 1
+            for k in range(1, K):
+                prepare(frontier)
+                eng.slice(k * B, B)
+                sk = timed_hop2()
+                if sk is None:     # a chunk full of hubs: leave it out, say so
+                    continue
+                us_sum += allmax(sk["device_us"]); by_sum += allsum(sk["algo_bytes"])
+                in_sum += allsum(sk["in_rows"]); out_sum += allsum(sk["out_rows"])
+                done += 1
+            fan = max(1.0, out_sum / max(1.0, in_sum)) * 1.5
+            line["hop2"] = {"us_max_rank": round(us_sum, 2), "in_rows": int(in_sum), "out_rows": int(out_sum), "algo_bytes": int(by_sum),
+                            "gbs_all_gpus": round(by_sum / us_sum / 1e3, 1), "gbs_per_gpu": round(by_sum / world / us_sum / 1e3, 1),
+                            "pct_of_hbm_peak_per_gpu": round(100 * by_sum / world / us_sum / 1e3 / peak, 1),
+                            "chunked": {"rows_per_chunk_per_rank": B, "chunks_timed": done, "chunks_total": int(nchunks_all),
+                                        "note": "sum over the timed chunks of the slowest rank's time; every chunk after its own L2 flush"}}
+        else:
+            line["note"] = "second hop: no chunk size down to 1024 rows fits the result buffers"
     if rank == 0:
         print(json.dumps(line), flush=True)
 eng.close()

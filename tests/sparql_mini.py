@@ -27,7 +27,7 @@ LUBM_INDEX = ["__PREDICATE__", RDF_TYPE] + [UB + n + ">" for n in (
 
 VID_BASE = 1 << 17
 UNIV_BASE = VID_BASE + (1 << 17)
-UNIV_BLOCK = 1 << 17
+UNIV_BLOCK = (1 << 17) - 1
 
 
 def lubm_str2id(s):

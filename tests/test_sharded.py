@@ -175,11 +175,15 @@ def _spill_plan():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_local_group_single_gpu(world):
+@pytest.mark.parametrize("world,resident", [(2, 1), (3, 1), (2, 0)])
+def test_sharded_local_group_single_gpu(world, resident):
     """Q1-Q7 x 3 plan sets + a const-start plan that outgrows shared memory, `world` shards on device 0: exchange through
-    the single-pass peer-memory push, light plans in place on the constant's owner, all against the brute-force joiner"""
+    the single-pass peer-memory push, light plans in place on the constant's owner -- by the resident servers of all shards
+    (owner walks the shards, peers wait for its verdict, nobody launches) or by one launch per rank -- all against the
+    brute-force joiner"""
     stores, engs = _local_group(world)
+    for e in engs:
+        e.set_resident(bool(resident))
     queries = {"q%d_%s" % (q, plan): load_query(q, plan)[:3] for q in range(1, 8) for plan in PLANS}
     queries["spill"] = _spill_plan()
 
@@ -192,10 +196,13 @@ def test_sharded_local_group_single_gpu(world):
             rc, rows_b, _, _ = eng.query_sharded(pats, nvars, req, blind=True)
             assert rc == 0 and rows_b == rows, name
         res["__stats__"] = eng.comm_stats()
+        res["__requests__"] = eng.get_option(capi.WK_INFO_RESIDENT_REQUESTS)
         return res
 
     res = _run_ranks(engs, run)
     _check_against_bruteforce(res, 2, 7)
+    for r in res:   # every rank's server took part in every light query (as owner or as waiter), or none did
+        assert (r["__requests__"] >= 2 * 3 * 3) if resident else (r["__requests__"] == 0), r["__requests__"]
     want = _spill_want(datagen.lubm(2, seed=7))
     got = np.concatenate([r["spill"].reshape(-1, 3) for r in res])
     assert want.shape[0] > 1024 and rows_equal(got, want)

@@ -63,11 +63,14 @@ static inline const char *lubm_index_string(int id) {
 
 // ---- normal vertex ids ---------------------------------------------------------------------
 //  [VID_BASE, VID_BASE + 2^17)            shared literal pool (telephone, names, research interests)
-//  [UNIV_BASE + u*2^17, +2^17)            block of university u
+//  [UNIV_BASE + u*(2^17-1), +2^17-1)      block of university u.  The block length is odd (a Mersenne prime) on purpose: with a
+//                                         power of two every university -- and every d-th department -- would land on the same
+//                                         shard of a vid % n cluster, which ids handed out in order of first appearance (the
+//                                         reference's id mapping of real UBA output) never do
 //      local 0       the university       local 1  its name literal
 //      local 2+d     department d (d<25)  local 64.. everything else, in generation order
 #define LUBM_VID_BASE (1u << 17)
-#define LUBM_UNIV_BLOCK (1u << 17)
+#define LUBM_UNIV_BLOCK ((1u << 17) - 1u)
 #define LUBM_UNIV_BASE (LUBM_VID_BASE + (1u << 17))
 #define LUBM_LOCAL_UNIV_NAME 1u
 #define LUBM_LOCAL_DEPT0 2u

@@ -587,6 +587,7 @@ struct wk_engine {
         uint64_t seq = 0;                // sequence number of the last request posted (QUIT included)
         uint64_t launch_id = 0;          // 0: never launched
         bool quitting = false;           // a QUIT is on its way: wait for the exit word before relaunching
+        bool sharded = false;            // the last instance launched is the sharded server (peer view, verdict flags)
         uint64_t launches = 0, requests = 0;
         uint64_t last_ns = 0;            // in-kernel span of the last request
         int variant = 0;                 // WK_OPT_RESIDENT_VARIANT (default 0; A/B on B200 in profiles/r2_light_ab.json): 0 = 1024 threads + warp mode, 1 = 256 + warp mode, 2 = 256, block steps only, 3 = 512 + warp mode
@@ -609,6 +610,7 @@ struct wk_engine {
 
 extern "C" {   // defined inside the extern "C" block below
 static void srv_park(wk_engine *e);   // resident light-query server: leave before a grid-filling kernel
+static int srv_fill_peers(wk_engine *e, SrvPeers &Q);   // after wk_sharded.cuh
 static void srv_stop(wk_engine *e);
 static bool srv_exited(const wk_engine *e);
 }
@@ -1757,6 +1759,7 @@ static int srv_init(wk_engine *e) {
     CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
     CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
     CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)light_server_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrvSmemSharded)));
     if (!e->d_trace) {
         CUDA_TRY(cudaMalloc((void **)&e->d_trace, LIGHT_TRACE_WORDS * sizeof(long long)));
         CUDA_TRY(cudaMemset(e->d_trace, 0, LIGHT_TRACE_WORDS * sizeof(long long)));
@@ -1770,7 +1773,7 @@ static bool srv_exited(const wk_engine *e) {
     return *(const volatile uint64_t *)&e->srv.h_box->exit_word == e->srv.launch_id;
 }
 
-static int srv_launch(wk_engine *e, uint64_t first_seq) {
+static int srv_launch(wk_engine *e, uint64_t first_seq, bool sharded = false) {
     SrvParams P;
     memset(&P, 0, sizeof(P));
     P.vertices = e->store->d_vertices;
@@ -1795,7 +1798,12 @@ static int srv_launch(wk_engine *e, uint64_t first_seq) {
     P.launch_id = ++e->srv.launch_id;
     P.idle_ns = e->srv.idle_ns;
     P.trace = e->d_trace;
-    switch (e->srv.variant) {   // WK_SRV_VARIANT, for A/B runs: threads of the server CTA x warp mode of the interpreter
+    if (sharded) {
+        SrvPeers Q;
+        int rc = srv_fill_peers(e, Q);
+        if (rc) return rc;
+        light_server_sharded_kernel<<<1, LIGHT_SRV_THREADS, sizeof(SrvSmemSharded), e->srv.stream>>>(P, Q);
+    } else switch (e->srv.variant) {   // WK_SRV_VARIANT, for A/B runs: threads of the server CTA x warp mode of the interpreter
     case 1: light_server_kernel<256, true><<<1, 256, sizeof(SrvSmem), e->srv.stream>>>(P); break;
     case 2: light_server_kernel<256, false><<<1, 256, sizeof(SrvSmem), e->srv.stream>>>(P); break;
     case 3: light_server_kernel<512, true><<<1, 512, sizeof(SrvSmem), e->srv.stream>>>(P); break;
@@ -1805,6 +1813,7 @@ static int srv_launch(wk_engine *e, uint64_t first_seq) {
     e->launches++;
     e->srv.launches++;
     e->srv.quitting = false;
+    e->srv.sharded = sharded;
     return WK_SUCCESS;
 }
 
@@ -1821,16 +1830,22 @@ static int srv_wait_exit(wk_engine *e) {
     return WK_SUCCESS;
 }
 
-static int srv_ensure_running(wk_engine *e, uint64_t first_seq) {
+static int srv_ensure_running(wk_engine *e, uint64_t first_seq, bool sharded = false) {
     int rc = srv_init(e);
     if (rc) return rc;
+    if (!e->srv.quitting && !srv_exited(e) && e->srv.sharded != sharded) {
+        // the other kind of server is resident (a plain query on an engine of a sharded group, or the reverse): swap.
+        // The QUIT takes a sequence number; the caller's first_seq was computed before it.
+        srv_park(e);
+        first_seq = e->srv.seq + 1;
+    }
     if (e->srv.quitting) {
         rc = srv_wait_exit(e);
         if (rc) return rc;
         e->srv.quitting = false;
-        return srv_launch(e, first_seq);
+        return srv_launch(e, first_seq, sharded);
     }
-    if (srv_exited(e)) return srv_launch(e, first_seq);
+    if (srv_exited(e)) return srv_launch(e, first_seq, sharded);
     return WK_SUCCESS;
 }
 
@@ -1866,8 +1881,42 @@ static bool srv_usable(const wk_engine *e) {
     return e->srv.enabled && e->store->nsegslots > 0 && e->store->nsegslots < (1 << 15) && e->store->d_segtab;
 }
 
+// post one request to the (right kind of) server and wait for its record; an instance that idled out is replaced
+static int srv_roundtrip(wk_engine *e, const SrvChunk *ch, int nsteps, int table_cols, bool sharded, RecView &rv) {
+    int rc = srv_ensure_running(e, e->srv.seq + 1, sharded);
+    if (rc) return rc;
+    const uint64_t seq = ++e->srv.seq;
+    srv_post(e, ch, seq);
+    e->srv.requests++;
+    const volatile uint64_t *rec = (const volatile uint64_t *)&e->srv.h_box->rec;
+    uint32_t spins = 0;
+    while (!record_valid_at(rec, e, seq, nsteps, table_cols, rv)) {
+        if ((++spins & 0xFFF) != 0) continue;
+        if (srv_exited(e)) {
+            // the instance idled out (or was leaving) without seeing this request: a new one picks it up
+            if (record_valid_at(rec, e, seq, nsteps, table_cols, rv)) break;
+            rc = srv_launch(e, seq, sharded);
+            if (rc) return rc;
+        } else if ((spins & 0xFFFFF) == 0) {
+            cudaError_t q = cudaStreamQuery(e->srv.stream);
+            if (q == cudaSuccess) {   // the kernel is gone although its exit word never showed up
+                if (record_valid_at(rec, e, seq, nsteps, table_cols, rv)) break;
+                rc = srv_launch(e, seq, sharded);
+                if (rc) return rc;
+            } else if (q != cudaErrorNotReady) {
+                CUDA_TRY(q);
+            }
+        }
+    }
+    const volatile uint64_t *t = (const volatile uint64_t *)e->srv.h_box->times;
+    const uint64_t t0 = t[0], t1 = t[1];
+    e->srv.last_ns = t1 >= t0 ? t1 - t0 : 0;
+    return WK_SUCCESS;
+}
+
+// epoch != 0: this engine is one shard of a group and owns the query's constant (in-place execution over peer memory)
 static int run_light_resident(wk_engine *e, const std::vector<PlannedStep> &steps, bool project,
-                              const std::vector<int32_t> &proj_cols, RecView &rv) {
+                              const std::vector<int32_t> &proj_cols, RecView &rv, uint64_t epoch = 0) {
     SrvChunk ch[SRV_CHUNKS];
     memset(ch, 0, sizeof(ch));
     const uint32_t flags = (project ? SRV_F_PROJECT : 0u) | (e->profiling >= 2 ? SRV_F_STATS : 0u) | (e->profiling >= 3 ? SRV_F_TRACE : 0u);
@@ -1890,37 +1939,10 @@ static int run_light_resident(wk_engine *e, const std::vector<PlannedStep> &step
         c.w1 = seed ? (uint32_t)ps.vid : ps.end_const;
         c.w2 = (ps.pid & 0x1FFFFu) | ((uint32_t)slot << 17);
     }
-    int rc = srv_ensure_running(e, e->srv.seq + 1);
+    ch[0].w1 = (uint32_t)epoch;
+    ch[0].w2 = (uint32_t)(epoch >> 32);
+    int rc = srv_roundtrip(e, ch, (int)steps.size(), project ? (int)proj_cols.size() : 0, epoch != 0, rv);
     if (rc) return rc;
-    const uint64_t seq = ++e->srv.seq;
-    srv_post(e, ch, seq);
-    e->srv.requests++;
-    const volatile uint64_t *rec = (const volatile uint64_t *)&e->srv.h_box->rec;
-    const int table_cols = project ? (int)proj_cols.size() : 0;
-    uint32_t spins = 0;
-    while (!record_valid_at(rec, e, seq, (int)steps.size(), table_cols, rv)) {
-        if ((++spins & 0xFFF) != 0) continue;
-        if (srv_exited(e)) {
-            // the instance idled out (or was leaving) without seeing this request: a new one picks it up
-            if (record_valid_at(rec, e, seq, (int)steps.size(), table_cols, rv)) break;
-            rc = srv_launch(e, seq);
-            if (rc) return rc;
-        } else if ((spins & 0xFFFFF) == 0) {
-            cudaError_t q = cudaStreamQuery(e->srv.stream);
-            if (q == cudaSuccess) {   // the kernel is gone although its exit word never showed up
-                if (record_valid_at(rec, e, seq, (int)steps.size(), table_cols, rv)) break;
-                rc = srv_launch(e, seq);
-                if (rc) return rc;
-            } else if (q != cudaErrorNotReady) {
-                CUDA_TRY(q);
-            }
-        }
-    }
-    {
-        const volatile uint64_t *t = (const volatile uint64_t *)e->srv.h_box->times;
-        const uint64_t t0 = t[0], t1 = t[1];
-        e->srv.last_ns = t1 >= t0 ? t1 - t0 : 0;
-    }
     for (int i = 0; i < rv.resume && i < (int)steps.size(); i++) {
         e->recs.emplace_back();
         StepRecord &r = e->recs.back();
@@ -2306,6 +2328,50 @@ int wk_engine_last_query_device_us(wk_engine_t *e, float *us) {
 
 static uint64_t comm_bytes_pushed(const wk_engine *e) { return e->comm ? e->comm->bytes_pushed : 0; }
 
+// the sharded light-query server's view of the group (wk_server.cuh)
+static int srv_fill_peers(wk_engine *e, SrvPeers &Q) {
+    memset(&Q, 0, sizeof(Q));
+    wk_comm *c = e->comm;
+    if (!c || !c->peer_stores || !c->p2p || !c->d_xctl || !c->d_segr_tab || c->nranks > LIGHT_PEERS) return WK_ERR_BAD_ARG;
+    for (int r = 0; r < c->nranks; r++) {
+        Q.pv[r] = c->peer_v[r];
+        Q.pe[r] = c->peer_e[r];
+        Q.peer_flag[r] = (r == c->rank) ? nullptr : &c->p2p->ctl[r]->flagL[c->rank];
+    }
+    Q.my_flag = c->d_xctl->flagL;
+    Q.segr_tab = c->d_segr_tab;
+    Q.nranks = (uint32_t)c->nranks;
+    Q.rank = (uint32_t)c->rank;
+    return WK_SUCCESS;
+}
+
+// [my segment slot][rank]: bucket range and modulo magic of that (index, pid, dir) segment in every shard.  A shard without
+// the segment gets bucket 0 of its store, whose keys belong to another (pid, dir) and never compare equal: the probe misses.
+static int comm_build_segr_tab(wk_engine *e) {
+    wk_comm *c = e->comm;
+    srv_stop(e);   // a resident sharded server reads the old table
+    if (c->d_segr_tab) { cudaFree(c->d_segr_tab); c->d_segr_tab = nullptr; }
+    const int ns = e->store->nsegslots;
+    if (ns <= 0 || (int)c->peer_segs.size() < c->nranks) return WK_SUCCESS;
+    SegLite none;
+    memset(&none, 0, sizeof(none));
+    none.bucket_start = 0;
+    none.fm = make_fastmod(1);
+    std::vector<SegLite> tab((size_t)ns * LIGHT_PEERS, none);
+    for (auto &kv : e->store->seg_slot) {
+        for (int r = 0; r < c->nranks; r++) {
+            auto it = c->peer_segs[r].find(kv.first);
+            if (it == c->peer_segs[r].end() || it->second.num_buckets == 0) continue;
+            SegLite &sl = tab[(size_t)kv.second * LIGHT_PEERS + r];
+            sl.bucket_start = it->second.bucket_start;
+            sl.fm = make_fastmod(it->second.num_buckets);
+        }
+    }
+    CUDA_TRY(cudaMalloc((void **)&c->d_segr_tab, tab.size() * sizeof(SegLite)));
+    CUDA_TRY(cudaMemcpy(c->d_segr_tab, tab.data(), tab.size() * sizeof(SegLite), cudaMemcpyHostToDevice));
+    return WK_SUCCESS;
+}
+
 static void comm_free(wk_engine *e) {
     wk_comm *c = e->comm;
     if (!c) return;
@@ -2317,6 +2383,7 @@ static void comm_free(wk_engine *e) {
     if (c->h_matrix) cudaFreeHost(c->h_matrix);
     if (c->d_xctl) cudaFree(c->d_xctl);
     if (c->d_p2p_local) cudaFree(c->d_p2p_local);
+    if (c->d_segr_tab) cudaFree(c->d_segr_tab);
     delete c->p2p;
     delete c;
     e->comm = nullptr;
@@ -2572,7 +2639,7 @@ int wk_comm_p2p_import_store(wk_engine_t *e, const void *blobs, const uint64_t *
         c->peer_e[r] = (const uint32_t *)q[1];
     }
     c->peer_stores = true;
-    return WK_SUCCESS;
+    return comm_build_segr_tab(e);
 }
 
 // Engines of ONE process as a group (several shards per GPU, or one thread per GPU): the peers' buffers, control blocks
@@ -2636,6 +2703,9 @@ int wk_comm_local_group(wk_engine_t **engines, int n) {
         c->local_group = true;
         c->p2p_ready = true;
         c->peer_stores = true;
+        CUDA_TRY(cudaSetDevice(e->store->device));
+        int rc = comm_build_segr_tab(e);
+        if (rc) return rc;
     }
     return WK_SUCCESS;
 }
@@ -2799,7 +2869,55 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
     if (in_place) {
         const int owner = (int)(steps[0].vid % (uint64_t)n);
         const uint64_t epoch = ++e->comm->epoch;
-        if (me == owner) {
+        // resident servers on every rank (wk_server.cuh): the owner's server walks the shards, the peers' servers wait for
+        // its verdict; nobody launches anything.  The phase trace (profiling 3) stays on the launch path.
+        const bool resident = srv_usable(e) && e->comm->d_segr_tab != nullptr && e->profiling < 3;
+        e->last_resident = false;
+        if (resident) {
+            e->step = 0;
+            e->recs.clear();
+            e->event_next = 0;
+            RecView rv;
+            if (me == owner) {
+                rc = run_light_resident(e, steps, want_table, proj_cols, rv, epoch);
+                if (rc == WK_ERR_NO_SEGMENT) {   // nothing was posted; the peers are waiting for a verdict: "answered"
+                    p2p_light_verdict_kernel<<<1, 64, 0, e->stream>>>(*e->comm->p2p, 2 * epoch);
+                    e->launches++;
+                }
+                if (rc) return rc;
+                if (rv.status & 1u) return WK_ERR_RBUF_OVERFLOW;
+                if (rv.resume == (int)steps.size()) {
+                    e->last_resident = true;
+                    const uint64_t rows = rv.rows;
+                    const int cols = (want_table && rows > 0) ? nrequired : final_cols;
+                    if (out_rows) *out_rows = rows;
+                    if (out_cols) *out_cols = cols;
+                    if (no_required && rows > 0) return WK_NO_REQUIRED_VAR;
+                    if (want_table && rows > 0 && table) {
+                        const uint64_t words = rows * (uint64_t)cols;
+                        if (words > cap_words) return WK_ERR_BAD_ARG;
+                        memcpy(table, e->h_stage, words * sizeof(uint32_t));
+                    }
+                    return WK_SUCCESS;
+                }
+                // outgrew shared memory: every peer has been told; fall through to the collective plan
+            } else {
+                SrvChunk ch[SRV_CHUNKS];
+                memset(ch, 0, sizeof(ch));
+                ch[0].w0 = ((uint32_t)SRV_F_WAIT << 8) | ((uint32_t)owner << 16);
+                ch[0].w1 = (uint32_t)epoch;
+                ch[0].w2 = (uint32_t)(epoch >> 32);
+                rc = srv_roundtrip(e, ch, -1, 0, true, rv);
+                if (rc) return rc;
+                if (rv.status & 2u) { e->comm->poisoned = true; return WK_ERR_COMM; }
+                if (!(rv.status & 4u)) {   // answered by the owner: this shard contributes no rows
+                    e->last_resident = true;
+                    if (out_rows) *out_rows = 0;
+                    if (out_cols) *out_cols = want_table ? nrequired : final_cols;
+                    return WK_SUCCESS;
+                }
+            }
+        } else if (me == owner) {
             LightPlanSharded sp;
             memset(&sp, 0, sizeof(sp));
             LightPlan &lp = sp.lp;
@@ -2938,6 +3056,11 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
     if (rc == WK_ERR_COMM) e->comm->poisoned = true;
     if (rc) return rc;
     if (e->profiling) e->q_timed = true;
+    // the device is idle again: bring this shard's light-query server back while the result is copied out
+    if (e->srv.enabled && e->srv.launch_id != 0 && srv_usable(e) && e->comm->peer_stores && e->comm->d_segr_tab) {
+        rc = srv_ensure_running(e, e->srv.seq + 1, true);
+        if (rc) return rc;
+    }
     const int cols = want_table ? nrequired : final_cols;
     if (out_rows) *out_rows = rows;
     if (out_cols) *out_cols = cols;
@@ -2984,7 +3107,8 @@ static int preload_kernels(wk_engine *e) {
                           (const void *)p2p_push_kernel<2>, (const void *)p2p_push_kernel<4>, (const void *)p2p_light_wait_kernel,
                           (const void *)p2p_light_verdict_kernel, (const void *)p2p_wait_kernel, (const void *)light_query_kernel,
                           (const void *)light_sharded_kernel, (const void *)light_batch_kernel, (const void *)light_server_kernel<LIGHT_SRV_THREADS, true>,
-                          (const void *)light_server_kernel<256, true>, (const void *)light_server_kernel<256, false>, (const void *)light_server_kernel<512, true>};
+                          (const void *)light_server_kernel<256, true>, (const void *)light_server_kernel<256, false>, (const void *)light_server_kernel<512, true>,
+                          (const void *)light_server_sharded_kernel};
     for (const void *f : rest) fns.push_back(f);
     for (const void *f : fns) {
         cudaFuncAttributes a;

@@ -89,6 +89,23 @@ __device__ __forceinline__ void st_sys_v2u64(uint64_t *p, uint64_t a, uint64_t b
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
+__device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= want; bounded (about 2 s) so that a dead peer cannot hang the GPU
+__device__ __forceinline__ bool wait_flag(const uint64_t *p, uint64_t want) {
+    for (uint32_t i = 0; i < (1u << 23); i++) {
+        if (ld_sys_u64(p) >= want) return true;
+        __nanosleep(200);
+    }
+    return false;
+}
+
 struct LightSmem {
     uint32_t tab[2][LIGHT_WORDS];
     uint64_t ptr[LIGHT_ROWS];       // raw iptr_t of each row's key (0 = miss)

@@ -21,7 +21,7 @@ namespace wk {
 
 enum { SRV_HDR_CHUNKS = 4, SRV_CHUNKS = SRV_HDR_CHUNKS + MAX_LIGHT_STEPS, SRV_SMEM_SEGS = 160 };
 static_assert(SRV_CHUNKS <= 32, "one lane of the polling warp per request chunk");
-enum { SRV_F_PROJECT = 1, SRV_F_STATS = 2, SRV_F_QUIT = 4, SRV_F_TRACE = 8 };
+enum { SRV_F_PROJECT = 1, SRV_F_STATS = 2, SRV_F_QUIT = 4, SRV_F_TRACE = 8, SRV_F_WAIT = 16 };
 
 struct SrvChunk { uint32_t w0, w1, w2, tag; };
 
@@ -59,6 +59,19 @@ struct SrvParams {
     long long *trace;            // device buffer of LIGHT_TRACE_WORDS phase clocks (requests with SRV_F_TRACE)
 };
 
+// A sharded store (wk_sharded.cuh): the server of the rank that owns a light query's constant walks the other shards through
+// peer memory exactly like light_sharded_kernel and tells the peers its verdict; the peers' servers answer a WAIT request
+// (header chunk: w0 = SRV_F_WAIT << 8 | owner << 16, w1 / w2 = epoch) by spinning on that verdict -- so an in-place light
+// query costs no launch on any rank.  Owner requests carry the epoch in w1 / w2 of the header chunk as well.
+struct SrvPeers {
+    const uint4 *pv[LIGHT_PEERS];
+    const uint32_t *pe[LIGHT_PEERS];
+    uint64_t *peer_flag[LIGHT_PEERS];   // &XchCtl::flagL[me] inside every peer's control block (nullptr for myself)
+    const uint64_t *my_flag;            // my XchCtl::flagL, indexed by owner
+    const SegLite *segr_tab;            // [my segment slot][LIGHT_PEERS]: where every shard keeps that (pid, dir) segment
+    uint32_t nranks, rank;
+};
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -85,10 +98,13 @@ struct SrvSmem {
     uint32_t ctrl;                  // 0 run, 1 leave
 };
 
-template <int NT, bool WARPM>
-__global__ void __launch_bounds__(NT) light_server_kernel(const __grid_constant__ SrvParams P) {
-    extern __shared__ __align__(16) unsigned char srv_dyn[];
-    SrvSmem &S = *reinterpret_cast<SrvSmem *>(srv_dyn);
+struct SrvSmemSharded {
+    SrvSmem base;
+    SegLite segr[LIGHT_SHARDED_STEPS][LIGHT_PEERS];
+};
+
+template <int NT, bool WARPM, bool SHARDED>
+__device__ __forceinline__ void light_server_body(const SrvParams &P, const SrvPeers *Q, SrvSmem &S, SegLite (*segr)[LIGHT_PEERS]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // constant part of the plan header and the segment table
     for (int i = tid; i < P.nsegs && i < SRV_SMEM_SEGS; i += NT) S.seg[i] = P.segtab[i];
@@ -157,6 +173,25 @@ __global__ void __launch_bounds__(NT) light_server_kernel(const __grid_constant_
         const uint32_t hdr = S.chunk[0].w0;
         const int nsteps = (int)(hdr & 0xFF);
         const uint32_t flags = (hdr >> 8) & 0xFF;
+        if (SHARDED && (flags & SRV_F_WAIT)) {
+            // a peer owns this query: wait for its verdict (bounded), report it in the record's status word
+            // (2 = the owner never answered, 4 = the table outgrew the owner's shared memory: redo collectively)
+            if (tid == 0) {
+                const uint64_t epoch = (uint64_t)S.chunk[0].w1 | ((uint64_t)S.chunk[0].w2 << 32);
+                const uint32_t owner = (hdr >> 16) & 0xFF;
+                uint64_t status = 0;
+                if (!wait_flag(Q->my_flag + owner, 2 * epoch)) status = 2;
+                else if (ld_sys_u64(Q->my_flag + owner) == 2 * epoch + 1) status = 4;
+                uint64_t *rec = (uint64_t *)P.rec;
+                st_sys_v2u64(P.times, t_acq, globaltimer_ns());
+                st_sys_v2u64(rec + 2, status, record_check(seq, 0, status, 0));
+                st_sys_v2u64(rec, seq, 0);
+            }
+            seq++;
+            t_idle0 = globaltimer_ns();
+            __syncthreads();
+            continue;
+        }
         if (tid < nsteps) {
             const SrvChunk c = S.chunk[SRV_HDR_CHUNKS + tid];
             LightStep &ls = S.plan.steps[tid];
@@ -178,6 +213,13 @@ __global__ void __launch_bounds__(NT) light_server_kernel(const __grid_constant_
             ls.mt_factor = 1;
             ls.key = (ls.kind == LKIND_C2U) ? make_key(c.w1, ls.seg.pid, ls.seg.dir) : 0;
         }
+        if (SHARDED) {   // where every shard keeps the segment of every step
+            for (int i = tid - 128; i >= 0 && i < nsteps * LIGHT_PEERS; i += NT) {
+                const int st = i / LIGHT_PEERS, r = i - st * LIGHT_PEERS;
+                const uint32_t slot = S.chunk[SRV_HDR_CHUNKS + st].w2 >> 17;
+                if (st < LIGHT_SHARDED_STEPS && r < (int)Q->nranks) segr[st][r] = Q->segr_tab[slot * LIGHT_PEERS + r];
+            }
+        }
         if (tid >= 32 && tid < 32 + 3 * 12) {   // projection columns: 12 per chunk
             const int j = tid - 32;
             const SrvChunk &c = S.chunk[1 + j / 12];
@@ -194,11 +236,38 @@ __global__ void __launch_bounds__(NT) light_server_kernel(const __grid_constant_
             if (S.plan.trace) S.plan.trace[29] = clock64();
         }
         __syncthreads();
-        light_run<NT, LocalView, WARPM>(S.plan, S.plan.steps, sv, S.light, (flags & SRV_F_STATS) != 0, P.times, t_acq);
+        if (SHARDED) {
+            PeerView pvw;
+            pvw.v = Q->pv;
+            pvw.e = Q->pe;
+            pvw.segr = segr;
+            pvw.n = Q->nranks;
+            const bool spilled = light_run<NT, PeerView, WARPM>(S.plan, S.plan.steps, pvw, S.light, (flags & SRV_F_STATS) != 0, P.times, t_acq);
+            if (tid < (int)Q->nranks && Q->peer_flag[tid] != nullptr) {
+                const uint64_t epoch = (uint64_t)S.chunk[0].w1 | ((uint64_t)S.chunk[0].w2 << 32);
+                st_sys_u64_light(Q->peer_flag[tid], 2 * epoch + (spilled ? 1 : 0));
+            }
+        } else {
+            light_run<NT, LocalView, WARPM>(S.plan, S.plan.steps, sv, S.light, (flags & SRV_F_STATS) != 0, P.times, t_acq);
+        }
         seq++;
         t_idle0 = globaltimer_ns();
         __syncthreads();
     }
+}
+
+template <int NT, bool WARPM>
+__global__ void __launch_bounds__(NT) light_server_kernel(const __grid_constant__ SrvParams P) {
+    extern __shared__ __align__(16) unsigned char srv_dyn[];
+    SrvSmem &S = *reinterpret_cast<SrvSmem *>(srv_dyn);
+    light_server_body<NT, WARPM, false>(P, nullptr, S, nullptr);
+}
+
+// the server of one shard of a vid % n group (peer memory mapped: wk_comm_p2p_import_store / wk_comm_local_group)
+__global__ void __launch_bounds__(LIGHT_SRV_THREADS) light_server_sharded_kernel(const __grid_constant__ SrvParams P, const __grid_constant__ SrvPeers Q) {
+    extern __shared__ __align__(16) unsigned char srv_dyn[];
+    SrvSmemSharded &S = *reinterpret_cast<SrvSmemSharded *>(srv_dyn);
+    light_server_body<LIGHT_SRV_THREADS, true, true>(P, &Q, S.base, S.segr);
 }
 
 }  // namespace wk

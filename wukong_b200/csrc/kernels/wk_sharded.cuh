@@ -140,6 +140,7 @@ struct wk_comm {
     const uint4 *peer_v[8] = {nullptr};
     const uint32_t *peer_e[8] = {nullptr};
     std::vector<std::map<std::tuple<int, uint32_t, int>, wk_segmeta_t>> peer_segs;
+    SegLite *d_segr_tab = nullptr;      // [segment slot of my store][LIGHT_PEERS]: the sharded light-query server's segment directory
 };
 
 // Which steps need an exchange: out[i] = -1 none, -2 replicate to every rank, c >= 0 re-shard by column c.
@@ -199,22 +200,7 @@ struct P2PLocal {                            // device scratch of one rank
     uint64_t sent_mark;                      // rows_sent when the running exchange began
 };
 
-__device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-// spin until *p >= want; bounded (about 2 s) so that a dead peer cannot hang the GPU
-__device__ __forceinline__ bool wait_flag(const uint64_t *p, uint64_t want) {
-    for (uint32_t i = 0; i < (1u << 23); i++) {
-        if (ld_sys_u64(p) >= want) return true;
-        __nanosleep(200);
-    }
-    return false;
-}
+// st_sys_u64 / ld_sys_u64 / wait_flag (bounded spin on a peer-written flag): wk_light.cuh
 
 // barrier A.  A rank that gives up poisons the whole group: a late peer must not push into a buffer that may already
 // hold another query's table.

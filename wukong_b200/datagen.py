@@ -66,13 +66,14 @@ def lubm_shard(num_univs, nranks, rank, seed=1, chunk=128):
 RMAT_PRED, RMAT_TYPE, RMAT_NUM_NORMAL_PREDS = 2, 3, 3   # str_index: __PREDICATE__, rdf:type, <edge>, <Vertex>
 
 
-def rmat(scale, nedges, seed=42, a=0.57, b=0.19, c=0.19, typed=True):
-    """R-MAT power-law graph as ID triples: (s, 2, o) edges, plus (v, 1, 3) for every vertex that occurs."""
+def rmat(scale, nedges, seed=42, a=0.57, b=0.19, c=0.19, typed=True, scramble=True):
+    """R-MAT power-law graph as ID triples: (s, 2, o) edges, plus (v, 1, 3) for every vertex that occurs.  scramble: relabel the
+    vertices through a bijection (as Graph500 does), so that the degree is not readable from the low bits of the id."""
     L = lib()
     L.wkgen_rmat_edges.restype = C.c_uint64
-    L.wkgen_rmat_edges.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    L.wkgen_rmat_edges.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
     out = np.empty((nedges, 3), dtype=np.uint32)
-    L.wkgen_rmat_edges(scale, nedges, seed, a, b, c, out.ctypes.data_as(C.c_void_p))
+    L.wkgen_rmat_edges(scale, nedges, seed, a, b, c, 1 if scramble else 0, out.ctypes.data_as(C.c_void_p))
     if not typed:
         return out
     verts = np.unique(np.concatenate([out[:, 0], out[:, 2]]))
