@@ -19,8 +19,9 @@ Contract (Measurement):
              vs the measured HBM peak in MEASURED_PEAKS.json
   cpu_baseline / --impl reference : the reference's OWN engine (oracle/_ref) on the host cores this process may use
              (sched_getaffinity capped by the cgroup CPU quota), best mt_factor per heavy query from a sweep, blind and
-             non-blind latencies; `value` of the reference line is the blind geomean, `e2e.value` the non-blind one, so
-             that value/value and e2e/e2e each compare equal work.
+             non-blind latencies; `value` of the reference line is the NON-blind geomean (= its `e2e.value`, as the contract
+             asks: the CPU engine's result is in host memory either way), `value_blind` the blind one, so that e2e/e2e and
+             value/value_blind each compare equal work.
   parity   = at full scale: an order-independent digest of every query's non-blind table from the GPU engine equals the
              CPU arm's digest of its own table (not only the row counts).
 """
@@ -41,6 +42,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 
 HEAVY = (1, 2, 3, 7)
+LIGHT = (4, 5, 6)
 QUERIES = (1, 2, 3, 4, 5, 6, 7)
 
 
@@ -467,7 +469,7 @@ class SpinBarrier:
         self.dist.barrier()
         if self.a is None:
             return
-        self.gen += 1
+        self.gen = int(self.a[self.rank * 8]) + 1     # the native timer (host.ShardedTimer) advances the same counters
         g = self.gen
         self.a[self.rank * 8] = g
         t0 = time.monotonic()
@@ -522,35 +524,31 @@ def run_sharded(args, rank, world, local_rank, dist):
     dev_us = {q: [] for q in QUERIES}
     wall_us = {q: [] for q in QUERIES}
     e2e_us = {q: [] for q in QUERIES}
+    srv_ns = {q: [] for q in QUERIES}
     resident = {}
+    # native timed calls (wkh_time_query_sharded): the L2 flush must be over on EVERY rank before anyone starts -- a rank still
+    # flushing would make its peers' exchange waits absorb its flush -- so: flush, stream sync, spin barrier, clock, query
+    timer = host.ShardedTimer(eng, bar.a, rank, world)
+    bar.wait()
     for _ in range(args.steps):
         for q in QUERIES:
             pats, nvars, req = plans[q]
-            eng.flush_l2()
-            eng.sync()        # the flush must be over on EVERY rank before anyone starts: a rank still flushing would
-            bar.wait()        # make its peers' exchange waits (and their device times) absorb its flush
-            w0 = time.perf_counter_ns()
-            rc, r, c, _ = eng.query_sharded(pats, nvars, req, blind=True)
-            w1 = time.perf_counter_ns()
-            assert rc == 0, rc
-            resident[q] = bool(eng.get_option(capi.WK_INFO_LAST_RESIDENT))
-            wall_us[q].append((w1 - w0) / 1e3)
+            w, d, r, c, res, ns = timer.time(pats, nvars, req, blind=True)
+            assert r == rows[q], (q, r, rows[q])
+            resident[q] = res
+            wall_us[q].append(w)
             # a light plan answered by the resident servers has no launch to bracket with events: its term is the wall clock
             # of the call (doorbell -> record), like at N = 1
-            dev_us[q].append((w1 - w0) / 1e3 if resident[q] else eng.last_query_device_us())
+            dev_us[q].append(d)
+            srv_ns[q].append(ns)
     eng.set_profiling(0)
     # end to end: non-blind, every rank receives its share of the projected table in pinned host memory
     for _ in range(args.steps):
         for q in QUERIES:
             pats, nvars, req = plans[q]
-            eng.flush_l2()
-            eng.sync()
-            bar.wait()
-            w0 = time.perf_counter_ns()
-            rc, r, c, _ = eng.query_sharded(pats, nvars, req, out=out_tbl)
-            w1 = time.perf_counter_ns()
-            assert rc == 0 and r == rows[q], (rc, r, rows[q])
-            e2e_us[q].append((w1 - w0) / 1e3)
+            w, _, r, c, _, _ = timer.time(pats, nvars, req, blind=False, table=out_tbl)
+            assert r == rows[q], (q, r, rows[q])
+            e2e_us[q].append(w)
     eng.sync(); dist.barrier(); torch.cuda.synchronize()
     t_region = time.time() - t_region0
     clocks = sampler.stop()
@@ -602,6 +600,11 @@ def run_sharded(args, rank, world, local_rank, dist):
                             "exchanges, barriers included; peak = measured peer copy per direction (B200_PROFILING.md), 900 GB/s nominal"}
     t = torch.tensor([np.mean(dev_us[q]) for q in QUERIES] + [np.mean(wall_us[q]) for q in QUERIES] + [np.mean(e2e_us[q]) for q in QUERIES] +
                      [1.0 if resident.get(q) else 0.0 for q in QUERIES], device="cuda", dtype=torch.float64)
+    # per rank, for the record: blind wall clock and in-kernel span of the server request of the light plans (owner vs waiting peers)
+    per_rank = torch.zeros((world, 2 * len(LIGHT)), device="cuda", dtype=torch.float64)
+    per_rank[rank] = torch.tensor([np.mean(wall_us[q]) for q in LIGHT] + [np.mean(srv_ns[q]) / 1e3 for q in LIGHT], dtype=torch.float64)
+    dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    per_rank = per_rank.cpu().numpy()
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     lat = t.cpu().numpy()
     rr = torch.tensor([rows[q] for q in QUERIES] + [stats["rows_sent"] - st0["rows_sent"], launches, bytes_pushed, sum(nb_words.values()) * 4],
@@ -626,14 +629,19 @@ def run_sharded(args, rank, world, local_rank, dist):
                            "value_mode": "blind (row count only), shards resident in HBM, max over ranks; CUDA events, except light plans answered "
                                          "in place by the resident servers (no launch on any rank: wall clock of the call, doorbell -> record)",
                            "e2e_mode": "non-blind: every rank's share of the projected table D2H into pinned memory, host wall clock, max over ranks",
-                           "barrier": "dist.barrier + shared-memory spin barrier before every timed query"},
+                           "barrier": "L2 flush, stream sync, shared-memory spin barrier, then the clock: all in native code (wkh_time_query_sharded)"},
                 "e2e": {"value": geomean(1e6 / e2e_mean), "unit": "queries/s", "h2d_bytes_per_step": 584 * world,
                         "d2h_bytes_per_step": int(rr[10]) + 32 * len(QUERIES) * world},
                 "gpu_launches": int(rr[8]), "clocks": clocks,
                 "latency_us": {"device": {"q%d" % q: round(float(dev_mean[i]), 2) for i, q in enumerate(QUERIES)},
                                "wall": {"q%d" % q: round(float(wall_mean[i]), 2) for i, q in enumerate(QUERIES)},
                                "e2e": {"q%d" % q: round(float(e2e_mean[i]), 2) for i, q in enumerate(QUERIES)}},
-                "light_path": {"resident_servers": {"q%d" % q: bool(res[i] > 0) for i, q in enumerate(QUERIES)}},
+                "light_path": {"resident_servers": {"q%d" % q: bool(res[i] > 0) for i, q in enumerate(QUERIES)},
+                               "per_rank": {"q%d" % q: {"wall_us": [round(float(x), 2) for x in per_rank[:, j]],
+                                                        "server_us": [round(float(x), 2) for x in per_rank[:, len(LIGHT) + j]]}
+                                            for j, q in enumerate(LIGHT)},
+                               "note": "in-place plans: the constant's owner walks the shards through peer loads, the other ranks wait for its "
+                                       "verdict; server_us = in-kernel span of that rank's server request (0: launch path)"},
                 "rows": {"q%d" % q: int(rr[i]) for i, q in enumerate(QUERIES)},
                 "comm": {"rows_pushed_all_ranks": int(rr[7]), "bytes_pushed_all_ranks": int(rr[9]),
                          "bytes_pushed_per_step_all_ranks": int(rr[9] // max(1, args.steps)),

@@ -224,7 +224,8 @@ def test_exchange_local_group_tables_and_overflow():
     world = 3
     stores, engs = _local_group(world, univs=1, seed=1, rbuf=8 << 20)
     rng = np.random.default_rng(5)
-    for C, n in ((1, 70001), (3, 50000), (5, 33333), (9, 4099), (2, 0)):
+    # 700 K and 400 K rows: more tiles than the grid has CTAs, so space is reserved per chunk of several tiles (wk_sharded.cuh)
+    for C, n in ((1, 700001), (2, 400003), (3, 50000), (5, 33333), (9, 4099), (2, 0)):
         tabs = [rng.integers(1 << 17, 1 << 26, (n + 13 * r, C), dtype=np.uint32) for r in range(world)]
         col = C // 2
 
@@ -241,6 +242,20 @@ def test_exchange_local_group_tables_and_overflow():
             assert got[r].shape[0] == want.shape[0], (C, n, r)
             if want.shape[0]:
                 assert rows_equal(got[r].reshape(-1, C), want), (C, n, r)
+    # replicate mode (the table of a type-index lookup, sparql.hpp:1091-1110): every rank ends up with every rank's rows;
+    # 250 K rows per rank = more tiles than CTAs (chunked reservations), 1 000 rows = one tile per rank
+    for nrep in (250007, 1000):
+        tabs = [rng.integers(1 << 17, 1 << 26, (nrep + 5 * r, 2), dtype=np.uint32) for r in range(world)]
+
+        def run_dup(rank, eng, tabs=tabs):
+            eng.upload(tabs[rank], ncols=2)
+            rows = eng.exchange_p2p(-2)
+            return eng.download()[:rows]
+
+        got = _run_ranks(engs, run_dup)
+        allrows = np.concatenate(tabs)
+        for r in range(world):
+            assert got[r].shape[0] == allrows.shape[0] and rows_equal(got[r].reshape(-1, 2), allrows), (nrep, r)
     # overflow: 2 M words per buffer; rank 0 would receive 3 x 300 K rows x 3 columns
     tabs = [np.full((300000, 3), 3 * 1000 + 0, dtype=np.uint32) for _ in range(world)]   # every row is owned by rank 0
 

@@ -90,6 +90,51 @@ int wkh_time_query(wk_engine_t *e, const wk_pattern_t *pats, int npat, int nvars
     return WK_SUCCESS;
 }
 
+// One timed collective query of a sharded group, called by every rank of the group at the same time.  L2 flush and stream
+// sync first, then a spin barrier on `slots` (shared memory, one generation counter per rank, `stride` int64 apart; release skew
+// well below a microsecond), then the clock around wk_query_execute_sharded.  resident: the call was answered by the resident
+// servers (no launch to bracket with events: dev_us = wall_us then); server_ns: in-kernel span of this rank's server request.
+int wkh_time_query_sharded(wk_engine_t *e, const wk_pattern_t *pats, int npat, int nvars, const int32_t *req, int nreq, int blind,
+                           wk_sid_t *table, uint64_t cap_words, int flush, volatile int64_t *slots, int stride, int rank, int world,
+                           int64_t gen, double *wall_us, float *dev_us, uint64_t *rows, int *cols, int *resident, uint64_t *server_ns) {
+    if (flush) {
+        int rc = wk_engine_flush_l2(e);
+        if (rc) return rc;
+    }
+    int rc = wk_engine_sync(e);
+    if (rc) return rc;
+    if (slots) {
+        slots[(size_t)rank * stride] = gen;
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        const auto tb = std::chrono::steady_clock::now();
+        uint64_t spins = 0;
+        for (int r = 0; r < world; r++) {
+            while (slots[(size_t)r * stride] < gen) {
+                if ((++spins & 0xFFFFF) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count() > 120.0) return WK_ERR_COMM;
+            }
+        }
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = wk_query_execute_sharded(e, pats, npat, nvars, req, nreq, 0, 1, blind, table, cap_words, rows, cols);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc) return rc;
+    const double w = std::chrono::duration<double, std::micro>(t1 - t0).count();
+    if (wall_us) *wall_us = w;
+    int64_t res = 0, ns = 0;
+    wk_engine_get_option(e, WK_INFO_LAST_RESIDENT, &res);
+    wk_engine_get_option(e, WK_INFO_LAST_RESIDENT_NS, &ns);
+    if (resident) *resident = (int)res;
+    if (server_ns) *server_ns = res ? (uint64_t)ns : 0;
+    if (dev_us) {
+        if (res) *dev_us = (float)w;
+        else {
+            rc = wk_engine_last_query_device_us(e, dev_us);
+            if (rc) return rc;
+        }
+    }
+    return WK_SUCCESS;
+}
+
 // ---- Wukong-surface environment: config + string server + graph + engine + proxy of one server ----
 struct HostEnv {
     wukong::Global global;

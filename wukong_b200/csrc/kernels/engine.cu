@@ -2856,6 +2856,7 @@ int wk_query_execute_sharded(wk_engine_t *e, const wk_pattern_t *patterns, int n
         }
     }
     e->q_timed = false;
+    e->last_resident = false;
     if (e->profiling) CUDA_TRY(cudaEventRecord(e->q_ev0, e->stream));
     const int n = e->comm->nranks, me = e->comm->rank;
     // In-place execution of a light query (the reference answers small tables with one-sided remote reads instead of a

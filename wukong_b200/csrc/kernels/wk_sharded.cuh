@@ -191,6 +191,7 @@ struct P2PTable {
     int nranks, rank;
 };
 enum { P2P_MAX_RANKS = MAX_PARTS / 4 };
+enum { P2P_CHUNK_TILES = 16 };   // tiles per reservation of the push kernel (see p2p_push_kernel)
 
 struct P2PLocal {                            // device scratch of one rank
     uint32_t done_ctas;
@@ -232,8 +233,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, Xc
     extern __shared__ uint32_t p2p_dyn[];
     constexpr uint32_t TILE = CTA_THREADS * RPT;
     uint32_t *rows = p2p_dyn, *stage = p2p_dyn + (size_t)TILE * C;
-    __shared__ uint32_t hist[P2P_MAX_RANKS], off[P2P_MAX_RANKS + 1];
-    __shared__ uint64_t base[P2P_MAX_RANKS];
+    __shared__ uint32_t hist[P2P_MAX_RANKS], off[P2P_MAX_RANKS + 1], chist[P2P_MAX_RANKS], crun[P2P_MAX_RANKS];
+    __shared__ uint64_t base[P2P_MAX_RANKS], cbase[P2P_MAX_RANKS];
     __shared__ uint32_t last, s_ovf;
     __shared__ int s_ok;
     const uint32_t n = (uint32_t)t.nranks;
@@ -261,73 +262,121 @@ __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, Xc
     const uint64_t N = bad ? 0 : ld_count(in_count);
     if (tid == 0) s_ovf = (__ldcg(status) & 1u) ? 1u : 0u;
     uint64_t sent = 0, kept = 0;
+    // Space in the owners' buffers is reserved once per CHUNK of G consecutive tiles, not per tile: the reservation is an atomic on
+    // ONE word per owner that every CTA of every rank hits, and same-address atomics retire one after the other (measured: the
+    // per-tile version spent ~6 ns per tile and owner, 0.6 ms of a 107 M-row exchange).  The chunk is counted first (key column
+    // only), then its tiles are loaded again -- from L2 -- grouped and pushed.  G grows with the table so that small tables
+    // still spread over the whole grid.
+    const uint64_t tiles_total = (N + TILE - 1) / TILE;
+    uint32_t G = (uint32_t)((tiles_total + gridDim.x - 1) / gridDim.x);
+    G = G < 1 ? 1 : (G > P2P_CHUNK_TILES ? P2P_CHUNK_TILES : G);
+    const uint64_t CH = (uint64_t)G * TILE;
+    const uint32_t lane = tid & 31u;
     __syncthreads();
-    for (uint64_t t0 = (uint64_t)blockIdx.x * TILE; t0 < N; t0 += (uint64_t)gridDim.x * TILE) {
-        const uint32_t nrows = (uint32_t)((N - t0 < TILE) ? (N - t0) : TILE);
-        const uint32_t words = nrows * (uint32_t)C;
-        if (tid < P2P_MAX_RANKS) hist[tid] = 0;
-        const uint32_t *src = in + t0 * (uint64_t)C;
-        for (uint32_t w = tid; w < words; w += CTA_THREADS) rows[w] = ld_table(src + w);
+    for (uint64_t c0 = (uint64_t)blockIdx.x * CH; c0 < N; c0 += (uint64_t)gridDim.x * CH) {
+        const uint32_t crows = (uint32_t)((N - c0 < CH) ? (N - c0) : CH);
+        // ---- count the chunk and reserve ---------------------------------------------------------------------------------
+        if (tid < P2P_MAX_RANKS) { chist[tid] = 0; crun[tid] = 0; }
         __syncthreads();
         if (!dup) {
-            uint32_t d[RPT], local[RPT];
-#pragma unroll
-            for (int j = 0; j < RPT; j++) {
-                const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
-                d[j] = 0; local[j] = 0;
-                if (r < nrows) {
-                    d[j] = rows[r * C + col] % n;
-                    local[j] = atomicAdd(&hist[d[j]], 1u);
+            if (G > 1) {
+                const uint32_t *key = in + c0 * (uint64_t)C + col;
+                for (uint32_t r0 = 0; r0 < crows; r0 += CTA_THREADS) {
+                    const uint32_t r = r0 + tid;
+                    const uint32_t d = r < crows ? ld_table(key + (uint64_t)r * C) % n : 0xFFFFFFFFu;
+                    for (uint32_t dd = 0; dd < n; dd++) {
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, d == dd);
+                        if (lane == 0 && m) atomicAdd(&chist[dd], __popc(m));
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t run = 0;
-                for (uint32_t dd = 0; dd < n; dd++) { off[dd] = run * (uint32_t)C; run += hist[dd]; }   // in words
-                off[n] = run * (uint32_t)C;
-            }
+        } else if (tid < n) {
+            chist[tid] = crows;
+        }
+        if (dup || G > 1) {
+            if (dup) __syncthreads();
             if (tid < n) {
                 uint64_t b = 0;
-                if (hist[tid]) {
-                    b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)hist[tid]);
-                    if (b + hist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }   // the owner's buffer is full: drop the run, flag it
-                    else if (tid != (uint32_t)t.rank) sent += hist[tid];
-                    else kept += hist[tid];
+                if (chist[tid]) {
+                    b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)chist[tid]);
+                    if (b + chist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }   // the owner's buffer is full: drop the run, flag it
+                    else if (tid != (uint32_t)t.rank) sent += chist[tid];
+                    else kept += chist[tid];
                 }
-                base[tid] = b;
+                cbase[tid] = b;
             }
             __syncthreads();
-#pragma unroll
-            for (int j = 0; j < RPT; j++) {
-                const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
-                if (r < nrows) {
-                    uint32_t *q = stage + off[d[j]] + local[j] * (uint32_t)C;
-                    for (int c = 0; c < C; c++) q[c] = rows[r * C + c];
-                }
-            }
-            __syncthreads();
-            for (uint32_t w = tid; w < words; w += CTA_THREADS) {
-                uint32_t dd = 0;
-                while (w >= off[dd + 1]) dd++;
-                const uint64_t b = base[dd];
-                if (b != ~0ull) t.buf[dst_buf][dd][b * (uint64_t)C + (w - off[dd])] = stage[w];
-            }
-        } else {
-            if (tid < n) {
-                uint64_t b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)nrows);
-                if (b + nrows > cap_rows) { b = ~0ull; s_ovf = 1; }
-                else if (tid != (uint32_t)t.rank) sent += nrows;
-                else kept += nrows;
-                base[tid] = b;
-            }
-            __syncthreads();
-            for (uint32_t dd = 0; dd < n; dd++) {
-                if (base[dd] == ~0ull) continue;
-                uint32_t *dst = t.buf[dst_buf][dd] + base[dd] * (uint64_t)C;
-                for (uint32_t w = tid; w < words; w += CTA_THREADS) dst[w] = rows[w];
-            }
         }
-        __syncthreads();
+        // ---- the chunk's tiles -------------------------------------------------------------------------------------------
+        for (uint32_t q0 = 0; q0 < crows; q0 += TILE) {
+            const uint64_t t0 = c0 + q0;
+            const uint32_t nrows = (crows - q0 < TILE) ? (crows - q0) : TILE;
+            const uint32_t words = nrows * (uint32_t)C;
+            if (tid < P2P_MAX_RANKS) hist[tid] = 0;
+            const uint32_t *src = in + t0 * (uint64_t)C;
+            for (uint32_t w = tid; w < words; w += CTA_THREADS) rows[w] = ld_table(src + w);
+            __syncthreads();
+            if (!dup) {
+                uint32_t d[RPT], local[RPT];
+#pragma unroll
+                for (int j = 0; j < RPT; j++) {
+                    const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
+                    d[j] = r < nrows ? rows[r * C + col] % n : 0xFFFFFFFFu;
+                    local[j] = 0;
+                    // rank of the row among the tile's rows of the same owner: one shared-memory atomic per warp and owner
+                    for (uint32_t dd = 0; dd < n; dd++) {
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, d[j] == dd);
+                        uint32_t wb = 0;
+                        if (lane == 0 && m) wb = atomicAdd(&hist[dd], __popc(m));
+                        wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
+                        if (d[j] == dd) local[j] = wb + __popc(m & ((1u << lane) - 1u));
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t run = 0;
+                    for (uint32_t dd = 0; dd < n; dd++) { off[dd] = run * (uint32_t)C; run += hist[dd]; }   // in words
+                    off[n] = run * (uint32_t)C;
+                }
+                if (tid < n) {
+                    uint64_t b = 0;
+                    if (G > 1) {
+                        b = cbase[tid] == ~0ull ? ~0ull : cbase[tid] + crun[tid];
+                        crun[tid] += hist[tid];
+                    } else if (hist[tid]) {
+                        b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)hist[tid]);
+                        if (b + hist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }
+                        else if (tid != (uint32_t)t.rank) sent += hist[tid];
+                        else kept += hist[tid];
+                    }
+                    base[tid] = b;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < RPT; j++) {
+                    const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
+                    if (r < nrows) {
+                        uint32_t *q = stage + off[d[j]] + local[j] * (uint32_t)C;
+                        for (int c = 0; c < C; c++) q[c] = rows[r * C + c];
+                    }
+                }
+                __syncthreads();
+                for (uint32_t w = tid; w < words; w += CTA_THREADS) {
+                    uint32_t dd = 0;
+                    while (w >= off[dd + 1]) dd++;
+                    const uint64_t b = base[dd];
+                    if (b != ~0ull) t.buf[dst_buf][dd][b * (uint64_t)C + (w - off[dd])] = stage[w];
+                }
+            } else {
+                for (uint32_t dd = 0; dd < n; dd++) {
+                    if (cbase[dd] == ~0ull) continue;
+                    uint32_t *dst = t.buf[dst_buf][dd] + (cbase[dd] + q0) * (uint64_t)C;
+                    for (uint32_t w = tid; w < words; w += CTA_THREADS) dst[w] = rows[w];
+                }
+            }
+            __syncthreads();
+        }
     }
     if (sent) {
         atomicAdd((unsigned long long *)&loc->rows_sent, (unsigned long long)sent);

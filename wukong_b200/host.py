@@ -31,6 +31,8 @@ def lib():
     L.wkh_store_upload.argtypes = [vp, ci, C.POINTER(vp)]
     L.wkh_time_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, u64, ci, ci, vp, vp, C.POINTER(u64),
                                  C.POINTER(ci)]
+    L.wkh_time_query_sharded.argtypes = [vp, vp, ci, ci, vp, ci, ci, vp, u64, ci, vp, ci, ci, ci, C.c_int64, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(ci), C.POINTER(ci), C.POINTER(u64)]
     L.wkh_env_create.restype = vp
     L.wkh_env_create.argtypes = [C.c_char_p, ci]
     L.wkh_env_destroy.argtypes = [vp]
@@ -131,6 +133,33 @@ def time_query(engine, patterns, nvars, required_vars, reps, blind=True, table=N
                               C.byref(rows), C.byref(cols))
     capi._check(rc, "wkh_time_query")
     return wall, dev, rows.value, cols.value
+
+
+class ShardedTimer:
+    """Timed collective queries of a sharded group in native code (wkh_time_query_sharded): L2 flush, stream sync, a spin barrier
+    over `slots` (a shared int64 array, rank r's generation counter at slots[8 * r]), then the clock around
+    wk_query_execute_sharded.  Every rank calls time() for the same query at the same time."""
+
+    def __init__(self, engine, slots, rank, world):
+        self.engine, self.slots, self.rank, self.world, self.gen = engine, slots, rank, world, 0
+        if slots is not None:
+            self.gen = int(slots[8 * rank])
+
+    def time(self, patterns, nvars, required_vars, blind=True, table=None, flush=True):
+        """-> (wall_us, dev_us, rows, cols, resident, server_ns)"""
+        p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+        rv = np.array(required_vars, dtype=np.int32)
+        wall, dev = C.c_double(0), C.c_float(0)
+        rows, cols, res, ns = C.c_uint64(0), C.c_int(0), C.c_int(0), C.c_uint64(0)
+        self.gen += 1
+        rc = lib().wkh_time_query_sharded(self.engine.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars, rv.ctypes.data_as(C.c_void_p),
+                                          len(rv), 1 if blind else 0, table.ctypes.data_as(C.c_void_p) if table is not None else None,
+                                          table.size if table is not None else 0, 1 if flush else 0,
+                                          self.slots.ctypes.data_as(C.c_void_p) if self.slots is not None else None, 8, self.rank,
+                                          self.world, self.gen, C.byref(wall), C.byref(dev), C.byref(rows), C.byref(cols),
+                                          C.byref(res), C.byref(ns))
+        capi._check(rc, "wkh_time_query_sharded")
+        return wall.value, dev.value, rows.value, cols.value, bool(res.value), ns.value
 
 
 CONFIG_ITEMS = ["num_servers", "num_threads", "num_proxies", "num_engines", "data_port_base", "ctrl_port_base", "rdma_buf_size_mb",
