@@ -1,5 +1,6 @@
 """CPU: the JSON line bench.py prints -- keys and types the driver reads.  The reference arm runs here (tiny scale); the
-GPU arm's line is checked on the committed output of the round's final run (profiles/r1_bench_lubm2560.json)."""
+GPU arm's line is checked on the committed output of the round's 1-GPU run (profiles/r2_bench_lubm2560.json) and, when
+present, on the committed sharded lines (profiles/r2_bench_sharded_*gpu_lubm10240.json)."""
 import json
 import os
 import subprocess
@@ -37,7 +38,7 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_lubm2560.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_lubm2560.json")))
     _check_base(d)
     assert "impl" not in d or d["impl"] != "reference"
     assert d["n_gpus"] == 1 and d["dtype"] == "u32" and d["data"] == "synthetic" and d["gpu_launches"] > 0
@@ -51,4 +52,21 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert c["sm_mhz"] and c["sm_max_mhz"] and isinstance(c["reasons"], list)
     assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
-    assert d["value"] / d["cpu_baseline"]["value"] >= 10    # the north-star's throughput bar, same box
+    assert d["value"] / d["cpu_baseline"]["value"] >= 10    # the north-star's throughput bar, same box: blind vs blind
+    assert d["e2e"]["value"] / d["cpu_baseline"]["e2e_value"] >= 10    # ... and non-blind end to end vs the CPU arm's non-blind
+    assert d["parity"]["match"] is True and d["parity"]["queries"] == 7   # table digests equal the CPU arm's at full scale
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == d["cpu_baseline"]["host_cpus"]["usable"]
+
+
+def test_committed_sharded_lines_have_the_contract_keys():
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_bench_sharded_*gpu_lubm10240.json")))
+    for f in files:
+        d = json.load(open(f))
+        for k, t in BASE_KEYS.items():
+            assert k in d and isinstance(d[k], t), (f, k)
+        assert d["n_gpus"] > 1 and d["scaling"] == "strong" and "LUBM-10240" in d["config"]["workload"] and "sharded" in d["config"]["parallelism"]
+        assert d["comm"]["bytes_pushed_per_step_all_ranks"] > 0 and d["comm"]["nvlink"]["achieved_gbs_per_gpu_per_direction"] > 0
+        one = d["secondary"]["single_gpu_same_store"]
+        assert d["rows"] == one["rows"], f                  # every row count equals the single-GPU run of the same store
+        assert d["gpu_launches"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0

@@ -2508,16 +2508,22 @@ static int exchange_table_p2p(wk_engine *e, int col) {
     // tile = 1024 / 512 / 256 rows so that the two staging areas stay within 32 KB of shared memory
     const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
     const size_t smem = 2 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
-    void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, uint32_t *, int) =
+    void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, uint32_t *, int, int, int) =
         rpt == 4 ? p2p_push_kernel<4> : (rpt == 2 ? p2p_push_kernel<2> : p2p_push_kernel<1>);
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // many tiles in flight per SM hide the round trip of the remote reservations
     int per_sm = (int)std::min<size_t>(6, std::max<size_t>(1, (200 * 1024) / std::max<size_t>(smem, 1)));
+    // experiment knobs of scripts/exchange_bench.py: tiles per reservation, CTAs per SM, timing-only debug modes
+    const char *ev_g = getenv("WK_P2P_G"), *ev_c = getenv("WK_P2P_CTAS"), *ev_d = getenv("WK_P2P_DEBUG");
+    const int k_gmax = ev_g ? std::max(1, atoi(ev_g)) : (int)P2P_CHUNK_TILES;
+    const int k_ctas = ev_c ? atoi(ev_c) : 0;
+    const int k_dbg = ev_d ? atoi(ev_d) : 0;
+    if (k_ctas > 0) per_sm = std::min(per_sm, k_ctas);
     const int grid = c->local_group ? std::max(1, e->num_sms * 4 / std::max(1, c->nranks)) : e->num_sms * per_sm;
     StepRecord &r = begin_step(e, KIND_EXCHANGE, C);
     if (!ready_inside) p2p_ready_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, &e->d_ctl->status);
     kfn<<<grid, CTA_THREADS, smem, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
-                                                dup ? 1 : 0, (s + 1) & 1, epoch, cap_rows, &e->d_ctl->status, ready_inside ? 1 : 0);
+                                                dup ? 1 : 0, (s + 1) & 1, epoch, cap_rows, &e->d_ctl->status, ready_inside ? 1 : 0, k_gmax, k_dbg);
     p2p_wait_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, cap_rows, &e->d_ctl->counts[s + 1], &e->d_ctl->status,
                                              &e->d_ctl->stats[2 * s]);
     CUDA_TRY(cudaGetLastError());

@@ -229,7 +229,10 @@ __global__ void p2p_ready_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t
 template <int RPT>
 __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
                                                                   int C, int col, int dup, int dst_buf, uint64_t epoch, uint64_t cap_rows,
-                                                                  uint32_t *status, int ready_inside) {
+                                                                  uint32_t *status, int ready_inside, int gmax, int dbg) {
+    // gmax: most tiles per reservation (P2P_CHUNK_TILES; WK_P2P_G overrides it for experiments).  dbg (WK_P2P_DEBUG, timing
+    // experiments of scripts/exchange_bench.py only -- the received tables are garbage): 1 = rows owned by peers are not stored,
+    // 2 = no reservations (every tile writes at its own row index).
     extern __shared__ uint32_t p2p_dyn[];
     constexpr uint32_t TILE = CTA_THREADS * RPT;
     uint32_t *rows = p2p_dyn, *stage = p2p_dyn + (size_t)TILE * C;
@@ -268,8 +271,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, Xc
     // only), then its tiles are loaded again -- from L2 -- grouped and pushed.  G grows with the table so that small tables
     // still spread over the whole grid.
     const uint64_t tiles_total = (N + TILE - 1) / TILE;
-    uint32_t G = (uint32_t)((tiles_total + gridDim.x - 1) / gridDim.x);
-    G = G < 1 ? 1 : (G > P2P_CHUNK_TILES ? P2P_CHUNK_TILES : G);
+    uint32_t G = (uint32_t)(tiles_total / ((uint64_t)gridDim.x * 4));      // at least ~4 chunks per CTA: no long tail
+    G = G < 1 ? 1 : (G > (uint32_t)gmax ? (uint32_t)gmax : G);
     const uint64_t CH = (uint64_t)G * TILE;
     const uint32_t lane = tid & 31u;
     __syncthreads();
@@ -298,7 +301,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, Xc
             if (dup) __syncthreads();
             if (tid < n) {
                 uint64_t b = 0;
-                if (chist[tid]) {
+                if (dbg & 2) {
+                    b = c0;
+                } else if (chist[tid]) {
                     b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)chist[tid]);
                     if (b + chist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }   // the owner's buffer is full: drop the run, flag it
                     else if (tid != (uint32_t)t.rank) sent += chist[tid];
@@ -344,6 +349,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, Xc
                     if (G > 1) {
                         b = cbase[tid] == ~0ull ? ~0ull : cbase[tid] + crun[tid];
                         crun[tid] += hist[tid];
+                    } else if (dbg & 2) {
+                        b = t0;
                     } else if (hist[tid]) {
                         b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)hist[tid]);
                         if (b + hist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, Xc
                     uint32_t dd = 0;
                     while (w >= off[dd + 1]) dd++;
                     const uint64_t b = base[dd];
-                    if (b != ~0ull) t.buf[dst_buf][dd][b * (uint64_t)C + (w - off[dd])] = stage[w];
+                    if (b != ~0ull && !((dbg & 1) && dd != (uint32_t)t.rank)) t.buf[dst_buf][dd][b * (uint64_t)C + (w - off[dd])] = stage[w];
                 }
             } else {
                 for (uint32_t dd = 0; dd < n; dd++) {
