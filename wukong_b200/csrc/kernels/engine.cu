@@ -2505,14 +2505,15 @@ static int exchange_table_p2p(wk_engine *e, int col) {
     // kernel from becoming resident) and the grid leaves room for the peers; ranks on devices of their own take barrier A
     // inside the push kernel (one launch less)
     const bool ready_inside = !c->local_group;
-    // tile = 1024 / 512 / 256 rows so that the two staging areas stay within 32 KB of shared memory
-    const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
-    const size_t smem = 2 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
+    // tile = 1024 / 512 / 256 rows: two row buffers (the next tile is in flight while this one is grouped) + the staging area
+    // stay within ~30 KB of shared memory for up to 9 columns, so 5-6 CTAs fit an SM
+    const int rpt = C <= 2 ? 4 : (C <= 5 ? 2 : 1);
+    const size_t smem = 3 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
     void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, uint32_t *, int, int, int) =
         rpt == 4 ? p2p_push_kernel<4> : (rpt == 2 ? p2p_push_kernel<2> : p2p_push_kernel<1>);
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // many tiles in flight per SM hide the round trip of the remote reservations
-    int per_sm = (int)std::min<size_t>(6, std::max<size_t>(1, (200 * 1024) / std::max<size_t>(smem, 1)));
+    // several CTAs per SM hide the barriers of the tile pipeline and the round trip of the remote reservations
+    int per_sm = (int)std::min<size_t>(5, std::max<size_t>(1, (200 * 1024) / std::max<size_t>(smem + 1024, 1)));
     // experiment knobs of scripts/exchange_bench.py: tiles per reservation, CTAs per SM, timing-only debug modes
     const char *ev_g = getenv("WK_P2P_G"), *ev_c = getenv("WK_P2P_CTAS"), *ev_d = getenv("WK_P2P_DEBUG");
     const int k_gmax = ev_g ? std::max(1, atoi(ev_g)) : (int)P2P_CHUNK_TILES;

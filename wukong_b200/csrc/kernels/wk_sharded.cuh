@@ -222,26 +222,56 @@ __global__ void p2p_ready_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t
     }
 }
 
+// L words of shared memory -> global words dst[0 .. L): the head up to the first 16-byte boundary of dst and the tail as
+// 4-byte stores, the body as 16-byte stores (one 512-byte request per warp instead of four 128-byte ones: what crosses NVLink
+// is full-width).  All threads of the CTA take part.
+__device__ __forceinline__ void push_run(uint32_t *dst, const uint32_t *src, uint32_t L, uint32_t tid) {
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3u);
+    uint32_t head = (4u - mis) & 3u;
+    if (head > L) head = L;
+    const uint32_t nvec = (L - head) >> 2, tail = L - head - (nvec << 2);
+    if (tid < head) dst[tid] = src[tid];
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t *sv = src + head;
+    for (uint32_t v = tid; v < nvec; v += CTA_THREADS) {
+        uint4 x;
+        x.x = sv[4 * v]; x.y = sv[4 * v + 1]; x.z = sv[4 * v + 2]; x.w = sv[4 * v + 3];
+        dv[v] = x;
+    }
+    if (tid < tail) dst[head + (nvec << 2) + tid] = src[head + (nvec << 2) + tid];
+}
+
 // one pass: tile -> group by owner -> reserve -> push.  RPT rows per thread: tile = 256 * RPT rows.
 // ready_inside: barrier A is taken inside this kernel (one launch less per exchange): CTA 0 tells every peer that this rank's
 // earlier kernels are done, and every CTA waits for all peers' word before its first store into a peer's buffer.  Only for
 // ranks on different devices: on a shared device a grid of waiting CTAs could keep a peer's kernel from becoming resident.
+//
+// Pipeline of a CTA (measured on 2 B200s, scripts/exchange_bench.py --variants: with the reservations and the remote stores
+// switched off the first version of this kernel still took 3/4 of its time -- it was bound by its own load -> sync -> rank ->
+// sync -> reserve -> sync -> stage -> sync -> store -> sync chain, 13 us per tile, not by NVLink):
+//   * tiles are fetched with 16-byte cp.async into a double buffer: tile i + 1 is in flight while tile i is grouped;
+//   * three barriers per tile: rows landed | ranks known | staged; every warp derives the run offsets it needs from the
+//     tile's histogram by a shuffle scan, only warp 0 publishes them (and reserves) for the store phase;
+//   * the reservation of a tile's space is either free (chunk mode: G > 1 consecutive tiles were counted and reserved at
+//     once) or a remote atomic issued by warp 0 while the other warps stage;
+//   * runs leave as 16-byte stores (push_run).
+// gmax: most tiles per reservation (P2P_CHUNK_TILES; WK_P2P_G overrides it for experiments).  dbg (WK_P2P_DEBUG, timing
+// experiments of scripts/exchange_bench.py only -- the received tables are garbage): 1 = rows owned by peers are not stored,
+// 2 = no reservations (every tile writes at its own row index).
 template <int RPT>
-__global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
+__global__ void __launch_bounds__(CTA_THREADS, 5) p2p_push_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
                                                                   int C, int col, int dup, int dst_buf, uint64_t epoch, uint64_t cap_rows,
                                                                   uint32_t *status, int ready_inside, int gmax, int dbg) {
-    // gmax: most tiles per reservation (P2P_CHUNK_TILES; WK_P2P_G overrides it for experiments).  dbg (WK_P2P_DEBUG, timing
-    // experiments of scripts/exchange_bench.py only -- the received tables are garbage): 1 = rows owned by peers are not stored,
-    // 2 = no reservations (every tile writes at its own row index).
-    extern __shared__ uint32_t p2p_dyn[];
+    extern __shared__ __align__(16) uint32_t p2p_dyn[];
     constexpr uint32_t TILE = CTA_THREADS * RPT;
-    uint32_t *rows = p2p_dyn, *stage = p2p_dyn + (size_t)TILE * C;
-    __shared__ uint32_t hist[P2P_MAX_RANKS], off[P2P_MAX_RANKS + 1], chist[P2P_MAX_RANKS], crun[P2P_MAX_RANKS];
-    __shared__ uint64_t base[P2P_MAX_RANKS], cbase[P2P_MAX_RANKS];
+    const uint32_t tile_words = TILE * (uint32_t)C;
+    uint32_t *stage = p2p_dyn + 2 * (size_t)tile_words;
+    __shared__ uint32_t hist[2][P2P_MAX_RANKS], off[P2P_MAX_RANKS + 1], chist[P2P_MAX_RANKS];
+    __shared__ uint64_t base[P2P_MAX_RANKS];
     __shared__ uint32_t last, s_ovf;
     __shared__ int s_ok;
     const uint32_t n = (uint32_t)t.nranks;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
     if (ready_inside) {
         if (tid == 0) s_ok = 1;
         __syncthreads();
@@ -264,127 +294,169 @@ __global__ void __launch_bounds__(CTA_THREADS, 6) p2p_push_kernel(P2PTable t, Xc
     const bool bad = __ldcg(status) != 0 || ld_sys_u64(&my->poison) != 0;
     const uint64_t N = bad ? 0 : ld_count(in_count);
     if (tid == 0) s_ovf = (__ldcg(status) & 1u) ? 1u : 0u;
-    uint64_t sent = 0, kept = 0;
-    // Space in the owners' buffers is reserved once per CHUNK of G consecutive tiles, not per tile: the reservation is an atomic on
-    // ONE word per owner that every CTA of every rank hits, and same-address atomics retire one after the other (measured: the
-    // per-tile version spent ~6 ns per tile and owner, 0.6 ms of a 107 M-row exchange).  The chunk is counted first (key column
-    // only), then its tiles are loaded again -- from L2 -- grouped and pushed.  G grows with the table so that small tables
-    // still spread over the whole grid.
+    if (tid < P2P_MAX_RANKS) { hist[0][tid] = 0; hist[1][tid] = 0; }
+    uint64_t sent = 0, kept = 0;      // threads tid < n: rows reserved at owner tid
+    uint64_t cbase = 0;               // threads tid < n: start of the running chunk's reservation at owner tid (~0: refused)
+    uint32_t crun = 0;                //                  rows of the chunk already placed there
+    // Space in the owners' buffers is reserved per CHUNK of G consecutive tiles when the table is long enough: the reservation
+    // is an atomic on ONE word per owner that every CTA of every rank hits.  The chunk is counted first (key column only),
+    // its tiles then come from L2.  G grows with the table so that every CTA still gets several chunks.
     const uint64_t tiles_total = (N + TILE - 1) / TILE;
-    uint32_t G = (uint32_t)(tiles_total / ((uint64_t)gridDim.x * 4));      // at least ~4 chunks per CTA: no long tail
+    uint32_t G = (uint32_t)(tiles_total / ((uint64_t)gridDim.x * 4));
     G = G < 1 ? 1 : (G > (uint32_t)gmax ? (uint32_t)gmax : G);
-    const uint64_t CH = (uint64_t)G * TILE;
-    const uint32_t lane = tid & 31u;
+    const uint64_t CH = (uint64_t)G * TILE, stride = (uint64_t)gridDim.x * CH;
+    const bool chunked = dup || G > 1;
+
+    // fetch rows [t0, t0 + nrows) into buffer b; one cp.async group per tile (empty groups keep the count regular)
+    auto fetch = [&](uint32_t b, uint64_t t0, uint32_t nrows) {
+        const uint32_t words = nrows * (uint32_t)C;
+        const uint32_t *src = in + t0 * (uint64_t)C;
+        if (nrows == TILE && (tile_words & 3u) == 0) {
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(p2p_dyn + (size_t)b * tile_words);
+            for (uint32_t v = tid; v < (words >> 2); v += CTA_THREADS) cp_async16(d0 + v * 16, src + v * 4);
+        } else {
+            uint32_t *dstw = p2p_dyn + (size_t)b * tile_words;
+            for (uint32_t w = tid; w < words; w += CTA_THREADS) dstw[w] = ld_table(src + w);
+        }
+        cp_async_commit();
+    };
+    uint64_t c0 = (uint64_t)blockIdx.x * CH;     // start of the running chunk
+    uint32_t q0 = 0, p = 0;                      // running tile's offset inside the chunk; its buffer
+    if (c0 < N) fetch(0, c0, (uint32_t)((N - c0 < TILE) ? (N - c0) : TILE));
     __syncthreads();
-    for (uint64_t c0 = (uint64_t)blockIdx.x * CH; c0 < N; c0 += (uint64_t)gridDim.x * CH) {
+    while (c0 < N) {
         const uint32_t crows = (uint32_t)((N - c0 < CH) ? (N - c0) : CH);
-        // ---- count the chunk and reserve ---------------------------------------------------------------------------------
-        if (tid < P2P_MAX_RANKS) { chist[tid] = 0; crun[tid] = 0; }
-        __syncthreads();
-        if (!dup) {
-            if (G > 1) {
+        // ---- chunk prologue: count and reserve ----------------------------------------------------------------------------
+        if (q0 == 0 && chunked) {
+            if (!dup) {
+                if (tid < P2P_MAX_RANKS) chist[tid] = 0;
+                __syncthreads();
                 const uint32_t *key = in + c0 * (uint64_t)C + col;
-                for (uint32_t r0 = 0; r0 < crows; r0 += CTA_THREADS) {
-                    const uint32_t r = r0 + tid;
-                    const uint32_t d = r < crows ? ld_table(key + (uint64_t)r * C) % n : 0xFFFFFFFFu;
-                    for (uint32_t dd = 0; dd < n; dd++) {
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, d == dd);
-                        if (lane == 0 && m) atomicAdd(&chist[dd], __popc(m));
+                for (uint32_t r0 = 0; r0 < crows; r0 += 4 * CTA_THREADS) {
+                    uint32_t d[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t r = r0 + (uint32_t)j * CTA_THREADS + tid;
+                        d[j] = r < crows ? ld_table(key + (uint64_t)r * C) : 0xFFFFFFFFu;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t dj = d[j] == 0xFFFFFFFFu ? 0xFFFFFFFFu : d[j] % n;
+                        for (uint32_t dd = 0; dd < n; dd++) {
+                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, dj == dd);
+                            if (lane == 0 && m) atomicAdd(&chist[dd], __popc(m));
+                        }
                     }
                 }
                 __syncthreads();
             }
-        } else if (tid < n) {
-            chist[tid] = crows;
-        }
-        if (dup || G > 1) {
-            if (dup) __syncthreads();
             if (tid < n) {
+                const uint32_t want = dup ? crows : chist[tid];
                 uint64_t b = 0;
                 if (dbg & 2) {
                     b = c0;
-                } else if (chist[tid]) {
-                    b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)chist[tid]);
-                    if (b + chist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }   // the owner's buffer is full: drop the run, flag it
-                    else if (tid != (uint32_t)t.rank) sent += chist[tid];
-                    else kept += chist[tid];
+                } else if (want) {
+                    b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)want);
+                    if (b + want > cap_rows) { b = ~0ull; s_ovf = 1; }   // the owner's buffer is full: drop the run, flag it
+                    else if (tid != (uint32_t)t.rank) sent += want;
+                    else kept += want;
                 }
-                cbase[tid] = b;
+                cbase = b;
+                crun = 0;
             }
-            __syncthreads();
         }
-        // ---- the chunk's tiles -------------------------------------------------------------------------------------------
-        for (uint32_t q0 = 0; q0 < crows; q0 += TILE) {
-            const uint64_t t0 = c0 + q0;
-            const uint32_t nrows = (crows - q0 < TILE) ? (crows - q0) : TILE;
-            const uint32_t words = nrows * (uint32_t)C;
-            if (tid < P2P_MAX_RANKS) hist[tid] = 0;
-            const uint32_t *src = in + t0 * (uint64_t)C;
-            for (uint32_t w = tid; w < words; w += CTA_THREADS) rows[w] = ld_table(src + w);
-            __syncthreads();
-            if (!dup) {
-                uint32_t d[RPT], local[RPT];
+        // ---- the running tile; the next one (same chunk, or the first of this CTA's next chunk) is fetched meanwhile -------
+        const uint64_t t0 = c0 + q0;
+        const uint32_t nrows = (crows - q0 < TILE) ? (crows - q0) : TILE;
+        const uint32_t words = nrows * (uint32_t)C;
+        uint64_t nc0 = c0;
+        uint32_t nq0 = q0 + TILE;
+        if (nq0 >= crows) { nc0 = c0 + stride; nq0 = 0; }
+        if (nc0 < N) {
+            const uint64_t left = N - (nc0 + nq0);
+            const uint64_t cleft = ((N - nc0 < CH) ? (N - nc0) : CH) - nq0;
+            const uint64_t m = left < cleft ? left : cleft;
+            fetch(p ^ 1u, nc0 + nq0, (uint32_t)(m < TILE ? m : TILE));
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                                            // (A) the tile's rows are in shared memory
+        const uint32_t *rows = p2p_dyn + (size_t)p * tile_words;
+        if (!dup) {
+            if (tid < P2P_MAX_RANKS) hist[p ^ 1u][tid] = 0;       // the next tile's histogram
+            uint32_t d[RPT], local[RPT];
 #pragma unroll
-                for (int j = 0; j < RPT; j++) {
-                    const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
-                    d[j] = r < nrows ? rows[r * C + col] % n : 0xFFFFFFFFu;
-                    local[j] = 0;
-                    // rank of the row among the tile's rows of the same owner: one shared-memory atomic per warp and owner
-                    for (uint32_t dd = 0; dd < n; dd++) {
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, d[j] == dd);
-                        uint32_t wb = 0;
-                        if (lane == 0 && m) wb = atomicAdd(&hist[dd], __popc(m));
-                        wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
-                        if (d[j] == dd) local[j] = wb + __popc(m & ((1u << lane) - 1u));
-                    }
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    uint32_t run = 0;
-                    for (uint32_t dd = 0; dd < n; dd++) { off[dd] = run * (uint32_t)C; run += hist[dd]; }   // in words
-                    off[n] = run * (uint32_t)C;
-                }
-                if (tid < n) {
-                    uint64_t b = 0;
-                    if (G > 1) {
-                        b = cbase[tid] == ~0ull ? ~0ull : cbase[tid] + crun[tid];
-                        crun[tid] += hist[tid];
-                    } else if (dbg & 2) {
-                        b = t0;
-                    } else if (hist[tid]) {
-                        b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)hist[tid]);
-                        if (b + hist[tid] > cap_rows) { b = ~0ull; s_ovf = 1; }
-                        else if (tid != (uint32_t)t.rank) sent += hist[tid];
-                        else kept += hist[tid];
-                    }
-                    base[tid] = b;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < RPT; j++) {
-                    const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
-                    if (r < nrows) {
-                        uint32_t *q = stage + off[d[j]] + local[j] * (uint32_t)C;
-                        for (int c = 0; c < C; c++) q[c] = rows[r * C + c];
-                    }
-                }
-                __syncthreads();
-                for (uint32_t w = tid; w < words; w += CTA_THREADS) {
-                    uint32_t dd = 0;
-                    while (w >= off[dd + 1]) dd++;
-                    const uint64_t b = base[dd];
-                    if (b != ~0ull && !((dbg & 1) && dd != (uint32_t)t.rank)) t.buf[dst_buf][dd][b * (uint64_t)C + (w - off[dd])] = stage[w];
-                }
-            } else {
+            for (int j = 0; j < RPT; j++) {
+                const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
+                d[j] = r < nrows ? rows[r * C + col] % n : 0xFFFFFFFFu;
+                local[j] = 0;
+                // rank of the row among the tile's rows of the same owner: one shared-memory atomic per warp and owner
                 for (uint32_t dd = 0; dd < n; dd++) {
-                    if (cbase[dd] == ~0ull) continue;
-                    uint32_t *dst = t.buf[dst_buf][dd] + (cbase[dd] + q0) * (uint64_t)C;
-                    for (uint32_t w = tid; w < words; w += CTA_THREADS) dst[w] = rows[w];
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, d[j] == dd);
+                    uint32_t wb = 0;
+                    if (lane == 0 && m) wb = atomicAdd(&hist[p][dd], __popc(m));
+                    wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
+                    if (d[j] == dd) local[j] = wb + __popc(m & ((1u << lane) - 1u));
                 }
             }
+            __syncthreads();                                        // (B) the histogram is complete
+            // exclusive prefix of the histogram (rows), by every warp for itself: lane dd holds owner dd's run start
+            const uint32_t hv = lane < n ? hist[p][lane] : 0;
+            uint32_t incl = hv;
+#pragma unroll
+            for (int o = 1; o < P2P_MAX_RANKS; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((int)lane >= o) incl += y;
+            }
+            const uint32_t excl = incl - hv;
+            if (tid < n) {                                          // warp 0 publishes run offsets and destinations
+                off[tid] = excl * (uint32_t)C;
+                if (tid == n - 1) off[n] = incl * (uint32_t)C;
+                uint64_t b = 0;
+                if (chunked) {
+                    b = cbase == ~0ull ? ~0ull : cbase + crun;
+                    crun += hv;
+                } else if (dbg & 2) {
+                    b = t0;
+                } else if (hv) {
+                    b = atomicAdd_system((unsigned long long *)&t.ctl[tid]->recv_count, (unsigned long long)hv);
+                    if (b + hv > cap_rows) { b = ~0ull; s_ovf = 1; }
+                    else if (tid != (uint32_t)t.rank) sent += hv;
+                    else kept += hv;
+                }
+                base[tid] = b;
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
+                const uint32_t o = __shfl_sync(0xFFFFFFFFu, excl, d[j] & 31u);
+                if (r < nrows) {
+                    uint32_t *q = stage + (o + local[j]) * (uint32_t)C;
+                    for (int c = 0; c < C; c++) q[c] = rows[r * C + c];
+                }
+            }
+            __syncthreads();                                        // (C) staged, destinations known
+            for (uint32_t dd = 0; dd < n; dd++) {
+                const uint64_t b = base[dd];
+                const uint32_t L = off[dd + 1] - off[dd];
+                if (b == ~0ull || L == 0 || ((dbg & 1) && dd != (uint32_t)t.rank)) continue;
+                push_run(t.buf[dst_buf][dd] + b * (uint64_t)C, stage + off[dd], L, tid);
+            }
+        } else {
+            if (tid < n) base[tid] = cbase == ~0ull ? ~0ull : cbase + q0;
             __syncthreads();
+            for (uint32_t dd = 0; dd < n; dd++) {
+                if (base[dd] == ~0ull || ((dbg & 1) && dd != (uint32_t)t.rank)) continue;
+                push_run(t.buf[dst_buf][dd] + base[dd] * (uint64_t)C, rows, words, tid);
+            }
+            __syncthreads();   // base[] is rewritten by the next tile before its first barrier
         }
+        c0 = nc0;
+        q0 = nq0;
+        p ^= 1u;
     }
+    cp_async_wait<0>();
     if (sent) {
         atomicAdd((unsigned long long *)&loc->rows_sent, (unsigned long long)sent);
         atomicAdd((unsigned long long *)&loc->bytes_pushed, (unsigned long long)(sent * (uint64_t)C * 4ull));
