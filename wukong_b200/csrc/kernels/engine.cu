@@ -2506,8 +2506,9 @@ static int exchange_table_p2p(wk_engine *e, int col) {
     // inside the push kernel (one launch less)
     const bool ready_inside = !c->local_group;
     // tile = 1024 / 512 / 256 rows: two row buffers (the next tile is in flight while this one is grouped) + the staging area
-    // stay within ~30 KB of shared memory for up to 9 columns, so 5-6 CTAs fit an SM
-    const int rpt = C <= 2 ? 4 : (C <= 5 ? 2 : 1);
+    // = 36 KB of shared memory for three columns, 4-5 CTAs per SM (large tiles: the fetch of the next tile has a whole tile's
+    // work to hide behind)
+    const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
     const size_t smem = 3 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
     void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, uint32_t *, int, int, int) =
         rpt == 4 ? p2p_push_kernel<4> : (rpt == 2 ? p2p_push_kernel<2> : p2p_push_kernel<1>);

@@ -299,10 +299,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) p2p_push_kernel(P2PTable t, Xc
     uint64_t cbase = 0;               // threads tid < n: start of the running chunk's reservation at owner tid (~0: refused)
     uint32_t crun = 0;                //                  rows of the chunk already placed there
     // Space in the owners' buffers is reserved per CHUNK of G consecutive tiles when the table is long enough: the reservation
-    // is an atomic on ONE word per owner that every CTA of every rank hits.  The chunk is counted first (key column only),
-    // its tiles then come from L2.  G grows with the table so that every CTA still gets several chunks.
+    // is an atomic on ONE word per owner that every CTA of every rank hits (measured on 2 GPUs, 64 M rows: one reservation per
+    // tile costs 0.34 ms of 1.10 ms).  The chunk is counted first (key column only: that pass also pulls the chunk into L2),
+    // its tiles then come from L2.  G grows with the table: a table of up to one tile per CTA keeps per-tile reservations.
     const uint64_t tiles_total = (N + TILE - 1) / TILE;
-    uint32_t G = (uint32_t)(tiles_total / ((uint64_t)gridDim.x * 4));
+    uint32_t G = (uint32_t)(tiles_total / (uint64_t)gridDim.x);
     G = G < 1 ? 1 : (G > (uint32_t)gmax ? (uint32_t)gmax : G);
     const uint64_t CH = (uint64_t)G * TILE, stride = (uint64_t)gridDim.x * CH;
     const bool chunked = dup || G > 1;
@@ -332,15 +333,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) p2p_push_kernel(P2PTable t, Xc
                 if (tid < P2P_MAX_RANKS) chist[tid] = 0;
                 __syncthreads();
                 const uint32_t *key = in + c0 * (uint64_t)C + col;
-                for (uint32_t r0 = 0; r0 < crows; r0 += 4 * CTA_THREADS) {
-                    uint32_t d[4];
+                for (uint32_t r0 = 0; r0 < crows; r0 += 16 * CTA_THREADS) {      // 16 independent loads in flight per thread
+                    uint32_t d[16];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < 16; j++) {
                         const uint32_t r = r0 + (uint32_t)j * CTA_THREADS + tid;
                         d[j] = r < crows ? ld_table(key + (uint64_t)r * C) : 0xFFFFFFFFu;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < 16; j++) {
                         const uint32_t dj = d[j] == 0xFFFFFFFFu ? 0xFFFFFFFFu : d[j] % n;
                         for (uint32_t dd = 0; dd < n; dd++) {
                             const uint32_t m = __ballot_sync(0xFFFFFFFFu, dj == dd);
