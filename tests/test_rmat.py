@@ -73,3 +73,39 @@ def test_rmat_device_built_store(rmat_mid):
     assert np.array_equal(np.sort(subj), np.sort(hs.get_edges(0, P, O.IN)))
     eng.close()
     gst.close()
+
+
+def test_scramble_is_a_relabelling_and_streams_do_not_depend_on_threads():
+    """CPU: the Graph500-style scramble permutes vertex labels (same degree multiset as the raw R-MAT graph, no longer
+    readable from the low id bits), and the edge list is a function of (scale, edges, seed) only -- ranks of a sharded run
+    generate it with different thread counts and must agree"""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    scale, ne = 12, 200000
+    raw = datagen.rmat(scale, ne, seed=5, typed=False, scramble=False)
+    scr = datagen.rmat(scale, ne, seed=5, typed=False, scramble=True)
+    assert raw.shape == scr.shape == (ne, 3)
+    base = 1 << 17
+    assert scr[:, [0, 2]].min() >= base and scr[:, [0, 2]].max() < base + (1 << scale)
+    for c in (0, 2):
+        d_raw = np.sort(np.unique(raw[:, c], return_counts=True)[1])
+        d_scr = np.sort(np.unique(scr[:, c], return_counts=True)[1])
+        assert np.array_equal(d_raw, d_scr)
+    # the same edge keeps its place in the list, so the relabelling is one map for subjects and objects alike
+    m = {}
+    for a, b in zip(raw[:, 0].tolist() + raw[:, 2].tolist(), scr[:, 0].tolist() + scr[:, 2].tolist()):
+        assert m.setdefault(a, b) == b
+    assert len(set(m.values())) == len(m)
+    # raw ids: the out-degree mass of ids = 0 mod 8 is several times 1/8; scrambled: close to 1/8
+    share_raw = float((raw[:, 0] % 8 == 0).mean())
+    share_scr = float((scr[:, 0] % 8 == 0).mean())
+    assert share_raw > 0.3 and abs(share_scr - 0.125) < 0.05, (share_raw, share_scr)
+    code = ("import sys, hashlib; sys.path.insert(0, %r); from wukong_b200 import datagen; "
+            "print(hashlib.sha256(datagen.rmat(%d, %d, seed=5, typed=False).tobytes()).hexdigest())" % (ROOT, scale, ne))
+    outs = set()
+    for nt in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=nt)
+        outs.add(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300).stdout.strip())
+    assert len(outs) == 1 and len(next(iter(outs))) == 64, outs
