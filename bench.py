@@ -542,6 +542,8 @@ def run_sharded(args, rank, world, local_rank, dist):
             dev_us[q].append(d)
             srv_ns[q].append(ns)
     eng.set_profiling(0)
+    stats = eng.comm_stats()       # communication of the K blind steps (the end-to-end pass below repeats the same exchanges)
+    bytes_pushed = (eng.get_option(capi.WK_INFO_COMM_BYTES_PUSHED) - bytes0) if args.exchange == "p2p" else 0
     # end to end: non-blind, every rank receives its share of the projected table in pinned host memory
     for _ in range(args.steps):
         for q in QUERIES:
@@ -553,8 +555,6 @@ def run_sharded(args, rank, world, local_rank, dist):
     t_region = time.time() - t_region0
     clocks = sampler.stop()
     launches = eng.launch_count() - launches0
-    stats = eng.comm_stats()
-    bytes_pushed = (eng.get_option(capi.WK_INFO_COMM_BYTES_PUSHED) - bytes0) if args.exchange == "p2p" else 0
     # ---- per-step pass (CUDA events per step and per exchange): where the time goes, NVLink GB/s of the exchanges ----------
     eng.set_profiling(2)
     agg = {}

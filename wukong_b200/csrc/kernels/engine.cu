@@ -2510,7 +2510,7 @@ static int exchange_table_p2p(wk_engine *e, int col) {
     // work to hide behind)
     const int rpt = C <= 4 ? 4 : (C <= 8 ? 2 : 1);
     const size_t smem = 3 * (size_t)CTA_THREADS * rpt * C * sizeof(uint32_t);
-    void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, uint32_t *, int, int, int) =
+    void (*kfn)(P2PTable, XchCtl *, P2PLocal *, const uint32_t *, const uint64_t *, int, int, int, int, uint64_t, uint64_t, uint32_t *, int, int, int, uint32_t) =
         rpt == 4 ? p2p_push_kernel<4> : (rpt == 2 ? p2p_push_kernel<2> : p2p_push_kernel<1>);
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // several CTAs per SM hide the barriers of the tile pipeline and the round trip of the remote reservations
@@ -2525,7 +2525,8 @@ static int exchange_table_p2p(wk_engine *e, int col) {
     StepRecord &r = begin_step(e, KIND_EXCHANGE, C);
     if (!ready_inside) p2p_ready_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, &e->d_ctl->status);
     kfn<<<grid, CTA_THREADS, smem, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, e->buf[s & 1], &e->d_ctl->counts[s], C, dup ? 0 : col,
-                                                dup ? 1 : 0, (s + 1) & 1, epoch, cap_rows, &e->d_ctl->status, ready_inside ? 1 : 0, k_gmax, k_dbg);
+                                                dup ? 1 : 0, (s + 1) & 1, epoch, cap_rows, &e->d_ctl->status, ready_inside ? 1 : 0, k_gmax, k_dbg,
+                                                c->nranks > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)c->nranks - 1) / (uint64_t)c->nranks) : 0u);
     p2p_wait_kernel<<<1, 64, 0, e->stream>>>(*c->p2p, c->d_xctl, c->d_p2p_local, epoch, cap_rows, &e->d_ctl->counts[s + 1], &e->d_ctl->status,
                                              &e->d_ctl->stats[2 * s]);
     CUDA_TRY(cudaGetLastError());

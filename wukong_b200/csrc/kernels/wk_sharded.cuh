@@ -191,7 +191,7 @@ struct P2PTable {
     int nranks, rank;
 };
 enum { P2P_MAX_RANKS = MAX_PARTS / 4 };
-enum { P2P_CHUNK_TILES = 16 };   // tiles per reservation of the push kernel (see p2p_push_kernel)
+enum { P2P_CHUNK_TILES = 8 };    // tiles per reservation of the push kernel (see p2p_push_kernel): the chunks of all CTAs together must stay in L2
 
 struct P2PLocal {                            // device scratch of one rank
     uint32_t done_ctas;
@@ -220,6 +220,14 @@ __global__ void p2p_ready_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t
         if (p < t.nranks) st_sys_u64(&t.ctl[p]->poison, 1);
         if (p == 0) atomicOr(status, 2u);
     }
+}
+
+// x % n for n <= 2^16 without a division: magic = ceil(2^32 / n) (host side; n = 1 is handled by the caller)
+__device__ __forceinline__ uint32_t mod_small(uint32_t x, uint32_t n, uint32_t magic) {
+    const uint32_t q = __umulhi(x, magic);       // floor(x / n) or one more
+    int32_t r = (int32_t)(x - q * n);
+    if (r < 0) r += (int32_t)n;
+    return (uint32_t)r;
 }
 
 // L words of shared memory -> global words dst[0 .. L): the head up to the first 16-byte boundary of dst and the tail as
@@ -261,7 +269,7 @@ __device__ __forceinline__ void push_run(uint32_t *dst, const uint32_t *src, uin
 template <int RPT>
 __global__ void __launch_bounds__(CTA_THREADS, 5) p2p_push_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, const uint32_t *in, const uint64_t *in_count,
                                                                   int C, int col, int dup, int dst_buf, uint64_t epoch, uint64_t cap_rows,
-                                                                  uint32_t *status, int ready_inside, int gmax, int dbg) {
+                                                                  uint32_t *status, int ready_inside, int gmax, int dbg, uint32_t nmagic) {
     extern __shared__ __align__(16) uint32_t p2p_dyn[];
     constexpr uint32_t TILE = CTA_THREADS * RPT;
     const uint32_t tile_words = TILE * (uint32_t)C;
@@ -342,11 +350,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) p2p_push_kernel(P2PTable t, Xc
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        const uint32_t dj = d[j] == 0xFFFFFFFFu ? 0xFFFFFFFFu : d[j] % n;
-                        for (uint32_t dd = 0; dd < n; dd++) {
-                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, dj == dd);
-                            if (lane == 0 && m) atomicAdd(&chist[dd], __popc(m));
-                        }
+                        // lanes with the same owner elect one of them to add their number (rows past the end share owner ~0)
+                        const uint32_t dj = d[j] == 0xFFFFFFFFu ? 0xFFFFFFFFu : (n == 1 ? 0u : mod_small(d[j], n, nmagic));
+                        const uint32_t m = __match_any_sync(0xFFFFFFFFu, dj);
+                        if (lane == (uint32_t)__ffs(m) - 1u && dj != 0xFFFFFFFFu) atomicAdd(&chist[dj], __popc(m));
                     }
                 }
                 __syncthreads();
@@ -390,16 +397,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) p2p_push_kernel(P2PTable t, Xc
 #pragma unroll
             for (int j = 0; j < RPT; j++) {
                 const uint32_t r = tid + (uint32_t)j * CTA_THREADS;
-                d[j] = r < nrows ? rows[r * C + col] % n : 0xFFFFFFFFu;
-                local[j] = 0;
-                // rank of the row among the tile's rows of the same owner: one shared-memory atomic per warp and owner
-                for (uint32_t dd = 0; dd < n; dd++) {
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, d[j] == dd);
-                    uint32_t wb = 0;
-                    if (lane == 0 && m) wb = atomicAdd(&hist[p][dd], __popc(m));
-                    wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
-                    if (d[j] == dd) local[j] = wb + __popc(m & ((1u << lane) - 1u));
-                }
+                d[j] = r < nrows ? (n == 1 ? 0u : mod_small(rows[r * C + col], n, nmagic)) : 0xFFFFFFFFu;
+                // rank of the row among the tile's rows of the same owner: the lanes of a warp that share an owner elect a leader,
+                // which takes their places with one shared-memory atomic
+                const uint32_t m = __match_any_sync(0xFFFFFFFFu, d[j]);
+                const uint32_t leader = (uint32_t)__ffs(m) - 1u;
+                uint32_t wb = 0;
+                if (lane == leader && d[j] != 0xFFFFFFFFu) wb = atomicAdd(&hist[p][d[j]], __popc(m));
+                wb = __shfl_sync(0xFFFFFFFFu, wb, leader);
+                local[j] = wb + __popc(m & ((1u << lane) - 1u));
             }
             __syncthreads();                                        // (B) the histogram is complete
             // exclusive prefix of the histogram (rows), by every warp for itself: lane dd holds owner dd's run start
