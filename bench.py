@@ -57,7 +57,7 @@ def load_plans(plan):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and clock-event (throttle) reasons of one GPU sampled DURING the timed region: NVML in this process every 10 ms
+    """SM clock and clock-event (throttle) reasons of one GPU sampled DURING the timed region: NVML in this process every 25 ms
     (the counters nvidia-smi prints; a subprocess of nvidia-smi -lms needs seconds to deliver its first line on an 8-GPU
     host, longer than a sharded run's timed region), falling back to `nvidia-smi -lms 20` when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -92,7 +92,7 @@ class ClockSampler(threading.Thread):
             sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
             bits = int(get(h))
             self.rows.append((time.time(), sm, mx, {nm for nm, b in self.BITS if bits & b}))
-            self.quit.wait(0.01)
+            self.quit.wait(0.025)
 
     def run_smi(self):
         self.source = "nvidia-smi"
@@ -130,7 +130,7 @@ class ClockSampler(threading.Thread):
             reasons |= r[3]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": (max(r[2] for r in use) if use else None),
                 "reasons": sorted(reasons), "samples": len(rows), "samples_in_timed_region": len(timed), "source": self.source,
-                "note": "sampled from the start of warm-up to the end of the timed region (NVML every 10 ms); sm_mhz / reasons over the "
+                "note": "sampled from the start of warm-up to the end of the timed region (NVML every 25 ms); sm_mhz / reasons over the "
                         "samples inside the timed region when there are any"}
 
 
