@@ -12,8 +12,60 @@ LIB = os.path.join(HERE, "_ref", "libwukong_ref.so")
 _lib = None
 
 
+GPU_LIB = os.path.join(HERE, "_ref", "libwukong_ref_gpu.so")
+_gpu_lib = None
+
+
 def available():
     return os.path.exists(LIB)
+
+
+def gpu_binding_available():
+    return os.path.exists(GPU_LIB)
+
+
+def gpu_lib():
+    """the reference's GPUEngine over integration/gpu_engine_cuda.hpp (ref_gpu_engine_shim.cpp); needs a GPU to run a query"""
+    global _gpu_lib
+    if _gpu_lib is None:
+        L = C.CDLL(GPU_LIB)
+        u64, vp, ci = C.c_uint64, C.c_void_p, C.c_int
+        L.refs_build.restype = vp
+        L.refs_build.argtypes = [vp, u64, ci, ci, ci, ci, ci]
+        L.refg_query.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, vp, u64, C.POINTER(u64), C.POINTER(ci)]
+        L.refs_get_edges.restype = u64
+        L.refs_get_edges.argtypes = [vp, C.c_uint32, C.c_uint32, ci, C.POINTER(vp)]
+        _gpu_lib = L
+    return _gpu_lib
+
+
+class RefGpuEngine:
+    """a store built by the reference's StaticGStore::init, queried through the reference's GPUEngine::execute_one_pattern
+    whose backend is the replacement GPUEngineCuda (calls into libwukong_b200.so)"""
+
+    def __init__(self, triples, num_normal_preds=31, memstore_gb=1):
+        t = np.ascontiguousarray(triples, dtype=np.uint32).reshape(-1, 3)
+        self.h = gpu_lib().refs_build(t.ctypes.data_as(C.c_void_p), t.shape[0], 1, 0, 1, memstore_gb, num_normal_preds)
+        self._out = np.empty(1 << 24, dtype=np.uint32)
+
+    def get_edges(self, vid, pid, d):
+        """GStore::get_edges of the store built under -DUSE_GPU (CPU probe)"""
+        p = C.c_void_p()
+        n = gpu_lib().refs_get_edges(self.h, vid, pid, d, C.byref(p))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+
+    def query(self, patterns, nvars, required, blind=False, rbuf_mb=64):
+        """-> (status, rows, cols, raw table of the pattern phase: one column per bound variable, in binding order)"""
+        p = np.array(patterns, dtype=np.int32).reshape(-1, 4)
+        rq = np.array(required, dtype=np.int32)
+        rows, cols = C.c_uint64(0), C.c_int(0)
+        rc = gpu_lib().refg_query(self.h, p.ctypes.data_as(C.c_void_p), p.shape[0], nvars, rq.ctypes.data_as(C.c_void_p) if len(rq) else None,
+                                  len(rq), 1 if blind else 0, rbuf_mb, self._out.ctypes.data_as(C.c_void_p), self._out.size,
+                                  C.byref(rows), C.byref(cols))
+        tbl = None
+        if rc == 0 and not blind and cols.value:
+            tbl = self._out[: rows.value * cols.value].reshape(rows.value, cols.value).copy()
+        return rc, rows.value, cols.value, tbl
 
 
 def build():

@@ -66,9 +66,10 @@ void *refs_build(const uint32_t *tr, uint64_t n, int num_servers, int sid, int n
         const segid_t &id = kv.first;
         const rdf_seg_meta_t &m = kv.second;
         uint64_t e0s = 0, e0n = 0;
-        if (!m.ext_bucket_list.empty()) { e0s = m.ext_bucket_list[0].start; e0n = m.ext_bucket_list[0].num_ext_buckets; }
+        // get_ext_bucket_list_size(): the list is a vector in the CPU build and a fixed array under -DUSE_GPU (meta.hpp:86-111)
+        if (m.get_ext_bucket_list_size() > 0) { e0s = m.ext_bucket_list[0].start; e0n = m.ext_bucket_list[0].num_ext_buckets; }
         const uint64_t row[11] = {(uint64_t)id.index, (uint64_t)id.dir, (uint64_t)id.pid, m.num_keys, m.num_buckets, m.bucket_start,
-                                  m.num_edges, m.edge_start, (uint64_t)m.ext_bucket_list.size(), e0s, e0n};
+                                  m.num_edges, m.edge_start, (uint64_t)m.get_ext_bucket_list_size(), e0s, e0n};
         r->segs.insert(r->segs.end(), row, row + 11);
     }
     return r;
