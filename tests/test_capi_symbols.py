@@ -45,6 +45,11 @@ def test_device_arithmetic_matches_oracle():
         ns += [(int(x) << 1) | 1 for x in rng.integers(1 << 62, 1 << 63, 100)]
         for n in ns:
             assert L.wk_selftest_fastmod(n, d) == n % d, (n, d)
+    # the exchange's owner function (row[col] % nranks by multiply-shift with magic = ceil(2^32 / n)), every n a box can hold
+    xs = [0, 1, 2, 15, 16, 17, (1 << 17), (1 << 31) - 1, 1 << 31, (1 << 32) - 2, (1 << 32) - 1] + [int(x) for x in rng.integers(0, 1 << 32, 3000)]
+    for n in range(1, 17):
+        for x in xs:
+            assert L.wk_selftest_owner(x, n) == x % n, (x, n)
 
 
 def test_compute_fails_loudly_without_gpu():

@@ -152,6 +152,8 @@ def lib():
     L.wk_selftest_ptr_off.argtypes = [u64]
     L.wk_selftest_make_key.restype = u64
     L.wk_selftest_make_key.argtypes = [u64, u32, u32]
+    L.wk_selftest_owner.restype = u64
+    L.wk_selftest_owner.argtypes = [u64, u64]
     _lib = L
     return L
 

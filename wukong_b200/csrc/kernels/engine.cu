@@ -3090,6 +3090,11 @@ uint64_t wk_selftest_fastmod(uint64_t n, uint64_t d) { FastMod f = make_fastmod(
 uint64_t wk_selftest_make_key(uint64_t vid, uint32_t pid, uint32_t dir) { return make_key(vid, pid, dir); }
 uint64_t wk_selftest_ptr_size(uint64_t raw) { return ptr_size(raw); }
 uint64_t wk_selftest_ptr_off(uint64_t raw) { return ptr_off(raw); }
+// owner of a row in the exchange's push kernel: x % n by multiply-shift (wk_sharded.cuh), with the magic the host passes
+uint64_t wk_selftest_owner(uint64_t x, uint64_t n) {
+    if (n <= 1) return 0;
+    return mod_small((uint32_t)x, (uint32_t)n, (uint32_t)(((1ull << 32) + n - 1) / n));
+}
 
 }  // extern "C"
 

@@ -167,10 +167,11 @@ static void plan_exchanges(const std::vector<PlannedStep> &steps, std::vector<in
 // Peer-memory exchange (NVLink / NVSwitch, no NCCL, no host synchronisation), ONE pass over the table:
 //   ready   (1 CTA)  every rank tells every peer "all my earlier kernels are done" and waits for the same from them:
 //                    the peers' next-table buffers and receive counters may now be written;
-//   push    (grid)   a tile of rows is loaded with coalesced reads, grouped by owner in shared memory, space for every
-//                    owner's run is reserved with ONE atomic per (tile, owner) on the owner's receive counter -- a remote
-//                    atomic over NVLink for the peers -- and the runs are stored STRAIGHT INTO the owners' next-table
-//                    buffers as contiguous words; the last CTA fences system-wide and raises the "pushed" flags;
+//   push    (grid)   tiles of rows are fetched with cp.async into a double buffer, grouped by owner in shared memory, space
+//                    for the owners' runs is reserved with ONE atomic per (chunk of up to 8 tiles, owner) on the owner's
+//                    receive counter -- a remote atomic over NVLink for the peers -- and the runs are stored STRAIGHT INTO
+//                    the owners' next-table buffers as 16-byte stores; the last CTA fences system-wide and raises the
+//                    "pushed" flags (multi-device groups take barrier "ready" inside this kernel);
 //   wait    (1 CTA)  every peer has pushed: the receive counter is the new row count.
 // No count pass, no count matrix, no second pass over the table (round 1: count -> publish -> scatter -> wait).
 // Buffers and control blocks of the peers are mapped with CUDA IPC (one process per GPU) or wired directly for engines
@@ -223,8 +224,12 @@ __global__ void p2p_ready_kernel(P2PTable t, XchCtl *my, P2PLocal *loc, uint64_t
 }
 
 // x % n for n <= 2^16 without a division: magic = ceil(2^32 / n) (host side; n = 1 is handled by the caller)
-__device__ __forceinline__ uint32_t mod_small(uint32_t x, uint32_t n, uint32_t magic) {
+__host__ __device__ __forceinline__ uint32_t mod_small(uint32_t x, uint32_t n, uint32_t magic) {
+#ifdef __CUDA_ARCH__
     const uint32_t q = __umulhi(x, magic);       // floor(x / n) or one more
+#else
+    const uint32_t q = (uint32_t)(((uint64_t)x * magic) >> 32);
+#endif
     int32_t r = (int32_t)(x - q * n);
     if (r < 0) r += (int32_t)n;
     return (uint32_t)r;
