@@ -600,6 +600,11 @@ def run_sharded(args, rank, world, local_rank, dist):
                             "exchanges, barriers included; peak = measured peer copy per direction (B200_PROFILING.md), 900 GB/s nominal"}
     t = torch.tensor([np.mean(dev_us[q]) for q in QUERIES] + [np.mean(wall_us[q]) for q in QUERIES] + [np.mean(e2e_us[q]) for q in QUERIES] +
                      [1.0 if resident.get(q) else 0.0 for q in QUERIES], device="cuda", dtype=torch.float64)
+    # samples far off their query's median (a descheduled host thread stalls every rank of a collective query): reported, not removed
+    outl = torch.tensor([float(sum(1 for x in dev_us[q] if x > 3.0 * float(np.median(dev_us[q])))) for q in QUERIES] +
+                        [float(np.median(dev_us[q])) for q in QUERIES], device="cuda", dtype=torch.float64)
+    dist.all_reduce(outl, op=dist.ReduceOp.MAX)
+    outl = outl.cpu().numpy()
     # per rank, for the record: blind wall clock and in-kernel span of the server request of the light plans (owner vs waiting peers)
     per_rank = torch.zeros((world, 2 * len(LIGHT)), device="cuda", dtype=torch.float64)
     per_rank[rank] = torch.tensor([np.mean(wall_us[q]) for q in LIGHT] + [np.mean(srv_ns[q]) / 1e3 for q in LIGHT], dtype=torch.float64)
@@ -635,7 +640,9 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "gpu_launches": int(rr[8]), "clocks": clocks,
                 "latency_us": {"device": {"q%d" % q: round(float(dev_mean[i]), 2) for i, q in enumerate(QUERIES)},
                                "wall": {"q%d" % q: round(float(wall_mean[i]), 2) for i, q in enumerate(QUERIES)},
-                               "e2e": {"q%d" % q: round(float(e2e_mean[i]), 2) for i, q in enumerate(QUERIES)}},
+                               "e2e": {"q%d" % q: round(float(e2e_mean[i]), 2) for i, q in enumerate(QUERIES)},
+                               "device_median": {"q%d" % q: round(float(outl[7 + i]), 2) for i, q in enumerate(QUERIES)},
+                               "samples_over_3x_median": {"q%d" % q: int(outl[i]) for i, q in enumerate(QUERIES)}},
                 "light_path": {"resident_servers": {"q%d" % q: bool(res[i] > 0) for i, q in enumerate(QUERIES)},
                                "per_rank": {"q%d" % q: {"wall_us": [round(float(x), 2) for x in per_rank[:, j]],
                                                         "server_us": [round(float(x), 2) for x in per_rank[:, len(LIGHT) + j]]}
