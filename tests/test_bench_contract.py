@@ -72,3 +72,39 @@ def test_committed_sharded_lines_have_the_contract_keys():
         if d.get("secondary"):                              # the line carries the single-GPU run of the same store itself
             assert d["secondary"]["single_gpu_same_store"]["rows"] == want, f
         assert d["gpu_launches"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+
+
+def test_spin_barrier_of_the_sharded_bench_on_two_gloo_ranks(tmp_path):
+    """CPU: bench.SpinBarrier (dist.barrier + a generation counter per rank in /dev/shm, spun on) with two gloo ranks: no rank
+    passes generation g before every rank has reached it, the shared file is gone afterwards"""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    code = r'''
+import os, sys, time
+sys.path.insert(0, %r)
+import numpy as np
+import torch.distributed as dist
+import bench
+rank, world = int(sys.argv[1]), 2
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d", rank=rank, world_size=world)
+bar = bench.SpinBarrier(rank, world, dist)
+assert bar.a is not None and bar.a.shape[0] == 8 * world
+seen = []
+for g in range(1, 51):
+    if rank == 1 and g %% 10 == 0:
+        time.sleep(0.02)                     # a late rank: the other one must wait for it
+    bar.wait()
+    seen.append([int(x) for x in bar.slots])
+    assert min(seen[-1]) >= g, (g, seen[-1])  # nobody is past a barrier the other has not reached
+dist.barrier()
+assert not [f for f in os.listdir("/dev/shm") if f.startswith("wk_bench_%%d_" %% os.getpid())]
+dist.destroy_process_group()
+print("ok", rank)
+''' % (ROOT, port)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, cwd=ROOT) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o[-2000:]
