@@ -2,7 +2,7 @@
 """Counts, per kernel of libwukong_b200.so, the SASS instructions that prove which data-movement hardware a kernel uses
 (cuobjdump -sass, sm_100a): UBLKCP (cp.async.bulk, the TMA engine's 1-D copies), SYNCS (mbarrier), LDGSTS (cp.async),
 ACQBULK (griddepcontrol.wait of programmatic dependent launch), ATOMG...SYS (remote reservations over NVLink), CCTL.IVALL (L1
-invalidation of a gpu / system fence).  Writes the markdown table of profiles/r2_sass_evidence.md to stdout."""
+invalidation of a gpu / system fence), MATCH.ANY (the warp-level owner grouping of the exchange), STG.E.128 (its 16-byte stores).  Writes the markdown table of profiles/r2_sass_evidence.md to stdout."""
 import collections
 import os
 import re
@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "wukong_b200", "libwukong_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(["c++filt"], input="\n".join(re.findall(r"Function : (\S+)", txt)), capture_output=True, text=True).stdout.split("\n")
-PAT = re.compile(r"\b(UBLKCP(?:\.\w+)*|UTMALDG(?:\.\w+)*|SYNCS(?:\.\w+)*|LDGSTS(?:\.\w+)*|ACQBULK|ATOMG(?:\.\w+)*\.SYS|CCTL\.IVALL)\b")
+PAT = re.compile(r"\b(UBLKCP(?:\.\w+)*|UTMALDG(?:\.\w+)*|SYNCS(?:\.\w+)*|LDGSTS(?:\.\w+)*|ACQBULK|ATOMG(?:\.\w+)*\.SYS|CCTL\.IVALL|MATCH\.ANY|STG\.E\.128)\b")
 counts = collections.OrderedDict()
 cur, k = None, -1
 for line in txt.split("\n"):
